@@ -1,0 +1,61 @@
+"""ctypes binding of libbdm_b200.so (the C-ABI declared in include/bdm_b200.h).
+
+There is NO fallback: if the library is missing or does not load, importing this module raises.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "libbdm_b200.so")
+
+if not os.path.exists(SO_PATH):
+    raise ImportError(
+        f"{SO_PATH} not found: build it with `python -m bdm_b200.build` (nvcc, sm_100a). "
+        "bdm_b200 has no CPU or PyTorch fallback for its kernels.")
+
+lib = ctypes.CDLL(SO_PATH)
+
+_i = ctypes.c_int
+_f = ctypes.c_float
+_p = ctypes.c_void_p
+_z = ctypes.c_size_t
+
+_PROTOS = {
+    "bdm_abi_version": (ctypes.c_int, []),
+    "bdm_error_string": (ctypes.c_char_p, [_i]),
+    "bdm_avg_voxelize_workspace_bytes": (_z, [_i, _i, _i]),
+    "bdm_avg_voxelize": (_i, [_i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _z, _p]),
+    "bdm_avg_voxelize_grad": (_i, [_i, _i, _i, _i, _p, _p, _p, _p, _p]),
+    "bdm_trilinear_devoxelize": (_i, [_i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p]),
+    "bdm_trilinear_devoxelize_grad": (_i, [_i, _i, _i, _i, _p, _p, _p, _p, _p]),
+    "bdm_gather_features": (_i, [_i, _i, _i, _i, _p, _p, _p, _p]),
+    "bdm_gather_features_grad": (_i, [_i, _i, _i, _i, _p, _p, _p, _p]),
+    "bdm_furthest_point_sampling_workspace_bytes": (_z, [_i, _i]),
+    "bdm_furthest_point_sampling": (_i, [_i, _i, _i, _p, _p, _p, _z, _p]),
+    "bdm_ball_query": (_i, [_i, _i, _i, _f, _i, _p, _p, _p, _p]),
+    "bdm_grouping": (_i, [_i, _i, _i, _i, _i, _p, _p, _p, _p]),
+    "bdm_grouping_grad": (_i, [_i, _i, _i, _i, _i, _p, _p, _p, _p]),
+    "bdm_three_nearest_neighbors_interpolate": (_i, [_i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p]),
+    "bdm_three_nn_search": (_i, [_i, _i, _i, _p, _p, _p, _p, _p]),
+    "bdm_three_nn_interpolate": (_i, [_i, _i, _i, _i, _p, _p, _p, _p, _p]),
+    "bdm_three_nearest_neighbors_interpolate_grad": (_i, [_i, _i, _i, _i, _p, _p, _p, _p, _p]),
+    "bdm_surface_projection": (_i, [_i, _i, _i, _i, _i, _f, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "bdm_surface_projection_hwc": (_i, [_i, _i, _i, _i, _i, _f, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "bdm_nn_f64": (_i, [_i, _i, _i, _i, _p, _p, _p, _p, _p]),
+}
+
+EXPORTS = tuple(_PROTOS)
+
+for _name, (_res, _args) in _PROTOS.items():
+    _fn = getattr(lib, _name)  # AttributeError here == a symbol of the header is missing: fail loudly
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+ABI_VERSION = lib.bdm_abi_version()
+
+
+def check(rc):
+    """Turn a non-zero return code of any bdm_* call into a RuntimeError (the reference's wrappers
+    raise RuntimeError through TORCH_CHECK, src/utils.hpp:7-18)."""
+    if rc != 0:
+        raise RuntimeError(f"bdm_b200 error {rc}: {lib.bdm_error_string(rc).decode()}")

@@ -1,0 +1,317 @@
+"""`_backend`: the reference's 12-function native module, served by libbdm_b200.so.
+
+Mirrors the pybind module `_pvcnn_backend`
+(/root/reference/experiments/model/pvcnn/modules/functional/src/bindings.cpp:10-37; loaded by
+functional/backend.py:12-31 as `_backend`): same function names, same positional arguments, same
+return structure, same input checks (CUDA / contiguous / dtype -> RuntimeError, src/utils.hpp:7-18).
+
+Differences that are invisible to callers: outputs are allocated with torch.empty (every kernel
+writes its whole output; the reference zero-fills first), all launches go to the *current* stream of
+the tensor's device (the reference mixes the legacy default stream and the current stream, and never
+sets the device), and launch failures raise instead of calling exit(-1).
+
+Extras beyond the 12 names (used by bdm_b200.modules to avoid duplicated work, never required):
+three_nn_search, three_nn_interpolate, surface_projection, nn_f64.
+"""
+import numpy as np
+import torch
+
+from . import _lib
+
+_L = _lib.lib
+_check = _lib.check
+_I32 = torch.int32
+_F32 = torch.float32
+
+
+def _req(cond, msg):
+    if not cond:
+        raise RuntimeError(msg)
+
+
+def _chk_float(x, name):
+    _req(x.is_cuda, f"{name} must be a CUDA tensor")
+    _req(x.is_contiguous(), f"{name} must be a contiguous tensor")
+    _req(x.dtype == _F32, f"{name} must be a float tensor")
+
+
+def _chk_int(x, name):
+    _req(x.is_cuda, f"{name} must be a CUDA tensor")
+    _req(x.is_contiguous(), f"{name} must be a contiguous tensor")
+    _req(x.dtype == _I32, f"{name} must be an int tensor")
+
+
+class _Launch:
+    """Device guard + current stream of the device that owns `ref`."""
+    __slots__ = ("dev", "prev", "stream")
+
+    def __init__(self, ref):
+        self.dev = ref.device.index
+        self.prev = None
+
+    def __enter__(self):
+        cur = torch.cuda.current_device()
+        if cur != self.dev:
+            self.prev = cur
+            torch.cuda.set_device(self.dev)
+        self.stream = torch.cuda.current_stream().cuda_stream
+        return self.stream
+
+    def __exit__(self, *exc):
+        if self.prev is not None:
+            torch.cuda.set_device(self.prev)
+        return False
+
+
+def _workspace(nbytes, device):
+    # torch's caching allocator makes this stream-safe and cheap; contents are irrelevant
+    return torch.empty((max(int(nbytes), 16),), dtype=torch.uint8, device=device)
+
+
+# ---------------------------------------------------------------------------------------------
+# voxelization  (vox.cpp:17-43, :54-76)
+# ---------------------------------------------------------------------------------------------
+def avg_voxelize_forward(features, coords, resolution):
+    _chk_float(features, "features")
+    _chk_int(coords, "coords")
+    b, c, n = features.shape
+    r = int(resolution)
+    r3 = r * r * r
+    dev = features.device
+    out = torch.empty((b, c, r3), dtype=_F32, device=dev)
+    ind = torch.empty((b, n), dtype=_I32, device=dev)
+    cnt = torch.empty((b, r3), dtype=_I32, device=dev)
+    nws = _L.bdm_avg_voxelize_workspace_bytes(b, n, r)
+    ws = _workspace(nws, dev)
+    with _Launch(features) as st:
+        _check(_L.bdm_avg_voxelize(b, c, n, r, coords.data_ptr(), features.data_ptr(), ind.data_ptr(),
+                                   cnt.data_ptr(), out.data_ptr(), ws.data_ptr(), ws.numel(), st))
+    return [out, ind, cnt]
+
+
+def avg_voxelize_backward(grad_y, indices, cnt):
+    _chk_float(grad_y, "grad_y")
+    _chk_int(indices, "indices")
+    _chk_int(cnt, "cnt")
+    b, c, s = grad_y.shape
+    n = indices.shape[1]
+    grad_x = torch.empty((b, c, n), dtype=_F32, device=grad_y.device)
+    with _Launch(grad_y) as st:
+        _check(_L.bdm_avg_voxelize_grad(b, c, n, s, indices.data_ptr(), cnt.data_ptr(), grad_y.data_ptr(),
+                                        grad_x.data_ptr(), st))
+    return grad_x
+
+
+# ---------------------------------------------------------------------------------------------
+# devoxelization  (trilinear_devox.cpp:18-55, :68-94)
+# ---------------------------------------------------------------------------------------------
+def trilinear_devoxelize_forward(r, is_training, coords, features):
+    _chk_float(features, "features")
+    _chk_float(coords, "coords")
+    b, c = features.shape[0], features.shape[1]
+    n = coords.shape[2]
+    r = int(r)
+    dev = features.device
+    outs = torch.empty((b, c, n), dtype=_F32, device=dev)
+    if is_training:
+        inds = torch.empty((b, 8, n), dtype=_I32, device=dev)
+        wgts = torch.empty((b, 8, n), dtype=_F32, device=dev)
+        ip, wp = inds.data_ptr(), wgts.data_ptr()
+    else:  # the reference returns 1-element dummies (trilinear_devox.cpp:45-53)
+        inds = torch.zeros((1,), dtype=_I32, device=dev)
+        wgts = torch.zeros((1,), dtype=_F32, device=dev)
+        ip, wp = None, None
+    with _Launch(features) as st:
+        _check(_L.bdm_trilinear_devoxelize(b, c, n, r, 1 if is_training else 0, coords.data_ptr(),
+                                           features.data_ptr(), ip, wp, outs.data_ptr(), st))
+    return [outs, inds, wgts]
+
+
+def trilinear_devoxelize_backward(grad_y, indices, weights, r):
+    _chk_float(grad_y, "grad_y")
+    _chk_float(weights, "weights")
+    _chk_int(indices, "indices")
+    b, c, n = grad_y.shape
+    r3 = int(r) ** 3
+    grad_x = torch.empty((b, c, r3), dtype=_F32, device=grad_y.device)
+    with _Launch(grad_y) as st:
+        _check(_L.bdm_trilinear_devoxelize_grad(b, c, n, r3, indices.data_ptr(), weights.data_ptr(),
+                                                grad_y.data_ptr(), grad_x.data_ptr(), st))
+    return grad_x
+
+
+# ---------------------------------------------------------------------------------------------
+# sampling  (sampling.cpp:6-58)
+# ---------------------------------------------------------------------------------------------
+def gather_features_forward(features, indices):
+    _chk_float(features, "features")
+    _chk_int(indices, "indices")
+    b, c, n = features.shape
+    m = indices.shape[1]
+    out = torch.empty((b, c, m), dtype=_F32, device=features.device)
+    with _Launch(features) as st:
+        _check(_L.bdm_gather_features(b, c, n, m, features.data_ptr(), indices.data_ptr(), out.data_ptr(), st))
+    return out
+
+
+def gather_features_backward(grad_y, indices, n):
+    _chk_float(grad_y, "grad_y")
+    _chk_int(indices, "indices")
+    b, c = grad_y.shape[0], grad_y.shape[1]
+    m = indices.shape[1]
+    n = int(n)
+    grad_x = torch.empty((b, c, n), dtype=_F32, device=grad_y.device)
+    with _Launch(grad_y) as st:
+        _check(_L.bdm_gather_features_grad(b, c, n, m, grad_y.data_ptr(), indices.data_ptr(),
+                                           grad_x.data_ptr(), st))
+    return grad_x
+
+
+def furthest_point_sampling(coords, num_samples):
+    _chk_float(coords, "coords")
+    b, n = coords.shape[0], coords.shape[2]
+    m = int(num_samples)
+    dev = coords.device
+    if m <= 0 or b == 0:
+        return torch.zeros((b, max(m, 0)), dtype=_I32, device=dev)
+    indices = torch.empty((b, m), dtype=_I32, device=dev)
+    ws = _workspace(_L.bdm_furthest_point_sampling_workspace_bytes(b, n), dev)
+    with _Launch(coords) as st:
+        _check(_L.bdm_furthest_point_sampling(b, n, m, coords.data_ptr(), indices.data_ptr(), ws.data_ptr(),
+                                              ws.numel(), st))
+    return indices
+
+
+# ---------------------------------------------------------------------------------------------
+# ball query  (ball_query.cpp:6-30)
+# ---------------------------------------------------------------------------------------------
+def ball_query(centers_coords, points_coords, radius, num_neighbors):
+    _chk_float(centers_coords, "centers_coords")
+    _chk_float(points_coords, "points_coords")
+    b, m = centers_coords.shape[0], centers_coords.shape[2]
+    n = points_coords.shape[2]
+    u = int(num_neighbors)
+    r = np.float32(radius)
+    r2 = float(r * r)  # fp32 product, like `radius * radius` at ball_query.cpp:24
+    out = torch.empty((b, m, u), dtype=_I32, device=centers_coords.device)
+    with _Launch(centers_coords) as st:
+        _check(_L.bdm_ball_query(b, n, m, r2, u, centers_coords.data_ptr(), points_coords.data_ptr(),
+                                 out.data_ptr(), st))
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# grouping  (grouping.cpp:6-43)
+# ---------------------------------------------------------------------------------------------
+def grouping_forward(features, indices):
+    _chk_float(features, "features")
+    _chk_int(indices, "indices")
+    b, c, n = features.shape
+    m, u = indices.shape[1], indices.shape[2]
+    out = torch.empty((b, c, m, u), dtype=_F32, device=features.device)
+    with _Launch(features) as st:
+        _check(_L.bdm_grouping(b, c, n, m, u, features.data_ptr(), indices.data_ptr(), out.data_ptr(), st))
+    return out
+
+
+def grouping_backward(grad_y, indices, n):
+    _chk_float(grad_y, "grad_y")
+    _chk_int(indices, "indices")
+    b, c = grad_y.shape[0], grad_y.shape[1]
+    m, u = indices.shape[1], indices.shape[2]
+    n = int(n)
+    grad_x = torch.empty((b, c, n), dtype=_F32, device=grad_y.device)
+    with _Launch(grad_y) as st:
+        _check(_L.bdm_grouping_grad(b, c, n, m, u, grad_y.data_ptr(), indices.data_ptr(), grad_x.data_ptr(), st))
+    return grad_x
+
+
+# ---------------------------------------------------------------------------------------------
+# three nearest neighbours  (neighbor_interpolate.cpp:6-66)
+# ---------------------------------------------------------------------------------------------
+def three_nn_search(points_coords, centers_coords):
+    """-> (indices int32[B,3,N], weights f32[B,3,N]); the search half of the reference op."""
+    _chk_float(points_coords, "points_coords")
+    _chk_float(centers_coords, "centers_coords")
+    b, n = points_coords.shape[0], points_coords.shape[2]
+    m = centers_coords.shape[2]
+    dev = points_coords.device
+    indices = torch.empty((b, 3, n), dtype=_I32, device=dev)
+    weights = torch.empty((b, 3, n), dtype=_F32, device=dev)
+    with _Launch(points_coords) as st:
+        _check(_L.bdm_three_nn_search(b, n, m, points_coords.data_ptr(), centers_coords.data_ptr(),
+                                      weights.data_ptr(), indices.data_ptr(), st))
+    return indices, weights
+
+
+def three_nn_interpolate(centers_features, indices, weights):
+    _chk_float(centers_features, "centers_features")
+    _chk_int(indices, "indices")
+    _chk_float(weights, "weights")
+    b, c, m = centers_features.shape
+    n = indices.shape[2]
+    out = torch.empty((b, c, n), dtype=_F32, device=centers_features.device)
+    with _Launch(centers_features) as st:
+        _check(_L.bdm_three_nn_interpolate(b, c, m, n, centers_features.data_ptr(), indices.data_ptr(),
+                                           weights.data_ptr(), out.data_ptr(), st))
+    return out
+
+
+def three_nearest_neighbors_interpolate_forward(points_coords, centers_coords, centers_features):
+    _chk_float(centers_features, "centers_features")
+    indices, weights = three_nn_search(points_coords, centers_coords)
+    return [three_nn_interpolate(centers_features, indices, weights), indices, weights]
+
+
+def three_nearest_neighbors_interpolate_backward(grad_y, indices, weights, m):
+    _chk_float(grad_y, "grad_y")
+    _chk_int(indices, "indices")
+    _chk_float(weights, "weights")
+    b, c, n = grad_y.shape
+    m = int(m)
+    grad_x = torch.empty((b, c, m), dtype=_F32, device=grad_y.device)
+    with _Launch(grad_y) as st:
+        _check(_L.bdm_three_nearest_neighbors_interpolate_grad(b, c, n, m, grad_y.data_ptr(), indices.data_ptr(),
+                                                               weights.data_ptr(), grad_x.data_ptr(), st))
+    return grad_x
+
+
+# ---------------------------------------------------------------------------------------------
+# secondary boundaries
+# ---------------------------------------------------------------------------------------------
+def surface_projection(points, R, T, focal, principal, feat, radius, feat_is_hwc=False):
+    """points f32[B,N,3]; R [B,3,3]; T [B,3]; focal, principal [B,2]; feat [B,C,H,W] (or [B,H,W,C]
+    when feat_is_hwc) -> (out f32[B,N,C], pix int32[B,N]: lowest won pixel index or -1)"""
+    for x, nm in ((points, "points"), (R, "R"), (T, "T"), (focal, "focal"), (principal, "principal"),
+                  (feat, "feat")):
+        _chk_float(x, nm)
+    b, n = points.shape[0], points.shape[1]
+    if feat_is_hwc:
+        H, W, C = feat.shape[1], feat.shape[2], feat.shape[3]
+    else:
+        C, H, W = feat.shape[1], feat.shape[2], feat.shape[3]
+    dev = points.device
+    zbuf = torch.empty((b, H, W), dtype=torch.int64, device=dev)
+    pix = torch.empty((b, n), dtype=_I32, device=dev)
+    out = torch.empty((b, n, C), dtype=_F32, device=dev)
+    fn = _L.bdm_surface_projection_hwc if feat_is_hwc else _L.bdm_surface_projection
+    with _Launch(points) as st:
+        _check(fn(b, n, C, H, W, float(radius), points.data_ptr(), R.data_ptr(), T.data_ptr(), focal.data_ptr(),
+                  principal.data_ptr(), feat.data_ptr(), zbuf.data_ptr(), pix.data_ptr(), out.data_ptr(), st))
+    return out, pix
+
+
+def nn_f64(src, tgt, expanded=False, return_index=True):
+    """src f64[B,N,3], tgt f64[B,M,3] -> (min squared distance f64[B,N], argmin int32[B,N] | None)"""
+    for x, nm in ((src, "src"), (tgt, "tgt")):
+        _req(x.is_cuda, f"{nm} must be a CUDA tensor")
+        _req(x.is_contiguous(), f"{nm} must be a contiguous tensor")
+        _req(x.dtype == torch.float64, f"{nm} must be a double tensor")
+    b, n = src.shape[0], src.shape[1]
+    m = tgt.shape[1]
+    dist = torch.empty((b, n), dtype=torch.float64, device=src.device)
+    idx = torch.empty((b, n), dtype=_I32, device=src.device) if return_index else None
+    with _Launch(src) as st:
+        _check(_L.bdm_nn_f64(b, n, m, 1 if expanded else 0, src.data_ptr(), tgt.data_ptr(), dist.data_ptr(),
+                             idx.data_ptr() if idx is not None else None, st))
+    return dist, idx

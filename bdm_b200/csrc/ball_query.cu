@@ -1,0 +1,124 @@
+// ball_query.cu -- ball query for sm_100a.
+//
+// Replaces ball_query_kernel
+// (experiments/model/pvcnn/modules/functional/src/ball_query/ball_query.cu:19-50; one CTA per batch
+// element, one thread per centre walking all N points from global memory).
+//
+// Semantics kept bit-exact: d2 = fma(dz,dz, fma(dx,dx, dy*dy)) with d = centre - point (:35-38 as
+// contracted by nvcc); hit iff d2 < r2 (strict); the row holds the first <=U hits in ascending point
+// index, padded with the first hit; all zeros when there is no hit (wrapper zero-fills, .cpp:20-22).
+//
+// Design: the op is compute-bound on B*M*N distance tests (algorithmic bytes are ~4 MB per call).
+// One warp = 32 centres (one per lane) x one contiguous SPLIT of the point range; all lanes read the
+// same point -> uniform 128-bit loads of 4 consecutive x / y / z values (L1 broadcast), 7 FP32
+// instructions per test, no ballot / compaction in the inner loop.  A CTA is SPLITS warps working on
+// the same 32 centres; hits go to per-(centre,split) lists in shared memory and are concatenated in
+// split order (= ascending point index) when the row is written, as one coalesced 128-byte store
+// per centre for U = 32.
+#include "common.cuh"
+
+namespace bdm {
+
+constexpr int kBqMaxSplits = 8;
+
+template <bool VEC4>
+__global__ void __launch_bounds__(32 * kBqMaxSplits)
+ball_query_kernel(int n, int m, float r2, int u, int splits, const float *__restrict__ centers,
+                  const float *__restrict__ points, int *__restrict__ neighbors) {
+  const int b = blockIdx.y;
+  const int lane = threadIdx.x & 31, split = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + lane;  // centre handled by this lane
+  centers += (size_t)b * 3 * m;
+  points += (size_t)b * 3 * n;
+  neighbors += (size_t)b * m * u;
+
+  extern __shared__ int s_hits[];                 // [splits][32 centres][us], us = u|1 (odd stride:
+                                                  // simultaneous appends of different lanes hit different banks)
+  __shared__ int s_cnt[kBqMaxSplits][32];
+  const int us = u | 1;
+  int *my = s_hits + ((size_t)split * 32 + lane) * us;
+
+  const bool valid = j < m;
+  const float cx = valid ? centers[j] : 0.0f;
+  const float cy = valid ? centers[j + m] : 0.0f;
+  const float cz = valid ? centers[j + m + m] : 0.0f;
+
+  // contiguous point range of this split, multiple of 4 so vector loads stay aligned
+  int len = ceil_div(n, splits);
+  len = (len + 3) & ~3;
+  const int k0 = min(split * len, n), k1 = min(k0 + len, n);
+
+  int cnt = valid ? 0 : u;  // lanes without a centre are "full" from the start
+  int k = k0;
+  if (VEC4) {
+    for (; k + 4 <= k1; k += 4) {
+      if (__all_sync(0xffffffffu, cnt >= u)) break;
+      const float4 X = __ldg(reinterpret_cast<const float4 *>(points + k));
+      const float4 Y = __ldg(reinterpret_cast<const float4 *>(points + n + k));
+      const float4 Z = __ldg(reinterpret_cast<const float4 *>(points + 2 * (size_t)n + k));
+      const float d0 = sqdist_ref(__fsub_rn(cx, X.x), __fsub_rn(cy, Y.x), __fsub_rn(cz, Z.x));
+      const float d1 = sqdist_ref(__fsub_rn(cx, X.y), __fsub_rn(cy, Y.y), __fsub_rn(cz, Z.y));
+      const float d2 = sqdist_ref(__fsub_rn(cx, X.z), __fsub_rn(cy, Y.z), __fsub_rn(cz, Z.z));
+      const float d3 = sqdist_ref(__fsub_rn(cx, X.w), __fsub_rn(cy, Y.w), __fsub_rn(cz, Z.w));
+      if (d0 < r2 && cnt < u) my[cnt++] = k;
+      if (d1 < r2 && cnt < u) my[cnt++] = k + 1;
+      if (d2 < r2 && cnt < u) my[cnt++] = k + 2;
+      if (d3 < r2 && cnt < u) my[cnt++] = k + 3;
+    }
+  }
+  for (; k < k1; ++k) {
+    if (__all_sync(0xffffffffu, cnt >= u)) break;
+    const float d = sqdist_ref(__fsub_rn(cx, __ldg(points + k)), __fsub_rn(cy, __ldg(points + n + k)),
+                               __fsub_rn(cz, __ldg(points + 2 * (size_t)n + k)));
+    if (d < r2 && cnt < u) my[cnt++] = k;
+  }
+  s_cnt[split][lane] = valid ? cnt : 0;
+  __syncthreads();
+
+  // merge: warp `split` writes rows split, split+splits, ... ; lane = output slot (strided over u)
+  for (int row = split; row < 32; row += splits) {
+    const int jj = blockIdx.x * 32 + row;
+    if (jj >= m) break;
+    int first = 0;
+    bool have_first = false;
+    for (int s = 0; s < splits && !have_first; ++s)
+      if (s_cnt[s][row] > 0) { first = s_hits[((size_t)s * 32 + row) * us]; have_first = true; }
+    for (int slot = lane; slot < u; slot += 32) {
+      int val = first, rem = slot;
+      for (int s = 0; s < splits; ++s) {
+        const int cs = s_cnt[s][row];
+        if (rem < cs) { val = s_hits[((size_t)s * 32 + row) * us + rem]; break; }
+        rem -= cs;
+      }
+      neighbors[(size_t)jj * u + slot] = val;
+    }
+  }
+}
+
+}  // namespace bdm
+
+extern "C" int bdm_ball_query(int b, int n, int m, float r2, int u, const float *centers_coords,
+                              const float *points_coords, int *neighbors_indices,
+                              bdm_stream_t stream) {
+  using namespace bdm;
+  BDM_CHECK_SIZE(b >= 0 && n >= 0 && m >= 0 && u >= 0 && b <= 65535);
+  if (b == 0 || m == 0 || u == 0) return BDM_OK;
+  BDM_CHECK_PTR(centers_coords); BDM_CHECK_PTR(neighbors_indices);
+  if (n > 0) BDM_CHECK_PTR(points_coords);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  // enough warps to fill the machine (>= 8 warps per SM), at most kBqMaxSplits per CTA, and at
+  // least 256 points per split so the per-row merge stays negligible
+  const int ctas = ceil_div(m, 32) * b;
+  int splits = 1;
+  while (splits < kBqMaxSplits && ctas * splits < 8 * sm_count() && n / (splits * 2) >= 256) splits *= 2;
+  size_t smem = sizeof(int) * (size_t)splits * 32 * (u | 1);
+  while (smem > 200 * 1024 && splits > 1) { splits /= 2; smem = sizeof(int) * (size_t)splits * 32 * (u | 1); }
+  BDM_CHECK_SIZE(smem <= 200 * 1024);
+  const bool vec4 = (n % 4 == 0) && ((reinterpret_cast<uintptr_t>(points_coords) & 15) == 0);
+  auto kern = vec4 ? ball_query_kernel<true> : ball_query_kernel<false>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  kern<<<dim3(ceil_div(m, 32), b), 32 * splits, smem, st>>>(n, m, r2, u, splits, centers_coords, points_coords,
+                                                            neighbors_indices);
+  BDM_RETURN_LAUNCH_STATUS();
+}

@@ -1,0 +1,72 @@
+// common.cuh -- shared helpers for the sm_100a kernels of libbdm_b200.so
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/bdm_b200.h"
+
+#define BDM_CHECK_PTR(p) \
+  do {                   \
+    if ((p) == nullptr) return BDM_ERR_NULL_POINTER; \
+  } while (0)
+
+#define BDM_CHECK_SIZE(cond) \
+  do {                       \
+    if (!(cond)) return BDM_ERR_BAD_SIZE; \
+  } while (0)
+
+// Every launcher ends with this: a launch error becomes the (positive) return code.
+#define BDM_RETURN_LAUNCH_STATUS()           \
+  do {                                       \
+    cudaError_t e__ = cudaGetLastError();    \
+    return e__ == cudaSuccess ? BDM_OK : (int)e__; \
+  } while (0)
+
+namespace bdm {
+
+constexpr int kWarp = 32;
+
+__host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+__host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Number of SMs of the current device (148 on B200); cached per process.
+inline int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+// The reference's squared distance `dx*dx + dy*dy + dz*dz` as nvcc contracts it (SASS of the
+// reference: FMUL dy*dy, FFMA dx*dx+t, FFMA dz*dz+t).  Spelled with intrinsics so that the result
+// does not depend on this file's optimisation flags: bit-exact integer outputs hinge on it.
+__device__ __forceinline__ float sqdist_ref(float dx, float dy, float dz) {
+  float t = __fmul_rn(dy, dy);
+  t = __fmaf_rn(dx, dx, t);
+  return __fmaf_rn(dz, dz, t);
+}
+
+// Streaming 128-bit store / read-only 128-bit load (no L1 allocation for data touched once).
+__device__ __forceinline__ void st_stream_f4(float *p, float4 v) {
+  asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ float4 ld_stream_f4(const float *p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float ld_stream_f1(const float *p) {
+  float v;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+
+}  // namespace bdm

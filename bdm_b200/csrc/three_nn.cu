@@ -1,0 +1,204 @@
+// three_nn.cu -- three nearest neighbours + inverse-distance interpolation (fwd/bwd) for sm_100a.
+//
+// Replaces three_nearest_neighbors_kernel, three_nearest_neighbors_interpolate_kernel and
+// three_nearest_neighbors_interpolate_grad_kernel
+// (experiments/model/pvcnn/modules/functional/src/interpolate/neighbor_interpolate.cu:20-75, :90-116,
+// :145-170; one CTA per batch element, serial scan of the centres from global memory).
+//
+// Bit-exact contract for the search:
+//   d = fma(dz,dz, fma(dx,dx, dy*dy)) with d = point - centre (:43 as contracted by nvcc);
+//   the reference compares the float d against double bests initialised to 1e40 with strict '<'
+//   (:44-57).  float -> double widening is exact, and 1e40 only ever compares against finite floats
+//   or +inf/NaN, for which `d < 1e40` and `d < +inf` agree -- so float bests initialised to +inf give
+//   the same insertion decisions.  The clamp and the three pair products are evaluated in double and
+//   rounded to float (:61-66), the rest in fp32 (:67-72) -- reproduced literally.
+// Interpolation: out = f[i1]*w1 + f[i2]*w2 + f[i3]*w3, contracted as fma(f3,w3, fma(f1,w1, f2*w2)).
+//
+// Search: one lane per point, uniform 128-bit loads of 4 consecutive centre x/y/z values.
+// Interpolation: one thread per point, (idx,w) in registers, CT channels per CTA, coalesced stores.
+#include "common.cuh"
+
+namespace bdm {
+
+constexpr int kNnThreads = 128;
+constexpr int kNnCT = 8;
+
+__device__ __forceinline__ void nn3_insert(float d, int k, float &b0, float &b1, float &b2, int &i0,
+                                           int &i1, int &i2) {
+  if (d < b2) {
+    b2 = d; i2 = k;
+    if (d < b1) {
+      b2 = b1; i2 = i1; b1 = d; i1 = k;
+      if (d < b0) { b1 = b0; i1 = i0; b0 = d; i0 = k; }
+    }
+  }
+}
+
+template <bool VEC4>
+__global__ void __launch_bounds__(kNnThreads)
+three_nn_kernel(int n, int m, const float *__restrict__ points, const float *__restrict__ centers,
+                float *__restrict__ weights, int *__restrict__ indices) {
+  const int b = blockIdx.y;
+  const int j = blockIdx.x * kNnThreads + threadIdx.x;
+  points += (size_t)b * 3 * n;
+  centers += (size_t)b * 3 * m;
+  weights += (size_t)b * 3 * n;
+  indices += (size_t)b * 3 * n;
+  const bool valid = j < n;
+  const float ux = valid ? points[j] : 0.0f;
+  const float uy = valid ? points[j + n] : 0.0f;
+  const float uz = valid ? points[j + n + n] : 0.0f;
+
+  float b0 = __int_as_float(0x7f800000), b1 = b0, b2 = b0;
+  int i0 = 0, i1 = 0, i2 = 0;
+  int k = 0;
+  if (VEC4) {
+    for (; k + 4 <= m; k += 4) {
+      const float4 X = __ldg(reinterpret_cast<const float4 *>(centers + k));
+      const float4 Y = __ldg(reinterpret_cast<const float4 *>(centers + m + k));
+      const float4 Z = __ldg(reinterpret_cast<const float4 *>(centers + 2 * (size_t)m + k));
+      const float d0 = sqdist_ref(__fsub_rn(ux, X.x), __fsub_rn(uy, Y.x), __fsub_rn(uz, Z.x));
+      const float d1 = sqdist_ref(__fsub_rn(ux, X.y), __fsub_rn(uy, Y.y), __fsub_rn(uz, Z.y));
+      const float d2 = sqdist_ref(__fsub_rn(ux, X.z), __fsub_rn(uy, Y.z), __fsub_rn(uz, Z.z));
+      const float d3 = sqdist_ref(__fsub_rn(ux, X.w), __fsub_rn(uy, Y.w), __fsub_rn(uz, Z.w));
+      nn3_insert(d0, k, b0, b1, b2, i0, i1, i2);
+      nn3_insert(d1, k + 1, b0, b1, b2, i0, i1, i2);
+      nn3_insert(d2, k + 2, b0, b1, b2, i0, i1, i2);
+      nn3_insert(d3, k + 3, b0, b1, b2, i0, i1, i2);
+    }
+  }
+  for (; k < m; ++k) {
+    const float d = sqdist_ref(__fsub_rn(ux, __ldg(centers + k)), __fsub_rn(uy, __ldg(centers + m + k)),
+                               __fsub_rn(uz, __ldg(centers + 2 * (size_t)m + k)));
+    nn3_insert(d, k, b0, b1, b2, i0, i1, i2);
+  }
+  if (!valid) return;
+  // neighbor_interpolate.cu:61-72.  An unset best is 1e40 in the reference and +inf here; both clamp
+  // to 1e10.  NaN bests follow CUDA's max/min (non-NaN operand wins) in both.
+  const double lo = (double)1e-10f, hi = (double)1e10f;
+  const double e0 = fmax(fmin(hi, (double)b0), lo);
+  const double e1 = fmax(fmin(hi, (double)b1), lo);
+  const double e2 = fmax(fmin(hi, (double)b2), lo);
+  const float d0d1 = __double2float_rn(__dmul_rn(e0, e1));
+  const float d0d2 = __double2float_rn(__dmul_rn(e0, e2));
+  const float d1d2 = __double2float_rn(__dmul_rn(e1, e2));
+  const float inv = __fdiv_rn(1.0f, __fadd_rn(__fadd_rn(d0d1, d0d2), d1d2));
+  weights[j] = __fmul_rn(d1d2, inv);
+  indices[j] = i0;
+  weights[j + n] = __fmul_rn(d0d2, inv);
+  indices[j + n] = i1;
+  weights[j + n + n] = __fmul_rn(d0d1, inv);
+  indices[j + n + n] = i2;
+}
+
+__global__ void __launch_bounds__(kNnThreads)
+three_interp_kernel(int c, int m, int n, const float *__restrict__ feat,
+                    const int *__restrict__ indices, const float *__restrict__ weights,
+                    float *__restrict__ out) {
+  const int b = blockIdx.z;
+  const int j = blockIdx.x * kNnThreads + threadIdx.x;
+  if (j >= n) return;
+  const int *ix = indices + (size_t)b * 3 * n;
+  const float *w = weights + (size_t)b * 3 * n;
+  const int i1 = __ldg(ix + j), i2 = __ldg(ix + j + n), i3 = __ldg(ix + j + n + n);
+  const float w1 = __ldg(w + j), w2 = __ldg(w + j + n), w3 = __ldg(w + j + n + n);
+  const int c0 = blockIdx.y * kNnCT;
+  const int c1 = min(c0 + kNnCT, c);
+  const float *f = feat + ((size_t)b * c + c0) * m;
+  float *o = out + ((size_t)b * c + c0) * n + j;
+  for (int cc = c0; cc < c1; ++cc) {
+    float acc = __fmul_rn(__ldg(f + i2), w2);
+    acc = __fmaf_rn(__ldg(f + i1), w1, acc);
+    acc = __fmaf_rn(__ldg(f + i3), w3, acc);
+    *o = acc;
+    f += m;
+    o += n;
+  }
+}
+
+// backward (neighbor_interpolate.cu:155-169): 3 atomic scatter-adds of fl(g*w) per (point, channel)
+__global__ void __launch_bounds__(kNnThreads)
+three_interp_grad_kernel(int c, int n, int m, const float *__restrict__ grad_y,
+                         const int *__restrict__ indices, const float *__restrict__ weights,
+                         float *__restrict__ grad_x) {
+  const int b = blockIdx.z;
+  const int j = blockIdx.x * kNnThreads + threadIdx.x;
+  if (j >= n) return;
+  const int *ix = indices + (size_t)b * 3 * n;
+  const float *w = weights + (size_t)b * 3 * n;
+  const int i1 = ix[j], i2 = ix[j + n], i3 = ix[j + n + n];
+  const float w1 = w[j], w2 = w[j + n], w3 = w[j + n + n];
+  const int c0 = blockIdx.y * kNnCT;
+  const int c1 = min(c0 + kNnCT, c);
+  for (int cc = c0; cc < c1; ++cc) {
+    const float g = grad_y[((size_t)b * c + cc) * n + j];
+    float *gx = grad_x + ((size_t)b * c + cc) * m;
+    atomicAdd(gx + i1, __fmul_rn(g, w1));
+    atomicAdd(gx + i2, __fmul_rn(g, w2));
+    atomicAdd(gx + i3, __fmul_rn(g, w3));
+  }
+}
+
+}  // namespace bdm
+
+extern "C" int bdm_three_nn_search(int b, int n, int m, const float *points_coords,
+                                   const float *centers_coords, float *weights, int *indices,
+                                   bdm_stream_t stream) {
+  using namespace bdm;
+  BDM_CHECK_SIZE(b >= 0 && n >= 0 && m >= 0 && b <= 65535);
+  if (b == 0 || n == 0) return BDM_OK;
+  BDM_CHECK_PTR(points_coords); BDM_CHECK_PTR(weights); BDM_CHECK_PTR(indices);
+  if (m > 0) BDM_CHECK_PTR(centers_coords);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const bool vec4 = (m % 4 == 0) && ((reinterpret_cast<uintptr_t>(centers_coords) & 15) == 0);
+  if (vec4)
+    three_nn_kernel<true><<<dim3(ceil_div(n, kNnThreads), b), kNnThreads, 0, st>>>(n, m, points_coords,
+                                                                                 centers_coords, weights, indices);
+  else
+    three_nn_kernel<false><<<dim3(ceil_div(n, kNnThreads), b), kNnThreads, 0, st>>>(n, m, points_coords,
+                                                                                  centers_coords, weights, indices);
+  BDM_RETURN_LAUNCH_STATUS();
+}
+
+extern "C" int bdm_three_nn_interpolate(int b, int c, int m, int n, const float *centers_features,
+                                        const int *indices, const float *weights, float *out,
+                                        bdm_stream_t stream) {
+  using namespace bdm;
+  BDM_CHECK_SIZE(b >= 0 && c >= 0 && n >= 0 && m >= 0 && b <= 65535);
+  if (b == 0 || c == 0 || n == 0) return BDM_OK;
+  BDM_CHECK_PTR(centers_features); BDM_CHECK_PTR(indices); BDM_CHECK_PTR(weights); BDM_CHECK_PTR(out);
+  BDM_CHECK_SIZE(ceil_div(c, kNnCT) <= 65535);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  three_interp_kernel<<<dim3(ceil_div(n, kNnThreads), ceil_div(c, kNnCT), b), kNnThreads, 0, st>>>(
+      c, m, n, centers_features, indices, weights, out);
+  BDM_RETURN_LAUNCH_STATUS();
+}
+
+extern "C" int bdm_three_nearest_neighbors_interpolate(int b, int c, int m, int n,
+                                                       const float *points_coords,
+                                                       const float *centers_coords,
+                                                       const float *centers_features, int *indices,
+                                                       float *weights, float *out,
+                                                       bdm_stream_t stream) {
+  int rc = bdm_three_nn_search(b, n, m, points_coords, centers_coords, weights, indices, stream);
+  if (rc != BDM_OK) return rc;
+  return bdm_three_nn_interpolate(b, c, m, n, centers_features, indices, weights, out, stream);
+}
+
+extern "C" int bdm_three_nearest_neighbors_interpolate_grad(int b, int c, int n, int m,
+                                                            const float *grad_y, const int *indices,
+                                                            const float *weights, float *grad_x,
+                                                            bdm_stream_t stream) {
+  using namespace bdm;
+  BDM_CHECK_SIZE(b >= 0 && c >= 0 && n >= 0 && m >= 0 && b <= 65535);
+  if (b == 0 || c == 0 || m == 0) return BDM_OK;
+  BDM_CHECK_PTR(grad_x);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  cudaMemsetAsync(grad_x, 0, sizeof(float) * (size_t)b * c * m, st);
+  if (n > 0) {
+    BDM_CHECK_PTR(grad_y); BDM_CHECK_PTR(indices); BDM_CHECK_PTR(weights);
+    three_interp_grad_kernel<<<dim3(ceil_div(n, kNnThreads), ceil_div(c, kNnCT), b), kNnThreads, 0, st>>>(
+        c, n, m, grad_y, indices, weights, grad_x);
+  }
+  BDM_RETURN_LAUNCH_STATUS();
+}

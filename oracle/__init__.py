@@ -1,0 +1,296 @@
+"""oracle -- CPU restatement of the reference's hot-path ops.  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / `--impl reference` legs may import
+this package; nothing under bdm_b200/ does (tests/test_boundary.py greps for it).  The C file
+bdm_oracle.c holds the algorithms (each citing the reference file:line it follows); this module is
+the numpy/ctypes binding plus the few pieces of reference *Python* glue that sit on the path
+(`Voxelization.forward`, Chamfer / F-score reductions).
+
+All functions take and return numpy arrays with the reference's layouts ([B,C,N] channel-first,
+[B,3,N] coordinate planes, int32 indices).
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SRC = os.path.join(_HERE, "bdm_oracle.c")
+_SO = os.path.join(_HERE, "_build", "libbdm_oracle.so")
+_lib = None
+
+
+def build(force=False):
+    """gcc -O2 -fopenmp -ffp-contract=off (every fma in the C file is explicit)."""
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(_SRC):
+        os.makedirs(os.path.dirname(_SO), exist_ok=True)
+        subprocess.check_call(["gcc", "-O2", "-fopenmp", "-ffp-contract=off", "-fno-fast-math", "-fPIC",
+                               "-shared", "-o", _SO, _SRC, "-lm"])
+    return _SO
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = ctypes.CDLL(build())
+    return _lib
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _p(a):
+    return ctypes.c_void_p(a.ctypes.data)
+
+
+_I = ctypes.c_int
+_F = ctypes.c_float
+
+
+# ------------------------------------------------------------------------------------------------
+# the 7 forward ops (+ 5 backward)
+# ------------------------------------------------------------------------------------------------
+def avg_voxelize_forward(features, coords, r):
+    """vox.cpp:17-43 -> (out[B,C,R^3], ind[B,N], cnt[B,R^3])"""
+    features, coords = _f32(features), _i32(coords)
+    b, c, n = features.shape
+    r3 = r * r * r
+    out = np.empty((b, c, r3), np.float32)
+    ind = np.empty((b, n), np.int32)
+    cnt = np.empty((b, r3), np.int32)
+    lib().orc_avg_voxelize_forward(_I(b), _I(c), _I(n), _I(r), _p(coords), _p(features), _p(ind), _p(cnt), _p(out))
+    return out, ind, cnt
+
+
+def avg_voxelize_backward(grad_y, ind, cnt):
+    """vox.cpp:54-76"""
+    grad_y, ind, cnt = _f32(grad_y), _i32(ind), _i32(cnt)
+    b, c, s = grad_y.shape
+    n = ind.shape[1]
+    gx = np.empty((b, c, n), np.float32)
+    lib().orc_avg_voxelize_backward(_I(b), _I(c), _I(n), _I(s), _p(ind), _p(cnt), _p(grad_y), _p(gx))
+    return gx
+
+
+def trilinear_devoxelize_forward(r, is_training, coords, features):
+    """trilinear_devox.cpp:18-55 -> (outs[B,C,N], inds, wgts); inds/wgts are [1] zeros when not training"""
+    coords, features = _f32(coords), _f32(features)
+    b, c = features.shape[:2]
+    n = coords.shape[2]
+    outs = np.empty((b, c, n), np.float32)
+    if is_training:
+        inds = np.empty((b, 8, n), np.int32)
+        wgts = np.empty((b, 8, n), np.float32)
+    else:
+        inds = np.zeros((1,), np.int32)
+        wgts = np.zeros((1,), np.float32)
+    lib().orc_trilinear_devoxelize_forward(_I(b), _I(c), _I(n), _I(r), _I(1 if is_training else 0), _p(coords),
+                                           _p(features), _p(inds), _p(wgts), _p(outs))
+    return outs, inds, wgts
+
+
+def trilinear_devoxelize_backward(grad_y, inds, wgts, r):
+    """trilinear_devox.cpp:68-94"""
+    grad_y, inds, wgts = _f32(grad_y), _i32(inds), _f32(wgts)
+    b, c, n = grad_y.shape
+    r3 = r * r * r
+    gx = np.empty((b, c, r3), np.float32)
+    lib().orc_trilinear_devoxelize_backward(_I(b), _I(c), _I(n), _I(r3), _p(inds), _p(wgts), _p(grad_y), _p(gx))
+    return gx
+
+
+def gather_features_forward(features, indices):
+    """sampling.cpp:6-23"""
+    features, indices = _f32(features), _i32(indices)
+    b, c, n = features.shape
+    m = indices.shape[1]
+    out = np.empty((b, c, m), np.float32)
+    lib().orc_gather_features_forward(_I(b), _I(c), _I(n), _I(m), _p(features), _p(indices), _p(out))
+    return out
+
+
+def gather_features_backward(grad_y, indices, n):
+    """sampling.cpp:25-41"""
+    grad_y, indices = _f32(grad_y), _i32(indices)
+    b, c, m = grad_y.shape
+    gx = np.empty((b, c, n), np.float32)
+    lib().orc_gather_features_backward(_I(b), _I(c), _I(n), _I(m), _p(grad_y), _p(indices), _p(gx))
+    return gx
+
+
+def furthest_point_sampling(coords, m):
+    """sampling.cpp:43-58 -> int32[B,M]"""
+    coords = _f32(coords)
+    b, _, n = coords.shape
+    idx = np.zeros((b, max(m, 0)), np.int32)
+    lib().orc_furthest_point_sampling(_I(b), _I(n), _I(m), _p(coords), _p(idx))
+    return idx
+
+
+def ball_query(centers, points, radius, u):
+    """ball_query.cpp:6-30 -> int32[B,M,U]; r2 = radius*radius in fp32 like the host wrapper (:24)"""
+    centers, points = _f32(centers), _f32(points)
+    b, _, m = centers.shape
+    n = points.shape[2]
+    r2 = np.float32(radius) * np.float32(radius)
+    out = np.empty((b, m, u), np.int32)
+    lib().orc_ball_query(_I(b), _I(n), _I(m), _F(float(r2)), _I(u), _p(centers), _p(points), _p(out))
+    return out
+
+
+def grouping_forward(features, indices):
+    """grouping.cpp:6-24"""
+    features, indices = _f32(features), _i32(indices)
+    b, c, n = features.shape
+    _, m, u = indices.shape
+    out = np.empty((b, c, m, u), np.float32)
+    lib().orc_grouping_forward(_I(b), _I(c), _I(n), _I(m), _I(u), _p(features), _p(indices), _p(out))
+    return out
+
+
+def grouping_backward(grad_y, indices, n):
+    """grouping.cpp:26-43"""
+    grad_y, indices = _f32(grad_y), _i32(indices)
+    b, c, m, u = grad_y.shape
+    gx = np.empty((b, c, n), np.float32)
+    lib().orc_grouping_backward(_I(b), _I(c), _I(n), _I(m), _I(u), _p(grad_y), _p(indices), _p(gx))
+    return gx
+
+
+def three_nn(points, centers):
+    """neighbor_interpolate.cu:20-75 -> (idx int32[B,3,N], w f32[B,3,N])"""
+    points, centers = _f32(points), _f32(centers)
+    b, _, n = points.shape
+    m = centers.shape[2]
+    w = np.empty((b, 3, n), np.float32)
+    idx = np.empty((b, 3, n), np.int32)
+    lib().orc_three_nn(_I(b), _I(n), _I(m), _p(points), _p(centers), _p(w), _p(idx))
+    return idx, w
+
+
+def three_interpolate(features, idx, w):
+    """neighbor_interpolate.cu:90-116"""
+    features, idx, w = _f32(features), _i32(idx), _f32(w)
+    b, c, m = features.shape
+    n = idx.shape[2]
+    out = np.empty((b, c, n), np.float32)
+    lib().orc_three_interpolate(_I(b), _I(c), _I(m), _I(n), _p(features), _p(idx), _p(w), _p(out))
+    return out
+
+
+def three_nearest_neighbors_interpolate_forward(points, centers, features):
+    """neighbor_interpolate.cpp:6-40 -> (out[B,C,N], idx[B,3,N], w[B,3,N])"""
+    idx, w = three_nn(points, centers)
+    return three_interpolate(features, idx, w), idx, w
+
+
+def three_nearest_neighbors_interpolate_backward(grad_y, idx, w, m):
+    """neighbor_interpolate.cpp:42-66"""
+    grad_y, idx, w = _f32(grad_y), _i32(idx), _f32(w)
+    b, c, n = grad_y.shape
+    gx = np.empty((b, c, m), np.float32)
+    lib().orc_three_interpolate_backward(_I(b), _I(c), _I(n), _I(m), _p(grad_y), _p(idx), _p(w), _p(gx))
+    return gx
+
+
+# ------------------------------------------------------------------------------------------------
+# Reference Python glue on the path
+# ------------------------------------------------------------------------------------------------
+def voxelization_coords(coords, r, normalize=True, eps=0.0):
+    """modules/voxelization.py:16-25 restated with torch CPU ops in the same order (the reference
+    runs the very same torch ops, on the GPU).  -> (vox int32[B,3,N], norm_coords f32[B,3,N])"""
+    import torch
+    c = torch.as_tensor(np.asarray(coords, dtype=np.float32))
+    nc = c - c.mean(2, keepdim=True)
+    if normalize:
+        nc = nc / (nc.norm(dim=1, keepdim=True).max(dim=2, keepdim=True).values * 2.0 + eps) + 0.5
+    else:
+        nc = (nc + 1) / 2.0
+    nc = torch.clamp(nc * r, 0, r - 1)
+    vox = torch.round(nc).to(torch.int32)
+    return vox.numpy(), nc.numpy()
+
+
+# ------------------------------------------------------------------------------------------------
+# Projection conditioning (PARITY UNPINNED: pytorch3d is not vendored; see bdm_oracle.c)
+# ------------------------------------------------------------------------------------------------
+def project_points(points, R, T, focal, pp):
+    """points [B,N,3] -> ndc xy + view z [B,N,3]"""
+    points, R, T, focal, pp = _f32(points), _f32(R), _f32(T), _f32(focal), _f32(pp)
+    b, n, _ = points.shape
+    ndc = np.empty((b, n, 3), np.float32)
+    lib().orc_project_points(_I(b), _I(n), _p(points), _p(R), _p(T), _p(focal), _p(pp), _p(ndc))
+    return ndc
+
+
+def rasterize_points(ndc, H, W, radius):
+    """-> int32[B,H,W] winning point index or -1 (K=1, nearest z, earlier index wins ties)"""
+    ndc = _f32(ndc)
+    b, n, _ = ndc.shape
+    zi = np.empty((b, H, W), np.int32)
+    lib().orc_rasterize_points(_I(b), _I(n), _I(H), _I(W), _F(radius), _p(ndc), _p(zi))
+    return zi
+
+
+def surface_projection(points, R, T, focal, pp, local_features, radius=0.0075, scale_factor=1.0):
+    """projection_model.py:127-157 -> (out f32[B,N,C], zbuf_idx int32[B,H,W])"""
+    local_features = _f32(local_features)
+    b, C, H, W = local_features.shape
+    T = _f32(T) * np.float32(scale_factor)  # projection_model.py:136-137
+    ndc = project_points(points, R, T, focal, pp)
+    zi = rasterize_points(ndc, H, W, radius)
+    n = ndc.shape[1]
+    out = np.empty((b, n, C), np.float32)
+    lib().orc_splat_features(_I(b), _I(n), _I(C), _I(H), _I(W), _p(zi), _p(local_features), _p(out))
+    return out, zi
+
+
+# ------------------------------------------------------------------------------------------------
+# Evaluation (fp64)
+# ------------------------------------------------------------------------------------------------
+def nn_direct(src, tgt):
+    """src [B,N,3], tgt [B,M,3] (fp64) -> (min squared distance [B,N], argmin int32[B,N])"""
+    src, tgt = _f64(src), _f64(tgt)
+    b, n, _ = src.shape
+    m = tgt.shape[1]
+    d = np.empty((b, n), np.float64)
+    i = np.empty((b, n), np.int32)
+    lib().orc_nn_direct_f64(_I(b), _I(n), _I(m), _p(src), _p(tgt), _p(d), _p(i))
+    return d, i
+
+
+def nn_expanded(src, tgt):
+    """evaluation_f1.py:90-98 compute_pc_to_pc_dist, batched: -> min clamped squared distance [B,N]"""
+    src, tgt = _f64(src), _f64(tgt)
+    b, n, _ = src.shape
+    m = tgt.shape[1]
+    d = np.empty((b, n), np.float64)
+    lib().orc_nn_expanded_f64(_I(b), _I(n), _I(m), _p(src), _p(tgt), _p(d))
+    return d
+
+
+def chamfer_distance(pred, gt):
+    """evaluation_cd.py:111-125: inputs are mean-centred by the caller; pytorch3d chamfer_distance
+    defaults (squared L2, point_reduction='mean', batch_reduction='mean') -> per-pair CD [B]"""
+    d1, _ = nn_direct(pred, gt)
+    d2, _ = nn_direct(gt, pred)
+    return d1.mean(axis=1) + d2.mean(axis=1)
+
+
+def fscore(gt, pred, thr=0.01):
+    """evaluation_f1.py:101-110 cal_fscore, batched -> per-pair F [B]"""
+    d1 = nn_expanded(gt, pred)
+    d2 = nn_expanded(pred, gt)
+    precision = (d1 < thr).sum(axis=1) / float(d1.shape[1])
+    recall = (d2 < thr).sum(axis=1) / float(d2.shape[1])
+    return 2 * recall * precision / (recall + precision + 1e-12)

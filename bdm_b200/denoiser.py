@@ -1,0 +1,302 @@
+"""Point-voxel denoisers of BDM on the B200 hot path: the callers either side of the sparse ops.
+
+Three networks, all with the reference's module tree (attribute names, Sequential positions and
+therefore state_dict keys), so reference checkpoints load with `load_state_dict`:
+
+  PVCNN2_PC2   projection-conditioned reconstruction denoiser
+               (reference: experiments/model/pvcnn/pvcnn.py:10-150, builders pvcnn_utils.py:14-185)
+  PVCNN2_PVD   unconditional prior denoiser -- same architecture, no extra feature channels
+               (reference: experiments/pvd/model/pvcnn_generation.py:172-245, pvd/__init__.py:300-332)
+  PVCNNFuse    BDM-Merging network: PC^2 encoder + PVD encoder, 4 zero-initialised 1x1-conv
+               projections, shared decoder   (reference: experiments/model/pvcnn/pvcnn_fuse.py:14-237)
+
+The dense layers (Conv3d / GroupNorm / attention / 1x1 convs) run on cuDNN / cuBLAS through torch; every
+sparse op goes through bdm_b200.modules -> bdm_b200.functional -> libbdm_b200.so.
+
+The layer tables and the two builder functions below restate the reference's construction rules,
+including its quirks, because they decide the parameter shapes:
+  * in an SA stage after the first, only the FIRST PVConv of the configured `num_blocks` is
+    instantiated (pvcnn_utils.py:98-103 `elif k == 0`);
+  * the FP-stage attention predicate can never be true (pvcnn_utils.py:149 compares against the length
+    of a list it has just shadowed), so FP PVConvs never carry attention;
+  * the SA module's input width counts the time embedding only when the stage has no PVConv (:118).
+"""
+import math
+
+import torch
+import torch.nn as nn
+
+from .modules import Attention, PointNetAModule, PointNetFPModule, PointNetSAModule, PVConv, SharedMLP
+
+# ((conv out_channels, num_blocks, voxel_resolution) | None, (num_centers, radius, num_neighbors, mlp widths))
+SA_BLOCKS = [
+    ((32, 2, 32), (1024, 0.1, 32, (32, 64))),
+    ((64, 3, 16), (256, 0.2, 32, (64, 128))),
+    ((128, 3, 8), (64, 0.4, 32, (128, 256))),
+    (None, (16, 0.8, 32, (256, 256, 512))),
+]
+# (fp mlp widths, (conv out_channels, num_blocks, voxel_resolution) | None)
+FP_BLOCKS = [
+    ((256, 256), (256, 3, 8)),
+    ((256, 256), (256, 3, 8)),
+    ((256, 128), (128, 2, 16)),
+    ((128, 128, 64), (64, 2, 32)),
+]
+
+
+def timestep_embedding(embed_dim, timesteps, device):
+    """Sinusoidal embedding [B] -> [B, embed_dim]: sin half then cos half, frequencies
+    exp(-i * ln(1e4)/(half-1)).  reference: pvcnn_utils.py:171-185 (computed through float64 numpy
+    then cast to fp32, reproduced with the same dtype path)."""
+    assert timesteps.dim() == 1
+    half = embed_dim // 2
+    step = math.log(10000) / (half - 1)
+    freqs = torch.exp(torch.arange(half, dtype=torch.float64) * -step).float().to(device)
+    arg = timesteps[:, None] * freqs[None, :]
+    emb = torch.cat([torch.sin(arg), torch.cos(arg)], dim=1)
+    if embed_dim % 2 == 1:
+        emb = nn.functional.pad(emb, (0, 1), "constant", 0)
+    return emb
+
+
+def _scaled(widths, r):
+    return [[int(r * w) for w in ws] if isinstance(ws, (list, tuple)) else int(r * ws) for ws in widths]
+
+
+def build_sa_layers(sa_blocks, extra_feature_channels, embed_dim=64, use_att=False, dropout=0.1, with_se=False,
+                    normalize=True, eps=0, width_multiplier=1, voxel_resolution_multiplier=1):
+    """-> (list of stages, input width of every stage, output width, number of final centres)"""
+    r, vr = width_multiplier, voxel_resolution_multiplier
+    width = extra_feature_channels + 3
+    stages, stage_in_widths = [], []
+    num_centers = None
+    for stage_idx, (conv_cfg, sa_cfg) in enumerate(sa_blocks):
+        stage_in_widths.append(width)
+        parts = []
+        convs_configured = 0
+        feat_width = extra_feature_channels if stage_idx == 0 else width
+        if conv_cfg is not None:
+            c_out, num_blocks, resolution = conv_cfg
+            c_out = int(r * c_out)
+            for p in range(num_blocks):
+                attention = (stage_idx + 1) % 2 == 0 and use_att and p == 0
+
+                def make(c_in, c_out=c_out, attention=attention):
+                    if resolution is None:
+                        return SharedMLP(c_in, c_out)
+                    return PVConv(c_in, c_out, kernel_size=3, resolution=int(vr * resolution), attention=attention,
+                                  dropout=dropout, with_se=with_se, with_se_relu=True, normalize=normalize, eps=eps)
+
+                if stage_idx == 0:
+                    parts.append(make(width))
+                elif convs_configured == 0:
+                    parts.append(make(width + embed_dim))
+                width = c_out
+                convs_configured += 1
+            feat_width = width
+        num_centers, radius, num_neighbors, mlp_widths = sa_cfg
+        mlp_widths = _scaled(mlp_widths, r)
+        sa_in = feat_width + (embed_dim if convs_configured == 0 else 0)
+        if num_centers is None:
+            parts.append(PointNetAModule(in_channels=sa_in, out_channels=mlp_widths, include_coordinates=True))
+        else:
+            parts.append(PointNetSAModule(num_centers=num_centers, radius=radius, num_neighbors=num_neighbors,
+                                          in_channels=sa_in, out_channels=mlp_widths, include_coordinates=True))
+        width = parts[-1].out_channels
+        stages.append(parts[0] if len(parts) == 1 else nn.Sequential(*parts))
+    return stages, stage_in_widths, width, (1 if num_centers is None else num_centers)
+
+
+def build_fp_layers(fp_blocks, in_channels, sa_in_channels, embed_dim=64, use_att=False, dropout=0.1,
+                    with_se=False, normalize=True, eps=0, width_multiplier=1, voxel_resolution_multiplier=1):
+    """-> (list of stages, output width).  `use_att` is accepted for signature parity; the reference's
+    predicate never enables attention in FP stages (see module docstring)."""
+    r, vr = width_multiplier, voxel_resolution_multiplier
+    width = in_channels
+    stages = []
+    for fp_idx, (fp_widths, conv_cfg) in enumerate(fp_blocks):
+        fp_widths = tuple(int(r * w) for w in fp_widths)
+        parts = [PointNetFPModule(in_channels=width + sa_in_channels[-1 - fp_idx] + embed_dim, out_channels=fp_widths)]
+        width = fp_widths[-1]
+        if conv_cfg is not None:
+            c_out, num_blocks, resolution = conv_cfg
+            c_out = int(r * c_out)
+            for _ in range(num_blocks):
+                if resolution is None:
+                    parts.append(SharedMLP(width, c_out))
+                else:
+                    parts.append(PVConv(width, c_out, kernel_size=3, resolution=int(vr * resolution),
+                                        attention=False, dropout=dropout, with_se=with_se, with_se_relu=True,
+                                        normalize=normalize, eps=eps))
+                width = c_out
+        stages.append(parts[0] if len(parts) == 1 else nn.Sequential(*parts))
+    return stages, width
+
+
+def build_classifier(in_channels, num_classes, dropout, width_multiplier=1):
+    """SharedMLP(in,128) -> Dropout -> Conv1d(128,num_classes,1)   (pvcnn_utils.py:14-46 with
+    out_channels=[128, dropout, num_classes], classifier=True, dim=2)"""
+    hidden = int(width_multiplier * 128)
+    return nn.Sequential(SharedMLP(in_channels, hidden), nn.Dropout(dropout), nn.Conv1d(hidden, num_classes, 1))
+
+
+def _time_mlp(embed_dim):
+    return nn.Sequential(nn.Linear(embed_dim, embed_dim), nn.LeakyReLU(0.1, inplace=True),
+                         nn.Linear(embed_dim, embed_dim))
+
+
+def _encode(sa_layers, features, coords, temb):
+    """Run the SA pyramid; returns the bottleneck state and the per-stage (coords, input features)."""
+    coords_per_stage, feats_per_stage = [], []
+    for i, stage in enumerate(sa_layers):
+        feats_per_stage.append(features)
+        coords_per_stage.append(coords)
+        stage_in = features if i == 0 else torch.cat([features, temb], dim=1)
+        features, coords, temb = stage((stage_in, coords, temb))
+    return features, coords, temb, coords_per_stage, feats_per_stage
+
+
+def _decode(fp_layers, features, coords, temb, coords_per_stage, skips_per_stage):
+    for fp_idx, stage in enumerate(fp_layers):
+        features, coords, temb = stage((coords_per_stage[-1 - fp_idx], coords, torch.cat([features, temb], dim=1),
+                                        skips_per_stage[-1 - fp_idx], temb))
+    return features
+
+
+class PVCNN2(nn.Module):
+    """U-shaped point-voxel denoiser: 4 set-abstraction stages, global attention, 4 feature-propagation
+    stages, per-point classifier.  forward(inputs f32[B,3+S,N], t [B]) -> f32[B,num_classes,N]."""
+    sa_blocks = SA_BLOCKS
+    fp_blocks = FP_BLOCKS
+
+    def __init__(self, num_classes, embed_dim, use_att=True, dropout=0.1, extra_feature_channels=3,
+                 width_multiplier=1, voxel_resolution_multiplier=1):
+        super().__init__()
+        assert extra_feature_channels >= 0
+        self.embed_dim = embed_dim
+        self.dropout = dropout
+        self.width_multiplier = width_multiplier
+        self.in_channels = extra_feature_channels + 3
+        common = dict(embed_dim=embed_dim, use_att=use_att, dropout=dropout, with_se=True,
+                      width_multiplier=width_multiplier, voxel_resolution_multiplier=voxel_resolution_multiplier)
+        sa_layers, sa_in_widths, bottleneck, _ = build_sa_layers(self.sa_blocks, extra_feature_channels, **common)
+        self.sa_layers = nn.ModuleList(sa_layers)
+        self.global_att = Attention(bottleneck, 8, D=1) if use_att else None
+        sa_in_widths[0] = extra_feature_channels  # the last FP stage sees only the extra features
+        fp_layers, fp_width = build_fp_layers(self.fp_blocks, bottleneck, sa_in_widths, **common)
+        self.fp_layers = nn.ModuleList(fp_layers)
+        self.channels_fp_features = fp_width
+        self.classifier = build_classifier(fp_width, num_classes, dropout, width_multiplier)
+        self.embedf = _time_mlp(embed_dim)
+
+    def forward(self, inputs, t):
+        temb = self.embedf(timestep_embedding(self.embed_dim, t, inputs.device).float())
+        temb = temb[:, :, None].expand(-1, -1, inputs.shape[-1])
+        coords = inputs[:, :3, :].contiguous()
+        features, coords, temb, coords_per_stage, feats_per_stage = _encode(self.sa_layers, inputs, coords, temb)
+        feats_per_stage[0] = inputs[:, 3:, :].contiguous()
+        if self.global_att is not None:
+            features = self.global_att(features)
+        features = _decode(self.fp_layers, features, coords, temb, coords_per_stage, feats_per_stage)
+        return self.classifier(features)
+
+
+class PVCNN2_PC2(PVCNN2):
+    """reference: experiments/model/pvcnn/pvcnn.py:130-150"""
+
+
+class PVCNN2_PVD(PVCNN2):
+    """reference: experiments/pvd/__init__.py:300-332 (use_att and dropout are positional there)"""
+
+    def __init__(self, num_classes, embed_dim, use_att, dropout, extra_feature_channels=3, width_multiplier=1,
+                 voxel_resolution_multiplier=1):
+        super().__init__(num_classes, embed_dim, use_att, dropout, extra_feature_channels, width_multiplier,
+                         voxel_resolution_multiplier)
+
+
+class PointCloudModel(nn.Module):
+    """(B,N,C) <-> (B,C,N) adapter around PVCNN2_PC2 with the reference's output-layer initialisation.
+    reference: experiments/model/point_cloud_model.py:14-65 (model_type='pvcnn' only; fp32 is forced
+    there through an autocast context, here simply by running in fp32)."""
+
+    def __init__(self, in_channels=3, out_channels=3, embed_dim=64, dropout=0.1, width_multiplier=1,
+                 voxel_resolution_multiplier=1):
+        super().__init__()
+        self.model = PVCNN2_PC2(num_classes=out_channels, embed_dim=embed_dim, extra_feature_channels=in_channels - 3,
+                                dropout=dropout, width_multiplier=width_multiplier,
+                                voxel_resolution_multiplier=voxel_resolution_multiplier)
+        self.model.classifier[-1].bias.data.normal_(0, 1e-6)
+        self.model.classifier[-1].weight.data.normal_(0, 1e-6)
+
+    def forward(self, inputs, t):
+        return self.model(inputs.transpose(1, 2), t).transpose(1, 2)
+
+
+class PVCNNFuse(nn.Module):
+    """BDM-Merging network.  The two encoders are the *shared* submodules of an existing PC^2 denoiser
+    and PVD denoiser (as in the reference, which aliases them: pvcnn_fuse.py:29-35); the decoder,
+    classifier and time MLP are initialised from the PC^2 network (:88, :100-104); `projs[k]` are
+    conv-LeakyReLU-conv-zero_conv stacks of widths 64/128/256/512 (:111-123).
+
+    forward(recon_inputs_with_cond f32[B,3+S,N], input_from_prior f32[B,3,N], t [B]) -> f32[B,3,N]
+
+    Defined behaviour where the reference has none: the reference feeds the PVD encoder the time
+    embedding left over from the PC^2 encoder, which by then is [B,64,16], and then gathers it with
+    neighbour indices up to N-1 (pvcnn_fuse.py:176-186 -> modules/ball_query.py:30): an out-of-bounds
+    read.  Here the PVD encoder gets the time embedding at full length N."""
+
+    def __init__(self, pvd_net, pc2_net, num_classes=3, embed_dim=64, use_att=True, dropout=0.1,
+                 extra_feature_channels=3, width_multiplier=1, voxel_resolution_multiplier=1):
+        super().__init__()
+        self.pvd_model_sa_layers = pvd_net.sa_layers
+        self.pvd_model_global_att = pvd_net.global_att
+        self.pc2_model_sa_layers = pc2_net.sa_layers
+        self.pc2_model_global_att = pc2_net.global_att
+        self.pc2_model_fp_layers = pc2_net.fp_layers
+        self.pc2_model_classiifier = pc2_net.classifier  # (sic) the reference's attribute name
+        self.pc2_model_embedf = pc2_net.embedf
+        self.embed_dim = embed_dim
+        common = dict(embed_dim=embed_dim, use_att=use_att, dropout=dropout, with_se=True,
+                      width_multiplier=width_multiplier, voxel_resolution_multiplier=voxel_resolution_multiplier)
+        _, sa_in_widths, bottleneck, _ = build_sa_layers(SA_BLOCKS, extra_feature_channels, **common)
+        sa_in_widths[0] = extra_feature_channels
+        fp_layers, fp_width = build_fp_layers(FP_BLOCKS, bottleneck, sa_in_widths, **common)
+        self.fusion_decoder_fp_layers = nn.ModuleList(fp_layers)
+        self.classifier = build_classifier(fp_width, num_classes, dropout, width_multiplier)
+        self.embedf = _time_mlp(embed_dim)
+        self.embedf.load_state_dict(self.pc2_model_embedf.state_dict())
+        self.fusion_decoder_fp_layers.load_state_dict(self.pc2_model_fp_layers.state_dict())
+        self.classifier.load_state_dict(self.pc2_model_classiifier.state_dict())
+        projs = []
+        for dim in (64, 128, 256, 512):
+            conv1, conv2, zero_conv = nn.Conv1d(dim, dim, 1), nn.Conv1d(dim, dim, 1), nn.Conv1d(dim, dim, 1)
+            for conv in (conv1, conv2):
+                nn.init.normal_(conv.weight, mean=0.0, std=math.sqrt(2 / dim))
+                nn.init.constant_(conv.bias, 0)
+            for p in zero_conv.parameters():
+                p.detach().zero_()
+            projs.append(nn.Sequential(conv1, nn.LeakyReLU(0.02, inplace=True), conv2, zero_conv))
+        self.projs = nn.ModuleList(projs)
+
+    def forward(self, recon_inputs_with_cond, input_from_prior, t, mode='fusion_nstep'):
+        n = recon_inputs_with_cond.shape[-1]
+        temb_vec = self.embedf(timestep_embedding(self.embed_dim, t, recon_inputs_with_cond.device).float())
+        temb_full = temb_vec[:, :, None].expand(-1, -1, n)
+        coords_pc2 = recon_inputs_with_cond[:, :3, :].contiguous()
+        coords_pvd = (input_from_prior if mode == 'fusion_nstep' else coords_pc2).clone()
+
+        f_pc2, c_pc2, temb, coords_per_stage, pc2_skips = _encode(self.pc2_model_sa_layers, recon_inputs_with_cond,
+                                                                 coords_pc2, temb_full)
+        pc2_skips[0] = recon_inputs_with_cond[:, 3:, :].contiguous()
+        if self.pc2_model_global_att is not None:
+            f_pc2 = self.pc2_model_global_att(f_pc2)
+
+        f_pvd, _, _, _, pvd_skips = _encode(self.pvd_model_sa_layers, coords_pvd.clone(), coords_pvd, temb_full)
+        if self.pvd_model_global_att is not None:
+            f_pvd = self.pvd_model_global_att(f_pvd)
+
+        features = self.projs[-1](f_pvd) + f_pc2
+        fused_skips = [pc2_skips[0]] + [proj(pvd_f) + pc2_f for pc2_f, pvd_f, proj in
+                                        zip(pc2_skips[1:], pvd_skips[1:], self.projs)]
+        features = _decode(self.fusion_decoder_fp_layers, features, c_pc2, temb, coords_per_stage, fused_skips)
+        return self.classifier(features)

@@ -1,0 +1,83 @@
+"""Dense building blocks of the point-voxel networks.  These run on cuDNN / cuBLAS through torch
+(the sparse hot path is elsewhere); they are restated here only so that the module tree -- class
+names, parameter names, layer order -- matches the reference's and its checkpoints load.
+
+reference: modules/shared_mlp.py:10-37, modules/se.py:8-19, modules/pvconv.py:12-63, modules/loss.py:8-10
+"""
+import torch
+import torch.nn as nn
+
+from .. import functional as F
+
+
+class Swish(nn.Module):
+    def forward(self, x):
+        return x * torch.sigmoid(x)
+
+
+class SharedMLP(nn.Module):
+    """Stack of (1x1 conv, GroupNorm(8), Swish) over points [B,C,N] (dim=1) or neighbourhoods
+    [B,C,M,U] (dim=2).  Parameters live at `layers.{3i}` (conv) and `layers.{3i+1}` (norm)."""
+
+    def __init__(self, in_channels, out_channels, dim=1):
+        super().__init__()
+        try:
+            conv = {1: nn.Conv1d, 2: nn.Conv2d}[dim]
+        except KeyError:
+            raise ValueError
+        widths = list(out_channels) if isinstance(out_channels, (list, tuple)) else [out_channels]
+        stack, c_in = [], in_channels
+        for c_out in widths:
+            stack += [conv(c_in, c_out, 1), nn.GroupNorm(8, c_out), Swish()]
+            c_in = c_out
+        self.layers = nn.Sequential(*stack)
+
+    def forward(self, inputs):
+        # tuples carry (features, *passthrough): only the features go through the MLP
+        if isinstance(inputs, (list, tuple)):
+            head, *rest = inputs
+            return (self.layers(head), *rest)
+        return self.layers(inputs)
+
+
+class SE3d(nn.Module):
+    """Squeeze-and-excitation gate over a voxel grid; two bias-free Linears at `fc.0` / `fc.2`."""
+
+    def __init__(self, channel, reduction=8, use_relu=False):
+        super().__init__()
+        hidden = channel // reduction
+        self.fc = nn.Sequential(nn.Linear(channel, hidden, bias=False),
+                                nn.ReLU(True) if use_relu else Swish(),
+                                nn.Linear(hidden, channel, bias=False),
+                                nn.Sigmoid())
+
+    def forward(self, inputs):
+        # three chained means (z, y, x) like the reference, for identical rounding
+        pooled = inputs.mean(-1).mean(-1).mean(-1)
+        return inputs * self.fc(pooled)[:, :, None, None, None]
+
+
+class Attention(nn.Module):
+    """Dense single-head self-attention with un-scaled logits over voxels (D=3) or points (D=1),
+    residual, GroupNorm, Swish.  Parameters: q, k, v, out (1x1 convs) and norm."""
+
+    def __init__(self, in_ch, num_groups, D=3):
+        super().__init__()
+        assert in_ch % num_groups == 0
+        conv = {3: nn.Conv3d, 1: nn.Conv1d}[D]
+        self.q, self.k, self.v, self.out = (conv(in_ch, in_ch, 1) for _ in range(4))
+        self.norm = nn.GroupNorm(num_groups, in_ch)
+        self.nonlin = Swish()
+        self.sm = nn.Softmax(-1)
+
+    def forward(self, x):
+        nb, nc = x.shape[:2]
+        q, k, v = (proj(x).reshape(nb, nc, -1) for proj in (self.q, self.k, self.v))
+        attn = self.sm(torch.matmul(q.transpose(1, 2), k))             # [B, T, T]
+        mixed = torch.matmul(v, attn.transpose(1, 2)).reshape(x.shape)  # [B, C, ...]
+        return self.nonlin(self.norm(self.out(mixed) + x))
+
+
+class KLLoss(nn.Module):
+    def forward(self, x, y):
+        return F.kl_loss(x, y)

@@ -1,0 +1,95 @@
+"""Voxelization and the point-voxel convolution block.
+
+reference: modules/voxelization.py:9-28, modules/pvconv.py:65-137
+"""
+import torch
+import torch.nn as nn
+
+from .. import functional as F
+from .layers import SE3d, Attention, SharedMLP, Swish
+
+
+def normalized_voxel_coords(coords, resolution, normalize=True, eps=0):
+    """Float coordinates in [0, R-1] for a cloud f32[B,3,N]: centre on the mean, scale by twice the
+    largest point norm, shift to [0,1], stretch to the grid and clamp.  This is deliberately the
+    reference's own sequence of torch ops (voxelization.py:17-23) -- mean, norm, max, divide, +0.5,
+    *R, clamp -- because the rounded integer coordinates, and every voxel index after them, must be
+    bit-identical."""
+    centred = coords - coords.mean(2, keepdim=True)
+    if normalize:
+        extent = centred.norm(dim=1, keepdim=True).max(dim=2, keepdim=True).values * 2.0 + eps
+        unit = centred / extent + 0.5
+    else:
+        unit = (centred + 1) / 2.0
+    return torch.clamp(unit * resolution, 0, resolution - 1)
+
+
+class Voxelization(nn.Module):
+    def __init__(self, resolution, normalize=True, eps=0):
+        super().__init__()
+        self.r = int(resolution)
+        self.normalize = normalize
+        self.eps = eps
+
+    def forward(self, features, coords):
+        """-> (voxel grid f32[B,C,R,R,R], float voxel coordinates f32[B,3,N])"""
+        norm_coords = normalized_voxel_coords(coords.detach(), self.r, self.normalize, self.eps)
+        vox_coords = torch.round(norm_coords).to(torch.int32)  # half-to-even, like the reference
+        return F.avg_voxelize(features, vox_coords, self.r), norm_coords
+
+    def extra_repr(self):
+        return 'resolution={}{}'.format(self.r, ', normalized eps = {}'.format(self.eps) if self.normalize else '')
+
+
+def _voxel_stack(c_in, c_out, k, attention, dropout, with_se, with_se_relu, make_norm, make_act):
+    """conv-norm-act-[dropout]-conv-norm-(attention|act)-[SE]; positions in the Sequential are the
+    reference's (pvconv.py:75-88) so `voxel_layers.{i}` keys line up."""
+    pad = k // 2
+    seq = [nn.Conv3d(c_in, c_out, k, stride=1, padding=pad), make_norm(c_out), make_act()]
+    if dropout is not None:
+        seq.append(nn.Dropout(dropout))
+    seq += [nn.Conv3d(c_out, c_out, k, stride=1, padding=pad), make_norm(c_out),
+            Attention(c_out, 8) if attention else make_act()]
+    if with_se:
+        seq.append(SE3d(c_out, use_relu=with_se_relu))
+    return nn.Sequential(*seq)
+
+
+class _PVConvBase(nn.Module):
+    def __init__(self, in_channels, out_channels, kernel_size, resolution, normalize, eps):
+        super().__init__()
+        self.in_channels = in_channels
+        self.out_channels = out_channels
+        self.kernel_size = kernel_size
+        self.resolution = resolution
+        self.voxelization = Voxelization(resolution, normalize=normalize, eps=eps)
+
+    def forward(self, inputs):
+        features, coords, temb = inputs
+        grid, grid_coords = self.voxelization(features, coords)
+        grid = self.voxel_layers(grid)
+        from_voxels = F.trilinear_devoxelize(grid, grid_coords, self.resolution, self.training)
+        return from_voxels + self.point_features(features), coords, temb
+
+
+class PVConv(_PVConvBase):
+    """voxelize -> 3-D convs (GroupNorm/Swish) -> trilinear devoxelize, fused with a point-wise MLP.
+    Submodules: voxelization, voxel_layers, point_features."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, resolution, attention=False,
+                 dropout=0.1, with_se=False, with_se_relu=False, normalize=True, eps=0):
+        super().__init__(in_channels, out_channels, kernel_size, resolution, normalize, eps)
+        self.voxel_layers = _voxel_stack(in_channels, out_channels, kernel_size, attention, dropout, with_se,
+                                         with_se_relu, lambda c: nn.GroupNorm(num_groups=8, num_channels=c), Swish)
+        self.point_features = SharedMLP(in_channels, out_channels)
+
+
+class PVConvReLU(_PVConvBase):
+    """BatchNorm / LeakyReLU variant of PVConv."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, resolution, attention=False, leak=0.2,
+                 dropout=0.1, with_se=False, with_se_relu=False, normalize=True, eps=0):
+        super().__init__(in_channels, out_channels, kernel_size, resolution, normalize, eps)
+        self.voxel_layers = _voxel_stack(in_channels, out_channels, kernel_size, attention, dropout, with_se,
+                                         with_se_relu, nn.BatchNorm3d, lambda: nn.LeakyReLU(leak, True))
+        self.point_features = SharedMLP(in_channels, out_channels)

@@ -1,0 +1,82 @@
+"""CPU: the drop-in boundary.  libbdm_b200.so loads and exports every symbol include/bdm_b200.h
+declares (no compute call is made: there is no GPU here); the product package never touches oracle/."""
+import ctypes
+import os
+import re
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "bdm_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(bdm_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from bdm_b200 import _lib
+    declared = _declared_symbols()
+    assert len(declared) >= 20
+    so = ctypes.CDLL(_lib.SO_PATH)
+    missing = [s for s in declared if not hasattr(so, s)]
+    assert not missing, f"declared in include/bdm_b200.h but not exported: {missing}"
+    assert sorted(_lib.EXPORTS) == declared, "ctypes prototypes and header disagree"
+    assert _lib.ABI_VERSION == 1
+
+
+def test_error_strings():
+    from bdm_b200 import _lib
+    assert _lib.lib.bdm_error_string(0) == b"success"
+    assert b"NULL" in _lib.lib.bdm_error_string(-1)
+    assert b"workspace" in _lib.lib.bdm_error_string(-3)
+
+
+def test_workspace_queries_need_no_gpu():
+    from bdm_b200 import _lib
+    L = _lib.lib
+    assert L.bdm_avg_voxelize_workspace_bytes(16, 4096, 32) >= 16 * (4096 + 2048 + 8192 + 8192)
+    assert L.bdm_avg_voxelize_workspace_bytes(1, 4096, 64) == 16          # generic path: no workspace
+    assert L.bdm_furthest_point_sampling_workspace_bytes(4, 4096) == 16   # register path
+    assert L.bdm_furthest_point_sampling_workspace_bytes(4, 20000) == 4 * 4 * 20000
+
+
+def test_argument_errors_do_not_need_a_gpu():
+    from bdm_b200 import _lib
+    L = _lib.lib
+    assert L.bdm_grouping(1, 1, 4, 2, 2, None, None, None, None) == -1          # NULL pointers
+    assert L.bdm_ball_query(-1, 4, 2, 0.1, 2, None, None, None, None) == -2     # bad size
+    assert L.bdm_grouping(0, 1, 4, 2, 2, None, None, None, None) == 0           # empty batch is a no-op
+
+
+def test_product_never_imports_oracle():
+    """A product path that routes through the oracle voids every parity claim: forbid it textually."""
+    offenders = []
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "bdm_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                src = open(os.path.join(dirpath, f)).read()
+                if re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M) or "libbdm_oracle" in src \
+                        or re.search(r"#include\s+[<\"].*oracle", src):
+                    offenders.append(os.path.join(dirpath, f))
+    assert not offenders, offenders
+
+
+def test_missing_library_fails_loudly(tmp_path, monkeypatch):
+    """bdm_b200._lib must raise, not fall back, when the .so is absent."""
+    import importlib
+    import sys
+    src = open(os.path.join(ROOT, "bdm_b200", "_lib.py")).read()
+    pkg = tmp_path / "fakepkg"
+    pkg.mkdir()
+    (pkg / "__init__.py").write_text("")
+    (pkg / "_lib.py").write_text(src)
+    monkeypatch.syspath_prepend(str(tmp_path))
+    try:
+        importlib.import_module("fakepkg._lib")
+        raised = False
+    except ImportError:
+        raised = True
+    finally:
+        sys.modules.pop("fakepkg._lib", None)
+        sys.modules.pop("fakepkg", None)
+    assert raised

@@ -1,0 +1,160 @@
+"""CPU tests of the host-side mirror: module tree / state_dict parity with the reference, drop-in
+injection, and forward equality of our modules vs the reference's own Python modules when both run
+on the same (oracle-backed) `_backend`.  The reference-dependent tests need /root/reference and are
+skipped where it does not exist (the GPU box)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+REF_EXP = "/root/reference/experiments"
+needs_ref = pytest.mark.skipif(not os.path.isdir(REF_EXP), reason="reference checkout not present")
+
+
+@pytest.fixture()
+def oracle_backend(monkeypatch):
+    from tests.oracle_backend import OracleBackend
+    import bdm_b200.functional.ops as ops
+    ob = OracleBackend()
+    monkeypatch.setattr(ops, "_B", ob)
+    return ob
+
+
+def test_public_surface():
+    import bdm_b200.functional as F
+    import bdm_b200.modules as M
+    for name in ['ball_query', 'trilinear_devoxelize', 'grouping', 'nearest_neighbor_interpolate', 'kl_loss',
+                 'huber_loss', 'gather', 'furthest_point_sample', 'logits_mask', 'avg_voxelize']:
+        assert callable(getattr(F, name)), name          # functional/__init__.py:1-7
+    for name in ['BallQuery', 'FrustumPointNetLoss', 'KLLoss', 'PointNetAModule', 'PointNetSAModule',
+                 'PointNetFPModule', 'PVConv', 'Attention', 'Swish', 'PVConvReLU', 'SE3d', 'SharedMLP',
+                 'Voxelization']:
+        assert hasattr(M, name), name                    # modules/__init__.py:1-8
+    from bdm_b200 import backend
+    for name in ['gather_features_forward', 'gather_features_backward', 'furthest_point_sampling', 'ball_query',
+                 'grouping_forward', 'grouping_backward', 'three_nearest_neighbors_interpolate_forward',
+                 'three_nearest_neighbors_interpolate_backward', 'trilinear_devoxelize_forward',
+                 'trilinear_devoxelize_backward', 'avg_voxelize_forward', 'avg_voxelize_backward']:
+        assert callable(getattr(backend, name)), name    # bindings.cpp:11-36
+
+
+def test_parameter_counts():
+    from bdm_b200.denoiser import PVCNN2_PC2, PVCNN2_PVD
+    pc2 = PVCNN2_PC2(num_classes=3, embed_dim=64, extra_feature_channels=387)
+    pvd = PVCNN2_PVD(3, 64, True, 0.1, extra_feature_channels=0)
+    assert sum(p.numel() for p in pc2.parameters()) == 28046275   # SURVEY.md section 3.1 (probe P3)
+    assert sum(p.numel() for p in pvd.parameters()) == 27649987
+
+
+def test_forward_counts_match_schedule():
+    from bdm_b200.diffusion import forward_counts
+    assert forward_counts(mode="blending") == dict(pc2=1000, pvd=80, fuse=0)
+    assert forward_counts(mode="merging") == dict(pc2=995, pvd=75, fuse=5)
+
+
+def test_backend_rejects_cpu_tensors():
+    """No CPU fallback: the product backend refuses non-CUDA inputs like the reference (utils.hpp:7)."""
+    from bdm_b200 import backend
+    with pytest.raises(RuntimeError):
+        backend.grouping_forward(torch.zeros(1, 2, 8), torch.zeros(1, 2, 2, dtype=torch.int32))
+    with pytest.raises(RuntimeError):
+        backend.furthest_point_sampling(torch.zeros(1, 3, 8), 4)
+
+
+def _small_inputs(b=2, n=96, extra=5, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(b, 3 + extra, n, generator=g), torch.tensor([500.0, 17.0])[:b]
+
+
+def test_denoiser_runs_on_oracle_backend(oracle_backend):
+    """Our module tree end to end on CPU (oracle-backed): shapes, op-call census of SURVEY.md section 3.1."""
+    from bdm_b200.denoiser import PVCNN2_PC2
+    torch.manual_seed(1)
+    net = PVCNN2_PC2(num_classes=3, embed_dim=64, extra_feature_channels=5).eval()
+    x, t = _small_inputs()
+    with torch.no_grad():
+        y = net(x, t)
+    assert y.shape == (2, 3, 96) and torch.isfinite(y).all()
+    names = [c[0] for c in oracle_backend.calls]
+    assert names.count("avg_voxelize_forward") == 14
+    assert names.count("trilinear_devoxelize_forward") == 14
+    assert names.count("furthest_point_sampling") == 4
+    assert names.count("ball_query") == 4
+    # the reference does 12 groupings and 8 three-NN calls per forward; the mirror drops the 4 groupings
+    # of the point-constant time embedding and searches once per FP stage
+    assert names.count("grouping_forward") == 8
+    assert names.count("three_nn_search") == 4 and names.count("three_nn_interpolate") == 8
+
+
+@needs_ref
+def test_state_dict_and_forward_match_reference_modules(oracle_backend):
+    """Reference PVCNN2_PC2 (its own Python, via bdm_b200.dropin with an oracle-backed _backend) vs
+    our PVCNN2_PC2 with the same weights: identical state_dict layout, bit-identical forward."""
+    from bdm_b200 import dropin
+    from bdm_b200.denoiser import PVCNN2_PC2
+    saved = {k: sys.modules.get(k) for k in ("model", "pvd") + dropin.BACKEND_MODULE_NAMES}
+    try:
+        dropin.install(REF_EXP, backend=oracle_backend, stub_packages=True)
+        from model.pvcnn.pvcnn import PVCNN2_PC2 as RefNet
+        torch.manual_seed(3)
+        ref = RefNet(num_classes=3, embed_dim=64, extra_feature_channels=5).eval()
+        ours = PVCNN2_PC2(num_classes=3, embed_dim=64, extra_feature_channels=5).eval()
+        rs, os_ = ref.state_dict(), ours.state_dict()
+        assert list(rs.keys()) == list(os_.keys())
+        assert all(rs[k].shape == os_[k].shape for k in rs)
+        ours.load_state_dict(rs)
+        x, t = _small_inputs(seed=4)
+        with torch.no_grad():
+            yr = ref(x, t)
+            yo = ours(x, t)
+        assert torch.equal(yr, yo)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+        for k in [k for k in sys.modules if k.startswith("model.") or k.startswith("pvd.")]:
+            sys.modules.pop(k, None)
+
+
+@needs_ref
+def test_pvd_state_dict_matches_reference():
+    from bdm_b200 import dropin
+    from bdm_b200.denoiser import PVCNN2_PVD
+    from tests.oracle_backend import OracleBackend
+    saved = {k: sys.modules.get(k) for k in ("model", "pvd") + dropin.BACKEND_MODULE_NAMES}
+    try:
+        dropin.install(REF_EXP, backend=OracleBackend(), stub_packages=True)
+        from pvd.model.pvcnn_generation import PVCNN2Base_PVD
+
+        class RefPVD(PVCNN2Base_PVD):
+            from bdm_b200.denoiser import FP_BLOCKS as fp_blocks, SA_BLOCKS as sa_blocks
+        ref = RefPVD(num_classes=3, embed_dim=64, use_att=True, dropout=0.1, extra_feature_channels=0)
+        ours = PVCNN2_PVD(3, 64, True, 0.1, extra_feature_channels=0)
+        assert [(k, tuple(v.shape)) for k, v in ref.state_dict().items()] == \
+               [(k, tuple(v.shape)) for k, v in ours.state_dict().items()]
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+        for k in [k for k in sys.modules if k.startswith("model.") or k.startswith("pvd.")]:
+            sys.modules.pop(k, None)
+
+
+def test_ddpm_schedule_properties():
+    from bdm_b200.diffusion import DDPMSchedule, PVDSchedule
+    s = DDPMSchedule()
+    assert s.timesteps[0] == 999 and s.timesteps[-1] == 0
+    sqrt_a, sqrt_b, c0, ct, sig = s.coefficients(0)
+    assert c0 == pytest.approx(1.0) and ct == pytest.approx(0.0) and sig == 0.0  # last step returns x0
+    x = torch.randn(2, 8, 3)
+    assert torch.allclose(s.step(torch.zeros_like(x), 0, x), x / sqrt_a)
+    p = PVDSchedule()
+    assert torch.allclose(p.step(torch.zeros(2, 3, 8), 0, x.transpose(1, 2)),
+                          float(p.coef1[0]) * float(p.sqrt_recip_ac[0]) * x.transpose(1, 2)
+                          + float(p.coef2[0]) * x.transpose(1, 2))

@@ -29,6 +29,52 @@ def _req(cond, msg):
         raise RuntimeError(msg)
 
 
+# ---------------------------------------------------------------------------------------------
+# launch accounting + optional per-call CUDA-event timing (used by bench.py; off by default)
+# ---------------------------------------------------------------------------------------------
+LAUNCHES = 0          # kernels of libbdm_b200.so enqueued by this process (memsets not counted)
+_PROFILE = None       # None, or {op name: [(start_event, end_event, shapes), ...]}
+
+
+def profile_start():
+    global _PROFILE
+    _PROFILE = {}
+
+
+def profile_stop():
+    """-> {op name: [(milliseconds, shapes), ...]}; synchronises the device."""
+    global _PROFILE
+    rec, _PROFILE = _PROFILE, None
+    torch.cuda.synchronize()
+    return {k: [(e0.elapsed_time(e1), shp) for e0, e1, shp in v] for k, v in (rec or {}).items()}
+
+
+def _op(launches):
+    """Decorator: count kernel launches; when profiling, bracket the call with CUDA events on the
+    current stream of the first tensor argument's device."""
+    def deco(fn):
+        name = fn.__name__
+
+        def wrapper(*args, **kwargs):
+            global LAUNCHES
+            LAUNCHES += launches
+            if _PROFILE is None:
+                return fn(*args, **kwargs)
+            shapes = tuple(tuple(a.shape) if isinstance(a, torch.Tensor) else a for a in args)
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = fn(*args, **kwargs)
+            e1.record()
+            _PROFILE.setdefault(name, []).append((e0, e1, shapes))
+            return out
+        wrapper.__name__ = name
+        wrapper.__doc__ = fn.__doc__
+        wrapper.__wrapped__ = fn
+        return wrapper
+    return deco
+
+
 def _chk_float(x, name):
     _req(x.is_cuda, f"{name} must be a CUDA tensor")
     _req(x.is_contiguous(), f"{name} must be a contiguous tensor")
@@ -71,6 +117,7 @@ def _workspace(nbytes, device):
 # ---------------------------------------------------------------------------------------------
 # voxelization  (vox.cpp:17-43, :54-76)
 # ---------------------------------------------------------------------------------------------
+@_op(2)
 def avg_voxelize_forward(features, coords, resolution):
     _chk_float(features, "features")
     _chk_int(coords, "coords")
@@ -89,6 +136,7 @@ def avg_voxelize_forward(features, coords, resolution):
     return [out, ind, cnt]
 
 
+@_op(1)
 def avg_voxelize_backward(grad_y, indices, cnt):
     _chk_float(grad_y, "grad_y")
     _chk_int(indices, "indices")
@@ -105,6 +153,7 @@ def avg_voxelize_backward(grad_y, indices, cnt):
 # ---------------------------------------------------------------------------------------------
 # devoxelization  (trilinear_devox.cpp:18-55, :68-94)
 # ---------------------------------------------------------------------------------------------
+@_op(1)
 def trilinear_devoxelize_forward(r, is_training, coords, features):
     _chk_float(features, "features")
     _chk_float(coords, "coords")
@@ -127,6 +176,7 @@ def trilinear_devoxelize_forward(r, is_training, coords, features):
     return [outs, inds, wgts]
 
 
+@_op(1)
 def trilinear_devoxelize_backward(grad_y, indices, weights, r):
     _chk_float(grad_y, "grad_y")
     _chk_float(weights, "weights")
@@ -143,6 +193,7 @@ def trilinear_devoxelize_backward(grad_y, indices, weights, r):
 # ---------------------------------------------------------------------------------------------
 # sampling  (sampling.cpp:6-58)
 # ---------------------------------------------------------------------------------------------
+@_op(1)
 def gather_features_forward(features, indices):
     _chk_float(features, "features")
     _chk_int(indices, "indices")
@@ -154,6 +205,7 @@ def gather_features_forward(features, indices):
     return out
 
 
+@_op(1)
 def gather_features_backward(grad_y, indices, n):
     _chk_float(grad_y, "grad_y")
     _chk_int(indices, "indices")
@@ -167,6 +219,7 @@ def gather_features_backward(grad_y, indices, n):
     return grad_x
 
 
+@_op(1)
 def furthest_point_sampling(coords, num_samples):
     _chk_float(coords, "coords")
     b, n = coords.shape[0], coords.shape[2]
@@ -185,6 +238,7 @@ def furthest_point_sampling(coords, num_samples):
 # ---------------------------------------------------------------------------------------------
 # ball query  (ball_query.cpp:6-30)
 # ---------------------------------------------------------------------------------------------
+@_op(1)
 def ball_query(centers_coords, points_coords, radius, num_neighbors):
     _chk_float(centers_coords, "centers_coords")
     _chk_float(points_coords, "points_coords")
@@ -203,6 +257,7 @@ def ball_query(centers_coords, points_coords, radius, num_neighbors):
 # ---------------------------------------------------------------------------------------------
 # grouping  (grouping.cpp:6-43)
 # ---------------------------------------------------------------------------------------------
+@_op(1)
 def grouping_forward(features, indices):
     _chk_float(features, "features")
     _chk_int(indices, "indices")
@@ -214,6 +269,7 @@ def grouping_forward(features, indices):
     return out
 
 
+@_op(1)
 def grouping_backward(grad_y, indices, n):
     _chk_float(grad_y, "grad_y")
     _chk_int(indices, "indices")
@@ -229,6 +285,7 @@ def grouping_backward(grad_y, indices, n):
 # ---------------------------------------------------------------------------------------------
 # three nearest neighbours  (neighbor_interpolate.cpp:6-66)
 # ---------------------------------------------------------------------------------------------
+@_op(1)
 def three_nn_search(points_coords, centers_coords):
     """-> (indices int32[B,3,N], weights f32[B,3,N]); the search half of the reference op."""
     _chk_float(points_coords, "points_coords")
@@ -244,6 +301,7 @@ def three_nn_search(points_coords, centers_coords):
     return indices, weights
 
 
+@_op(1)
 def three_nn_interpolate(centers_features, indices, weights):
     _chk_float(centers_features, "centers_features")
     _chk_int(indices, "indices")
@@ -263,6 +321,7 @@ def three_nearest_neighbors_interpolate_forward(points_coords, centers_coords, c
     return [three_nn_interpolate(centers_features, indices, weights), indices, weights]
 
 
+@_op(1)
 def three_nearest_neighbors_interpolate_backward(grad_y, indices, weights, m):
     _chk_float(grad_y, "grad_y")
     _chk_int(indices, "indices")
@@ -279,6 +338,7 @@ def three_nearest_neighbors_interpolate_backward(grad_y, indices, weights, m):
 # ---------------------------------------------------------------------------------------------
 # secondary boundaries
 # ---------------------------------------------------------------------------------------------
+@_op(4)
 def surface_projection(points, R, T, focal, principal, feat, radius, feat_is_hwc=False):
     """points f32[B,N,3]; R [B,3,3]; T [B,3]; focal, principal [B,2]; feat [B,C,H,W] (or [B,H,W,C]
     when feat_is_hwc) -> (out f32[B,N,C], pix int32[B,N]: lowest won pixel index or -1)"""
@@ -301,6 +361,7 @@ def surface_projection(points, R, T, focal, principal, feat, radius, feat_is_hwc
     return out, pix
 
 
+@_op(1)
 def nn_f64(src, tgt, expanded=False, return_index=True):
     """src f64[B,N,3], tgt f64[B,M,3] -> (min squared distance f64[B,N], argmin int32[B,N] | None)"""
     for x, nm in ((src, "src"), (tgt, "tgt")):

@@ -98,13 +98,19 @@ grouping = _Group.apply
 gather = _Gather.apply
 
 
+# When True the modules issue exactly the reference's native-call sequence (12 groupings and 8 three-NN
+# calls per denoiser forward) instead of skipping the redundant ones.  Used only to time the
+# reference's own kernels under the reference's own call pattern (bench.py `reference_cuda`).
+REFERENCE_CALL_PATTERN = False
+
+
 def group_time_embedding(temb, neighbor_indices):
     """`grouping(temb, idx)` as called at modules/ball_query.py:30.  The denoisers pass a time
     embedding that is an `expand` of one vector per shape (pvcnn.py:88): stride 0 along the point
     axis, so every gathered element is the same value and the grouped tensor is that vector
     broadcast to [B,C,M,U] -- bit-identical to the gather without moving 4*C*M*U bytes per shape.
     Any other layout takes the real gather."""
-    if temb.dim() == 3 and temb.size(-1) > 0 and temb.stride(-1) == 0:
+    if not REFERENCE_CALL_PATTERN and temb.dim() == 3 and temb.size(-1) > 0 and temb.stride(-1) == 0:
         m, u = neighbor_indices.shape[1], neighbor_indices.shape[2]
         return temb[:, :, :1].unsqueeze(-1).expand(-1, -1, m, u)
     return grouping(temb, neighbor_indices)

@@ -6,6 +6,7 @@ import torch
 import torch.nn as nn
 
 from .. import functional as F
+from ..functional import ops as _ops
 from .layers import SharedMLP
 
 
@@ -125,9 +126,13 @@ class PointNetFPModule(nn.Module):
             skip = None
         else:
             points_coords, centers_coords, centers_features, skip, temb = inputs
-        idx, w = F.three_nn_search(points_coords, centers_coords)
-        up = F.three_nn_interpolate(centers_features, idx, w)
-        up_temb = F.three_nn_interpolate(temb, idx, w)
+        if _ops.REFERENCE_CALL_PATTERN:
+            up = F.nearest_neighbor_interpolate(points_coords, centers_coords, centers_features)
+            up_temb = F.nearest_neighbor_interpolate(points_coords, centers_coords, temb)
+        else:
+            idx, w = F.three_nn_search(points_coords, centers_coords)
+            up = F.three_nn_interpolate(centers_features, idx, w)
+            up_temb = F.three_nn_interpolate(temb, idx, w)
         if skip is not None:
             up = torch.cat([up, skip], dim=1)
         return self.mlp(up), points_coords, up_temb

@@ -1,0 +1,122 @@
+"""GPU parity tests of the secondary boundaries (projection conditioning, evaluation kNN) and of the
+whole denoiser step, against the oracle."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _cams(b, seed):
+    import torch
+    from bdm_b200.projection import look_at_cameras
+    g = torch.Generator().manual_seed(seed)
+    return look_at_cameras(torch.rand(b, generator=g) * 360.0, 25.0 + 5.0 * torch.rand(b, generator=g),
+                           (0.65 + 0.30 * torch.rand(b, generator=g)) * 1.75)
+
+
+@pytest.mark.parametrize("hwc", [False, True])
+@pytest.mark.parametrize("n,C,H,radius", [(4096, 19, 224, 0.0075), (700, 5, 64, 0.03), (300, 3, 32, 0.2)])
+def test_surface_projection_vs_oracle(n, C, H, radius, hwc, cuda_backend):
+    import torch
+
+    import oracle as O
+    from tests.cases import cloud
+    b = 3
+    rng = np.random.default_rng(n + C)
+    pts = np.ascontiguousarray(cloud(rng, b, n, "shape").transpose(0, 2, 1)) * np.float32(0.35)
+    cams = _cams(b, n)
+    feat = rng.standard_normal((b, C, H, H)).astype(np.float32)
+    want, zi = O.surface_projection(pts, cams.R.numpy(), cams.T.numpy(), cams.focal.numpy(), cams.principal.numpy(),
+                                    feat, radius=radius)
+    f_t = torch.as_tensor(feat).cuda()
+    if hwc:
+        f_t = f_t.permute(0, 2, 3, 1).contiguous()
+    out, pix = cuda_backend.surface_projection(torch.as_tensor(pts).cuda(), cams.R.cuda(), cams.T.cuda(),
+                                               cams.focal.cuda(), cams.principal.cuda(), f_t, radius, feat_is_hwc=hwc)
+    # z-buffer winners: lowest pixel index won by each point, -1 if none -- integer, bit-exact
+    want_pix = np.full((b, n), -1, np.int32)
+    for bi in range(b):
+        flat = zi[bi].reshape(-1)
+        for q in range(flat.size - 1, -1, -1):
+            if flat[q] >= 0:
+                want_pix[bi, flat[q]] = q
+    assert np.array_equal(pix.cpu().numpy(), want_pix)
+    assert (want_pix >= 0).any() and (want_pix < 0).any()
+    assert np.array_equal(out.cpu().numpy(), want)   # pure copies / zeros: bit-exact
+
+
+def test_projection_points_behind_camera(cuda_backend):
+    import torch
+    b, n = 1, 64
+    pts = torch.zeros(b, n, 3, device="cuda")
+    R = torch.eye(3, device="cuda").unsqueeze(0).contiguous()
+    T = torch.tensor([[0.0, 0.0, -3.0]], device="cuda")      # every point at depth -3
+    f = torch.full((b, 2), 2.0, device="cuda")
+    p = torch.zeros(b, 2, device="cuda")
+    feat = torch.ones(b, 4, 16, 16, device="cuda")
+    out, pix = cuda_backend.surface_projection(pts, R, T, f, p, feat, 0.5)
+    assert (pix == -1).all() and (out == 0).all()
+
+
+@pytest.mark.parametrize("n,m", [(4096, 4096), (1000, 777), (5, 3)])
+def test_nn_f64_vs_oracle(n, m, cuda_backend):
+    import torch
+
+    import oracle as O
+    rng = np.random.default_rng(2003)   # the reference's eval seed (example_eval.sh:12)
+    b = 8 if n == 4096 else 2
+    gt = rng.standard_normal((b, m, 3))
+    src = (gt[:, rng.integers(0, m, n)] + 0.05 * rng.standard_normal((b, n, 3)))
+    s_t, g_t = torch.as_tensor(src).cuda(), torch.as_tensor(gt).cuda()
+    d, i = cuda_backend.nn_f64(s_t, g_t, expanded=False)
+    od, oi = O.nn_direct(src, gt)
+    assert np.array_equal(i.cpu().numpy(), oi)
+    assert np.array_equal(d.cpu().numpy(), od)          # same fp64 expression without fma: bit-exact
+    de, _ = cuda_backend.nn_f64(s_t, g_t, expanded=True, return_index=False)
+    assert np.array_equal(de.cpu().numpy(), O.nn_expanded(src, gt))
+
+
+def test_chamfer_fscore_config1(cuda_backend):
+    """BASELINE.json configs[0]: CD + F-score@0.01 on 8 synthetic 4096-point pairs."""
+    import torch
+
+    import oracle as O
+    from bdm_b200 import evaluation as E
+    from tests.cases import cloud
+    rng = np.random.default_rng(2003)
+    gt = cloud(rng, 8, 4096, "shape").transpose(0, 2, 1).astype(np.float64)
+    pred = gt[:, rng.permutation(4096)] + 0.05 * rng.standard_normal(gt.shape)
+    gt -= gt.mean(1, keepdims=True)
+    pred -= pred.mean(1, keepdims=True)
+    cd = E.chamfer_distance(torch.as_tensor(pred).cuda(), torch.as_tensor(gt).cuda()).cpu().numpy()
+    f1 = E.fscore(torch.as_tensor(gt).cuda(), torch.as_tensor(pred).cuda()).cpu().numpy()
+    assert np.allclose(cd, O.chamfer_distance(pred, gt), rtol=1e-12, atol=0)
+    assert np.allclose(f1, O.fscore(gt, pred), rtol=1e-12, atol=0)
+    assert 0.0 < f1.mean() < 1.0
+    # symmetry property of CD
+    cd2 = E.chamfer_distance(torch.as_tensor(gt).cuda(), torch.as_tensor(pred).cuda()).cpu().numpy()
+    assert np.allclose(cd, cd2, rtol=1e-12)
+
+
+def test_denoiser_step_gpu_vs_cpu_oracle(cuda_backend, monkeypatch):
+    """Whole PC^2 denoiser forward: CUDA path vs the same module tree on CPU with every sparse op
+    routed to the oracle.  Integer decisions inside (FPS, ball query, 3-NN, voxel indices) are bit-exact
+    per op; the end-to-end comparison is bounded by the dense layers' fp32 reassociation on the GPU."""
+    import torch
+
+    import bdm_b200.functional.ops as ops
+    from bdm_b200.denoiser import PVCNN2_PC2
+    from oracle.torch_backend import OracleBackend
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(7)
+    net = PVCNN2_PC2(num_classes=3, embed_dim=64, extra_feature_channels=6).eval()
+    g = torch.Generator().manual_seed(8)
+    x = torch.randn(2, 9, 1024, generator=g)
+    t = torch.tensor([500.0, 3.0])
+    with torch.no_grad():
+        y_gpu = net.cuda()(x.cuda(), t.cuda()).cpu()
+        monkeypatch.setattr(ops, "_B", OracleBackend())
+        y_cpu = net.cpu()(x, t)
+    err = (y_gpu - y_cpu).abs().max().item() / y_cpu.abs().max().item()
+    assert err < 2e-3, err

@@ -15,7 +15,7 @@ needs_ref = pytest.mark.skipif(not os.path.isdir(REF_EXP), reason="reference che
 
 @pytest.fixture()
 def oracle_backend(monkeypatch):
-    from tests.oracle_backend import OracleBackend
+    from oracle.torch_backend import OracleBackend
     import bdm_b200.functional.ops as ops
     ob = OracleBackend()
     monkeypatch.setattr(ops, "_B", ob)
@@ -124,7 +124,7 @@ def test_state_dict_and_forward_match_reference_modules(oracle_backend):
 def test_pvd_state_dict_matches_reference():
     from bdm_b200 import dropin
     from bdm_b200.denoiser import PVCNN2_PVD
-    from tests.oracle_backend import OracleBackend
+    from oracle.torch_backend import OracleBackend
     saved = {k: sys.modules.get(k) for k in ("model", "pvd") + dropin.BACKEND_MODULE_NAMES}
     try:
         dropin.install(REF_EXP, backend=OracleBackend(), stub_packages=True)

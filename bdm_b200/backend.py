@@ -117,23 +117,50 @@ def _workspace(nbytes, device):
 # ---------------------------------------------------------------------------------------------
 # voxelization  (vox.cpp:17-43, :54-76)
 # ---------------------------------------------------------------------------------------------
-@_op(2)
+class VoxelPlan:
+    """Everything avg_voxelize derives from the coordinates alone: per-point voxel index, per-voxel
+    count, and the sorted lookup tables living in `workspace` (opaque)."""
+    __slots__ = ("b", "n", "r", "ind", "cnt", "workspace")
+
+    def __init__(self, b, n, r, ind, cnt, workspace):
+        self.b, self.n, self.r, self.ind, self.cnt, self.workspace = b, n, r, ind, cnt, workspace
+
+
+@_op(1)
+def voxel_plan(coords, resolution):
+    """coords int32[B,3,N] (voxel coordinates in [0,R)) -> VoxelPlan"""
+    _chk_int(coords, "coords")
+    b, n = coords.shape[0], coords.shape[2]
+    r = int(resolution)
+    dev = coords.device
+    ind = torch.empty((b, n), dtype=_I32, device=dev)
+    cnt = torch.empty((b, r * r * r), dtype=_I32, device=dev)
+    ws = _workspace(_L.bdm_avg_voxelize_workspace_bytes(b, n, r), dev)
+    with _Launch(coords) as st:
+        _check(_L.bdm_voxel_plan(b, n, r, coords.data_ptr(), ind.data_ptr(), cnt.data_ptr(), ws.data_ptr(),
+                                 ws.numel(), st))
+    return VoxelPlan(b, n, r, ind, cnt, ws)
+
+
+@_op(1)
+def avg_voxelize_fill(features, plan):
+    """features f32[B,C,N] + VoxelPlan -> dense grid f32[B,C,R^3]"""
+    _chk_float(features, "features")
+    b, c, n = features.shape
+    _req(b == plan.b and n == plan.n, "features do not match the voxel plan")
+    out = torch.empty((b, c, plan.r ** 3), dtype=_F32, device=features.device)
+    with _Launch(features) as st:
+        _check(_L.bdm_avg_voxelize_fill(b, c, n, plan.r, plan.ind.data_ptr(), plan.cnt.data_ptr(),
+                                        features.data_ptr(), out.data_ptr(), plan.workspace.data_ptr(),
+                                        plan.workspace.numel(), st))
+    return out
+
+
 def avg_voxelize_forward(features, coords, resolution):
     _chk_float(features, "features")
     _chk_int(coords, "coords")
-    b, c, n = features.shape
-    r = int(resolution)
-    r3 = r * r * r
-    dev = features.device
-    out = torch.empty((b, c, r3), dtype=_F32, device=dev)
-    ind = torch.empty((b, n), dtype=_I32, device=dev)
-    cnt = torch.empty((b, r3), dtype=_I32, device=dev)
-    nws = _L.bdm_avg_voxelize_workspace_bytes(b, n, r)
-    ws = _workspace(nws, dev)
-    with _Launch(features) as st:
-        _check(_L.bdm_avg_voxelize(b, c, n, r, coords.data_ptr(), features.data_ptr(), ind.data_ptr(),
-                                   cnt.data_ptr(), out.data_ptr(), ws.data_ptr(), ws.numel(), st))
-    return [out, ind, cnt]
+    plan = voxel_plan(coords, resolution)
+    return [avg_voxelize_fill(features, plan), plan.ind, plan.cnt]
 
 
 @_op(1)
@@ -153,7 +180,7 @@ def avg_voxelize_backward(grad_y, indices, cnt):
 # ---------------------------------------------------------------------------------------------
 # devoxelization  (trilinear_devox.cpp:18-55, :68-94)
 # ---------------------------------------------------------------------------------------------
-@_op(1)
+@_op(2)
 def trilinear_devoxelize_forward(r, is_training, coords, features):
     _chk_float(features, "features")
     _chk_float(coords, "coords")
@@ -170,9 +197,11 @@ def trilinear_devoxelize_forward(r, is_training, coords, features):
         inds = torch.zeros((1,), dtype=_I32, device=dev)
         wgts = torch.zeros((1,), dtype=_F32, device=dev)
         ip, wp = None, None
+    ws = _workspace(_L.bdm_trilinear_devoxelize_workspace_bytes(b, n, r), dev)
     with _Launch(features) as st:
         _check(_L.bdm_trilinear_devoxelize(b, c, n, r, 1 if is_training else 0, coords.data_ptr(),
-                                           features.data_ptr(), ip, wp, outs.data_ptr(), st))
+                                           features.data_ptr(), ip, wp, outs.data_ptr(), ws.data_ptr(),
+                                           ws.numel(), st))
     return [outs, inds, wgts]
 
 

@@ -48,11 +48,14 @@ ball_query_kernel(int n, int m, float r2, int u, int splits, const float *__rest
   len = (len + 3) & ~3;
   const int k0 = min(split * len, n), k1 = min(k0 + len, n);
 
-  int cnt = valid ? 0 : u;  // lanes without a centre are "full" from the start
+  // A lane that has no centre, or whose list is full, gets a negative threshold: no distance is
+  // below it, so the hot loop needs no `cnt < u` test.
+  int cnt = 0;
+  float thr = valid ? r2 : -1.0f;
   int k = k0;
   if (VEC4) {
     for (; k + 4 <= k1; k += 4) {
-      if (__all_sync(0xffffffffu, cnt >= u)) break;
+      if ((k & 127) == 0 && __all_sync(0xffffffffu, thr < 0.0f)) break;
       const float4 X = __ldg(reinterpret_cast<const float4 *>(points + k));
       const float4 Y = __ldg(reinterpret_cast<const float4 *>(points + n + k));
       const float4 Z = __ldg(reinterpret_cast<const float4 *>(points + 2 * (size_t)n + k));
@@ -60,17 +63,18 @@ ball_query_kernel(int n, int m, float r2, int u, int splits, const float *__rest
       const float d1 = sqdist_ref(__fsub_rn(cx, X.y), __fsub_rn(cy, Y.y), __fsub_rn(cz, Z.y));
       const float d2 = sqdist_ref(__fsub_rn(cx, X.z), __fsub_rn(cy, Y.z), __fsub_rn(cz, Z.z));
       const float d3 = sqdist_ref(__fsub_rn(cx, X.w), __fsub_rn(cy, Y.w), __fsub_rn(cz, Z.w));
-      if (d0 < r2 && cnt < u) my[cnt++] = k;
-      if (d1 < r2 && cnt < u) my[cnt++] = k + 1;
-      if (d2 < r2 && cnt < u) my[cnt++] = k + 2;
-      if (d3 < r2 && cnt < u) my[cnt++] = k + 3;
+      if (fminf(fminf(d0, d1), fminf(d2, d3)) < thr) {  // rare: balls hold a handful of points
+        if (d0 < thr) { my[cnt++] = k;     if (cnt == u) thr = -1.0f; }
+        if (d1 < thr) { my[cnt++] = k + 1; if (cnt == u) thr = -1.0f; }
+        if (d2 < thr) { my[cnt++] = k + 2; if (cnt == u) thr = -1.0f; }
+        if (d3 < thr) { my[cnt++] = k + 3; if (cnt == u) thr = -1.0f; }
+      }
     }
   }
   for (; k < k1; ++k) {
-    if (__all_sync(0xffffffffu, cnt >= u)) break;
     const float d = sqdist_ref(__fsub_rn(cx, __ldg(points + k)), __fsub_rn(cy, __ldg(points + n + k)),
                                __fsub_rn(cz, __ldg(points + 2 * (size_t)n + k)));
-    if (d < r2 && cnt < u) my[cnt++] = k;
+    if (d < thr) { my[cnt++] = k; if (cnt == u) thr = -1.0f; }
   }
   s_cnt[split][lane] = valid ? cnt : 0;
   __syncthreads();
@@ -110,13 +114,13 @@ extern "C" int bdm_ball_query(int b, int n, int m, float r2, int u, const float 
   // least 256 points per split so the per-row merge stays negligible
   const int ctas = ceil_div(m, 32) * b;
   int splits = 1;
-  while (splits < kBqMaxSplits && ctas * splits < 8 * sm_count() && n / (splits * 2) >= 256) splits *= 2;
+  while (splits < kBqMaxSplits && ctas * splits < 16 * sm_count() && n / (splits * 2) >= 256) splits *= 2;
   size_t smem = sizeof(int) * (size_t)splits * 32 * (u | 1);
   while (smem > 200 * 1024 && splits > 1) { splits /= 2; smem = sizeof(int) * (size_t)splits * 32 * (u | 1); }
   BDM_CHECK_SIZE(smem <= 200 * 1024);
   const bool vec4 = (n % 4 == 0) && ((reinterpret_cast<uintptr_t>(points_coords) & 15) == 0);
   auto kern = vec4 ? ball_query_kernel<true> : ball_query_kernel<false>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void *>(kern), smem);
   if (e != cudaSuccess) return (int)e;
   kern<<<dim3(ceil_div(m, 32), b), 32 * splits, smem, st>>>(n, m, r2, u, splits, centers_coords, points_coords,
                                                             neighbors_indices);

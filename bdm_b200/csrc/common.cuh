@@ -3,6 +3,10 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <map>
+#include <mutex>
+#include <utility>
+
 #include "../../include/bdm_b200.h"
 
 #define BDM_CHECK_PTR(p) \
@@ -39,6 +43,22 @@ inline int sm_count() {
     if (n <= 0) n = 148;
   }
   return n;
+}
+
+// Opt a kernel in to `bytes` of dynamic shared memory (> 48 KB needs it) once per (kernel, device);
+// cudaFuncSetAttribute is too slow to repeat on every launch and is a per-device setting.
+inline cudaError_t ensure_dynamic_smem(const void *func, size_t bytes) {
+  if (bytes <= 48 * 1024) return cudaSuccess;
+  static std::mutex mu;
+  static std::map<std::pair<const void *, int>, size_t> configured;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lock(mu);
+  size_t &have = configured[std::make_pair(func, dev)];
+  if (bytes <= have) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e == cudaSuccess) have = bytes;
+  return e;
 }
 
 // The reference's squared distance `dx*dx + dy*dy + dz*dz` as nvcc contracts it (SASS of the

@@ -12,8 +12,19 @@
 //         acc = w001*f001;  acc = fma(w000,f000,acc);  acc = fma(w010,f010,acc); ... ; fma(w111,f111,acc)
 //
 // Kernels:
-//   devox_gather_kernel   generic path: thread per point, channel chunk per blockIdx.y, 8 read-only
-//                         gathers per channel, 4 channels in flight.
+//   devox_bin_kernel +    inference fast path (R <= 32, N <= ~12k).  The 8 corner reads of a point are
+//   devox_slice_kernel    random addresses in a 4*R^3-byte channel row: served from global memory every
+//                         warp-level gather costs up to 32 L1 wavefronts and the kernel is L1-bound at
+//                         ~30 % of the HBM roofline (measured, profiles/).  Instead: points are binned
+//                         by x-slice once per call (one small CTA per shape); then one CTA per
+//                         (shape, CT channels) streams the grid through shared memory one x-slice at a
+//                         time -- coalesced loads, channel-interleaved [R^2][CT] layout so that one
+//                         LDS.128 fetches a corner for 4 channels, a 3-slice ring with register
+//                         prefetch of slice x+2 while bin x is processed -- and gathers from there.
+//                         Results go to a [CT][N] shared tile in original point order and leave as
+//                         coalesced 128-bit stores.  HBM traffic = the grid once + the output once.
+//   devox_gather_kernel   generic path (training: also writes inds/wgts; large R or N): thread per
+//                         point, channel chunk per blockIdx.y, 8 read-only gathers per channel.
 #include "common.cuh"
 
 namespace bdm {
@@ -63,6 +74,200 @@ __device__ __forceinline__ float devox_blend(const float *__restrict__ f, const 
 
 constexpr int kDevoxThreads = 128;
 constexpr int kDevoxChunk = 8;  // channels per CTA in the generic path
+
+// ------------------------------------------------------------------------------------------------
+// fast path: x-slice binning + slice-ring gather
+// ------------------------------------------------------------------------------------------------
+constexpr int kSliceThreads = 256;
+constexpr int kSliceMaxR = 32;
+constexpr int kSliceSlots = (kSliceMaxR * kSliceMaxR) / kSliceThreads;  // yz entries per thread per slice
+constexpr int kBinThreads = 1024;
+
+struct DevoxPlanLayout {
+  size_t xstart;  // i32[r+1]
+  size_t spid;    // i32[n]   sorted position -> point
+  size_t sxyz;    // f32[3][n] coordinates in sorted order
+  size_t stride;
+};
+
+__host__ __device__ inline DevoxPlanLayout devox_plan_layout(int n, int r) {
+  DevoxPlanLayout L;
+  size_t off = 0;
+  L.xstart = off; off = align_up(off + sizeof(int) * (r + 1), 16);
+  L.spid = off;   off = align_up(off + sizeof(int) * (size_t)n, 16);
+  L.sxyz = off;   off = align_up(off + sizeof(float) * 3 * (size_t)n, 16);
+  L.stride = off;
+  return L;
+}
+
+__device__ __forceinline__ int devox_xbin(float x, int r) { return min(max((int)floorf(x), 0), r - 1); }
+
+__global__ void __launch_bounds__(kBinThreads)
+devox_bin_kernel(int n, int r, const float *__restrict__ coords, unsigned char *__restrict__ ws,
+                 DevoxPlanLayout L) {
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x;
+  coords += (size_t)b * 3 * n;
+  ws += (size_t)b * L.stride;
+  int *g_xstart = reinterpret_cast<int *>(ws + L.xstart);
+  int *g_spid = reinterpret_cast<int *>(ws + L.spid);
+  float *g_sxyz = reinterpret_cast<float *>(ws + L.sxyz);
+  __shared__ int hist[kSliceMaxR];
+  __shared__ int cursor[kSliceMaxR];
+  if (tid < kSliceMaxR) hist[tid] = 0;
+  __syncthreads();
+  for (int i = tid; i < n; i += kBinThreads) atomicAdd(&hist[devox_xbin(coords[i], r)], 1);
+  __syncthreads();
+  if (tid < 32) {  // kSliceMaxR == 32: one warp scans the bins
+    const int c = tid < r ? hist[tid] : 0;
+    int incl = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, d);
+      if (tid >= d) incl += t;
+    }
+    cursor[tid] = incl - c;
+    if (tid < r) g_xstart[tid] = incl - c;
+    if (tid == 31) g_xstart[r] = n;
+  }
+  __syncthreads();
+  for (int i = tid; i < n; i += kBinThreads) {
+    const float x = coords[i], y = coords[i + n], z = coords[i + n + n];
+    const int pos = atomicAdd(&cursor[devox_xbin(x, r)], 1);
+    g_spid[pos] = i;
+    g_sxyz[pos] = x;
+    g_sxyz[pos + n] = y;
+    g_sxyz[pos + 2 * (size_t)n] = z;
+  }
+}
+
+template <int CT> struct VecOf;
+template <> struct VecOf<4> { using type = float4; };
+template <> struct VecOf<2> { using type = float2; };
+template <> struct VecOf<1> { using type = float; };
+
+template <int CT>
+__device__ __forceinline__ void lds_vec(const float *p, float (&v)[CT]) {
+  using V = typename VecOf<CT>::type;
+  const V t = *reinterpret_cast<const V *>(p);
+  const float *tf = reinterpret_cast<const float *>(&t);
+#pragma unroll
+  for (int q = 0; q < CT; ++q) v[q] = tf[q];
+}
+
+template <int CT>
+__global__ void __launch_bounds__(kSliceThreads)
+devox_slice_kernel(int c, int n, int r, const float *__restrict__ feat,
+                   const unsigned char *__restrict__ ws, DevoxPlanLayout L, float *__restrict__ outs) {
+  const int b = blockIdx.y;
+  const int c0 = blockIdx.x * CT;
+  const int nch = min(CT, c - c0);
+  const int tid = threadIdx.x;
+  const int r2 = r * r;
+  const size_t r3 = (size_t)r2 * r;
+
+  extern __shared__ __align__(16) float smem_f[];
+  float *ring = smem_f;                         // [3][r2][CT]  channel-interleaved slices
+  float *sout = ring + ((3 * (size_t)r2 * CT + 3) & ~(size_t)3);  // [CT][n] results, original point order
+  int *xs = reinterpret_cast<int *>(sout + (size_t)CT * n);  // [r+1]
+
+  ws += (size_t)b * L.stride;
+  const int *g_xstart = reinterpret_cast<const int *>(ws + L.xstart);
+  const int *g_spid = reinterpret_cast<const int *>(ws + L.spid);
+  const float *g_sx = reinterpret_cast<const float *>(ws + L.sxyz);
+  const float *g_sy = g_sx + n;
+  const float *g_sz = g_sy + n;
+  for (int i = tid; i <= r; i += kSliceThreads) xs[i] = g_xstart[i];
+
+  const float *fbase = feat + ((size_t)b * c + c0) * r3;
+  float regs[kSliceSlots][CT];
+
+  auto load_slice = [&](int x) {
+#pragma unroll
+    for (int s = 0; s < kSliceSlots; ++s) {
+      const int yz = tid + s * kSliceThreads;
+#pragma unroll
+      for (int cc = 0; cc < CT; ++cc)
+        regs[s][cc] = (yz < r2 && cc < nch) ? ld_stream_f1(fbase + (size_t)cc * r3 + (size_t)x * r2 + yz) : 0.0f;
+    }
+  };
+  auto store_slice = [&](int stage) {
+    float *dst = ring + (size_t)stage * r2 * CT;
+#pragma unroll
+    for (int s = 0; s < kSliceSlots; ++s) {
+      const int yz = tid + s * kSliceThreads;
+      if (yz < r2) {
+        using V = typename VecOf<CT>::type;
+        V t;
+        float *tf = reinterpret_cast<float *>(&t);
+#pragma unroll
+        for (int cc = 0; cc < CT; ++cc) tf[cc] = regs[s][cc];
+        *reinterpret_cast<V *>(dst + (size_t)yz * CT) = t;
+      }
+    }
+  };
+
+  load_slice(0);
+  store_slice(0);
+  if (r > 1) {
+    load_slice(1);
+    store_slice(1);
+  }
+  __syncthreads();
+
+  for (int x = 0; x < r; ++x) {
+    const bool more = x + 2 < r;
+    if (more) load_slice(x + 2);  // in flight while bin x is processed
+    const float *A = ring + (size_t)(x % 3) * r2 * CT;
+    const float *Bn = ring + (size_t)((x + 1) % 3) * r2 * CT;
+    for (int p = xs[x] + tid; p < xs[x + 1]; p += kSliceThreads) {
+      const float px = g_sx[p], py = g_sy[p], pz = g_sz[p];
+      const int pid = g_spid[p];
+      // trilinear_devox.cu:37-75 with slice-relative offsets
+      const float xl = floorf(px), yl = floorf(py), zl = floorf(pz);
+      const float xd1 = __fsub_rn(px, xl), yd1 = __fsub_rn(py, yl), zd1 = __fsub_rn(pz, zl);
+      const float xd0 = __fsub_rn(1.0f, xd1), yd0 = __fsub_rn(1.0f, yd1), zd0 = __fsub_rn(1.0f, zd1);
+      const float w00 = __fmul_rn(xd0, yd0), w01 = __fmul_rn(xd0, yd1);
+      const float w10 = __fmul_rn(xd1, yd0), w11 = __fmul_rn(xd1, yd1);
+      const float w0 = __fmul_rn(w00, zd0), w1 = __fmul_rn(w00, zd1), w2 = __fmul_rn(w01, zd0),
+                  w3 = __fmul_rn(w01, zd1), w4 = __fmul_rn(w10, zd0), w5 = __fmul_rn(w10, zd1),
+                  w6 = __fmul_rn(w11, zd0), w7 = __fmul_rn(w11, zd1);
+      const int ylo = min(max((int)yl, 0), r - 1), zlo = min(max((int)zl, 0), r - 1);
+      const int yo = (yd1 > 0.0f && ylo < r - 1) ? r : 0, zo = (zd1 > 0.0f && zlo < r - 1) ? 1 : 0;
+      const float *Hi = (xd1 > 0.0f) ? Bn : A;
+      const int o00 = (ylo * r + zlo) * CT, o01 = o00 + zo * CT, o10 = o00 + yo * CT, o11 = o10 + zo * CT;
+      float f0[CT], f1[CT], f2[CT], f3[CT], f4[CT], f5[CT], f6[CT], f7[CT];
+      lds_vec<CT>(A + o00, f0); lds_vec<CT>(A + o01, f1); lds_vec<CT>(A + o10, f2); lds_vec<CT>(A + o11, f3);
+      lds_vec<CT>(Hi + o00, f4); lds_vec<CT>(Hi + o01, f5); lds_vec<CT>(Hi + o10, f6); lds_vec<CT>(Hi + o11, f7);
+#pragma unroll
+      for (int cc = 0; cc < CT; ++cc) {
+        float acc = __fmul_rn(w1, f1[cc]);
+        acc = __fmaf_rn(w0, f0[cc], acc);
+        acc = __fmaf_rn(w2, f2[cc], acc);
+        acc = __fmaf_rn(w3, f3[cc], acc);
+        acc = __fmaf_rn(w4, f4[cc], acc);
+        acc = __fmaf_rn(w5, f5[cc], acc);
+        acc = __fmaf_rn(w6, f6[cc], acc);
+        acc = __fmaf_rn(w7, f7[cc], acc);
+        sout[(size_t)cc * n + pid] = acc;
+      }
+    }
+    // Stage (x+2)%3 held slice x-1, last read during bin x-1, i.e. before the barrier that ended the
+    // previous iteration: it can be overwritten now.  One barrier per slice then (a) publishes slice
+    // x+2 before bin x+1 reads it and (b) keeps the next iteration's store off stage x%3 until every
+    // thread is done with bin x.
+    if (more) store_slice((x + 2) % 3);
+    __syncthreads();
+  }
+
+  float *o = outs + ((size_t)b * c + c0) * n;
+  if ((n & 3) == 0 && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+    for (int q = tid; q < nch * (n / 4); q += kSliceThreads)
+      st_stream_f4(o + 4 * (size_t)q, reinterpret_cast<const float4 *>(sout)[q]);
+  } else {
+    for (int q = tid; q < nch * n; q += kSliceThreads) o[q] = sout[q];
+  }
+}
 
 __global__ void __launch_bounds__(kDevoxThreads)
 devox_gather_kernel(int c, int n, int r, int is_training, const float *__restrict__ coords,
@@ -132,9 +337,45 @@ devox_grad_kernel(int c, int n, int r3, const int *__restrict__ inds, const floa
 
 }  // namespace bdm
 
+namespace bdm {
+
+static size_t devox_slice_smem(int ct, int n, int r) {
+  return sizeof(float) * (((3 * (size_t)r * r * ct + 3) & ~(size_t)3) + (size_t)ct * n) + sizeof(int) * (r + 1);
+}
+
+// channel tile for the slice kernel, or 0 when the fast path does not apply
+static int devox_slice_ct(int b, int c, int n, int r, int is_training) {
+  if (is_training || r > kSliceMaxR || r < 1 || n < 1 || c < 1) return 0;
+  int ct = 4;
+  // keep >= ~1.5 CTAs per SM in flight, and two CTAs resident per SM (<= 113 KB each)
+  while (ct > 1 && (b * ceil_div(c, ct) < (3 * sm_count()) / 2 || devox_slice_smem(ct, n, r) > 113 * 1024)) ct >>= 1;
+  if (devox_slice_smem(ct, n, r) > 200 * 1024) return 0;
+  if (ceil_div(c, ct) > 65535 || b > 65535) return 0;
+  return ct;
+}
+
+template <int CT>
+static cudaError_t launch_slice(int b, int c, int n, int r, const float *feat, const unsigned char *ws,
+                                const DevoxPlanLayout &L, float *outs, cudaStream_t st) {
+  const size_t smem = devox_slice_smem(CT, n, r);
+  auto kern = devox_slice_kernel<CT>;
+  cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void *>(kern), smem);
+  if (e != cudaSuccess) return e;
+  kern<<<dim3(ceil_div(c, CT), b), kSliceThreads, smem, st>>>(c, n, r, feat, ws, L, outs);
+  return cudaGetLastError();
+}
+
+}  // namespace bdm
+
+extern "C" size_t bdm_trilinear_devoxelize_workspace_bytes(int b, int n, int r) {
+  if (b <= 0 || n <= 0 || r <= 0 || r > bdm::kSliceMaxR) return 16;
+  return bdm::devox_plan_layout(n, r).stride * (size_t)b;
+}
+
 extern "C" int bdm_trilinear_devoxelize(int b, int c, int n, int r, int is_training,
                                         const float *coords, const float *feat, int *inds,
-                                        float *wgts, float *outs, bdm_stream_t stream) {
+                                        float *wgts, float *outs, void *workspace,
+                                        size_t workspace_bytes, bdm_stream_t stream) {
   using namespace bdm;
   BDM_CHECK_SIZE(b >= 0 && c >= 0 && n >= 0 && r >= 1 && (long long)r * r * r <= 0x7fffffffLL);
   if (b == 0 || n == 0) return BDM_OK;
@@ -142,6 +383,21 @@ extern "C" int bdm_trilinear_devoxelize(int b, int c, int n, int r, int is_train
   if (c > 0) { BDM_CHECK_PTR(feat); BDM_CHECK_PTR(outs); }
   if (is_training) { BDM_CHECK_PTR(inds); BDM_CHECK_PTR(wgts); }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+
+  const int ct = devox_slice_ct(b, c, n, r, is_training);
+  const DevoxPlanLayout L = devox_plan_layout(n, r);
+  if (ct > 0 && workspace != nullptr && workspace_bytes >= L.stride * (size_t)b &&
+      (reinterpret_cast<uintptr_t>(workspace) & 15) == 0) {
+    unsigned char *ws = static_cast<unsigned char *>(workspace);
+    devox_bin_kernel<<<b, kBinThreads, 0, st>>>(n, r, coords, ws, L);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+    if (ct == 4) e = launch_slice<4>(b, c, n, r, feat, ws, L, outs, st);
+    else if (ct == 2) e = launch_slice<2>(b, c, n, r, feat, ws, L, outs, st);
+    else e = launch_slice<1>(b, c, n, r, feat, ws, L, outs, st);
+    return e == cudaSuccess ? BDM_OK : (int)e;
+  }
+
   const int cy = c > 0 ? ceil_div(c, kDevoxChunk) : 1;
   BDM_CHECK_SIZE(cy <= 65535 && b <= 65535);
   devox_gather_kernel<<<dim3(ceil_div(n, kDevoxThreads), cy, b), kDevoxThreads, 0, st>>>(

@@ -50,6 +50,36 @@ grouping_kernel(int c, int n, int mu, const float *__restrict__ features,
   }
 }
 
+// Shared-memory variant: the gathers of one output row hit random addresses of a feature row of n
+// floats.  From global memory each warp-level gather costs up to 32 L1 wavefronts; from shared memory
+// about 3.  A CTA stages CT rows [CT][n] and serves a chunk of the (m,u) index space from them:
+// one 128-bit index load, CT x 4 shared-memory reads, CT 128-bit streaming stores per thread step.
+template <int CT>
+__global__ void __launch_bounds__(kGrpThreads)
+grouping_rows_kernel(int c, int n, int mu, int chunk4, const float *__restrict__ features,
+                     const int *__restrict__ indices, float *__restrict__ out) {
+  extern __shared__ float rows[];  // [CT][n]
+  const int b = blockIdx.z;
+  const int c0 = blockIdx.y * CT;
+  const int nrows = min(CT, c - c0);
+  const float *f = features + ((size_t)b * c + c0) * n;
+  for (int q = threadIdx.x; q < nrows * n; q += kGrpThreads) rows[q] = ld_stream_f1(f + q);
+  __syncthreads();
+  const int4 *ix = reinterpret_cast<const int4 *>(indices + (size_t)b * mu);
+  float *o = out + ((size_t)b * c + c0) * mu;
+  const int g_end = min((blockIdx.x + 1) * chunk4, mu / 4);
+  for (int g = blockIdx.x * chunk4 + threadIdx.x; g < g_end; g += kGrpThreads) {
+    const int4 id = __ldg(ix + g);
+#pragma unroll
+    for (int cc = 0; cc < CT; ++cc) {
+      if (cc < nrows) {
+        const float *r = rows + cc * n;
+        st_stream_f4(o + (size_t)cc * mu + 4 * (size_t)g, make_float4(r[id.x], r[id.y], r[id.z], r[id.w]));
+      }
+    }
+  }
+}
+
 // backward: grad_x[b,c,indices[b,m,u]] += grad_y[b,c,m,u]   (grouping.cu:71-76)
 __global__ void __launch_bounds__(kGrpThreads)
 grouping_grad_kernel(int c, int n, int mu, const float *__restrict__ grad_y,
@@ -78,7 +108,28 @@ extern "C" int bdm_grouping(int b, int c, int n, int m, int u, const float *feat
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const bool vec4 = (mu % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0) &&
                     ((reinterpret_cast<uintptr_t>(indices) & 15) == 0);
-  if (vec4)
+  if (vec4 && n >= 1 && sizeof(float) * (size_t)n <= 64 * 1024 && mu / 4 >= kGrpThreads) {
+    int ct = 4;
+    while (ct > 1 && (sizeof(float) * (size_t)ct * n > 64 * 1024 || b * ceil_div(c, ct) < sm_count())) ct >>= 1;
+    const int tiles = ceil_div(c, ct) * b;
+    int chunks = 1;
+    while (tiles * chunks < 3 * sm_count() && ceil_div(mu / 4, chunks * 2) >= 4 * kGrpThreads) chunks *= 2;
+    const int chunk4 = ceil_div(mu / 4, chunks);
+    const size_t smem = sizeof(float) * (size_t)ct * n;
+    const dim3 grid(chunks, ceil_div(c, ct), b);
+    cudaError_t e;
+    if (ct == 4) {
+      e = ensure_dynamic_smem(reinterpret_cast<const void *>(grouping_rows_kernel<4>), smem);
+      if (e == cudaSuccess) grouping_rows_kernel<4><<<grid, kGrpThreads, smem, st>>>(c, n, mu, chunk4, features, indices, out);
+    } else if (ct == 2) {
+      e = ensure_dynamic_smem(reinterpret_cast<const void *>(grouping_rows_kernel<2>), smem);
+      if (e == cudaSuccess) grouping_rows_kernel<2><<<grid, kGrpThreads, smem, st>>>(c, n, mu, chunk4, features, indices, out);
+    } else {
+      e = ensure_dynamic_smem(reinterpret_cast<const void *>(grouping_rows_kernel<1>), smem);
+      if (e == cudaSuccess) grouping_rows_kernel<1><<<grid, kGrpThreads, smem, st>>>(c, n, mu, chunk4, features, indices, out);
+    }
+    if (e != cudaSuccess) return (int)e;
+  } else if (vec4)
     grouping_kernel<true><<<dim3(ceil_div(mu / 4, kGrpThreads), ceil_div(c, kGrpCT), b), kGrpThreads, 0, st>>>(
         c, n, mu, features, indices, out);
   else

@@ -23,9 +23,11 @@ namespace bdm {
 __device__ __forceinline__ unsigned fps_tie_key(int k) { return ((unsigned)(k & 511) << 22) | ((unsigned)k >> 9); }
 __device__ __forceinline__ int fps_tie_key_decode(unsigned t) { return (int)(((t & 0x3fffffu) << 9) | (t >> 22)); }
 
-// Register-resident FPS: PPT points per thread, T threads, n <= PPT*T.
-template <int PPT>
-__global__ void __launch_bounds__(1024, 1)
+// Register-resident FPS: PPT points per thread, T <= MAXT threads, n <= PPT*T.  A round is
+// issue-bound on one SM (every SMSP retires ~N*10/128 instructions) plus a fixed reduction/barrier
+// latency per warp, so few fat threads (PPT=16, 8 warps for N=4096) beat many thin ones.
+template <int PPT, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1)
 fps_register_kernel(int n, int m, const float *__restrict__ coords, int *__restrict__ indices) {
   const int b = blockIdx.x;
   const int T = blockDim.x;
@@ -147,12 +149,12 @@ __global__ void gather_grad_kernel(int c, int n, int m, const float *__restrict_
     atomicAdd(grad_x + ((size_t)b * c + cc) * n + dst, grad_y[((size_t)b * c + cc) * m + j]);
 }
 
-template <int PPT>
+template <int PPT, int MAXT>
 static cudaError_t launch_fps_reg(int b, int n, int m, int threads, const float *coords, int *indices,
                                   cudaStream_t st) {
   const size_t smem = sizeof(float) * 3 * (size_t)n;
-  auto kern = fps_register_kernel<PPT>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  auto kern = fps_register_kernel<PPT, MAXT>;
+  cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void *>(kern), smem);
   if (e != cudaSuccess) return e;
   kern<<<b, threads, smem, st>>>(n, m, coords, indices);
   return cudaGetLastError();
@@ -181,13 +183,14 @@ extern "C" int bdm_furthest_point_sampling(int b, int n, int m, const float *coo
   BDM_CHECK_PTR(coords);
   cudaError_t e;
   if (n <= BDM_FPS_REGISTER_MAX_N) {
-    // 4 points per thread up to 4096 points (fewer, smaller warps for the small pyramid levels),
-    // 8 per thread up to 8192.
-    if (n <= 4096) {
-      int threads = ((ceil_div(n, 4) + 31) / 32) * 32;
-      e = launch_fps_reg<4>(b, n, m, threads, coords, indices, st);
-    } else {
-      e = launch_fps_reg<8>(b, n, m, 1024, coords, indices, st);
+    if (n <= 1024) {         // small pyramid levels: 4 points per thread, <= 8 warps
+      const int threads = ((ceil_div(n, 4) + 31) / 32) * 32;
+      e = launch_fps_reg<4, 256>(b, n, m, threads, coords, indices, st);
+    } else if (n <= 4096) {  // 16 points per thread, <= 8 warps
+      const int threads = ((ceil_div(n, 16) + 31) / 32) * 32;
+      e = launch_fps_reg<16, 256>(b, n, m, threads, coords, indices, st);
+    } else {                 // <= 8192 points: 8 per thread, 32 warps (64-register budget)
+      e = launch_fps_reg<8, 1024>(b, n, m, 1024, coords, indices, st);
     }
   } else {
     if (workspace == nullptr) return BDM_ERR_NULL_POINTER;

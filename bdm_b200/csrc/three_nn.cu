@@ -34,12 +34,20 @@ __device__ __forceinline__ void nn3_insert(float d, int k, float &b0, float &b1,
   }
 }
 
+// One warp = 32 points (one per lane) x one contiguous SPLIT of the centre range; the SPLITS warps of
+// a CTA work on the same 32 points and merge their sorted top-3 lists through shared memory in split
+// order, which preserves the reference's "earlier index first on equal distance" rule because split
+// s only holds indices smaller than split s+1.
+constexpr int kNnMaxSplits = 8;
+
 template <bool VEC4>
-__global__ void __launch_bounds__(kNnThreads)
-three_nn_kernel(int n, int m, const float *__restrict__ points, const float *__restrict__ centers,
-                float *__restrict__ weights, int *__restrict__ indices) {
+__global__ void __launch_bounds__(32 * kNnMaxSplits)
+three_nn_kernel(int n, int m, int splits, const float *__restrict__ points,
+                const float *__restrict__ centers, float *__restrict__ weights,
+                int *__restrict__ indices) {
   const int b = blockIdx.y;
-  const int j = blockIdx.x * kNnThreads + threadIdx.x;
+  const int lane = threadIdx.x & 31, split = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + lane;
   points += (size_t)b * 3 * n;
   centers += (size_t)b * 3 * m;
   weights += (size_t)b * 3 * n;
@@ -49,11 +57,16 @@ three_nn_kernel(int n, int m, const float *__restrict__ points, const float *__r
   const float uy = valid ? points[j + n] : 0.0f;
   const float uz = valid ? points[j + n + n] : 0.0f;
 
-  float b0 = __int_as_float(0x7f800000), b1 = b0, b2 = b0;
+  int len = ceil_div(m, splits);
+  len = (len + 3) & ~3;
+  const int k0 = min(split * len, m), k1 = min(k0 + len, m);
+
+  const float inf = __int_as_float(0x7f800000);
+  float b0 = inf, b1 = inf, b2 = inf;
   int i0 = 0, i1 = 0, i2 = 0;
-  int k = 0;
+  int k = k0;
   if (VEC4) {
-    for (; k + 4 <= m; k += 4) {
+    for (; k + 4 <= k1; k += 4) {
       const float4 X = __ldg(reinterpret_cast<const float4 *>(centers + k));
       const float4 Y = __ldg(reinterpret_cast<const float4 *>(centers + m + k));
       const float4 Z = __ldg(reinterpret_cast<const float4 *>(centers + 2 * (size_t)m + k));
@@ -61,16 +74,37 @@ three_nn_kernel(int n, int m, const float *__restrict__ points, const float *__r
       const float d1 = sqdist_ref(__fsub_rn(ux, X.y), __fsub_rn(uy, Y.y), __fsub_rn(uz, Z.y));
       const float d2 = sqdist_ref(__fsub_rn(ux, X.z), __fsub_rn(uy, Y.z), __fsub_rn(uz, Z.z));
       const float d3 = sqdist_ref(__fsub_rn(ux, X.w), __fsub_rn(uy, Y.w), __fsub_rn(uz, Z.w));
-      nn3_insert(d0, k, b0, b1, b2, i0, i1, i2);
-      nn3_insert(d1, k + 1, b0, b1, b2, i0, i1, i2);
-      nn3_insert(d2, k + 2, b0, b1, b2, i0, i1, i2);
-      nn3_insert(d3, k + 3, b0, b1, b2, i0, i1, i2);
+      // none of the four can enter the top-3 unless the smallest beats the current third best
+      if (fminf(fminf(d0, d1), fminf(d2, d3)) < b2) {
+        nn3_insert(d0, k, b0, b1, b2, i0, i1, i2);
+        nn3_insert(d1, k + 1, b0, b1, b2, i0, i1, i2);
+        nn3_insert(d2, k + 2, b0, b1, b2, i0, i1, i2);
+        nn3_insert(d3, k + 3, b0, b1, b2, i0, i1, i2);
+      }
     }
   }
-  for (; k < m; ++k) {
+  for (; k < k1; ++k) {
     const float d = sqdist_ref(__fsub_rn(ux, __ldg(centers + k)), __fsub_rn(uy, __ldg(centers + m + k)),
                                __fsub_rn(uz, __ldg(centers + 2 * (size_t)m + k)));
     nn3_insert(d, k, b0, b1, b2, i0, i1, i2);
+  }
+
+  // merge the per-split top-3 lists (ascending split = ascending index, strict '<' keeps ties stable)
+  __shared__ float s_d[kNnMaxSplits][3][32];
+  __shared__ int s_i[kNnMaxSplits][3][32];
+  if (splits > 1) {
+    s_d[split][0][lane] = b0; s_d[split][1][lane] = b1; s_d[split][2][lane] = b2;
+    s_i[split][0][lane] = i0; s_i[split][1][lane] = i1; s_i[split][2][lane] = i2;
+    __syncthreads();
+    if (split != 0) return;
+    for (int s2 = 1; s2 < splits; ++s2) {
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        const float d = s_d[s2][q][lane];
+        // unset slots are +inf with index 0: never inserted (strict '<' against a finite or inf best)
+        nn3_insert(d, s_i[s2][q][lane], b0, b1, b2, i0, i1, i2);
+      }
+    }
   }
   if (!valid) return;
   // neighbor_interpolate.cu:61-72.  An unset best is 1e40 in the reference and +inf here; both clamp
@@ -116,6 +150,43 @@ three_interp_kernel(int c, int m, int n, const float *__restrict__ feat,
   }
 }
 
+// Shared-memory variant: the 3 gathers per output element hit random addresses of a feature row; from
+// global memory every warp-level gather costs up to 32 L1 wavefronts, from shared memory ~3 (bank
+// conflicts).  A CTA stages CT rows [CT][m] once and serves a chunk of points from them.
+constexpr int kNnRowThreads = 256;
+
+template <int CT>
+__global__ void __launch_bounds__(kNnRowThreads)
+three_interp_rows_kernel(int c, int m, int n, int chunk, const float *__restrict__ feat,
+                         const int *__restrict__ indices, const float *__restrict__ weights,
+                         float *__restrict__ out) {
+  extern __shared__ float rows[];  // [CT][m]
+  const int b = blockIdx.z;
+  const int c0 = blockIdx.y * CT;
+  const int nrows = min(CT, c - c0);
+  const float *f = feat + ((size_t)b * c + c0) * m;
+  for (int q = threadIdx.x; q < nrows * m; q += kNnRowThreads) rows[q] = ld_stream_f1(f + q);
+  __syncthreads();
+  const int *ix = indices + (size_t)b * 3 * n;
+  const float *w = weights + (size_t)b * 3 * n;
+  const int j_end = min((blockIdx.x + 1) * chunk, n);
+  for (int j = blockIdx.x * chunk + threadIdx.x; j < j_end; j += kNnRowThreads) {
+    const int i1 = __ldg(ix + j), i2 = __ldg(ix + j + n), i3 = __ldg(ix + j + n + n);
+    const float w1 = __ldg(w + j), w2 = __ldg(w + j + n), w3 = __ldg(w + j + n + n);
+    float *o = out + ((size_t)b * c + c0) * n + j;
+#pragma unroll
+    for (int cc = 0; cc < CT; ++cc) {
+      if (cc < nrows) {
+        const float *r = rows + cc * m;
+        float acc = __fmul_rn(r[i2], w2);
+        acc = __fmaf_rn(r[i1], w1, acc);
+        acc = __fmaf_rn(r[i3], w3, acc);
+        o[(size_t)cc * n] = acc;
+      }
+    }
+  }
+}
+
 // backward (neighbor_interpolate.cu:155-169): 3 atomic scatter-adds of fl(g*w) per (point, channel)
 __global__ void __launch_bounds__(kNnThreads)
 three_interp_grad_kernel(int c, int n, int m, const float *__restrict__ grad_y,
@@ -151,12 +222,16 @@ extern "C" int bdm_three_nn_search(int b, int n, int m, const float *points_coor
   if (m > 0) BDM_CHECK_PTR(centers_coords);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const bool vec4 = (m % 4 == 0) && ((reinterpret_cast<uintptr_t>(centers_coords) & 15) == 0);
+  // enough warps to fill the machine; at least 64 centres per split
+  const int ctas = ceil_div(n, 32) * b;
+  int splits = 1;
+  while (splits < kNnMaxSplits && ctas * splits < 12 * sm_count() && m / (splits * 2) >= 64) splits *= 2;
   if (vec4)
-    three_nn_kernel<true><<<dim3(ceil_div(n, kNnThreads), b), kNnThreads, 0, st>>>(n, m, points_coords,
-                                                                                 centers_coords, weights, indices);
+    three_nn_kernel<true><<<dim3(ceil_div(n, 32), b), 32 * splits, 0, st>>>(n, m, splits, points_coords,
+                                                                           centers_coords, weights, indices);
   else
-    three_nn_kernel<false><<<dim3(ceil_div(n, kNnThreads), b), kNnThreads, 0, st>>>(n, m, points_coords,
-                                                                                  centers_coords, weights, indices);
+    three_nn_kernel<false><<<dim3(ceil_div(n, 32), b), 32 * splits, 0, st>>>(n, m, splits, points_coords,
+                                                                            centers_coords, weights, indices);
   BDM_RETURN_LAUNCH_STATUS();
 }
 
@@ -169,6 +244,33 @@ extern "C" int bdm_three_nn_interpolate(int b, int c, int m, int n, const float 
   BDM_CHECK_PTR(centers_features); BDM_CHECK_PTR(indices); BDM_CHECK_PTR(weights); BDM_CHECK_PTR(out);
   BDM_CHECK_SIZE(ceil_div(c, kNnCT) <= 65535);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  // rows in shared memory when they fit (CT*m*4 <= 64 KB), else gathers straight from global
+  int ct = 8;
+  while (ct > 1 && sizeof(float) * (size_t)ct * m > 64 * 1024) ct >>= 1;
+  if (m >= 1 && sizeof(float) * (size_t)ct * m <= 64 * 1024 && ceil_div(c, ct) <= 65535) {
+    const int tiles = ceil_div(c, ct) * b;
+    int chunks = 1;
+    while (tiles * chunks < 2 * sm_count() && ceil_div(n, chunks * 2) >= 2 * kNnRowThreads) chunks *= 2;
+    const int chunk = ceil_div(n, chunks);
+    const size_t smem = sizeof(float) * (size_t)ct * m;
+    const dim3 grid(chunks, ceil_div(c, ct), b);
+    cudaError_t e = cudaSuccess;
+    if (ct == 8) {
+      e = ensure_dynamic_smem(reinterpret_cast<const void *>(three_interp_rows_kernel<8>), smem);
+      if (e == cudaSuccess) three_interp_rows_kernel<8><<<grid, kNnRowThreads, smem, st>>>(c, m, n, chunk, centers_features, indices, weights, out);
+    } else if (ct == 4) {
+      e = ensure_dynamic_smem(reinterpret_cast<const void *>(three_interp_rows_kernel<4>), smem);
+      if (e == cudaSuccess) three_interp_rows_kernel<4><<<grid, kNnRowThreads, smem, st>>>(c, m, n, chunk, centers_features, indices, weights, out);
+    } else if (ct == 2) {
+      e = ensure_dynamic_smem(reinterpret_cast<const void *>(three_interp_rows_kernel<2>), smem);
+      if (e == cudaSuccess) three_interp_rows_kernel<2><<<grid, kNnRowThreads, smem, st>>>(c, m, n, chunk, centers_features, indices, weights, out);
+    } else {
+      e = ensure_dynamic_smem(reinterpret_cast<const void *>(three_interp_rows_kernel<1>), smem);
+      if (e == cudaSuccess) three_interp_rows_kernel<1><<<grid, kNnRowThreads, smem, st>>>(c, m, n, chunk, centers_features, indices, weights, out);
+    }
+    if (e != cudaSuccess) return (int)e;
+    BDM_RETURN_LAUNCH_STATUS();
+  }
   three_interp_kernel<<<dim3(ceil_div(n, kNnThreads), ceil_div(c, kNnCT), b), kNnThreads, 0, st>>>(
       c, m, n, centers_features, indices, weights, out);
   BDM_RETURN_LAUNCH_STATUS();

@@ -14,12 +14,15 @@
 //                        tables per shape in the workspace: an occupancy bitmask (1 bit/voxel), the
 //                        occupied-rank base of every 32-voxel word, and the start offset of every
 //                        occupied voxel in the sorted order.
-//   2. vox_fill_kernel   one CTA per (shape, tile of CT channels): stages its channels' point
+//   2. vox_fill_kernel   one CTA per (shape, tile of CT channels): (a) stages its channels' point
 //                        features into shared memory *in sorted order* (coalesced global reads,
-//                        permuting shared-memory writes), then streams over the voxel grid four
-//                        voxels per thread: bitmask test -> zeros, or a short in-register sum over
-//                        the voxel's contiguous run of sorted points -> one st.global.cs.v4 per
-//                        channel.  HBM traffic = read feat once + write out once.
+//                        permuting shared-memory writes); (b) one thread per OCCUPIED voxel sums the
+//                        voxel's contiguous run of sorted points and compacts the averages in place
+//                        (value j of a channel = average of the j-th occupied voxel); (c) streams over
+//                        the voxel grid four voxels per thread: bitmask nibble == 0 -> zeros, else a
+//                        popcount-ranked look-up of the precomputed averages -> one st.global.cs.v4
+//                        per channel.  HBM traffic = read feat once + write out once; the streaming
+//                        loop is ~17 instructions per 4 x 512-byte warp stores.
 // Summation order inside a voxel is ascending point index (deterministic run to run); each addend is
 // fl(feat * fl(1/cnt)) exactly like the reference (vox.cu:66-68), so voxels holding one or two
 // points are bit-identical to the reference and the rest differ only by fp32 summation order
@@ -37,6 +40,7 @@ constexpr int kFastMaxR3 = 32768;
 constexpr int kFastMaxN = 16384;
 
 struct VoxAuxLayout {
+  size_t header;   // u32[4]: [0] = number of occupied voxels
   size_t bitmask;  // u32[nw]
   size_t obase;    // u16[nw]
   size_t ostart;   // u16[n+1]
@@ -49,6 +53,7 @@ __host__ __device__ inline VoxAuxLayout vox_aux_layout(int n, int r3) {
   VoxAuxLayout L;
   L.nw = (r3 + 31) / 32;
   size_t off = 0;
+  L.header = off;  off += 16;
   L.bitmask = off; off = align_up(off + sizeof(uint32_t) * L.nw, 16);
   L.obase = off;   off = align_up(off + sizeof(uint16_t) * L.nw, 16);
   L.ostart = off;  off = align_up(off + sizeof(uint16_t) * (n + 1), 16);
@@ -149,7 +154,10 @@ vox_sort_kernel(int n, int r, const int *__restrict__ coords, int *__restrict__ 
       obase[tid] = excl >> 16;
       g_bitmask[tid] = wmask[tid];
       g_obase[tid] = (uint16_t)(excl >> 16);
-      if (tid == nw - 1) g_ostart[(excl + val) >> 16] = (uint16_t)n;  // sentinel after the last run
+      if (tid == nw - 1) {
+        g_ostart[(excl + val) >> 16] = (uint16_t)n;  // sentinel after the last run
+        reinterpret_cast<uint32_t *>(ws + L.header)[0] = (excl + val) >> 16;
+      }
     }
   }
   __syncthreads();
@@ -196,7 +204,8 @@ vox_fill_kernel(int c, int n, int r3, const float *__restrict__ feat, float *__r
   const int nw = L.nw;
 
   extern __shared__ uint32_t smem_u32[];
-  float *sfeat = reinterpret_cast<float *>(smem_u32);                  // [CT][n]
+  float *buf = reinterpret_cast<float *>(smem_u32);                    // [CT][n] sorted features, then
+                                                                       //         per-voxel averages (in place)
   uint32_t *bitmask = smem_u32 + (size_t)CT * n;                       // [nw]
   uint16_t *obase = reinterpret_cast<uint16_t *>(bitmask + nw);        // [nw]
   uint16_t *ostart = obase + ((nw + 1) & ~1);                          // [n+1]
@@ -206,23 +215,49 @@ vox_fill_kernel(int c, int n, int r3, const float *__restrict__ feat, float *__r
   const uint16_t *g_obase = reinterpret_cast<const uint16_t *>(ws + L.obase);
   const uint16_t *g_ostart = reinterpret_cast<const uint16_t *>(ws + L.ostart);
   const uint16_t *g_rank = reinterpret_cast<const uint16_t *>(ws + L.rank);
+  const int nocc = (int)reinterpret_cast<const uint32_t *>(ws + L.header)[0];
 
   for (int w = tid; w < nw; w += kFillThreads) {
     bitmask[w] = g_bitmask[w];
     obase[w] = g_obase[w];
   }
-  for (int i = tid; i < n + 1; i += kFillThreads) ostart[i] = g_ostart[i];
+  for (int i = tid; i <= nocc; i += kFillThreads) ostart[i] = g_ostart[i];
 
-  // stage this tile's features in sorted order
+  // (a) stage this tile's features in sorted order
   const float *f = feat + ((size_t)b * c + c0) * n;
   for (int i = tid; i < n; i += kFillThreads) {
     const int rk = g_rank[i];
 #pragma unroll
     for (int cc = 0; cc < CT; ++cc)
-      if (c0 + cc < c) sfeat[cc * n + rk] = ld_stream_f1(f + (size_t)cc * n + i);
+      if (c0 + cc < c) buf[cc * n + rk] = ld_stream_f1(f + (size_t)cc * n + i);
   }
   __syncthreads();
 
+  // (b) one thread per occupied voxel: average of its run, compacted in place.  Voxel j's run starts
+  // at ostart[j] >= j, so chunk k (voxels [k*T,(k+1)*T)) only reads positions >= k*T and only writes
+  // positions < (k+1)*T: a barrier between the chunk's reads and its writes is all that is needed.
+  for (int base = 0; base < nocc; base += kFillThreads) {
+    const int j = base + tid;
+    float acc[CT];
+#pragma unroll
+    for (int cc = 0; cc < CT; ++cc) acc[cc] = 0.0f;
+    if (j < nocc) {
+      const int s = ostart[j], e = ostart[j + 1];
+      const float inv = __frcp_rn((float)(e - s));  // == 1.0 / float(cnt), vox.cu:65
+      for (int p = s; p < e; ++p) {
+#pragma unroll
+        for (int cc = 0; cc < CT; ++cc) acc[cc] = __fadd_rn(acc[cc], __fmul_rn(buf[cc * n + p], inv));
+      }
+    }
+    __syncthreads();
+    if (j < nocc) {
+#pragma unroll
+      for (int cc = 0; cc < CT; ++cc) buf[cc * n + j] = acc[cc];
+    }
+  }
+  __syncthreads();
+
+  // (c) stream the dense grid
   float *o = out + ((size_t)b * c + c0) * r3;
   const int ngroups = r3 / VEC;
   for (int g = tid; g < ngroups; g += kFillThreads) {
@@ -240,18 +275,8 @@ vox_fill_kernel(int c, int n, int r3, const float *__restrict__ feat, float *__r
 #pragma unroll
       for (int k = 0; k < VEC; ++k) {
         if ((nib >> k) & 1u) {
-          const int s = ostart[j], e = ostart[j + 1];
-          const float inv = __frcp_rn((float)(e - s));  // == 1.0 / float(cnt), vox.cu:65
-          float acc[CT];
 #pragma unroll
-          for (int cc = 0; cc < CT; ++cc) acc[cc] = 0.0f;
-          for (int p = s; p < e; ++p) {
-#pragma unroll
-            for (int cc = 0; cc < CT; ++cc)
-              acc[cc] = __fadd_rn(acc[cc], __fmul_rn(sfeat[cc * n + p], inv));
-          }
-#pragma unroll
-          for (int cc = 0; cc < CT; ++cc) val[cc][k] = acc[cc];
+          for (int cc = 0; cc < CT; ++cc) val[cc][k] = buf[cc * n + j];
           ++j;
         }
       }
@@ -316,6 +341,7 @@ __global__ void vox_grad_kernel(int c, int n, int s, const int *__restrict__ ind
   }
 }
 
+
 static bool vox_fast_path(int n, int r3) { return r3 <= kFastMaxR3 && n <= kFastMaxN && n >= 1; }
 
 template <int CT, int VEC>
@@ -324,11 +350,18 @@ static cudaError_t launch_fill(int b, int c, int n, int r3, const float *feat, f
   const size_t smem = sizeof(float) * (size_t)CT * n + sizeof(uint32_t) * L.nw +
                       sizeof(uint16_t) * (((L.nw + 1) & ~1) + n + 2);
   auto kern = vox_fill_kernel<CT, VEC>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
+  cudaError_t e0 = ensure_dynamic_smem(reinterpret_cast<const void *>(kern), smem);
+  if (e0 != cudaSuccess) return e0;
   dim3 grid(ceil_div(c, CT), b);
   kern<<<grid, kFillThreads, smem, st>>>(c, n, r3, feat, out, ws, L);
   return cudaGetLastError();
+}
+
+static int check_workspace(const VoxAuxLayout &L, int b, const void *workspace, size_t workspace_bytes) {
+  if (workspace == nullptr) return BDM_ERR_NULL_POINTER;
+  if (workspace_bytes < L.stride * (size_t)b) return BDM_ERR_WORKSPACE_TOO_SMALL;
+  if ((reinterpret_cast<uintptr_t>(workspace) & 15) != 0) return BDM_ERR_MISALIGNED;
+  return BDM_OK;
 }
 
 }  // namespace bdm
@@ -336,53 +369,76 @@ static cudaError_t launch_fill(int b, int c, int n, int r3, const float *feat, f
 extern "C" size_t bdm_avg_voxelize_workspace_bytes(int b, int n, int r) {
   if (b <= 0 || n <= 0 || r <= 0) return 16;
   const long long r3 = (long long)r * r * r;
-  if (!bdm::vox_fast_path(n, r3 > bdm::kFastMaxR3 ? bdm::kFastMaxR3 + 1 : (int)r3)) return 16;
+  if (r3 > bdm::kFastMaxR3 || !bdm::vox_fast_path(n, (int)r3)) return 16;
   return bdm::vox_aux_layout(n, (int)r3).stride * (size_t)b;
 }
 
-extern "C" int bdm_avg_voxelize(int b, int c, int n, int r, const int *coords, const float *feat,
-                                int *ind, int *cnt, float *out, void *workspace,
-                                size_t workspace_bytes, bdm_stream_t stream) {
+// Step 1 of avg_voxelize: everything that depends only on the coordinates (ind, cnt, and the sorted
+// plan in the workspace).  Callers that voxelize several feature tensors over the same coordinates
+// (consecutive PVConv blocks of one stage do) run this once.
+extern "C" int bdm_voxel_plan(int b, int n, int r, const int *coords, int *ind, int *cnt,
+                              void *workspace, size_t workspace_bytes, bdm_stream_t stream) {
   using namespace bdm;
-  BDM_CHECK_SIZE(b >= 0 && c >= 0 && n >= 0 && r >= 1);
+  BDM_CHECK_SIZE(b >= 0 && n >= 0 && r >= 1);
   const long long r3ll = (long long)r * r * r;
   BDM_CHECK_SIZE(r3ll <= 0x7fffffffLL);
   const int r3 = (int)r3ll;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (b == 0) return BDM_OK;
   BDM_CHECK_PTR(cnt);
-  if (c > 0) BDM_CHECK_PTR(out);
-  if (n > 0) { BDM_CHECK_PTR(coords); BDM_CHECK_PTR(ind); if (c > 0) BDM_CHECK_PTR(feat); }
-
-  if (n == 0) {  // empty clouds: all-zero grid
+  if (n == 0) {
     cudaMemsetAsync(cnt, 0, sizeof(int) * (size_t)b * r3, st);
-    if (c > 0) cudaMemsetAsync(out, 0, sizeof(float) * (size_t)b * c * r3, st);
     BDM_RETURN_LAUNCH_STATUS();
   }
-
+  BDM_CHECK_PTR(coords); BDM_CHECK_PTR(ind);
   if (vox_fast_path(n, r3)) {
     const VoxAuxLayout L = vox_aux_layout(n, r3);
-    if (workspace == nullptr) return BDM_ERR_NULL_POINTER;
-    if (workspace_bytes < L.stride * (size_t)b) return BDM_ERR_WORKSPACE_TOO_SMALL;
-    if ((reinterpret_cast<uintptr_t>(workspace) & 15) != 0) return BDM_ERR_MISALIGNED;
-    unsigned char *ws = static_cast<unsigned char *>(workspace);
+    const int rc = check_workspace(L, b, workspace, workspace_bytes);
+    if (rc != BDM_OK) return rc;
     const size_t smem_sort = sizeof(uint32_t) * ((size_t)L.nw * 32 + 3 * (size_t)L.nw) +
                              sizeof(uint16_t) * (2 * (size_t)((n + 1) & ~1));
-    cudaError_t e = cudaFuncSetAttribute(vox_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)smem_sort);
+    cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void *>(vox_sort_kernel), smem_sort);
     if (e != cudaSuccess) return (int)e;
-    vox_sort_kernel<<<b, kSortThreads, smem_sort, st>>>(n, r, coords, ind, cnt, ws, L);
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return (int)e;
-    if (c == 0) return BDM_OK;
+    vox_sort_kernel<<<b, kSortThreads, smem_sort, st>>>(n, r, coords, ind, cnt, static_cast<unsigned char *>(workspace), L);
+    BDM_RETURN_LAUNCH_STATUS();
+  }
+  cudaMemsetAsync(cnt, 0, sizeof(int) * (size_t)b * r3, st);
+  vox_stats_generic_kernel<<<dim3(ceil_div(n, 256), b), 256, 0, st>>>(n, r, coords, ind, cnt);
+  BDM_RETURN_LAUNCH_STATUS();
+}
+
+// Step 2 of avg_voxelize: the dense [b,c,r^3] grid from features + the plan of bdm_voxel_plan
+// (same b, n, r, workspace; ind/cnt are only read on the generic path).
+extern "C" int bdm_avg_voxelize_fill(int b, int c, int n, int r, const int *ind, const int *cnt,
+                                     const float *feat, float *out, const void *workspace,
+                                     size_t workspace_bytes, bdm_stream_t stream) {
+  using namespace bdm;
+  BDM_CHECK_SIZE(b >= 0 && c >= 0 && n >= 0 && r >= 1);
+  const long long r3ll = (long long)r * r * r;
+  BDM_CHECK_SIZE(r3ll <= 0x7fffffffLL);
+  const int r3 = (int)r3ll;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (b == 0 || c == 0) return BDM_OK;
+  BDM_CHECK_PTR(out);
+  if (n == 0) {
+    cudaMemsetAsync(out, 0, sizeof(float) * (size_t)b * c * r3, st);
+    BDM_RETURN_LAUNCH_STATUS();
+  }
+  BDM_CHECK_PTR(feat);
+  if (vox_fast_path(n, r3)) {
+    const VoxAuxLayout L = vox_aux_layout(n, r3);
+    const int rc = check_workspace(L, b, workspace, workspace_bytes);
+    if (rc != BDM_OK) return rc;
+    const unsigned char *ws = static_cast<const unsigned char *>(workspace);
     const bool vec4 = (r3 % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
-    // Channel tile: as large as possible (amortises the per-CTA lookup tables) while still giving
-    // every SM at least two CTAs.
+    // Channel tile: as large as possible (amortises the per-CTA lookup tables and the staging
+    // barrier) while still giving every SM at least two CTAs.
     const int want = 2 * sm_count();
     int ct = 4;
     if (b * ceil_div(c, 4) < want) ct = 2;
     if (b * ceil_div(c, 2) < want) ct = 1;
     if (sizeof(float) * (size_t)ct * n > 160 * 1024) ct = (n > 8192) ? 1 : 2;
+    cudaError_t e;
     if (vec4) {
       if (ct == 4) e = launch_fill<4, 4>(b, c, n, r3, feat, out, ws, L, st);
       else if (ct == 2) e = launch_fill<2, 4>(b, c, n, r3, feat, out, ws, L, st);
@@ -394,15 +450,18 @@ extern "C" int bdm_avg_voxelize(int b, int c, int n, int r, const int *coords, c
     }
     return e == cudaSuccess ? BDM_OK : (int)e;
   }
-
-  // generic path
-  cudaMemsetAsync(cnt, 0, sizeof(int) * (size_t)b * r3, st);
-  if (c > 0) cudaMemsetAsync(out, 0, sizeof(float) * (size_t)b * c * r3, st);
-  vox_stats_generic_kernel<<<dim3(ceil_div(n, 256), b), 256, 0, st>>>(n, r, coords, ind, cnt);
-  if (c > 0)
-    vox_scatter_generic_kernel<<<dim3(ceil_div(n, 256), ceil_div(c, 8), b), 256, 0, st>>>(c, n, r3, ind, cnt,
-                                                                                         feat, out);
+  BDM_CHECK_PTR(ind); BDM_CHECK_PTR(cnt);
+  cudaMemsetAsync(out, 0, sizeof(float) * (size_t)b * c * r3, st);
+  vox_scatter_generic_kernel<<<dim3(ceil_div(n, 256), ceil_div(c, 8), b), 256, 0, st>>>(c, n, r3, ind, cnt, feat, out);
   BDM_RETURN_LAUNCH_STATUS();
+}
+
+extern "C" int bdm_avg_voxelize(int b, int c, int n, int r, const int *coords, const float *feat,
+                                int *ind, int *cnt, float *out, void *workspace,
+                                size_t workspace_bytes, bdm_stream_t stream) {
+  const int rc = bdm_voxel_plan(b, n, r, coords, ind, cnt, workspace, workspace_bytes, stream);
+  if (rc != BDM_OK) return rc;
+  return bdm_avg_voxelize_fill(b, c, n, r, ind, cnt, feat, out, workspace, workspace_bytes, stream);
 }
 
 extern "C" int bdm_avg_voxelize_grad(int b, int c, int n, int s, const int *ind, const int *cnt,

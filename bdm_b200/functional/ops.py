@@ -55,8 +55,36 @@ class _TrilinearDevoxelize(Function):
         return g.view(grad_out.size(0), grad_out.size(1), r, r, r), None, None, None
 
 
+class _AvgVoxelizePlanned(Function):
+    """avg_voxelize for callers that already hold the coordinate-only half of the op (`voxel_plan`)."""
+
+    @staticmethod
+    def forward(ctx, features, plan):
+        feats = features.contiguous()
+        grid = _B.avg_voxelize_fill(feats, plan)
+        ctx.save_for_backward(plan.ind, plan.cnt)
+        r = plan.r
+        return grid.view(feats.shape[0], feats.shape[1], r, r, r)
+
+    @staticmethod
+    def backward(ctx, grad_grid):
+        point_voxel, voxel_count = ctx.saved_tensors
+        flat = grad_grid.contiguous().view(grad_grid.shape[0], grad_grid.shape[1], -1)
+        return _B.avg_voxelize_backward(flat, point_voxel, voxel_count), None
+
+
 avg_voxelize = _AvgVoxelize.apply
+avg_voxelize_planned = _AvgVoxelizePlanned.apply
 trilinear_devoxelize = _TrilinearDevoxelize.apply
+
+
+def voxel_plan(vox_coords, resolution):
+    """Coordinate-only half of avg_voxelize (voxel index, counts, sorted lookup tables), reusable for
+    every feature tensor voxelized over the same coordinates.  None when the active backend has no
+    such entry point (the reference's extension does not)."""
+    if REFERENCE_CALL_PATTERN or not hasattr(_B, "voxel_plan"):
+        return None
+    return _B.voxel_plan(vox_coords.int().contiguous(), resolution)
 
 
 # ----------------------------------------------------------------------------------------------

@@ -24,6 +24,36 @@ def normalized_voxel_coords(coords, resolution, normalize=True, eps=0):
     return torch.clamp(unit * resolution, 0, resolution - 1)
 
 
+class _CoordinatePlanCache:
+    """The last (coords tensor, resolution) -> (float voxel coords, voxel plan).  Consecutive PVConv
+    blocks of one stage receive the SAME coords tensor object (PVConv.forward passes it through), so
+    2-3 voxelizations per stage share one normalisation (~8 small torch launches) and one index/sort
+    kernel.  Holding a reference to the coords tensor keeps its storage from being recycled; the
+    version counter catches in-place edits.  Results are bit-identical to recomputing."""
+
+    def __init__(self):
+        self.key = None
+        self.coords = None
+        self.value = None
+
+    def lookup(self, coords, r, normalize, eps):
+        key = (coords.data_ptr(), coords._version, tuple(coords.shape), coords.device, r, normalize, eps)
+        if self.coords is coords and self.key == key:
+            return self.value
+        norm_coords = normalized_voxel_coords(coords.detach(), r, normalize, eps)
+        vox_coords = torch.round(norm_coords).to(torch.int32)  # half-to-even, like the reference
+        plan = F.voxel_plan(vox_coords, r)
+        self.key, self.coords = key, coords
+        self.value = (norm_coords, vox_coords, plan)
+        return self.value
+
+    def clear(self):
+        self.key = self.coords = self.value = None
+
+
+_plan_cache = _CoordinatePlanCache()
+
+
 class Voxelization(nn.Module):
     def __init__(self, resolution, normalize=True, eps=0):
         super().__init__()
@@ -33,9 +63,10 @@ class Voxelization(nn.Module):
 
     def forward(self, features, coords):
         """-> (voxel grid f32[B,C,R,R,R], float voxel coordinates f32[B,3,N])"""
-        norm_coords = normalized_voxel_coords(coords.detach(), self.r, self.normalize, self.eps)
-        vox_coords = torch.round(norm_coords).to(torch.int32)  # half-to-even, like the reference
-        return F.avg_voxelize(features, vox_coords, self.r), norm_coords
+        norm_coords, vox_coords, plan = _plan_cache.lookup(coords, self.r, self.normalize, self.eps)
+        if plan is None:  # backend without the split entry points (e.g. the reference's own extension)
+            return F.avg_voxelize(features, vox_coords, self.r), norm_coords
+        return F.avg_voxelize_planned(features, plan), norm_coords
 
     def extra_repr(self):
         return 'resolution={}{}'.format(self.r, ', normalized eps = {}'.format(self.eps) if self.normalize else '')

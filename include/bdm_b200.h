@@ -52,6 +52,16 @@ size_t bdm_avg_voxelize_workspace_bytes(int b, int n, int r);
 int bdm_avg_voxelize(int b, int c, int n, int r, const int *coords, const float *feat, int *ind,
                      int *cnt, float *out, void *workspace, size_t workspace_bytes,
                      bdm_stream_t stream);
+/* The two halves of bdm_avg_voxelize, for callers that voxelize several feature tensors over the
+ * same coordinates (consecutive PVConv blocks of one stage do: modules/pvconv.py:91-97 is called 2-3
+ * times per stage with unchanged coords).  bdm_voxel_plan does everything that depends only on the
+ * coordinates (ind, cnt, the sorted plan kept in `workspace`); bdm_avg_voxelize_fill produces the
+ * dense grid for one feature tensor from that plan (same b, n, r and workspace). */
+int bdm_voxel_plan(int b, int n, int r, const int *coords, int *ind, int *cnt, void *workspace,
+                   size_t workspace_bytes, bdm_stream_t stream);
+int bdm_avg_voxelize_fill(int b, int c, int n, int r, const int *ind, const int *cnt,
+                          const float *feat, float *out, const void *workspace,
+                          size_t workspace_bytes, bdm_stream_t stream);
 /* replaces avg_voxelize_grad (src/voxelization/vox.cuh:7-8): grad_y f32[b,c,s] -> grad_x f32[b,c,n] */
 int bdm_avg_voxelize_grad(int b, int c, int n, int s, const int *ind, const int *cnt,
                           const float *grad_y, float *grad_x, bdm_stream_t stream);
@@ -61,10 +71,13 @@ int bdm_avg_voxelize_grad(int b, int c, int n, int s, const int *ind, const int 
  *              const float*coords,const float*feat,int*inds,float*wgts,float*outs)
  *                                                            (src/interpolate/trilinear_devox.cuh:5-8)
  *   coords f32[b,3,n] in [0,r-1]   feat f32[b,c,r^3]   outs f32[b,c,n]
- *   inds i32[b,8,n], wgts f32[b,8,n]: written iff is_training (may be NULL otherwise). */
+ *   inds i32[b,8,n], wgts f32[b,8,n]: written iff is_training (may be NULL otherwise).
+ * workspace: bdm_trilinear_devoxelize_workspace_bytes(b,n,r) bytes, 16-byte aligned (x-slice binning
+ * of the points for the shared-memory fast path); NULL selects the generic gather kernel. */
+size_t bdm_trilinear_devoxelize_workspace_bytes(int b, int n, int r);
 int bdm_trilinear_devoxelize(int b, int c, int n, int r, int is_training, const float *coords,
                              const float *feat, int *inds, float *wgts, float *outs,
-                             bdm_stream_t stream);
+                             void *workspace, size_t workspace_bytes, bdm_stream_t stream);
 /* replaces trilinear_devoxelize_grad (trilinear_devox.cuh:9-11): grad_x f32[b,c,r3] is zeroed here */
 int bdm_trilinear_devoxelize_grad(int b, int c, int n, int r3, const int *inds, const float *wgts,
                                   const float *grad_y, float *grad_x, bdm_stream_t stream);

@@ -145,6 +145,51 @@ def test_voxelize_deterministic(cuda_backend):
         assert torch.equal(a, cuda_backend.avg_voxelize_forward(feat, vt, 32)[0])
 
 
+@pytest.mark.parametrize("n,m", [(33, 20), (700, 90), (1024, 256), (1025, 64), (2500, 300), (4096, 1024), (6000, 128), (8192, 64)])
+def test_fps_every_launch_configuration(n, m, cuda_backend):
+    """each register-path instantiation (4/16/8 points per thread) against the oracle, with duplicates"""
+    import torch
+
+    import oracle as O
+    rng = np.random.default_rng(n * 31 + m)
+    co = cases.cloud(rng, 2, n, "shape")
+    co[:, :, rng.integers(0, n, n // 5)] = co[:, :, rng.integers(0, n, n // 5)]
+    idx = cuda_backend.furthest_point_sampling(torch.as_tensor(co).cuda(), m)
+    assert np.array_equal(idx.cpu().numpy(), O.furthest_point_sampling(co, m))
+
+
+@pytest.mark.parametrize("c,n,r", [(5, 777, 8), (7, 1000, 16), (64, 4096, 32), (3, 300, 5), (9, 5000, 32), (2, 100, 1)])
+@pytest.mark.parametrize("b", [1, 16, 60])
+def test_devoxelize_fast_path_vs_oracle(b, c, n, r, cuda_backend):
+    """slice-ring kernel (CT = 1, 2, 4 depending on b*c) and odd sizes, bit-exact against the oracle"""
+    import torch
+
+    import oracle as O
+    if b * c * r ** 3 > 40e6:
+        b = 4
+    rng = np.random.default_rng(b + c + n + r)
+    nc = (rng.random((b, 3, n)) * (r - 1)).astype(np.float32)
+    nc[:, :, : min(n, 16)] = np.round(nc[:, :, : min(n, 16)])
+    nc[0, :, -1] = r - 1
+    grid = rng.standard_normal((b, c, r ** 3)).astype(np.float32)
+    got = cuda_backend.trilinear_devoxelize_forward(r, False, torch.as_tensor(nc).cuda(), torch.as_tensor(grid).cuda())[0]
+    want = O.trilinear_devoxelize_forward(r, False, nc, grid)[0]
+    assert np.array_equal(got.cpu().numpy(), want)
+
+
+def test_voxel_plan_reuse(cuda_backend):
+    """one plan, several feature tensors == independent avg_voxelize calls"""
+    import torch
+    rng = np.random.default_rng(3)
+    co = cases.cloud(rng, 4, 2048, "shape")
+    vox, _ = cases.vox_coords(co, 16)
+    vt = torch.as_tensor(vox).cuda()
+    plan = cuda_backend.voxel_plan(vt, 16)
+    for c in (1, 3, 8, 33):
+        f = torch.randn(4, c, 2048, device="cuda")
+        assert torch.equal(cuda_backend.avg_voxelize_fill(f, plan), cuda_backend.avg_voxelize_forward(f, vt, 16)[0])
+
+
 def test_generic_paths(cuda_backend):
     """sizes outside the shared-memory fast paths: R^3 > 32768 (voxelize), N > 8192 (FPS)"""
     import torch

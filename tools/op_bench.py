@@ -45,10 +45,37 @@ def flush_l2():
     _flush.fill_(1)
 
 
+USE_GRAPH = True
+
+
 def timeit(fn, iters, warm=3):
+    """Device time per call.  With USE_GRAPH the `iters` calls are captured into one CUDA graph and
+    replayed, so Python / ctypes / allocator time between launches is not measured."""
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
+    if USE_GRAPH:
+        try:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                for _ in range(iters):
+                    fn()
+            g.replay()
+            torch.cuda.synchronize()
+            ts = []
+            for _ in range(3):
+                flush_l2()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                g.replay()
+                e1.record()
+                torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1) / iters)
+            del g
+            return min(ts)
+        except Exception as e:  # e.g. an op that cannot be captured: fall back to eager timing
+            print("graph capture failed:", repr(e)[:200], flush=True)
+            torch.cuda.synchronize()
     ts = []
     for _ in range(3):
         flush_l2()
@@ -68,9 +95,12 @@ def main():
     ap.add_argument("--regime", default="shape")
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--no-ref", action="store_true")
+    ap.add_argument("--eager", action="store_true", help="time eager launches instead of CUDA-graph replays")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "op_bench.json"))
     args = ap.parse_args()
     B = args.batch
+    global USE_GRAPH
+    USE_GRAPH = not args.eager
     from bdm_b200 import backend as ours
     ref = None
     if not args.no_ref:

@@ -48,7 +48,7 @@ inline int sm_count() {
 // Opt a kernel in to `bytes` of dynamic shared memory (> 48 KB needs it) once per (kernel, device);
 // cudaFuncSetAttribute is too slow to repeat on every launch and is a per-device setting.
 inline cudaError_t ensure_dynamic_smem(const void *func, size_t bytes) {
-  if (bytes <= 48 * 1024) return cudaSuccess;
+  if (bytes <= 32 * 1024) return cudaSuccess;  // static + dynamic stays under the default 48 KB cap
   static std::mutex mu;
   static std::map<std::pair<const void *, int>, size_t> configured;
   int dev = 0;

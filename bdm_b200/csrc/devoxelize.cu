@@ -146,13 +146,79 @@ template <> struct VecOf<4> { using type = float4; };
 template <> struct VecOf<2> { using type = float2; };
 template <> struct VecOf<1> { using type = float; };
 
+// CT consecutive floats from shared memory in as few (<= 128-bit) loads as possible
 template <int CT>
 __device__ __forceinline__ void lds_vec(const float *p, float (&v)[CT]) {
-  using V = typename VecOf<CT>::type;
-  const V t = *reinterpret_cast<const V *>(p);
-  const float *tf = reinterpret_cast<const float *>(&t);
+  if constexpr (CT > 4) {
 #pragma unroll
-  for (int q = 0; q < CT; ++q) v[q] = tf[q];
+    for (int h = 0; h < CT / 4; ++h) {
+      const float4 t = reinterpret_cast<const float4 *>(p)[h];
+      v[4 * h] = t.x; v[4 * h + 1] = t.y; v[4 * h + 2] = t.z; v[4 * h + 3] = t.w;
+    }
+  } else {
+    using V = typename VecOf<CT>::type;
+    const V t = *reinterpret_cast<const V *>(p);
+    const float *tf = reinterpret_cast<const float *>(&t);
+#pragma unroll
+    for (int q = 0; q < CT; ++q) v[q] = tf[q];
+  }
+}
+
+template <int CT>
+__device__ __forceinline__ void sts_vec(float *p, const float (&v)[CT]) {
+  if constexpr (CT > 4) {
+#pragma unroll
+    for (int h = 0; h < CT / 4; ++h)
+      reinterpret_cast<float4 *>(p)[h] = make_float4(v[4 * h], v[4 * h + 1], v[4 * h + 2], v[4 * h + 3]);
+  } else {
+    using V = typename VecOf<CT>::type;
+    V t;
+    float *tf = reinterpret_cast<float *>(&t);
+#pragma unroll
+    for (int q = 0; q < CT; ++q) tf[q] = v[q];
+    *reinterpret_cast<V *>(p) = t;
+  }
+}
+
+// Small grids (R^3 * CT * 4 <= 64 KB: R <= 16): the whole channel-interleaved grid tile [R^3][CT] sits
+// in shared memory, points are served in their original order (no binning pass, coalesced stores).
+constexpr int kGridThreads = 256;
+
+template <int CT>
+__global__ void __launch_bounds__(kGridThreads)
+devox_grid_kernel(int c, int n, int r, int chunk, const float *__restrict__ coords,
+                  const float *__restrict__ feat, float *__restrict__ outs) {
+  extern __shared__ __align__(16) float tile[];  // [r3][CT]
+  const int b = blockIdx.z;
+  const int c0 = blockIdx.x * CT;
+  const int nch = min(CT, c - c0);
+  const int r2 = r * r, r3 = r2 * r;
+  const float *fbase = feat + ((size_t)b * c + c0) * r3;
+  for (int v = threadIdx.x; v < r3; v += kGridThreads) {
+    float t[CT];
+#pragma unroll
+    for (int cc = 0; cc < CT; ++cc) t[cc] = cc < nch ? ld_stream_f1(fbase + (size_t)cc * r3 + v) : 0.0f;
+    sts_vec<CT>(tile + (size_t)v * CT, t);
+  }
+  __syncthreads();
+  const float *co = coords + (size_t)b * 3 * n;
+  float *o = outs + ((size_t)b * c + c0) * n;
+  const int i_end = min((blockIdx.y + 1) * chunk, n);
+  for (int i = blockIdx.y * chunk + threadIdx.x; i < i_end; i += kGridThreads) {
+    Corner8 k;
+    devox_corners(co[i], co[i + n], co[i + n + n], r, r2, k);
+    float f[8][CT];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) lds_vec<CT>(tile + (size_t)min(max(k.id[q], 0), r3 - 1) * CT, f[q]);
+#pragma unroll
+    for (int cc = 0; cc < CT; ++cc) {
+      float acc = __fmul_rn(k.w[1], f[1][cc]);
+      acc = __fmaf_rn(k.w[0], f[0][cc], acc);
+#pragma unroll
+      for (int q = 2; q < 8; ++q) acc = __fmaf_rn(k.w[q], f[q][cc], acc);
+      if (cc < nch) o[(size_t)cc * n + i] = acc;
+    }
+  }
 }
 
 template <int CT>
@@ -354,6 +420,31 @@ static int devox_slice_ct(int b, int c, int n, int r, int is_training) {
   return ct;
 }
 
+// channel tile for the whole-grid kernel, or 0 when the grid tile does not fit
+static int devox_grid_ct(int b, int c, int n, int r, int is_training) {
+  if (is_training || n < 1 || c < 1) return 0;
+  const size_t r3 = (size_t)r * r * r;
+  if (r3 * sizeof(float) > 64 * 1024) return 0;
+  int ct = 8;
+  while (ct > 1 && (r3 * ct * sizeof(float) > 64 * 1024 || b * ceil_div(c, ct) < 2 * sm_count())) ct >>= 1;
+  if (ceil_div(c, ct) > 65535 || b > 65535) return 0;
+  return ct;
+}
+
+template <int CT>
+static cudaError_t launch_grid(int b, int c, int n, int r, const float *coords, const float *feat, float *outs,
+                               cudaStream_t st) {
+  const size_t smem = sizeof(float) * (size_t)r * r * r * CT;
+  auto kern = devox_grid_kernel<CT>;
+  cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void *>(kern), smem);
+  if (e != cudaSuccess) return e;
+  const int tiles = ceil_div(c, CT) * b;
+  int chunks = 1;
+  while (tiles * chunks < 2 * sm_count() && ceil_div(n, chunks * 2) >= kGridThreads && chunks < 64) chunks *= 2;
+  kern<<<dim3(ceil_div(c, CT), chunks, b), kGridThreads, smem, st>>>(c, n, r, ceil_div(n, chunks), coords, feat, outs);
+  return cudaGetLastError();
+}
+
 template <int CT>
 static cudaError_t launch_slice(int b, int c, int n, int r, const float *feat, const unsigned char *ws,
                                 const DevoxPlanLayout &L, float *outs, cudaStream_t st) {
@@ -383,6 +474,16 @@ extern "C" int bdm_trilinear_devoxelize(int b, int c, int n, int r, int is_train
   if (c > 0) { BDM_CHECK_PTR(feat); BDM_CHECK_PTR(outs); }
   if (is_training) { BDM_CHECK_PTR(inds); BDM_CHECK_PTR(wgts); }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+
+  const int gct = devox_grid_ct(b, c, n, r, is_training);
+  if (gct > 0) {
+    cudaError_t e;
+    if (gct == 8) e = launch_grid<8>(b, c, n, r, coords, feat, outs, st);
+    else if (gct == 4) e = launch_grid<4>(b, c, n, r, coords, feat, outs, st);
+    else if (gct == 2) e = launch_grid<2>(b, c, n, r, coords, feat, outs, st);
+    else e = launch_grid<1>(b, c, n, r, coords, feat, outs, st);
+    return e == cudaSuccess ? BDM_OK : (int)e;
+  }
 
   const int ct = devox_slice_ct(b, c, n, r, is_training);
   const DevoxPlanLayout L = devox_plan_layout(n, r);

@@ -26,7 +26,11 @@ import math
 import torch
 import torch.nn as nn
 
+from . import functional as F
+from .functional import geometry
+from .functional import ops as _ops
 from .modules import Attention, PointNetAModule, PointNetFPModule, PointNetSAModule, PVConv, SharedMLP
+from .modules.point_voxel import coordinate_plan
 
 # ((conv out_channels, num_blocks, voxel_resolution) | None, (num_centers, radius, num_neighbors, mlp widths))
 SA_BLOCKS = [
@@ -145,6 +149,44 @@ def _time_mlp(embed_dim):
                          nn.Linear(embed_dim, embed_dim))
 
 
+def _stage_parts(stage):
+    return list(stage) if isinstance(stage, nn.Sequential) else [stage]
+
+
+def plan_geometry_ahead(cache, sa_layers, fp_layers, coords):
+    """Issue every coordinate-only op of the forward on the cache's side stream, in dependency order:
+    voxel plans of the first stage first (the main stream needs them immediately), then the FPS /
+    ball-query pyramid, then the 3-NN searches and the decoder's voxel plans."""
+    with cache.side_stream():
+        levels = [coords]
+        for stage in sa_layers:
+            pts = levels[-1]
+            for part in _stage_parts(stage):
+                if isinstance(part, PVConv):
+                    v = part.voxelization
+                    coordinate_plan(pts, v.r, v.normalize, v.eps)
+                elif isinstance(part, PointNetSAModule):
+                    cen = F.furthest_point_sample(pts, part.num_centers)
+                    for grouper in part.groupers:
+                        F.ball_query(cen, pts, grouper.radius, grouper.num_neighbors)
+                    levels.append(cen)
+        if fp_layers is not None and len(levels) == len(sa_layers) + 1:
+            cen = levels[-1]
+            for fp_idx, stage in enumerate(fp_layers):
+                pts = levels[-2 - fp_idx]
+                for part in _stage_parts(stage):
+                    if isinstance(part, PointNetFPModule):
+                        F.three_nn_search(pts, cen)
+                    elif isinstance(part, PVConv):
+                        v = part.voxelization
+                        coordinate_plan(pts, v.r, v.normalize, v.eps)
+                cen = pts
+
+
+def _ahead_enabled(x):
+    return x.is_cuda and not torch.is_grad_enabled() and not _ops.REFERENCE_CALL_PATTERN
+
+
 def _encode(sa_layers, features, coords, temb):
     """Run the SA pyramid; returns the bottleneck state and the per-stage (coords, input features)."""
     coords_per_stage, feats_per_stage = [], []
@@ -193,12 +235,15 @@ class PVCNN2(nn.Module):
         temb = self.embedf(timestep_embedding(self.embed_dim, t, inputs.device).float())
         temb = temb[:, :, None].expand(-1, -1, inputs.shape[-1])
         coords = inputs[:, :3, :].contiguous()
-        features, coords, temb, coords_per_stage, feats_per_stage = _encode(self.sa_layers, inputs, coords, temb)
-        feats_per_stage[0] = inputs[:, 3:, :].contiguous()
-        if self.global_att is not None:
-            features = self.global_att(features)
-        features = _decode(self.fp_layers, features, coords, temb, coords_per_stage, feats_per_stage)
-        return self.classifier(features)
+        with geometry.scope(_ahead_enabled(inputs)) as cache:
+            if cache is not None:
+                plan_geometry_ahead(cache, self.sa_layers, self.fp_layers, coords)
+            features, coords, temb, coords_per_stage, feats_per_stage = _encode(self.sa_layers, inputs, coords, temb)
+            feats_per_stage[0] = inputs[:, 3:, :].contiguous()
+            if self.global_att is not None:
+                features = self.global_att(features)
+            features = _decode(self.fp_layers, features, coords, temb, coords_per_stage, feats_per_stage)
+            return self.classifier(features)
 
 
 class PVCNN2_PC2(PVCNN2):
@@ -285,6 +330,13 @@ class PVCNNFuse(nn.Module):
         coords_pc2 = recon_inputs_with_cond[:, :3, :].contiguous()
         coords_pvd = (input_from_prior if mode == 'fusion_nstep' else coords_pc2).clone()
 
+        with geometry.scope(_ahead_enabled(recon_inputs_with_cond)) as cache:
+            if cache is not None:
+                plan_geometry_ahead(cache, self.pc2_model_sa_layers, self.fusion_decoder_fp_layers, coords_pc2)
+                plan_geometry_ahead(cache, self.pvd_model_sa_layers, None, coords_pvd)
+            return self._forward(recon_inputs_with_cond, coords_pc2, coords_pvd, temb_full)
+
+    def _forward(self, recon_inputs_with_cond, coords_pc2, coords_pvd, temb_full):
         f_pc2, c_pc2, temb, coords_per_stage, pc2_skips = _encode(self.pc2_model_sa_layers, recon_inputs_with_cond,
                                                                  coords_pc2, temb_full)
         pc2_skips[0] = recon_inputs_with_cond[:, 3:, :].contiguous()

@@ -10,6 +10,7 @@ import torch
 import torch.nn.functional as tnf
 from torch.autograd import Function
 
+from . import geometry
 from .backend import _backend as _B
 
 
@@ -147,12 +148,15 @@ def group_time_embedding(temb, neighbor_indices):
 def furthest_point_sample(coords, num_samples):
     """sampling.py:37-48.  coords f32[B,3,N] -> coordinates of the M sampled centres f32[B,3,M]"""
     pts = coords.contiguous()
-    return gather(pts, _B.furthest_point_sampling(pts, num_samples))
+    return geometry.memo("fps", (pts,), (int(num_samples),),
+                         lambda: gather(pts, _B.furthest_point_sampling(pts, num_samples)))
 
 
 def ball_query(centers_coords, points_coords, radius, num_neighbors):
     """ball_query.py:8-19.  (centres f32[B,3,M], points f32[B,3,N]) -> int32[B,M,U]"""
-    return _B.ball_query(centers_coords.contiguous(), points_coords.contiguous(), radius, num_neighbors)
+    cen, pts = centers_coords.contiguous(), points_coords.contiguous()
+    return geometry.memo("ball", (cen, pts), (float(radius), int(num_neighbors)),
+                         lambda: _B.ball_query(cen, pts, radius, num_neighbors))
 
 
 # ----------------------------------------------------------------------------------------------
@@ -201,7 +205,8 @@ three_nn_interpolate = _InterpolateWith.apply
 def three_nn_search(points_coords, centers_coords):
     """Search half alone -> (indices int32[B,3,N], weights f32[B,3,N]).  No gradient flows through
     the coordinates in the reference either (its backward returns None for both)."""
-    return _B.three_nn_search(points_coords.detach().contiguous(), centers_coords.detach().contiguous())
+    pts, cen = points_coords.detach().contiguous(), centers_coords.detach().contiguous()
+    return geometry.memo("nn3", (pts, cen), (), lambda: _B.three_nn_search(pts, cen))
 
 
 # ----------------------------------------------------------------------------------------------

@@ -6,6 +6,7 @@ import torch
 import torch.nn as nn
 
 from .. import functional as F
+from ..functional import geometry
 from .layers import SE3d, Attention, SharedMLP, Swish
 
 
@@ -24,34 +25,40 @@ def normalized_voxel_coords(coords, resolution, normalize=True, eps=0):
     return torch.clamp(unit * resolution, 0, resolution - 1)
 
 
-class _CoordinatePlanCache:
-    """The last (coords tensor, resolution) -> (float voxel coords, voxel plan).  Consecutive PVConv
-    blocks of one stage receive the SAME coords tensor object (PVConv.forward passes it through), so
-    2-3 voxelizations per stage share one normalisation (~8 small torch launches) and one index/sort
-    kernel.  Holding a reference to the coords tensor keeps its storage from being recycled; the
-    version counter catches in-place edits.  Results are bit-identical to recomputing."""
+def _coordinate_plan(coords, r, normalize, eps):
+    """(float voxel coords, int voxel coords, voxel plan) for one (coords tensor, resolution)."""
+    norm_coords = normalized_voxel_coords(coords.detach(), r, normalize, eps)
+    vox_coords = torch.round(norm_coords).to(torch.int32)  # half-to-even, like the reference
+    return norm_coords, vox_coords, F.voxel_plan(vox_coords, r)
+
+
+class _LastPlan:
+    """The last (coords tensor, resolution) -> plan outside a geometry scope.  Consecutive PVConv blocks
+    of one stage receive the SAME coords tensor object (PVConv.forward passes it through), so 2-3
+    voxelizations per stage share one normalisation (~8 small torch launches) and one index/sort
+    kernel.  Holding the coords tensor keeps its storage from being recycled; the version counter
+    catches in-place edits.  Results are bit-identical to recomputing."""
 
     def __init__(self):
-        self.key = None
-        self.coords = None
-        self.value = None
+        self.key = self.coords = self.value = None
 
     def lookup(self, coords, r, normalize, eps):
         key = (coords.data_ptr(), coords._version, tuple(coords.shape), coords.device, r, normalize, eps)
         if self.coords is coords and self.key == key:
             return self.value
-        norm_coords = normalized_voxel_coords(coords.detach(), r, normalize, eps)
-        vox_coords = torch.round(norm_coords).to(torch.int32)  # half-to-even, like the reference
-        plan = F.voxel_plan(vox_coords, r)
         self.key, self.coords = key, coords
-        self.value = (norm_coords, vox_coords, plan)
+        self.value = _coordinate_plan(coords, r, normalize, eps)
         return self.value
 
-    def clear(self):
-        self.key = self.coords = self.value = None
+
+_last_plan = _LastPlan()
 
 
-_plan_cache = _CoordinatePlanCache()
+def coordinate_plan(coords, r, normalize=True, eps=0):
+    if geometry.active() is not None:
+        return geometry.memo("vox", (coords,), (int(r), bool(normalize), float(eps)),
+                             lambda: _coordinate_plan(coords, r, normalize, eps))
+    return _last_plan.lookup(coords, r, normalize, eps)
 
 
 class Voxelization(nn.Module):
@@ -63,7 +70,7 @@ class Voxelization(nn.Module):
 
     def forward(self, features, coords):
         """-> (voxel grid f32[B,C,R,R,R], float voxel coordinates f32[B,3,N])"""
-        norm_coords, vox_coords, plan = _plan_cache.lookup(coords, self.r, self.normalize, self.eps)
+        norm_coords, vox_coords, plan = coordinate_plan(coords, self.r, self.normalize, self.eps)
         if plan is None:  # backend without the split entry points (e.g. the reference's own extension)
             return F.avg_voxelize(features, vox_coords, self.r), norm_coords
         return F.avg_voxelize_planned(features, plan), norm_coords

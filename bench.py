@@ -251,13 +251,31 @@ def run_ours(args):
         step_resident()
     step_e2e()
 
-    # ---- timed region 1: resident inputs (value) with clocks sampled and per-op events recorded ----
+    # ---- per-op CUDA events on eager launches (the roofline / sparse-path breakdown) ----
     launches0 = backend.LAUNCHES
     backend.profile_start()
+    for _ in range(args.steps):
+        step_resident()
+    prof = backend.profile_stop()
+    launches_per_step = (backend.LAUNCHES - launches0) // args.steps
+    ms_eager = timed(step_resident, args.steps)
+
+    graphed = False
+    if not args.no_graph:
+        try:
+            sampler.enable_cuda_graphs(x_dev)
+            graphed = True
+            for _ in range(3):
+                step_resident()
+            step_e2e()
+        except Exception as e:
+            print("CUDA graph capture failed, staying eager:", repr(e)[:300], file=sys.stderr)
+            sampler._graphs.clear()
+
+    # ---- timed region 1: resident inputs (value) with clocks sampled and per-op events recorded ----
     with ClockSampler(local) as clocks:
         ms_step = timed(step_resident, args.steps, final_gather=True)
-    prof = backend.profile_stop()
-    launches = backend.LAUNCHES - launches0
+    launches = launches_per_step * args.steps   # replayed from the graph: same kernels every step
 
     # ---- timed region 2: host buffers through the public API (e2e) ----
     ms_e2e = timed(step_e2e, args.steps)
@@ -294,14 +312,16 @@ def run_ours(args):
                    "points": N_POINTS, "image_feature_map": [C_IMG, IMG, IMG], "timestep": T_MID,
                    "steps_per_shape": STEPS_PER_SHAPE, "parallelism": f"shapes sharded over {world} rank(s), no per-step collective",
                    "l2": "per-step working set (1.2 GB feature map + >2 GB activations) exceeds the 126 MB L2; no flush",
-                   "dense_layers": "torch (cuDNN/cuBLAS, PyTorch default TF32 conv policy)"},
+                   "dense_layers": "torch (cuDNN/cuBLAS, PyTorch default TF32 conv policy)",
+                   "launch": "one CUDA graph per step" if graphed else "eager", "ms_per_step_eager": ms_eager},
         "clocks": clocks.summary(),
         "e2e": {"value": e2e_value, "unit": "shapes/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": x_host.numel() * 4 * world, "d2h_bytes_per_step": out_host.numel() * 4 * world},
         "gpu_launches": launches,
         "roofline": roofline,
         "sparse_path": {"ms_per_step_by_op": sparse_ms, "ms_per_step_total": sum(sparse_ms.values()),
-                        "share_of_step": sum(sparse_ms.values()) / ms_step},
+                        "share_of_step": sum(sparse_ms.values()) / ms_eager,
+                        "note": "per-op CUDA events on eager launches, host gaps inside an op included"},
     }
 
     # ---- reference CUDA kernels (recompiled for sm_100a) under the reference's call pattern ----
@@ -311,14 +331,16 @@ def run_ours(args):
             ref = build_ref.load_ref()
             if ref is not None:
                 import bdm_b200.functional.ops as ops
-                saved = (ops._B, ops.REFERENCE_CALL_PATTERN)
+                saved = (ops._B, ops.REFERENCE_CALL_PATTERN, dict(sampler._graphs))
                 ops._B, ops.REFERENCE_CALL_PATTERN = ref, True
+                sampler._graphs.clear()   # the reference launches on the legacy default stream: eager only
                 try:
                     for _ in range(3):
                         step_resident()
                     ms_ref = timed(step_resident, max(3, args.steps // 2))
                 finally:
-                    ops._B, ops.REFERENCE_CALL_PATTERN = saved
+                    ops._B, ops.REFERENCE_CALL_PATTERN = saved[0], saved[1]
+                    sampler._graphs.update(saved[2])
                 line["reference_cuda"] = {"what": "same step with the reference's own kernels (oracle/_ref, unmodified "
                                                   "sources recompiled for sm_100a) and its native-call pattern",
                                           "ms_per_step": ms_ref, "value": B / (STEPS_PER_SHAPE * ms_ref * 1e-3),
@@ -362,6 +384,7 @@ def main():
     ap.add_argument("--cpu-sample-shapes", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-cuda", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of one CUDA graph per step")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

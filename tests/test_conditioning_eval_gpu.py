@@ -120,3 +120,36 @@ def test_denoiser_step_gpu_vs_cpu_oracle(cuda_backend, monkeypatch):
         y_cpu = net.cpu()(x, t)
     err = (y_gpu - y_cpu).abs().max().item() / y_cpu.abs().max().item()
     assert err < 2e-3, err
+
+
+def test_plan_ahead_and_graph_replay_are_bit_identical(cuda_backend):
+    """Side-stream geometry plan-ahead, the inline order and a CUDA-graph replay all run the same kernels
+    on the same data: outputs must be bit-identical."""
+    import torch
+
+    from bdm_b200.denoiser import PVCNN2_PC2
+    from bdm_b200.diffusion import GraphedStep
+    from bdm_b200.functional import geometry
+    torch.manual_seed(11)
+    net = PVCNN2_PC2(num_classes=3, embed_dim=64, extra_feature_channels=6).cuda().eval()
+    x = torch.randn(4, 9, 2048, device="cuda")
+    t = torch.tensor([500.0, 3.0, 999.0, 0.0], device="cuda")
+    with torch.no_grad():
+        y_ahead = net(x, t)
+        # inline order: an already-active (dummy) scope disables the nested plan-ahead
+        saved = geometry._active
+        try:
+            geometry._active = None
+            import bdm_b200.denoiser as D
+            orig = D._ahead_enabled
+            D._ahead_enabled = lambda _x: False
+            y_inline = net(x, t)
+        finally:
+            D._ahead_enabled = orig
+            geometry._active = saved
+        g = GraphedStep(lambda a, b: net(a, b), x, t)
+        y_graph = g(x, t).clone()
+        y_graph2 = g(x, t).clone()
+    torch.cuda.synchronize()
+    assert torch.equal(y_ahead, y_inline)
+    assert torch.equal(y_ahead, y_graph) and torch.equal(y_graph, y_graph2)

@@ -53,12 +53,17 @@ ball_query_kernel(int n, int m, float r2, int u, int splits, const float *__rest
   int cnt = 0;
   float thr = valid ? r2 : -1.0f;
   int k = k0;
-  if (VEC4) {
+  if (VEC4 && k + 4 <= k1) {
+    // software pipeline: the next 4 points are in flight while the current 4 are tested
+    float4 X = __ldg(reinterpret_cast<const float4 *>(points + k));
+    float4 Y = __ldg(reinterpret_cast<const float4 *>(points + n + k));
+    float4 Z = __ldg(reinterpret_cast<const float4 *>(points + 2 * (size_t)n + k));
     for (; k + 4 <= k1; k += 4) {
       if ((k & 127) == 0 && __all_sync(0xffffffffu, thr < 0.0f)) break;
-      const float4 X = __ldg(reinterpret_cast<const float4 *>(points + k));
-      const float4 Y = __ldg(reinterpret_cast<const float4 *>(points + n + k));
-      const float4 Z = __ldg(reinterpret_cast<const float4 *>(points + 2 * (size_t)n + k));
+      const int kn = (k + 8 <= k1) ? k + 4 : k;  // clamp the prefetch at the end of the range
+      const float4 Xn = __ldg(reinterpret_cast<const float4 *>(points + kn));
+      const float4 Yn = __ldg(reinterpret_cast<const float4 *>(points + n + kn));
+      const float4 Zn = __ldg(reinterpret_cast<const float4 *>(points + 2 * (size_t)n + kn));
       const float d0 = sqdist_ref(__fsub_rn(cx, X.x), __fsub_rn(cy, Y.x), __fsub_rn(cz, Z.x));
       const float d1 = sqdist_ref(__fsub_rn(cx, X.y), __fsub_rn(cy, Y.y), __fsub_rn(cz, Z.y));
       const float d2 = sqdist_ref(__fsub_rn(cx, X.z), __fsub_rn(cy, Y.z), __fsub_rn(cz, Z.z));
@@ -69,6 +74,7 @@ ball_query_kernel(int n, int m, float r2, int u, int splits, const float *__rest
         if (d2 < thr) { my[cnt++] = k + 2; if (cnt == u) thr = -1.0f; }
         if (d3 < thr) { my[cnt++] = k + 3; if (cnt == u) thr = -1.0f; }
       }
+      X = Xn; Y = Yn; Z = Zn;
     }
   }
   for (; k < k1; ++k) {

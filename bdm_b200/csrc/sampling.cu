@@ -16,12 +16,38 @@
 // equal distances.  Net effect: among points with the maximal running distance the winner minimises
 // (k mod 512, k div 512) lexicographically.  tie_key(k) = (k & 511) << 22 | (k >> 9) encodes that
 // order in one unsigned int (k < 2^31 / ... fine for k < 2^22*512).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace bdm {
 
 __device__ __forceinline__ unsigned fps_tie_key(int k) { return ((unsigned)(k & 511) << 22) | ((unsigned)k >> 9); }
 __device__ __forceinline__ int fps_tie_key_decode(unsigned t) { return (int)(((t & 0x3fffffu) << 9) | (t >> 22)); }
+
+template <int N>
+__device__ __forceinline__ float tree_max(const float (&a)[N]) {
+  float t[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) t[i] = a[i];
+#pragma unroll
+  for (int w = N / 2; w >= 1; w >>= 1)
+#pragma unroll
+    for (int i = 0; i < w; ++i) t[i] = fmaxf(t[i], t[i + w]);
+  return t[0];
+}
+
+template <int N>
+__device__ __forceinline__ unsigned tree_min(const unsigned (&a)[N]) {
+  unsigned t[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) t[i] = a[i];
+#pragma unroll
+  for (int w = N / 2; w >= 1; w >>= 1)
+#pragma unroll
+    for (int i = 0; i < w; ++i) t[i] = min(t[i], t[i + w]);
+  return t[0];
+}
 
 // Register-resident FPS: PPT points per thread, T <= MAXT threads, n <= PPT*T.  A round is
 // issue-bound on one SM (every SMSP retires ~N*10/128 instructions) plus a fixed reduction/barrier
@@ -59,19 +85,18 @@ fps_register_kernel(int n, int m, const float *__restrict__ coords, int *__restr
   int old = 0;
   for (int s = 1; s < m; ++s) {
     const float x1 = sco[old], y1 = sco[old + n], z1 = sco[old + n + n];
-    float best = 0.0f;
 #pragma unroll
     for (int j = 0; j < PPT; ++j) {
       const float d = sqdist_ref(__fsub_rn(px[j], x1), __fsub_rn(py[j], y1), __fsub_rn(pz[j], z1));
       dist[j] = fminf(d, dist[j]);
-      best = fmaxf(best, dist[j]);
     }
+    // per-thread reductions as trees (log depth): the round is a dependent chain end to end
+    const float best = fmaxf(tree_max<PPT>(dist), 0.0f);  // slots without a point hold -1
     const unsigned wmax = __reduce_max_sync(0xffffffffu, __float_as_uint(best));
-    unsigned mykey = 0xffffffffu;
+    unsigned cand[PPT];
 #pragma unroll
-    for (int j = 0; j < PPT; ++j)
-      mykey = (__float_as_uint(dist[j]) == wmax) ? min(mykey, tk[j]) : mykey;
-    const unsigned wkey = __reduce_min_sync(0xffffffffu, mykey);
+    for (int j = 0; j < PPT; ++j) cand[j] = (__float_as_uint(dist[j]) == wmax) ? tk[j] : 0xffffffffu;
+    const unsigned wkey = __reduce_min_sync(0xffffffffu, tree_min<PPT>(cand));
     if (lane == 0) slot[s & 1][warp] = ((unsigned long long)wmax << 32) | (unsigned long long)(~wkey);
     __syncthreads();
     const unsigned long long v = (lane < nwarps) ? slot[s & 1][lane] : 0ull;
@@ -186,9 +211,15 @@ extern "C" int bdm_furthest_point_sampling(int b, int n, int m, const float *coo
     if (n <= 1024) {         // small pyramid levels: 4 points per thread, <= 8 warps
       const int threads = ((ceil_div(n, 4) + 31) / 32) * 32;
       e = launch_fps_reg<4, 256>(b, n, m, threads, coords, indices, st);
-    } else if (n <= 4096) {  // 16 points per thread, <= 8 warps
-      const int threads = ((ceil_div(n, 16) + 31) / 32) * 32;
-      e = launch_fps_reg<16, 256>(b, n, m, threads, coords, indices, st);
+    } else if (n <= 4096) {  // 16 points per thread, <= 8 warps (BDM_FPS_VARIANT: tuning hook)
+      static const char *variant = getenv("BDM_FPS_VARIANT");
+      if (variant != nullptr && variant[0] == '8') {
+        e = launch_fps_reg<8, 512>(b, n, m, ((ceil_div(n, 8) + 31) / 32) * 32, coords, indices, st);
+      } else if (variant != nullptr && variant[0] == '4') {
+        e = launch_fps_reg<4, 1024>(b, n, m, ((ceil_div(n, 4) + 31) / 32) * 32, coords, indices, st);
+      } else {
+        e = launch_fps_reg<16, 256>(b, n, m, ((ceil_div(n, 16) + 31) / 32) * 32, coords, indices, st);
+      }
     } else {                 // <= 8192 points: 8 per thread, 32 warps (64-register budget)
       e = launch_fps_reg<8, 1024>(b, n, m, 1024, coords, indices, st);
     }

@@ -225,7 +225,7 @@ extern "C" int bdm_three_nn_search(int b, int n, int m, const float *points_coor
   // enough warps to fill the machine; at least 64 centres per split
   const int ctas = ceil_div(n, 32) * b;
   int splits = 1;
-  while (splits < kNnMaxSplits && ctas * splits < 12 * sm_count() && m / (splits * 2) >= 64) splits *= 2;
+  while (splits < kNnMaxSplits && ctas * splits < 48 * sm_count() && m / (splits * 2) >= 64) splits *= 2;  // warps
   if (vec4)
     three_nn_kernel<true><<<dim3(ceil_div(n, 32), b), 32 * splits, 0, st>>>(n, m, splits, points_coords,
                                                                            centers_coords, weights, indices);

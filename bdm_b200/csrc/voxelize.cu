@@ -208,7 +208,6 @@ vox_fill_kernel(int c, int n, int r3, const float *__restrict__ feat, float *__r
                                                                        //         per-voxel averages (in place)
   uint32_t *bitmask = smem_u32 + (size_t)CT * n;                       // [nw]
   uint16_t *obase = reinterpret_cast<uint16_t *>(bitmask + nw);        // [nw]
-  uint16_t *ostart = obase + ((nw + 1) & ~1);                          // [n+1]
 
   ws += (size_t)b * L.stride;
   const uint32_t *g_bitmask = reinterpret_cast<const uint32_t *>(ws + L.bitmask);
@@ -221,15 +220,35 @@ vox_fill_kernel(int c, int n, int r3, const float *__restrict__ feat, float *__r
     bitmask[w] = g_bitmask[w];
     obase[w] = g_obase[w];
   }
-  for (int i = tid; i <= nocc; i += kFillThreads) ostart[i] = g_ostart[i];
 
-  // (a) stage this tile's features in sorted order
+  // (a) stage this tile's features in sorted order: 4 points per step (one 64-bit load of 4 ranks,
+  // one 128-bit load per channel), all loads of a step in flight together
   const float *f = feat + ((size_t)b * c + c0) * n;
-  for (int i = tid; i < n; i += kFillThreads) {
-    const int rk = g_rank[i];
+  if ((n & 3) == 0 && (reinterpret_cast<uintptr_t>(f) & 15) == 0) {
+    const int ng = n >> 2;
+#pragma unroll 2
+    for (int g = tid; g < ng; g += kFillThreads) {
+      const uint2 rk = __ldg(reinterpret_cast<const uint2 *>(g_rank) + g);
+      float4 v[CT];
 #pragma unroll
-    for (int cc = 0; cc < CT; ++cc)
-      if (c0 + cc < c) buf[cc * n + rk] = ld_stream_f1(f + (size_t)cc * n + i);
+      for (int cc = 0; cc < CT; ++cc)
+        v[cc] = (c0 + cc < c) ? ld_stream_f4(f + (size_t)cc * n + 4 * (size_t)g) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const int r0 = rk.x & 0xffffu, r1 = rk.x >> 16, r2 = rk.y & 0xffffu, r3_ = rk.y >> 16;
+#pragma unroll
+      for (int cc = 0; cc < CT; ++cc) {
+        buf[cc * n + r0] = v[cc].x;
+        buf[cc * n + r1] = v[cc].y;
+        buf[cc * n + r2] = v[cc].z;
+        buf[cc * n + r3_] = v[cc].w;
+      }
+    }
+  } else {
+    for (int i = tid; i < n; i += kFillThreads) {
+      const int rk = g_rank[i];
+#pragma unroll
+      for (int cc = 0; cc < CT; ++cc)
+        if (c0 + cc < c) buf[cc * n + rk] = ld_stream_f1(f + (size_t)cc * n + i);
+    }
   }
   __syncthreads();
 
@@ -242,7 +261,7 @@ vox_fill_kernel(int c, int n, int r3, const float *__restrict__ feat, float *__r
 #pragma unroll
     for (int cc = 0; cc < CT; ++cc) acc[cc] = 0.0f;
     if (j < nocc) {
-      const int s = ostart[j], e = ostart[j + 1];
+      const int s = __ldg(g_ostart + j), e = __ldg(g_ostart + j + 1);  // L2-resident, read once per tile
       const float inv = __frcp_rn((float)(e - s));  // == 1.0 / float(cnt), vox.cu:65
       for (int p = s; p < e; ++p) {
 #pragma unroll
@@ -348,7 +367,7 @@ template <int CT, int VEC>
 static cudaError_t launch_fill(int b, int c, int n, int r3, const float *feat, float *out,
                                const unsigned char *ws, const VoxAuxLayout &L, cudaStream_t st) {
   const size_t smem = sizeof(float) * (size_t)CT * n + sizeof(uint32_t) * L.nw +
-                      sizeof(uint16_t) * (((L.nw + 1) & ~1) + n + 2);
+                      sizeof(uint16_t) * ((L.nw + 1) & ~1);
   auto kern = vox_fill_kernel<CT, VEC>;
   cudaError_t e0 = ensure_dynamic_smem(reinterpret_cast<const void *>(kern), smem);
   if (e0 != cudaSuccess) return e0;

@@ -48,14 +48,28 @@ FP_BLOCKS = [
 ]
 
 
+_FREQ_TABLES = {}
+
+
+def _frequency_table(embed_dim, device):
+    """exp(-i * ln(1e4)/(half-1)) computed on the host in float64 and cast to fp32, like the reference's
+    numpy expression; cached per device so that no host->device copy happens inside a forward (a
+    pageable copy would break CUDA-graph capture)."""
+    key = (embed_dim, str(device))
+    tab = _FREQ_TABLES.get(key)
+    if tab is None:
+        half = embed_dim // 2
+        step = math.log(10000) / (half - 1)
+        tab = torch.exp(torch.arange(half, dtype=torch.float64) * -step).float().to(device)
+        _FREQ_TABLES[key] = tab
+    return tab
+
+
 def timestep_embedding(embed_dim, timesteps, device):
-    """Sinusoidal embedding [B] -> [B, embed_dim]: sin half then cos half, frequencies
-    exp(-i * ln(1e4)/(half-1)).  reference: pvcnn_utils.py:171-185 (computed through float64 numpy
-    then cast to fp32, reproduced with the same dtype path)."""
+    """Sinusoidal embedding [B] -> [B, embed_dim]: sin half then cos half.
+    reference: pvcnn_utils.py:171-185"""
     assert timesteps.dim() == 1
-    half = embed_dim // 2
-    step = math.log(10000) / (half - 1)
-    freqs = torch.exp(torch.arange(half, dtype=torch.float64) * -step).float().to(device)
+    freqs = _frequency_table(embed_dim, device)
     arg = timesteps[:, None] * freqs[None, :]
     emb = torch.cat([torch.sin(arg), torch.cos(arg)], dim=1)
     if embed_dim % 2 == 1:

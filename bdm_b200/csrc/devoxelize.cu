@@ -415,7 +415,7 @@ static int devox_slice_ct(int b, int c, int n, int r, int is_training) {
   int ct = 4;
   // every CTA walks its R slices serially (load -> gather -> barrier), so latency is hidden by CTAs,
   // not by warps: keep >= 3 CTAs per SM in flight (smaller channel tiles when b*c is small)
-  while (ct > 1 && (b * ceil_div(c, ct) < 3 * sm_count() || devox_slice_smem(ct, n, r) > 75 * 1024)) ct >>= 1;
+  while (ct > 1 && (b * ceil_div(c, ct) < (3 * sm_count()) / 2 || devox_slice_smem(ct, n, r) > 113 * 1024)) ct >>= 1;
   if (devox_slice_smem(ct, n, r) > 200 * 1024) return 0;
   if (ceil_div(c, ct) > 65535 || b > 65535) return 0;
   return ct;

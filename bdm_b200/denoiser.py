@@ -22,6 +22,7 @@ including its quirks, because they decide the parameter shapes:
   * the SA module's input width counts the time embedding only when the stage has no PVConv (:118).
 """
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -197,8 +198,11 @@ def plan_geometry_ahead(cache, sa_layers, fp_layers, coords):
                 cen = pts
 
 
+PLAN_AHEAD = os.environ.get("BDM_PLAN_AHEAD", "1") != "0"   # module switch (tests / A-B timing)
+
+
 def _ahead_enabled(x):
-    return x.is_cuda and not torch.is_grad_enabled() and not _ops.REFERENCE_CALL_PATTERN
+    return PLAN_AHEAD and x.is_cuda and not torch.is_grad_enabled() and not _ops.REFERENCE_CALL_PATTERN
 
 
 def _encode(sa_layers, features, coords, temb):

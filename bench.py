@@ -251,7 +251,11 @@ def run_ours(args):
         step_resident()
     step_e2e()
 
-    # ---- per-op CUDA events on eager launches (the roofline / sparse-path breakdown) ----
+    # ---- per-op CUDA events on eager, single-stream launches (the roofline / sparse-path breakdown) ----
+    import bdm_b200.denoiser as denoiser_mod
+    plan_ahead_default = denoiser_mod.PLAN_AHEAD
+    denoiser_mod.PLAN_AHEAD = False          # events on one stream: clean per-op durations
+    step_resident()
     launches0 = backend.LAUNCHES
     backend.profile_start()
     for _ in range(args.steps):
@@ -259,6 +263,7 @@ def run_ours(args):
     prof = backend.profile_stop()
     launches_per_step = (backend.LAUNCHES - launches0) // args.steps
     ms_eager = timed(step_resident, args.steps)
+    denoiser_mod.PLAN_AHEAD = plan_ahead_default and not args.no_plan_ahead
 
     graphed = False
     if not args.no_graph:
@@ -313,7 +318,8 @@ def run_ours(args):
                    "steps_per_shape": STEPS_PER_SHAPE, "parallelism": f"shapes sharded over {world} rank(s), no per-step collective",
                    "l2": "per-step working set (1.2 GB feature map + >2 GB activations) exceeds the 126 MB L2; no flush",
                    "dense_layers": "torch (cuDNN/cuBLAS, PyTorch default TF32 conv policy)",
-                   "launch": "one CUDA graph per step" if graphed else "eager", "ms_per_step_eager": ms_eager},
+                   "launch": "one CUDA graph per step" if graphed else "eager", "ms_per_step_eager": ms_eager,
+                   "geometry_plan_ahead": bool(denoiser_mod.PLAN_AHEAD)},
         "clocks": clocks.summary(),
         "e2e": {"value": e2e_value, "unit": "shapes/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": x_host.numel() * 4 * world, "d2h_bytes_per_step": out_host.numel() * 4 * world},
@@ -385,6 +391,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-cuda", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of one CUDA graph per step")
+    ap.add_argument("--no-plan-ahead", action="store_true", help="keep the coordinate-only ops inline on one stream")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -1,0 +1,19 @@
+"""One warm-up step + one measured PC^2 step, eager, single stream: the command whose launch list
+(ncu --metrics gpu__time_duration.sum) is committed under profiles/."""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+import bdm_b200.denoiser as D  # noqa: E402
+
+D.PLAN_AHEAD = False
+x, feats, cams = bench.make_inputs(16, 1234, "cuda:0")
+sampler = bench.build_sampler(x, feats, cams, "cuda:0")
+for _ in range(2):
+    with torch.no_grad():
+        sampler.pc2_step(x, 500)
+    torch.cuda.synchronize()

@@ -12,17 +12,16 @@
 //         acc = w001*f001;  acc = fma(w000,f000,acc);  acc = fma(w010,f010,acc); ... ; fma(w111,f111,acc)
 //
 // Kernels:
-//   devox_bin_kernel +    inference fast path (R <= 32, N <= ~12k).  The 8 corner reads of a point are
-//   devox_slice_kernel    random addresses in a 4*R^3-byte channel row: served from global memory every
-//                         warp-level gather costs up to 32 L1 wavefronts and the kernel is L1-bound at
-//                         ~30 % of the HBM roofline (measured, profiles/).  Instead: points are binned
-//                         by x-slice once per call (one small CTA per shape); then one CTA per
-//                         (shape, CT channels) streams the grid through shared memory one x-slice at a
-//                         time -- coalesced loads, channel-interleaved [R^2][CT] layout so that one
-//                         LDS.128 fetches a corner for 4 channels, a 3-slice ring with register
-//                         prefetch of slice x+2 while bin x is processed -- and gathers from there.
-//                         Results go to a [CT][N] shared tile in original point order and leave as
-//                         coalesced 128-bit stores.  HBM traffic = the grid once + the output once.
+//   devox_grid_kernel     inference, R <= 16: the whole channel-interleaved grid tile [R^3][CT] in shared
+//                         memory (one LDS.128 per corner for 4 channels), points in original order.
+//   devox_bin_kernel +    inference, R = 17..32.  The 8 corner reads of a point are random addresses in a
+//   devox_ring_kernel     4*R^3-byte channel row: served from global memory every warp-level gather costs up
+//                         to 32 L1 wavefronts and the kernel is L1-bound at ~30 % of the HBM roofline
+//                         (measured, profiles/).  Instead: points are binned by x-slice once per call (one
+//                         small CTA per shape); then one CTA per (shape, CT channels) streams the grid
+//                         through a 4-slice shared-memory ring with cp.async -- two slices in use, two in
+//                         flight -- and gathers from shared memory.  HBM traffic = the grid once + the
+//                         output once.
 //   devox_gather_kernel   generic path (training: also writes inds/wgts; large R or N): thread per
 //                         point, channel chunk per blockIdx.y, 8 read-only gathers per channel.
 #include "common.cuh"
@@ -221,21 +220,36 @@ devox_grid_kernel(int c, int n, int r, int chunk, const float *__restrict__ coor
   }
 }
 
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// R = 17..32 (even): the grid of CT channels is streamed through a ring of kRingDepth x-slices in shared
+// memory with cp.async (LDGSTS.128, no register staging): while bin x (the points with floor(x) == x)
+// gathers from slices x and x+1, slices x+2 and x+3 are in flight.  One barrier per slice.  Results are
+// stored straight to global memory by original point index (4-byte scattered stores: 16 MB for the
+// largest call, absorbed by L2).
+constexpr int kRingDepth = 4;
+
 template <int CT>
 __global__ void __launch_bounds__(kSliceThreads)
-devox_slice_kernel(int c, int n, int r, const float *__restrict__ feat,
-                   const unsigned char *__restrict__ ws, DevoxPlanLayout L, float *__restrict__ outs) {
+devox_ring_kernel(int c, int n, int r, const float *__restrict__ feat,
+                  const unsigned char *__restrict__ ws, DevoxPlanLayout L, float *__restrict__ outs) {
   const int b = blockIdx.y;
   const int c0 = blockIdx.x * CT;
   const int nch = min(CT, c - c0);
   const int tid = threadIdx.x;
   const int r2 = r * r;
   const size_t r3 = (size_t)r2 * r;
+  const int stage_floats = CT * r2;
 
   extern __shared__ __align__(16) float smem_f[];
-  float *ring = smem_f;                         // [3][r2][CT]  channel-interleaved slices
-  float *sout = ring + ((3 * (size_t)r2 * CT + 3) & ~(size_t)3);  // [CT][n] results, original point order
-  int *xs = reinterpret_cast<int *>(sout + (size_t)CT * n);  // [r+1]
+  float *ring = smem_f;                                                    // [kRingDepth][CT][r2]
+  int *xs = reinterpret_cast<int *>(ring + (size_t)kRingDepth * stage_floats);  // [r+1]
 
   ws += (size_t)b * L.stride;
   const int *g_xstart = reinterpret_cast<const int *>(ws + L.xstart);
@@ -246,49 +260,48 @@ devox_slice_kernel(int c, int n, int r, const float *__restrict__ feat,
   for (int i = tid; i <= r; i += kSliceThreads) xs[i] = g_xstart[i];
 
   const float *fbase = feat + ((size_t)b * c + c0) * r3;
-  float regs[kSliceSlots][CT];
-
-  auto load_slice = [&](int x) {
-#pragma unroll
-    for (int s = 0; s < kSliceSlots; ++s) {
-      const int yz = tid + s * kSliceThreads;
-#pragma unroll
-      for (int cc = 0; cc < CT; ++cc)
-        regs[s][cc] = (yz < r2 && cc < nch) ? ld_stream_f1(fbase + (size_t)cc * r3 + (size_t)x * r2 + yz) : 0.0f;
-    }
-  };
-  auto store_slice = [&](int stage) {
-    float *dst = ring + (size_t)stage * r2 * CT;
-#pragma unroll
-    for (int s = 0; s < kSliceSlots; ++s) {
-      const int yz = tid + s * kSliceThreads;
-      if (yz < r2) {
-        using V = typename VecOf<CT>::type;
-        V t;
-        float *tf = reinterpret_cast<float *>(&t);
-#pragma unroll
-        for (int cc = 0; cc < CT; ++cc) tf[cc] = regs[s][cc];
-        *reinterpret_cast<V *>(dst + (size_t)yz * CT) = t;
+  const int chunks_per_row = r2 >> 2;
+  auto issue = [&](int x) {  // one commit group per slice, empty past the end (keeps the group count uniform)
+    if (x < r) {
+      float *dst = ring + (size_t)(x % kRingDepth) * stage_floats;
+      const float *src = fbase + (size_t)x * r2;
+      for (int q = tid; q < nch * chunks_per_row; q += kSliceThreads) {
+        const int cc = q / chunks_per_row, k = q - cc * chunks_per_row;
+        cp_async16(dst + cc * r2 + 4 * k, src + (size_t)cc * r3 + 4 * k);
       }
     }
+    cp_async_commit();
   };
+#pragma unroll
+  for (int s = 0; s < kRingDepth; ++s) issue(s);
+  __syncthreads();  // xs visible
 
-  load_slice(0);
-  store_slice(0);
-  if (r > 1) {
-    load_slice(1);
-    store_slice(1);
+  // first point of the first bin, prefetched like every later bin's
+  float px = 0.f, py = 0.f, pz = 0.f;
+  int pid = 0;
+  {
+    const int p = xs[0] + tid;
+    if (p < xs[1]) { px = g_sx[p]; py = g_sy[p]; pz = g_sz[p]; pid = g_spid[p]; }
   }
-  __syncthreads();
 
+  float *obase = outs + ((size_t)b * c + c0) * n;
   for (int x = 0; x < r; ++x) {
-    const bool more = x + 2 < r;
-    if (more) load_slice(x + 2);  // in flight while bin x is processed
-    const float *A = ring + (size_t)(x % 3) * r2 * CT;
-    const float *Bn = ring + (size_t)((x + 1) % 3) * r2 * CT;
-    for (int p = xs[x] + tid; p < xs[x + 1]; p += kSliceThreads) {
-      const float px = g_sx[p], py = g_sy[p], pz = g_sz[p];
-      const int pid = g_spid[p];
+    cp_async_wait<kRingDepth - 3>();  // slices <= x+1 have landed (this thread's copies) ...
+    __syncthreads();                  // ... and everybody else's; also: everyone is done with bin x-1
+    if (x >= 1) issue(x - 1 + kRingDepth);  // refill the stage that held slice x-1
+
+    const float *A = ring + (size_t)(x % kRingDepth) * stage_floats;
+    const float *Bn = ring + (size_t)((x + 1) % kRingDepth) * stage_floats;
+    const int p_begin = xs[x], p_end = xs[x + 1];
+    // prefetch the first point of the next bin before working on this one
+    float nx = 0.f, ny = 0.f, nz = 0.f;
+    int npid = 0;
+    if (x + 1 < r) {
+      const int pn = p_end + tid;
+      if (pn < xs[x + 2]) { nx = g_sx[pn]; ny = g_sy[pn]; nz = g_sz[pn]; npid = g_spid[pn]; }
+    }
+    for (int p = p_begin + tid; p < p_end; p += kSliceThreads) {
+      if (p != p_begin + tid) { px = g_sx[p]; py = g_sy[p]; pz = g_sz[p]; pid = g_spid[p]; }
       // trilinear_devox.cu:37-75 with slice-relative offsets
       const float xl = floorf(px), yl = floorf(py), zl = floorf(pz);
       const float xd1 = __fsub_rn(px, xl), yd1 = __fsub_rn(py, yl), zd1 = __fsub_rn(pz, zl);
@@ -300,39 +313,25 @@ devox_slice_kernel(int c, int n, int r, const float *__restrict__ feat,
                   w6 = __fmul_rn(w11, zd0), w7 = __fmul_rn(w11, zd1);
       const int ylo = min(max((int)yl, 0), r - 1), zlo = min(max((int)zl, 0), r - 1);
       const int yo = (yd1 > 0.0f && ylo < r - 1) ? r : 0, zo = (zd1 > 0.0f && zlo < r - 1) ? 1 : 0;
-      const float *Hi = (xd1 > 0.0f) ? Bn : A;
-      const int o00 = (ylo * r + zlo) * CT, o01 = o00 + zo * CT, o10 = o00 + yo * CT, o11 = o10 + zo * CT;
-      float f0[CT], f1[CT], f2[CT], f3[CT], f4[CT], f5[CT], f6[CT], f7[CT];
-      lds_vec<CT>(A + o00, f0); lds_vec<CT>(A + o01, f1); lds_vec<CT>(A + o10, f2); lds_vec<CT>(A + o11, f3);
-      lds_vec<CT>(Hi + o00, f4); lds_vec<CT>(Hi + o01, f5); lds_vec<CT>(Hi + o10, f6); lds_vec<CT>(Hi + o11, f7);
+      const float *Hi = (xd1 > 0.0f && x + 1 < r) ? Bn : A;
+      const int o00 = ylo * r + zlo, o01 = o00 + zo, o10 = o00 + yo, o11 = o10 + zo;
 #pragma unroll
       for (int cc = 0; cc < CT; ++cc) {
-        float acc = __fmul_rn(w1, f1[cc]);
-        acc = __fmaf_rn(w0, f0[cc], acc);
-        acc = __fmaf_rn(w2, f2[cc], acc);
-        acc = __fmaf_rn(w3, f3[cc], acc);
-        acc = __fmaf_rn(w4, f4[cc], acc);
-        acc = __fmaf_rn(w5, f5[cc], acc);
-        acc = __fmaf_rn(w6, f6[cc], acc);
-        acc = __fmaf_rn(w7, f7[cc], acc);
-        sout[(size_t)cc * n + pid] = acc;
+        const float *a = A + cc * r2, *h = Hi + cc * r2;
+        float acc = __fmul_rn(w1, a[o01]);
+        acc = __fmaf_rn(w0, a[o00], acc);
+        acc = __fmaf_rn(w2, a[o10], acc);
+        acc = __fmaf_rn(w3, a[o11], acc);
+        acc = __fmaf_rn(w4, h[o00], acc);
+        acc = __fmaf_rn(w5, h[o01], acc);
+        acc = __fmaf_rn(w6, h[o10], acc);
+        acc = __fmaf_rn(w7, h[o11], acc);
+        if (cc < nch) obase[(size_t)cc * n + pid] = acc;
       }
     }
-    // Stage (x+2)%3 held slice x-1, last read during bin x-1, i.e. before the barrier that ended the
-    // previous iteration: it can be overwritten now.  One barrier per slice then (a) publishes slice
-    // x+2 before bin x+1 reads it and (b) keeps the next iteration's store off stage x%3 until every
-    // thread is done with bin x.
-    if (more) store_slice((x + 2) % 3);
-    __syncthreads();
+    px = nx; py = ny; pz = nz; pid = npid;
   }
-
-  float *o = outs + ((size_t)b * c + c0) * n;
-  if ((n & 3) == 0 && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
-    for (int q = tid; q < nch * (n / 4); q += kSliceThreads)
-      st_stream_f4(o + 4 * (size_t)q, reinterpret_cast<const float4 *>(sout)[q]);
-  } else {
-    for (int q = tid; q < nch * n; q += kSliceThreads) o[q] = sout[q];
-  }
+  cp_async_wait<0>();
 }
 
 __global__ void __launch_bounds__(kDevoxThreads)
@@ -406,16 +405,18 @@ devox_grad_kernel(int c, int n, int r3, const int *__restrict__ inds, const floa
 namespace bdm {
 
 static size_t devox_slice_smem(int ct, int n, int r) {
-  return sizeof(float) * (((3 * (size_t)r * r * ct + 3) & ~(size_t)3) + (size_t)ct * n) + sizeof(int) * (r + 1);
+  (void)n;
+  return sizeof(float) * (size_t)kRingDepth * r * r * ct + sizeof(int) * (r + 1);
 }
 
 // channel tile for the slice kernel, or 0 when the fast path does not apply
 static int devox_slice_ct(int b, int c, int n, int r, int is_training) {
   if (is_training || r > kSliceMaxR || r < 1 || n < 1 || c < 1) return 0;
+  if (((r * r) & 3) != 0) return 0;  // 16-byte cp.async chunks need r^2 % 4 == 0
   int ct = 4;
   // every CTA walks its R slices serially (load -> gather -> barrier), so latency is hidden by CTAs,
   // not by warps: keep >= 3 CTAs per SM in flight (smaller channel tiles when b*c is small)
-  while (ct > 1 && (b * ceil_div(c, ct) < (3 * sm_count()) / 2 || devox_slice_smem(ct, n, r) > 113 * 1024)) ct >>= 1;
+  while (ct > 1 && (b * ceil_div(c, ct) < (3 * sm_count()) / 2 || devox_slice_smem(ct, n, r) > 72 * 1024)) ct >>= 1;
   if (devox_slice_smem(ct, n, r) > 200 * 1024) return 0;
   if (ceil_div(c, ct) > 65535 || b > 65535) return 0;
   return ct;
@@ -450,7 +451,7 @@ template <int CT>
 static cudaError_t launch_slice(int b, int c, int n, int r, const float *feat, const unsigned char *ws,
                                 const DevoxPlanLayout &L, float *outs, cudaStream_t st) {
   const size_t smem = devox_slice_smem(CT, n, r);
-  auto kern = devox_slice_kernel<CT>;
+  auto kern = devox_ring_kernel<CT>;
   cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void *>(kern), smem);
   if (e != cudaSuccess) return e;
   kern<<<dim3(ceil_div(c, CT), b), kSliceThreads, smem, st>>>(c, n, r, feat, ws, L, outs);
@@ -489,7 +490,7 @@ extern "C" int bdm_trilinear_devoxelize(int b, int c, int n, int r, int is_train
   const int ct = devox_slice_ct(b, c, n, r, is_training);
   const DevoxPlanLayout L = devox_plan_layout(n, r);
   if (ct > 0 && workspace != nullptr && workspace_bytes >= L.stride * (size_t)b &&
-      (reinterpret_cast<uintptr_t>(workspace) & 15) == 0) {
+      (reinterpret_cast<uintptr_t>(workspace) & 15) == 0 && (reinterpret_cast<uintptr_t>(feat) & 15) == 0) {
     unsigned char *ws = static_cast<unsigned char *>(workspace);
     devox_bin_kernel<<<b, kBinThreads, 0, st>>>(n, r, coords, ws, L);
     cudaError_t e = cudaGetLastError();

@@ -15,12 +15,12 @@
 //   devox_grid_kernel     inference, R <= 16: the whole channel-interleaved grid tile [R^3][CT] in shared
 //                         memory (one LDS.128 per corner for 4 channels), points in original order.
 //   devox_bin_kernel +    inference, R = 17..32.  The 8 corner reads of a point are random addresses in a
-//   devox_ring_kernel     4*R^3-byte channel row: served from global memory every warp-level gather costs up
+//   devox_slab_kernel     4*R^3-byte channel row: served from global memory every warp-level gather costs up
 //                         to 32 L1 wavefronts and the kernel is L1-bound at ~30 % of the HBM roofline
 //                         (measured, profiles/).  Instead: points are binned by x-slice once per call (one
-//                         small CTA per shape); then one CTA per (shape, CT channels) streams the grid
-//                         through a 4-slice shared-memory ring with cp.async -- two slices in use, two in
-//                         flight -- and gathers from shared memory.  HBM traffic = the grid once + the
+//                         small CTA per shape); then one CTA per (shape, 2 channels, slab of 8 x-slices)
+//                         bulk-loads its slab + 1 halo slice into shared memory with cp.async and serves
+//                         the slab's points from there.  HBM traffic = the grid once (+12.5 % halo) + the
 //                         output once.
 //   devox_gather_kernel   generic path (training: also writes inds/wgts; large R or N): thread per
 //                         point, channel chunk per blockIdx.y, 8 read-only gathers per channel.
@@ -228,110 +228,90 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// R = 17..32 (even): the grid of CT channels is streamed through a ring of kRingDepth x-slices in shared
-// memory with cp.async (LDGSTS.128, no register staging): while bin x (the points with floor(x) == x)
-// gathers from slices x and x+1, slices x+2 and x+3 are in flight.  One barrier per slice.  Results are
-// stored straight to global memory by original point index (4-byte scattered stores: 16 MB for the
-// largest call, absorbed by L2).
-constexpr int kRingDepth = 4;
-
+// R = 17..32 (even): one CTA per (shape, CT channels, slab of XS x-slices).  The slab plus one halo
+// slice is bulk-loaded into shared memory with cp.async (LDGSTS.128: no register staging, every load of
+// the CTA in flight at once), one barrier, then the slab's points -- a contiguous run of the x-sorted
+// order -- gather their 8 corners from shared memory.  No per-slice pipeline: latency is hidden by the
+// three CTAs resident per SM.  Results are stored straight to global memory by original point index.
 template <int CT>
 __global__ void __launch_bounds__(kSliceThreads)
-devox_ring_kernel(int c, int n, int r, const float *__restrict__ feat,
+devox_slab_kernel(int c, int n, int r, int xs_per_slab, const float *__restrict__ feat,
                   const unsigned char *__restrict__ ws, DevoxPlanLayout L, float *__restrict__ outs) {
-  const int b = blockIdx.y;
+  const int b = blockIdx.z;
   const int c0 = blockIdx.x * CT;
   const int nch = min(CT, c - c0);
+  const int x0 = blockIdx.y * xs_per_slab;
+  const int x1 = min(x0 + xs_per_slab, r);           // slab = slices [x0, x1), halo = slice x1 (if < r)
+  const int nslices = min(x1 + 1, r) - x0;
   const int tid = threadIdx.x;
   const int r2 = r * r;
   const size_t r3 = (size_t)r2 * r;
-  const int stage_floats = CT * r2;
-
-  extern __shared__ __align__(16) float smem_f[];
-  float *ring = smem_f;                                                    // [kRingDepth][CT][r2]
-  int *xs = reinterpret_cast<int *>(ring + (size_t)kRingDepth * stage_floats);  // [r+1]
 
   ws += (size_t)b * L.stride;
   const int *g_xstart = reinterpret_cast<const int *>(ws + L.xstart);
+  const int p_begin = __ldg(g_xstart + x0), p_end = __ldg(g_xstart + x1);
+  if (p_begin == p_end) return;  // no point falls into this slab: nothing to read, nothing to write
+
+  extern __shared__ __align__(16) float slab[];        // [nslices][CT][r2]
+  const float *fbase = feat + ((size_t)b * c + c0) * r3 + (size_t)x0 * r2;
+  const int chunks_per_row = r2 >> 2;
+  for (int sl = 0; sl < nslices; ++sl)
+#pragma unroll
+    for (int cc = 0; cc < CT; ++cc)
+      if (cc < nch)
+        for (int k = tid; k < chunks_per_row; k += kSliceThreads)
+          cp_async16(slab + ((size_t)sl * CT + cc) * r2 + 4 * k, fbase + (size_t)cc * r3 + (size_t)sl * r2 + 4 * k);
+  cp_async_commit();
+
   const int *g_spid = reinterpret_cast<const int *>(ws + L.spid);
   const float *g_sx = reinterpret_cast<const float *>(ws + L.sxyz);
   const float *g_sy = g_sx + n;
   const float *g_sz = g_sy + n;
-  for (int i = tid; i <= r; i += kSliceThreads) xs[i] = g_xstart[i];
+  float *obase = outs + ((size_t)b * c + c0) * n;
 
-  const float *fbase = feat + ((size_t)b * c + c0) * r3;
-  const int chunks_per_row = r2 >> 2;
-  auto issue = [&](int x) {  // one commit group per slice, empty past the end (keeps the group count uniform)
-    if (x < r) {
-      float *dst = ring + (size_t)(x % kRingDepth) * stage_floats;
-      const float *src = fbase + (size_t)x * r2;
-      for (int q = tid; q < nch * chunks_per_row; q += kSliceThreads) {
-        const int cc = q / chunks_per_row, k = q - cc * chunks_per_row;
-        cp_async16(dst + cc * r2 + 4 * k, src + (size_t)cc * r3 + 4 * k);
-      }
-    }
-    cp_async_commit();
-  };
-#pragma unroll
-  for (int s = 0; s < kRingDepth; ++s) issue(s);
-  __syncthreads();  // xs visible
-
-  // first point of the first bin, prefetched like every later bin's
+  // the first point of every thread is fetched while the slab is in flight
+  int p = p_begin + tid;
   float px = 0.f, py = 0.f, pz = 0.f;
   int pid = 0;
-  {
-    const int p = xs[0] + tid;
-    if (p < xs[1]) { px = g_sx[p]; py = g_sy[p]; pz = g_sz[p]; pid = g_spid[p]; }
-  }
+  if (p < p_end) { px = g_sx[p]; py = g_sy[p]; pz = g_sz[p]; pid = g_spid[p]; }
+  cp_async_wait<0>();
+  __syncthreads();
 
-  float *obase = outs + ((size_t)b * c + c0) * n;
-  for (int x = 0; x < r; ++x) {
-    cp_async_wait<kRingDepth - 3>();  // slices <= x+1 have landed (this thread's copies) ...
-    __syncthreads();                  // ... and everybody else's; also: everyone is done with bin x-1
-    if (x >= 1) issue(x - 1 + kRingDepth);  // refill the stage that held slice x-1
-
-    const float *A = ring + (size_t)(x % kRingDepth) * stage_floats;
-    const float *Bn = ring + (size_t)((x + 1) % kRingDepth) * stage_floats;
-    const int p_begin = xs[x], p_end = xs[x + 1];
-    // prefetch the first point of the next bin before working on this one
+  while (p < p_end) {
+    const int pn = p + kSliceThreads;
     float nx = 0.f, ny = 0.f, nz = 0.f;
     int npid = 0;
-    if (x + 1 < r) {
-      const int pn = p_end + tid;
-      if (pn < xs[x + 2]) { nx = g_sx[pn]; ny = g_sy[pn]; nz = g_sz[pn]; npid = g_spid[pn]; }
-    }
-    for (int p = p_begin + tid; p < p_end; p += kSliceThreads) {
-      if (p != p_begin + tid) { px = g_sx[p]; py = g_sy[p]; pz = g_sz[p]; pid = g_spid[p]; }
-      // trilinear_devox.cu:37-75 with slice-relative offsets
-      const float xl = floorf(px), yl = floorf(py), zl = floorf(pz);
-      const float xd1 = __fsub_rn(px, xl), yd1 = __fsub_rn(py, yl), zd1 = __fsub_rn(pz, zl);
-      const float xd0 = __fsub_rn(1.0f, xd1), yd0 = __fsub_rn(1.0f, yd1), zd0 = __fsub_rn(1.0f, zd1);
-      const float w00 = __fmul_rn(xd0, yd0), w01 = __fmul_rn(xd0, yd1);
-      const float w10 = __fmul_rn(xd1, yd0), w11 = __fmul_rn(xd1, yd1);
-      const float w0 = __fmul_rn(w00, zd0), w1 = __fmul_rn(w00, zd1), w2 = __fmul_rn(w01, zd0),
-                  w3 = __fmul_rn(w01, zd1), w4 = __fmul_rn(w10, zd0), w5 = __fmul_rn(w10, zd1),
-                  w6 = __fmul_rn(w11, zd0), w7 = __fmul_rn(w11, zd1);
-      const int ylo = min(max((int)yl, 0), r - 1), zlo = min(max((int)zl, 0), r - 1);
-      const int yo = (yd1 > 0.0f && ylo < r - 1) ? r : 0, zo = (zd1 > 0.0f && zlo < r - 1) ? 1 : 0;
-      const float *Hi = (xd1 > 0.0f && x + 1 < r) ? Bn : A;
-      const int o00 = ylo * r + zlo, o01 = o00 + zo, o10 = o00 + yo, o11 = o10 + zo;
+    if (pn < p_end) { nx = g_sx[pn]; ny = g_sy[pn]; nz = g_sz[pn]; npid = g_spid[pn]; }
+    // trilinear_devox.cu:37-75 with slab-relative offsets
+    const float xl = floorf(px), yl = floorf(py), zl = floorf(pz);
+    const float xd1 = __fsub_rn(px, xl), yd1 = __fsub_rn(py, yl), zd1 = __fsub_rn(pz, zl);
+    const float xd0 = __fsub_rn(1.0f, xd1), yd0 = __fsub_rn(1.0f, yd1), zd0 = __fsub_rn(1.0f, zd1);
+    const float w00 = __fmul_rn(xd0, yd0), w01 = __fmul_rn(xd0, yd1);
+    const float w10 = __fmul_rn(xd1, yd0), w11 = __fmul_rn(xd1, yd1);
+    const float w0 = __fmul_rn(w00, zd0), w1 = __fmul_rn(w00, zd1), w2 = __fmul_rn(w01, zd0),
+                w3 = __fmul_rn(w01, zd1), w4 = __fmul_rn(w10, zd0), w5 = __fmul_rn(w10, zd1),
+                w6 = __fmul_rn(w11, zd0), w7 = __fmul_rn(w11, zd1);
+    const int xb = devox_xbin(px, r);  // the bin this point was sorted into: x0 <= xb < x1
+    const int ylo = min(max((int)yl, 0), r - 1), zlo = min(max((int)zl, 0), r - 1);
+    const int yo = (yd1 > 0.0f && ylo < r - 1) ? r : 0, zo = (zd1 > 0.0f && zlo < r - 1) ? 1 : 0;
+    const float *A = slab + (size_t)(xb - x0) * CT * r2;
+    const float *Hi = (xd1 > 0.0f && xb + 1 < r) ? A + (size_t)CT * r2 : A;
+    const int o00 = ylo * r + zlo, o01 = o00 + zo, o10 = o00 + yo, o11 = o10 + zo;
 #pragma unroll
-      for (int cc = 0; cc < CT; ++cc) {
-        const float *a = A + cc * r2, *h = Hi + cc * r2;
-        float acc = __fmul_rn(w1, a[o01]);
-        acc = __fmaf_rn(w0, a[o00], acc);
-        acc = __fmaf_rn(w2, a[o10], acc);
-        acc = __fmaf_rn(w3, a[o11], acc);
-        acc = __fmaf_rn(w4, h[o00], acc);
-        acc = __fmaf_rn(w5, h[o01], acc);
-        acc = __fmaf_rn(w6, h[o10], acc);
-        acc = __fmaf_rn(w7, h[o11], acc);
-        if (cc < nch) obase[(size_t)cc * n + pid] = acc;
-      }
+    for (int cc = 0; cc < CT; ++cc) {
+      const float *a = A + cc * r2, *h = Hi + cc * r2;
+      float acc = __fmul_rn(w1, a[o01]);
+      acc = __fmaf_rn(w0, a[o00], acc);
+      acc = __fmaf_rn(w2, a[o10], acc);
+      acc = __fmaf_rn(w3, a[o11], acc);
+      acc = __fmaf_rn(w4, h[o00], acc);
+      acc = __fmaf_rn(w5, h[o01], acc);
+      acc = __fmaf_rn(w6, h[o10], acc);
+      acc = __fmaf_rn(w7, h[o11], acc);
+      if (cc < nch) obase[(size_t)cc * n + pid] = acc;
     }
-    px = nx; py = ny; pz = nz; pid = npid;
+    p = pn; px = nx; py = ny; pz = nz; pid = npid;
   }
-  cp_async_wait<0>();
 }
 
 __global__ void __launch_bounds__(kDevoxThreads)
@@ -404,21 +384,23 @@ devox_grad_kernel(int c, int n, int r3, const int *__restrict__ inds, const floa
 
 namespace bdm {
 
-static size_t devox_slice_smem(int ct, int n, int r) {
-  (void)n;
-  return sizeof(float) * (size_t)kRingDepth * r * r * ct + sizeof(int) * (r + 1);
+// slab width (x-slices per CTA) such that slab + halo fits `budget` bytes of shared memory
+static int devox_slab_width(int ct, int r, size_t budget) {
+  const size_t per_slice = sizeof(float) * (size_t)ct * r * r;
+  const int fit = (int)(budget / per_slice) - 1;
+  return fit < 1 ? 0 : (fit > r ? r : fit);
 }
 
-// channel tile for the slice kernel, or 0 when the fast path does not apply
+// channel tile for the slab kernel, or 0 when the fast path does not apply
 static int devox_slice_ct(int b, int c, int n, int r, int is_training) {
   if (is_training || r > kSliceMaxR || r < 1 || n < 1 || c < 1) return 0;
   if (((r * r) & 3) != 0) return 0;  // 16-byte cp.async chunks need r^2 % 4 == 0
-  int ct = 4;
-  // every CTA walks its R slices serially (load -> gather -> barrier), so latency is hidden by CTAs,
-  // not by warps: keep >= 3 CTAs per SM in flight (smaller channel tiles when b*c is small)
-  while (ct > 1 && (b * ceil_div(c, ct) < (3 * sm_count()) / 2 || devox_slice_smem(ct, n, r) > 72 * 1024)) ct >>= 1;
-  if (devox_slice_smem(ct, n, r) > 200 * 1024) return 0;
-  if (ceil_div(c, ct) > 65535 || b > 65535) return 0;
+  if (b > 65535) return 0;
+  int ct = 2;                        // 2 channels x (8+1) slices x 4 KB = 72 KB at R=32: 3 CTAs per SM
+  if (c == 1) ct = 1;
+  if (devox_slab_width(ct, r, 72 * 1024) < 1) ct = 1;
+  if (devox_slab_width(ct, r, 72 * 1024) < 1) return 0;
+  if (ceil_div(c, ct) > 0x7fffffff) return 0;
   return ct;
 }
 
@@ -448,13 +430,15 @@ static cudaError_t launch_grid(int b, int c, int n, int r, const float *coords, 
 }
 
 template <int CT>
-static cudaError_t launch_slice(int b, int c, int n, int r, const float *feat, const unsigned char *ws,
-                                const DevoxPlanLayout &L, float *outs, cudaStream_t st) {
-  const size_t smem = devox_slice_smem(CT, n, r);
-  auto kern = devox_ring_kernel<CT>;
+static cudaError_t launch_slab(int b, int c, int n, int r, const float *feat, const unsigned char *ws,
+                               const DevoxPlanLayout &L, float *outs, cudaStream_t st) {
+  const int width = devox_slab_width(CT, r, 72 * 1024);
+  const int nslabs = ceil_div(r, width);
+  const size_t smem = sizeof(float) * (size_t)(width + 1) * CT * r * r;
+  auto kern = devox_slab_kernel<CT>;
   cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void *>(kern), smem);
   if (e != cudaSuccess) return e;
-  kern<<<dim3(ceil_div(c, CT), b), kSliceThreads, smem, st>>>(c, n, r, feat, ws, L, outs);
+  kern<<<dim3(ceil_div(c, CT), nslabs, b), kSliceThreads, smem, st>>>(c, n, r, width, feat, ws, L, outs);
   return cudaGetLastError();
 }
 
@@ -495,9 +479,8 @@ extern "C" int bdm_trilinear_devoxelize(int b, int c, int n, int r, int is_train
     devox_bin_kernel<<<b, kBinThreads, 0, st>>>(n, r, coords, ws, L);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
-    if (ct == 4) e = launch_slice<4>(b, c, n, r, feat, ws, L, outs, st);
-    else if (ct == 2) e = launch_slice<2>(b, c, n, r, feat, ws, L, outs, st);
-    else e = launch_slice<1>(b, c, n, r, feat, ws, L, outs, st);
+    if (ct == 2) e = launch_slab<2>(b, c, n, r, feat, ws, L, outs, st);
+    else e = launch_slab<1>(b, c, n, r, feat, ws, L, outs, st);
     return e == cudaSuccess ? BDM_OK : (int)e;
   }
 

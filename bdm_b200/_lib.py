@@ -29,7 +29,8 @@ _PROTOS = {
     "bdm_avg_voxelize_fill": (_i, [_i, _i, _i, _i, _p, _p, _p, _p, _p, _z, _p]),
     "bdm_avg_voxelize_grad": (_i, [_i, _i, _i, _i, _p, _p, _p, _p, _p]),
     "bdm_trilinear_devoxelize_workspace_bytes": (_z, [_i, _i, _i]),
-    "bdm_trilinear_devoxelize": (_i, [_i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _z, _p]),
+    "bdm_trilinear_devoxelize_plan": (_i, [_i, _i, _i, _p, _p, _z, _p]),
+    "bdm_trilinear_devoxelize": (_i, [_i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _z, _i, _p]),
     "bdm_trilinear_devoxelize_grad": (_i, [_i, _i, _i, _i, _p, _p, _p, _p, _p]),
     "bdm_gather_features": (_i, [_i, _i, _i, _i, _p, _p, _p, _p]),
     "bdm_gather_features_grad": (_i, [_i, _i, _i, _i, _p, _p, _p, _p]),

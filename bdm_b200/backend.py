@@ -180,8 +180,20 @@ def avg_voxelize_backward(grad_y, indices, cnt):
 # ---------------------------------------------------------------------------------------------
 # devoxelization  (trilinear_devox.cpp:18-55, :68-94)
 # ---------------------------------------------------------------------------------------------
-@_op(2)
-def trilinear_devoxelize_forward(r, is_training, coords, features):
+@_op(1)
+def devoxelize_plan(coords, r):
+    """Coordinate-only half of inference devoxelization (x-slice binning) -> opaque workspace tensor"""
+    _chk_float(coords, "coords")
+    b, n = coords.shape[0], coords.shape[2]
+    r = int(r)
+    ws = _workspace(_L.bdm_trilinear_devoxelize_workspace_bytes(b, n, r), coords.device)
+    with _Launch(coords) as st:
+        _check(_L.bdm_trilinear_devoxelize_plan(b, n, r, coords.data_ptr(), ws.data_ptr(), ws.numel(), st))
+    return ws
+
+
+@_op(1)
+def trilinear_devoxelize_forward(r, is_training, coords, features, plan=None):
     _chk_float(features, "features")
     _chk_float(coords, "coords")
     b, c = features.shape[0], features.shape[1]
@@ -197,11 +209,11 @@ def trilinear_devoxelize_forward(r, is_training, coords, features):
         inds = torch.zeros((1,), dtype=_I32, device=dev)
         wgts = torch.zeros((1,), dtype=_F32, device=dev)
         ip, wp = None, None
-    ws = _workspace(_L.bdm_trilinear_devoxelize_workspace_bytes(b, n, r), dev)
+    ws = plan if plan is not None else _workspace(_L.bdm_trilinear_devoxelize_workspace_bytes(b, n, r), dev)
     with _Launch(features) as st:
         _check(_L.bdm_trilinear_devoxelize(b, c, n, r, 1 if is_training else 0, coords.data_ptr(),
                                            features.data_ptr(), ip, wp, outs.data_ptr(), ws.data_ptr(),
-                                           ws.numel(), st))
+                                           ws.numel(), 1 if plan is not None else 0, st))
     return [outs, inds, wgts]
 
 

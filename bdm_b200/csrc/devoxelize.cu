@@ -115,7 +115,18 @@ devox_bin_kernel(int n, int r, const float *__restrict__ coords, unsigned char *
   __shared__ int cursor[kSliceMaxR];
   if (tid < kSliceMaxR) hist[tid] = 0;
   __syncthreads();
-  for (int i = tid; i < n; i += kBinThreads) atomicAdd(&hist[devox_xbin(coords[i], r)], 1);
+  // up to kBinKeep points per thread stay in registers between the histogram and the scatter pass
+  constexpr int kBinKeep = 4;
+  float kx[kBinKeep], ky[kBinKeep], kz[kBinKeep];
+#pragma unroll
+  for (int j = 0; j < kBinKeep; ++j) {
+    const int i = tid + j * kBinThreads;
+    if (i < n) {
+      kx[j] = coords[i]; ky[j] = coords[i + n]; kz[j] = coords[i + n + n];
+      atomicAdd(&hist[devox_xbin(kx[j], r)], 1);
+    }
+  }
+  for (int i = tid + kBinKeep * kBinThreads; i < n; i += kBinThreads) atomicAdd(&hist[devox_xbin(coords[i], r)], 1);
   __syncthreads();
   if (tid < 32) {  // kSliceMaxR == 32: one warp scans the bins
     const int c = tid < r ? hist[tid] : 0;
@@ -130,7 +141,18 @@ devox_bin_kernel(int n, int r, const float *__restrict__ coords, unsigned char *
     if (tid == 31) g_xstart[r] = n;
   }
   __syncthreads();
-  for (int i = tid; i < n; i += kBinThreads) {
+#pragma unroll
+  for (int j = 0; j < kBinKeep; ++j) {
+    const int i = tid + j * kBinThreads;
+    if (i < n) {
+      const int pos = atomicAdd(&cursor[devox_xbin(kx[j], r)], 1);
+      g_spid[pos] = i;
+      g_sxyz[pos] = kx[j];
+      g_sxyz[pos + n] = ky[j];
+      g_sxyz[pos + 2 * (size_t)n] = kz[j];
+    }
+  }
+  for (int i = tid + kBinKeep * kBinThreads; i < n; i += kBinThreads) {
     const float x = coords[i], y = coords[i + n], z = coords[i + n + n];
     const int pos = atomicAdd(&cursor[devox_xbin(x, r)], 1);
     g_spid[pos] = i;
@@ -220,17 +242,43 @@ devox_grid_kernel(int c, int n, int r, int chunk, const float *__restrict__ coor
   }
 }
 
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+// TMA 1-D bulk copy (cp.async.bulk, SASS UBLKCP) completing on an mbarrier: one instruction moves a
+// whole 4 KB slice row; the issuing thread needs no registers for the data and no address loop.
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count) : "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // init visible to the async proxy
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, unsigned bytes, uint64_t *bar) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d),
+               "l"(gmem_src), "r"(bytes), "r"(a)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  unsigned done;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(a), "r"(parity)
+        : "memory");
+  } while (!done);
+}
 
 // R = 17..32 (even): one CTA per (shape, CT channels, slab of XS x-slices).  The slab plus one halo
-// slice is bulk-loaded into shared memory with cp.async (LDGSTS.128: no register staging, every load of
-// the CTA in flight at once), one barrier, then the slab's points -- a contiguous run of the x-sorted
+// slice is bulk-loaded into shared memory by TMA (cp.async.bulk: one 4 KB copy per slice row issued by
+// one thread, completion on an mbarrier, no register staging), then the slab's points -- a contiguous run of the x-sorted
 // order -- gather their 8 corners from shared memory.  No per-slice pipeline: latency is hidden by the
 // three CTAs resident per SM.  Results are stored straight to global memory by original point index.
 template <int CT>
@@ -252,16 +300,18 @@ devox_slab_kernel(int c, int n, int r, int xs_per_slab, const float *__restrict_
   const int p_begin = __ldg(g_xstart + x0), p_end = __ldg(g_xstart + x1);
   if (p_begin == p_end) return;  // no point falls into this slab: nothing to read, nothing to write
 
-  extern __shared__ __align__(16) float slab[];        // [nslices][CT][r2]
+  extern __shared__ __align__(128) float slab[];       // [nslices][CT][r2]
+  __shared__ __align__(8) uint64_t mbar;
   const float *fbase = feat + ((size_t)b * c + c0) * r3 + (size_t)x0 * r2;
-  const int chunks_per_row = r2 >> 2;
-  for (int sl = 0; sl < nslices; ++sl)
-#pragma unroll
-    for (int cc = 0; cc < CT; ++cc)
-      if (cc < nch)
-        for (int k = tid; k < chunks_per_row; k += kSliceThreads)
-          cp_async16(slab + ((size_t)sl * CT + cc) * r2 + 4 * k, fbase + (size_t)cc * r3 + (size_t)sl * r2 + 4 * k);
-  cp_async_commit();
+  const unsigned row_bytes = (unsigned)(sizeof(float) * r2);
+  if (tid == 0) mbar_init(&mbar, 1);
+  __syncthreads();
+  if (tid == 0) {
+    mbar_expect_tx(&mbar, row_bytes * (unsigned)(nslices * nch));
+    for (int sl = 0; sl < nslices; ++sl)
+      for (int cc = 0; cc < nch; ++cc)
+        bulk_g2s(slab + ((size_t)sl * CT + cc) * r2, fbase + (size_t)cc * r3 + (size_t)sl * r2, row_bytes, &mbar);
+  }
 
   const int *g_spid = reinterpret_cast<const int *>(ws + L.spid);
   const float *g_sx = reinterpret_cast<const float *>(ws + L.sxyz);
@@ -274,8 +324,7 @@ devox_slab_kernel(int c, int n, int r, int xs_per_slab, const float *__restrict_
   float px = 0.f, py = 0.f, pz = 0.f;
   int pid = 0;
   if (p < p_end) { px = g_sx[p]; py = g_sy[p]; pz = g_sz[p]; pid = g_spid[p]; }
-  cp_async_wait<0>();
-  __syncthreads();
+  mbar_wait(&mbar, 0);
 
   while (p < p_end) {
     const int pn = p + kSliceThreads;
@@ -449,10 +498,29 @@ extern "C" size_t bdm_trilinear_devoxelize_workspace_bytes(int b, int n, int r) 
   return bdm::devox_plan_layout(n, r).stride * (size_t)b;
 }
 
+// Coordinate-only half of the inference fast path: x-slice binning of the points into `workspace`.
+// A no-op for sizes the slab kernel does not serve.  Callers that devoxelize several grids over the
+// same coordinates (consecutive PVConv blocks of a stage) run it once and pass planned=1 afterwards.
+extern "C" int bdm_trilinear_devoxelize_plan(int b, int n, int r, const float *coords, void *workspace,
+                                             size_t workspace_bytes, bdm_stream_t stream) {
+  using namespace bdm;
+  BDM_CHECK_SIZE(b >= 0 && n >= 0 && r >= 1);
+  if (b == 0 || n == 0 || r > kSliceMaxR || ((r * r) & 3) != 0) return BDM_OK;
+  if (sizeof(float) * (size_t)r * r * r <= 64 * 1024) return BDM_OK;  // served by devox_grid_kernel: no plan
+  BDM_CHECK_PTR(coords);
+  const DevoxPlanLayout L = devox_plan_layout(n, r);
+  if (workspace == nullptr) return BDM_ERR_NULL_POINTER;
+  if (workspace_bytes < L.stride * (size_t)b) return BDM_ERR_WORKSPACE_TOO_SMALL;
+  if ((reinterpret_cast<uintptr_t>(workspace) & 15) != 0) return BDM_ERR_MISALIGNED;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  devox_bin_kernel<<<b, kBinThreads, 0, st>>>(n, r, coords, static_cast<unsigned char *>(workspace), L);
+  BDM_RETURN_LAUNCH_STATUS();
+}
+
 extern "C" int bdm_trilinear_devoxelize(int b, int c, int n, int r, int is_training,
                                         const float *coords, const float *feat, int *inds,
                                         float *wgts, float *outs, void *workspace,
-                                        size_t workspace_bytes, bdm_stream_t stream) {
+                                        size_t workspace_bytes, int planned, bdm_stream_t stream) {
   using namespace bdm;
   BDM_CHECK_SIZE(b >= 0 && c >= 0 && n >= 0 && r >= 1 && (long long)r * r * r <= 0x7fffffffLL);
   if (b == 0 || n == 0) return BDM_OK;
@@ -476,9 +544,12 @@ extern "C" int bdm_trilinear_devoxelize(int b, int c, int n, int r, int is_train
   if (ct > 0 && workspace != nullptr && workspace_bytes >= L.stride * (size_t)b &&
       (reinterpret_cast<uintptr_t>(workspace) & 15) == 0 && (reinterpret_cast<uintptr_t>(feat) & 15) == 0) {
     unsigned char *ws = static_cast<unsigned char *>(workspace);
-    devox_bin_kernel<<<b, kBinThreads, 0, st>>>(n, r, coords, ws, L);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return (int)e;
+    cudaError_t e = cudaSuccess;
+    if (!planned) {
+      devox_bin_kernel<<<b, kBinThreads, 0, st>>>(n, r, coords, ws, L);
+      e = cudaGetLastError();
+      if (e != cudaSuccess) return (int)e;
+    }
     if (ct == 2) e = launch_slab<2>(b, c, n, r, feat, ws, L, outs, st);
     else e = launch_slab<1>(b, c, n, r, feat, ws, L, outs, st);
     return e == cudaSuccess ? BDM_OK : (int)e;

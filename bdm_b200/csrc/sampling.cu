@@ -62,8 +62,7 @@ fps_register_kernel(int n, int m, const float *__restrict__ coords, int *__restr
   indices += (size_t)b * m;
 
   extern __shared__ float sco[];  // [3][n] coordinate planes, for the winner look-up
-  __shared__ unsigned s_max[2][32];  // per-warp maximum (distance bit pattern), double-buffered by round parity
-  __shared__ unsigned s_key[2];      // minimum tie key among the points holding the global maximum
+  __shared__ unsigned long long slot[2][32];
 
   float px[PPT], py[PPT], pz[PPT], dist[PPT];
   unsigned tk[PPT];
@@ -80,37 +79,31 @@ fps_register_kernel(int n, int m, const float *__restrict__ coords, int *__restr
     dist[j] = ok ? 1e38f : -1.0f;
     tk[j] = ok ? fps_tie_key(k) : 0xffffffffu;
   }
-  if (tid == 0) { indices[0] = 0; s_key[0] = 0xffffffffu; s_key[1] = 0xffffffffu; }
+  if (tid == 0) indices[0] = 0;
   __syncthreads();
 
-  // A round on one SM is bound by the ALU pipe (min / max / compare / select run at half the FP32
-  // rate), so the tie-key search -- 3 ALU ops per point -- is done only by the warp(s) that hold the
-  // global maximum: phase 1 reduces the maximum alone, phase 2 resolves the key.  Two barriers per
-  // round, but 7 of 8 warps skip 48 ALU instructions per thread.
   int old = 0;
   for (int s = 1; s < m; ++s) {
-    const int par = s & 1;
     const float x1 = sco[old], y1 = sco[old + n], z1 = sco[old + n + n];
 #pragma unroll
     for (int j = 0; j < PPT; ++j) {
       const float d = sqdist_ref(__fsub_rn(px[j], x1), __fsub_rn(py[j], y1), __fsub_rn(pz[j], z1));
       dist[j] = fminf(d, dist[j]);
     }
+    // per-thread reductions as trees (log depth): the round is a dependent chain end to end
     const float best = fmaxf(tree_max<PPT>(dist), 0.0f);  // slots without a point hold -1
     const unsigned wmax = __reduce_max_sync(0xffffffffu, __float_as_uint(best));
-    if (lane == 0) s_max[par][warp] = wmax;
-    __syncthreads();
-    const unsigned gmax = __reduce_max_sync(0xffffffffu, lane < nwarps ? s_max[par][lane] : 0u);
-    if (wmax == gmax) {  // warp-uniform
-      unsigned cand[PPT];
+    unsigned cand[PPT];
 #pragma unroll
-      for (int j = 0; j < PPT; ++j) cand[j] = (__float_as_uint(dist[j]) == gmax) ? tk[j] : 0xffffffffu;
-      const unsigned wkey = __reduce_min_sync(0xffffffffu, tree_min<PPT>(cand));
-      if (lane == 0) atomicMin(&s_key[par], wkey);
-    }
-    if (tid == 0) s_key[par ^ 1] = 0xffffffffu;  // reset the other parity's slot for the next round
+    for (int j = 0; j < PPT; ++j) cand[j] = (__float_as_uint(dist[j]) == wmax) ? tk[j] : 0xffffffffu;
+    const unsigned wkey = __reduce_min_sync(0xffffffffu, tree_min<PPT>(cand));
+    if (lane == 0) slot[s & 1][warp] = ((unsigned long long)wmax << 32) | (unsigned long long)(~wkey);
     __syncthreads();
-    old = fps_tie_key_decode(s_key[par]);
+    const unsigned long long v = (lane < nwarps) ? slot[s & 1][lane] : 0ull;
+    const unsigned hi = (unsigned)(v >> 32), lo = (unsigned)v;
+    const unsigned gmax = __reduce_max_sync(0xffffffffu, hi);
+    const unsigned gkey = __reduce_max_sync(0xffffffffu, (hi == gmax && lane < nwarps) ? lo : 0u);
+    old = fps_tie_key_decode(~gkey);
     if (tid == 0) indices[s] = old;
   }
 }

@@ -179,7 +179,7 @@ def plan_geometry_ahead(cache, sa_layers, fp_layers, coords):
             for part in _stage_parts(stage):
                 if isinstance(part, PVConv):
                     v = part.voxelization
-                    coordinate_plan(pts, v.r, v.normalize, v.eps)
+                    F.devoxelize_plan(coordinate_plan(pts, v.r, v.normalize, v.eps)[0], v.r)
                 elif isinstance(part, PointNetSAModule):
                     cen = F.furthest_point_sample(pts, part.num_centers)
                     for grouper in part.groupers:
@@ -194,7 +194,7 @@ def plan_geometry_ahead(cache, sa_layers, fp_layers, coords):
                         F.three_nn_search(pts, cen)
                     elif isinstance(part, PVConv):
                         v = part.voxelization
-                        coordinate_plan(pts, v.r, v.normalize, v.eps)
+                        F.devoxelize_plan(coordinate_plan(pts, v.r, v.normalize, v.eps)[0], v.r)
                 cen = pts
 
 

@@ -42,7 +42,12 @@ class _TrilinearDevoxelize(Function):
     def forward(ctx, features, coords, resolution, is_training=True):
         nb, nc = features.shape[:2]
         flat = features.contiguous().view(nb, nc, -1)
-        outs, corner_idx, corner_w = _B.trilinear_devoxelize_forward(resolution, is_training, coords.contiguous(), flat)
+        pts = coords.contiguous()
+        plan = None if is_training else devoxelize_plan(pts, resolution)
+        if plan is not None:
+            outs, corner_idx, corner_w = _B.trilinear_devoxelize_forward(resolution, is_training, pts, flat, plan)
+        else:
+            outs, corner_idx, corner_w = _B.trilinear_devoxelize_forward(resolution, is_training, pts, flat)
         if is_training:
             ctx.save_for_backward(corner_idx, corner_w)
             ctx.r = resolution
@@ -77,6 +82,16 @@ class _AvgVoxelizePlanned(Function):
 avg_voxelize = _AvgVoxelize.apply
 avg_voxelize_planned = _AvgVoxelizePlanned.apply
 trilinear_devoxelize = _TrilinearDevoxelize.apply
+
+
+def devoxelize_plan(coords, resolution):
+    """Coordinate-only half of inference devoxelization, shared by every grid devoxelized over the same
+    coords tensor (memoised by tensor identity: geometry scope, else the last call).  None when the
+    active backend has no such entry point."""
+    if REFERENCE_CALL_PATTERN or not hasattr(_B, "devoxelize_plan"):
+        return None
+    return geometry.memo("devox", (coords,), (int(resolution),), lambda: _B.devoxelize_plan(coords, resolution),
+                         keep_last=True)
 
 
 def voxel_plan(vox_coords, resolution):

@@ -73,11 +73,16 @@ int bdm_avg_voxelize_grad(int b, int c, int n, int s, const int *ind, const int 
  *   coords f32[b,3,n] in [0,r-1]   feat f32[b,c,r^3]   outs f32[b,c,n]
  *   inds i32[b,8,n], wgts f32[b,8,n]: written iff is_training (may be NULL otherwise).
  * workspace: bdm_trilinear_devoxelize_workspace_bytes(b,n,r) bytes, 16-byte aligned (x-slice binning
- * of the points for the shared-memory fast path); NULL selects the generic gather kernel. */
+ * of the points for the shared-memory fast path); NULL selects the generic gather kernel.
+ * planned: 0 = bin the points into `workspace` first; 1 = `workspace` already holds the result of
+ * bdm_trilinear_devoxelize_plan for these coords (consecutive PVConv blocks of a stage share it). */
 size_t bdm_trilinear_devoxelize_workspace_bytes(int b, int n, int r);
+int bdm_trilinear_devoxelize_plan(int b, int n, int r, const float *coords, void *workspace,
+                                  size_t workspace_bytes, bdm_stream_t stream);
 int bdm_trilinear_devoxelize(int b, int c, int n, int r, int is_training, const float *coords,
                              const float *feat, int *inds, float *wgts, float *outs,
-                             void *workspace, size_t workspace_bytes, bdm_stream_t stream);
+                             void *workspace, size_t workspace_bytes, int planned,
+                             bdm_stream_t stream);
 /* replaces trilinear_devoxelize_grad (trilinear_devox.cuh:9-11): grad_x f32[b,c,r3] is zeroed here */
 int bdm_trilinear_devoxelize_grad(int b, int c, int n, int r3, const int *inds, const float *wgts,
                                   const float *grad_y, float *grad_x, bdm_stream_t stream);

@@ -295,36 +295,35 @@ devox_slab_kernel(int c, int n, int r, int xs_per_slab, const float *__restrict_
   const int r2 = r * r;
   const size_t r3 = (size_t)r2 * r;
 
+  // One mbarrier per slice: thread `sl` of warp 0 arms barrier sl and issues that slice's CT row copies.
+  // A point of bin xb only waits for slices xb and xb+1, so the gather on the first bins overlaps the
+  // arrival of the later slices (points are visited in x-sorted order).
+  extern __shared__ __align__(128) float slab[];       // [nslices][CT][r2]
+  __shared__ __align__(8) uint64_t mbar[kSliceMaxR + 1];
+  const float *fbase = feat + ((size_t)b * c + c0) * r3 + (size_t)x0 * r2;
+  const unsigned row_bytes = (unsigned)(sizeof(float) * r2);
+  if (tid < nslices) mbar_init(&mbar[tid], 1);
+  __syncthreads();
+  if (tid < nslices) {
+    mbar_expect_tx(&mbar[tid], row_bytes * (unsigned)nch);
+    for (int cc = 0; cc < nch; ++cc)
+      bulk_g2s(slab + ((size_t)tid * CT + cc) * r2, fbase + (size_t)cc * r3 + (size_t)tid * r2, row_bytes, &mbar[tid]);
+  }
+
   ws += (size_t)b * L.stride;
   const int *g_xstart = reinterpret_cast<const int *>(ws + L.xstart);
   const int p_begin = __ldg(g_xstart + x0), p_end = __ldg(g_xstart + x1);
-  if (p_begin == p_end) return;  // no point falls into this slab: nothing to read, nothing to write
-
-  extern __shared__ __align__(128) float slab[];       // [nslices][CT][r2]
-  __shared__ __align__(8) uint64_t mbar;
-  const float *fbase = feat + ((size_t)b * c + c0) * r3 + (size_t)x0 * r2;
-  const unsigned row_bytes = (unsigned)(sizeof(float) * r2);
-  if (tid == 0) mbar_init(&mbar, 1);
-  __syncthreads();
-  if (tid == 0) {
-    mbar_expect_tx(&mbar, row_bytes * (unsigned)(nslices * nch));
-    for (int sl = 0; sl < nslices; ++sl)
-      for (int cc = 0; cc < nch; ++cc)
-        bulk_g2s(slab + ((size_t)sl * CT + cc) * r2, fbase + (size_t)cc * r3 + (size_t)sl * r2, row_bytes, &mbar);
-  }
-
   const int *g_spid = reinterpret_cast<const int *>(ws + L.spid);
   const float *g_sx = reinterpret_cast<const float *>(ws + L.sxyz);
   const float *g_sy = g_sx + n;
   const float *g_sz = g_sy + n;
   float *obase = outs + ((size_t)b * c + c0) * n;
 
-  // the first point of every thread is fetched while the slab is in flight
   int p = p_begin + tid;
   float px = 0.f, py = 0.f, pz = 0.f;
   int pid = 0;
   if (p < p_end) { px = g_sx[p]; py = g_sy[p]; pz = g_sz[p]; pid = g_spid[p]; }
-  mbar_wait(&mbar, 0);
+  int ready = -1;  // slices [0, ready] are known to have landed
 
   while (p < p_end) {
     const int pn = p + kSliceThreads;
@@ -341,6 +340,8 @@ devox_slab_kernel(int c, int n, int r, int xs_per_slab, const float *__restrict_
                 w3 = __fmul_rn(w01, zd1), w4 = __fmul_rn(w10, zd0), w5 = __fmul_rn(w10, zd1),
                 w6 = __fmul_rn(w11, zd0), w7 = __fmul_rn(w11, zd1);
     const int xb = devox_xbin(px, r);  // the bin this point was sorted into: x0 <= xb < x1
+    const int need = min(xb - x0 + 1, nslices - 1);
+    while (ready < need) mbar_wait(&mbar[++ready], 0);
     const int ylo = min(max((int)yl, 0), r - 1), zlo = min(max((int)zl, 0), r - 1);
     const int yo = (yd1 > 0.0f && ylo < r - 1) ? r : 0, zo = (zd1 > 0.0f && zlo < r - 1) ? 1 : 0;
     const float *A = slab + (size_t)(xb - x0) * CT * r2;
@@ -361,6 +362,8 @@ devox_slab_kernel(int c, int n, int r, int xs_per_slab, const float *__restrict_
     }
     p = pn; px = nx; py = ny; pz = nz; pid = npid;
   }
+  // a CTA must not retire while bulk copies into its shared memory are still in flight
+  while (ready < nslices - 1) mbar_wait(&mbar[++ready], 0);
 }
 
 __global__ void __launch_bounds__(kDevoxThreads)

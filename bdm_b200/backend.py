@@ -377,6 +377,25 @@ def three_nearest_neighbors_interpolate_backward(grad_y, indices, weights, m):
 
 
 # ---------------------------------------------------------------------------------------------
+# dense side: fused GroupNorm (+ Swish)
+# ---------------------------------------------------------------------------------------------
+@_op(2)
+def groupnorm_act(x, num_groups, weight, bias, eps, swish=True):
+    """x f32[B,C,*] -> swish(group_norm(x)) (or group_norm(x) when swish=False), same shape"""
+    _chk_float(x, "x")
+    b, c = x.shape[0], x.shape[1]
+    s = x.numel() // max(b * c, 1)
+    y = torch.empty_like(x)
+    ws = _workspace(_L.bdm_groupnorm_workspace_bytes(b * int(num_groups)), x.device)
+    with _Launch(x) as st:
+        _check(_L.bdm_groupnorm_act(b, c, s, int(num_groups), float(eps), 1 if swish else 0, x.data_ptr(),
+                                    weight.data_ptr() if weight is not None else None,
+                                    bias.data_ptr() if bias is not None else None, y.data_ptr(), ws.data_ptr(),
+                                    ws.numel(), st))
+    return y
+
+
+# ---------------------------------------------------------------------------------------------
 # secondary boundaries
 # ---------------------------------------------------------------------------------------------
 @_op(4)

@@ -4,15 +4,55 @@ names, parameter names, layer order -- matches the reference's and its checkpoin
 
 reference: modules/shared_mlp.py:10-37, modules/se.py:8-19, modules/pvconv.py:12-63, modules/loss.py:8-10
 """
+import os
+
 import torch
 import torch.nn as nn
 
 from .. import functional as F
+from ..functional import ops as _ops
+
+# Fused GroupNorm+Swish kernel of libbdm_b200 for inference on CUDA (tolerance 1e-5 vs the torch pair,
+# tests/test_dense_fused_gpu.py).  BDM_FUSED_NORM=0, autograd, CPU tensors or a foreign `_backend`
+# (the reference's extension, the test oracle) fall back to nn.GroupNorm followed by Swish.
+FUSED_NORM_ACT = os.environ.get("BDM_FUSED_NORM", "1") != "0"
 
 
 class Swish(nn.Module):
     def forward(self, x):
         return x * torch.sigmoid(x)
+
+
+def _fusable(x):
+    return (FUSED_NORM_ACT and x.is_cuda and x.dtype == torch.float32 and x.dim() >= 3 and x.is_contiguous()
+            and not torch.is_grad_enabled() and not _ops.REFERENCE_CALL_PATTERN
+            and hasattr(_ops._B, "groupnorm_act"))
+
+
+def norm_act(norm, x, swish=True):
+    """swish(norm(x)) for an nn.GroupNorm `norm`, through the fused kernel when possible."""
+    if isinstance(norm, nn.GroupNorm) and _fusable(x):
+        return _ops._B.groupnorm_act(x, norm.num_groups, norm.weight, norm.bias, norm.eps, swish)
+    y = norm(x)
+    return y * torch.sigmoid(y) if swish else y
+
+
+class FusedSequential(nn.Sequential):
+    """nn.Sequential (same children, same state_dict keys) that runs every GroupNorm -> Swish pair as one
+    fused kernel when the input allows it."""
+
+    def forward(self, x):
+        mods = list(self)
+        i = 0
+        while i < len(mods):
+            m = mods[i]
+            if isinstance(m, nn.GroupNorm) and i + 1 < len(mods) and isinstance(mods[i + 1], Swish) and _fusable(x):
+                x = norm_act(m, x, True)
+                i += 2
+            else:
+                x = m(x)
+                i += 1
+        return x
 
 
 class SharedMLP(nn.Module):
@@ -30,7 +70,7 @@ class SharedMLP(nn.Module):
         for c_out in widths:
             stack += [conv(c_in, c_out, 1), nn.GroupNorm(8, c_out), Swish()]
             c_in = c_out
-        self.layers = nn.Sequential(*stack)
+        self.layers = FusedSequential(*stack)
 
     def forward(self, inputs):
         # tuples carry (features, *passthrough): only the features go through the MLP
@@ -75,7 +115,7 @@ class Attention(nn.Module):
         q, k, v = (proj(x).reshape(nb, nc, -1) for proj in (self.q, self.k, self.v))
         attn = self.sm(torch.matmul(q.transpose(1, 2), k))             # [B, T, T]
         mixed = torch.matmul(v, attn.transpose(1, 2)).reshape(x.shape)  # [B, C, ...]
-        return self.nonlin(self.norm(self.out(mixed) + x))
+        return norm_act(self.norm, self.out(mixed) + x, True)
 
 
 class KLLoss(nn.Module):

@@ -7,7 +7,7 @@ import torch.nn as nn
 
 from .. import functional as F
 from ..functional import geometry
-from .layers import SE3d, Attention, SharedMLP, Swish
+from .layers import SE3d, Attention, FusedSequential, SharedMLP, Swish
 
 
 def normalized_voxel_coords(coords, resolution, normalize=True, eps=0):
@@ -90,7 +90,7 @@ def _voxel_stack(c_in, c_out, k, attention, dropout, with_se, with_se_relu, make
             Attention(c_out, 8) if attention else make_act()]
     if with_se:
         seq.append(SE3d(c_out, use_relu=with_se_relu))
-    return nn.Sequential(*seq)
+    return FusedSequential(*seq)
 
 
 class _PVConvBase(nn.Module):

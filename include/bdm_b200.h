@@ -168,6 +168,17 @@ int bdm_surface_projection_hwc(int b, int n, int C, int H, int W, float radius, 
 int bdm_nn_f64(int b, int n, int m, int expanded, const double *src, const double *tgt,
                double *dist, int *idx, bdm_stream_t stream);
 
+/* ---- dense side: fused GroupNorm + Swish ------------------------------------
+ * replaces the nn.GroupNorm(8, C) -> Swish pair that follows every conv of the point-voxel blocks
+ * (modules/shared_mlp.py:25-31, modules/pvconv.py:75-88, :59-61): y = act(group_norm(x)) with biased
+ * variance and eps inside the sqrt, act = x*sigmoid(x) when swish != 0, identity otherwise.
+ *   x, y f32[b,c,s] (s = product of the trailing dims; y may alias x), gamma/beta f32[c] or NULL.
+ * workspace: bdm_groupnorm_workspace_bytes(b*groups) bytes, 16-byte aligned. */
+size_t bdm_groupnorm_workspace_bytes(long long rows);
+int bdm_groupnorm_act(int b, int c, long long s, int groups, float eps, int swish, const float *x,
+                      const float *gamma, const float *beta, float *y, void *workspace,
+                      size_t workspace_bytes, bdm_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -45,8 +45,9 @@ _PROTOS = {
     "bdm_three_nearest_neighbors_interpolate_grad": (_i, [_i, _i, _i, _i, _p, _p, _p, _p, _p]),
     "bdm_surface_projection": (_i, [_i, _i, _i, _i, _i, _f, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "bdm_surface_projection_hwc": (_i, [_i, _i, _i, _i, _i, _f, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
-    "bdm_groupnorm_workspace_bytes": (_z, [ctypes.c_longlong]),
-    "bdm_groupnorm_act": (_i, [_i, _i, ctypes.c_longlong, _i, _f, _i, _p, _p, _p, _p, _p, _z, _p]),
+    "bdm_groupnorm_workspace_bytes": (_z, [_i, _i, ctypes.c_longlong]),
+    "bdm_groupnorm_tiles": (_i, [_i, _i, ctypes.c_longlong]),
+    "bdm_groupnorm_act": (_i, [_i, _i, ctypes.c_longlong, _i, _f, _i, _i, _p, _p, _p, _p, _p, _p, _p, _z, _p]),
     "bdm_nn_f64": (_i, [_i, _i, _i, _i, _p, _p, _p, _p, _p]),
 }
 

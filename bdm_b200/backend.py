@@ -380,19 +380,34 @@ def three_nearest_neighbors_interpolate_backward(grad_y, indices, weights, m):
 # dense side: fused GroupNorm (+ Swish)
 # ---------------------------------------------------------------------------------------------
 @_op(2)
-def groupnorm_act(x, num_groups, weight, bias, eps, swish=True):
-    """x f32[B,C,*] -> swish(group_norm(x)) (or group_norm(x) when swish=False), same shape"""
+def groupnorm_act(x, num_groups, weight, bias, eps, swish=True, conv_bias=None, max_over_last=False,
+                  channel_sums=False):
+    """x f32[B,C,*] -> act(group_norm(x + conv_bias[c])), act = swish or identity.
+    max_over_last: return the max over the last dim instead (shape x.shape[:-1]).
+    channel_sums:  also return f32[B,C] sums of the output over the trailing dims (SE squeeze)."""
     _chk_float(x, "x")
     b, c = x.shape[0], x.shape[1]
     s = x.numel() // max(b * c, 1)
-    y = torch.empty_like(x)
-    ws = _workspace(_L.bdm_groupnorm_workspace_bytes(b * int(num_groups)), x.device)
+    dev = x.device
+    u = int(x.shape[-1]) if max_over_last else 0
+    y = torch.empty(x.shape[:-1] if max_over_last else x.shape, dtype=_F32, device=dev)
+    sums = None
+    if channel_sums:
+        sums = torch.empty((b * c, _L.bdm_groupnorm_tiles(b, c, s)), dtype=_F32, device=dev)
+    ws = _workspace(_L.bdm_groupnorm_workspace_bytes(b, c, s), dev)
     with _Launch(x) as st:
-        _check(_L.bdm_groupnorm_act(b, c, s, int(num_groups), float(eps), 1 if swish else 0, x.data_ptr(),
+        _check(_L.bdm_groupnorm_act(b, c, s, int(num_groups), float(eps), 1 if swish else 0, u, x.data_ptr(),
+                                    conv_bias.data_ptr() if conv_bias is not None else None,
                                     weight.data_ptr() if weight is not None else None,
-                                    bias.data_ptr() if bias is not None else None, y.data_ptr(), ws.data_ptr(),
-                                    ws.numel(), st))
+                                    bias.data_ptr() if bias is not None else None, y.data_ptr(),
+                                    sums.data_ptr() if sums is not None else None, ws.data_ptr(), ws.numel(), st))
+    if channel_sums:
+        return y, sums.sum(dim=1).view(b, c)
     return y
+
+
+def groupnorm_max_supported(u):
+    return 4 <= u <= 128 and (u & (u - 1)) == 0
 
 
 # ---------------------------------------------------------------------------------------------

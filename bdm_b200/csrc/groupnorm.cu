@@ -1,41 +1,46 @@
-// groupnorm.cu -- fused GroupNorm (+ Swish) for the dense side of the point-voxel blocks, sm_100a.
+// groupnorm.cu -- fused [conv bias +] GroupNorm [+ Swish] [+ max over neighbours | + channel sums], sm_100a.
 //
 // Every conv of the denoisers is followed by GroupNorm(8) and Swish (x * sigmoid(x)):
 // modules/shared_mlp.py:25-31 (1x1 conv -> GroupNorm -> Swish), modules/pvconv.py:75-88 (Conv3d -> GroupNorm
-// -> Swish), pvconv.py:59-61 (attention: GroupNorm -> Swish).  Through torch that is four kernels and
-// ~5 reads + 3 writes of the tensor (RowwiseMoments with ONE CTA per (sample, group) row of up to 512 KB,
-// the normalise pass, sigmoid, mul) -- 7 of the 17 ms of a PC^2 step at B=16.  Both ops are pure HBM
-// streaming; fused they are 2 reads + 1 write:
-//   gn_stats_kernel   each (sample, group) row -- cg*S contiguous floats -- is split over several CTAs;
+// -> Swish), pvconv.py:59-61 (attention: GroupNorm -> Swish).  Through torch that is a bias-add kernel
+// after the conv, then four kernels and ~5 reads + 3 writes of the tensor for norm + activation
+// (RowwiseMoments with ONE CTA per (sample, group) row of up to 512 KB, the normalise pass, sigmoid, mul),
+// often followed by yet another full pass: the max over the 32 neighbours in PointNetSAModule
+// (modules/pointnet.py:86) or the squeeze-excite mean (modules/se.py:19).  All of it is HBM streaming.
+// Fused here into 2 reads + (at most) 1 write:
+//   gn_stats_kernel   per (sample, channel) row of S contiguous floats, split over several CTAs when long:
 //                     per-thread fp32 partial sums over <= 64 elements, then double precision through the
-//                     warp / block reduction; one (sum, sumsq) partial per CTA (fixed slots: deterministic)
-//   gn_apply_kernel   one CTA per (sample, channel, tile): warp 0 folds the row's partials in a fixed
-//                     order into mean / rstd, then y = swish(x * (rstd*gamma) + (beta - mean*rstd*gamma))
-//                     with 128-bit loads and streaming stores.
-// Tolerance against torch (F.group_norm followed by x*sigmoid(x)): 1e-5 relative to the output's max
-// (tests/test_dense_fused_gpu.py); biased variance, eps inside the sqrt, like torch.
+//                     warp / block reduction; one (sum, sumsq) partial per CTA in a fixed slot
+//                     (deterministic).
+//   gn_apply_kernel   one CTA per (sample, channel, tile): warp 0 folds the group's partials -- and, when
+//                     the conv was run without its bias, the per-channel bias terms, analytically -- into
+//                     mean / rstd in double, then y = act((x + b_conv) * rstd*gamma + beta - mean*rstd*gamma)
+//                     with 128-bit loads; optionally reduces max over the innermost U (<= 128) values
+//                     instead of writing them all, or emits per-tile sums of y for the SE squeeze.
+// Tolerance against torch (conv bias add, F.group_norm, x*sigmoid(x), max / mean): 1e-5 relative to the
+// output's peak (tests/test_dense_fused_gpu.py); biased variance, eps inside the sqrt, like torch.
 #include "common.cuh"
 
 namespace bdm {
 
 constexpr int kGnThreads = 256;
-constexpr int kGnMaxChunks = 64;
+constexpr int kGnMaxChunks = 32;
 
 __global__ void __launch_bounds__(kGnThreads)
 gn_stats_kernel(long long row_len, int nchunks, const float *__restrict__ x, double2 *__restrict__ partials) {
   const long long row = blockIdx.y;
   const int chunk = blockIdx.x;
-  const long long per = (row_len + nchunks - 1) / nchunks;
-  const long long lo = chunk * per, hi = min(lo + per, row_len);
+  long long per = (row_len + nchunks - 1) / nchunks;
+  per = (per + 3) & ~3LL;  // chunks start on 16-byte boundaries when the row does
+  const long long lo = min(chunk * per, row_len), hi = min(lo + per, row_len);
   const float *p = x + row * row_len;
   float s = 0.0f, q = 0.0f;
   double ds = 0.0, dq = 0.0;
   int since = 0;
-  if (((row * row_len + lo) & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+  if ((reinterpret_cast<uintptr_t>(p + lo) & 15) == 0) {
     const long long n4 = (hi - lo) >> 2;
-    const float4 *p4 = reinterpret_cast<const float4 *>(p + lo);
     for (long long i = threadIdx.x; i < n4; i += kGnThreads) {
-      const float4 v = ld_stream_f4(reinterpret_cast<const float *>(p4 + i));
+      const float4 v = ld_stream_f4(p + lo + 4 * i);
       s += (v.x + v.y) + (v.z + v.w);
       q += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
       if (++since == 16) { ds += s; dq += q; s = q = 0.0f; since = 0; }  // bound the fp32 run length
@@ -66,94 +71,178 @@ gn_stats_kernel(long long row_len, int nchunks, const float *__restrict__ x, dou
   }
 }
 
-template <bool SWISH>
+// MODE 0: y[b,c,s] elementwise (+ optional per-tile sums of y);  MODE 1: y[b,c,s/u] = max over innermost u
+template <bool SWISH, int MODE>
 __global__ void __launch_bounds__(kGnThreads)
-gn_apply_kernel(int c, long long s, int groups, int nchunks, float eps, int tile4,
-                const float *__restrict__ x, const float *__restrict__ gamma,
-                const float *__restrict__ beta, const double2 *__restrict__ partials,
-                float *__restrict__ y) {
+gn_apply_kernel(int c, long long s, int groups, int nchunks, float eps, int tile4, int u,
+                const float *__restrict__ x, const float *__restrict__ conv_bias,
+                const float *__restrict__ gamma, const float *__restrict__ beta,
+                const double2 *__restrict__ partials, float *__restrict__ y, float *__restrict__ tile_sums) {
   const long long bc = blockIdx.x;       // sample * c + channel
   const int ch = (int)(bc % c);
   const long long sample = bc / c;
   const int cg = c / groups;
-  const long long row = sample * groups + ch / cg;
+  const int ch0 = (ch / cg) * cg;        // first channel of this channel's group
   __shared__ float s_ab[2];
+  __shared__ float s_red[kGnThreads / 32];
   if (threadIdx.x < 32) {
-    double a = 0.0, b2 = 0.0;
-    for (int k = threadIdx.x; k < nchunks; k += 32) { const double2 v = partials[row * nchunks + k]; a += v.x; b2 += v.y; }
+    // fold (sum, sumsq) of the group's channels; a conv bias b shifts a channel's sums analytically:
+    //   sum(x+b) = sum(x) + S b,   sum((x+b)^2) = sum(x^2) + 2 b sum(x) + S b^2
+    double S1 = 0.0, S2 = 0.0;
+    const double ds = (double)s;
+    for (int e = threadIdx.x; e < cg * nchunks; e += 32) {
+      const int cc = e / nchunks;
+      const double2 v = partials[(sample * c + ch0 + cc) * nchunks + (e - cc * nchunks)];
+      S1 += v.x; S2 += v.y;
+      if (conv_bias != nullptr) {
+        const double b = (double)conv_bias[ch0 + cc];
+        S2 += 2.0 * b * v.x;
+        if (e - cc * nchunks == 0) { S1 += ds * b; S2 += ds * b * b; }
+      }
+    }
 #pragma unroll
     for (int d = 16; d >= 1; d >>= 1) {
-      a += __shfl_xor_sync(0xffffffffu, a, d);
-      b2 += __shfl_xor_sync(0xffffffffu, b2, d);
+      S1 += __shfl_xor_sync(0xffffffffu, S1, d);
+      S2 += __shfl_xor_sync(0xffffffffu, S2, d);
     }
     if (threadIdx.x == 0) {
-      const double n = (double)cg * (double)s;
-      const double mean = a / n;
-      const double var = fmax(b2 / n - mean * mean, 0.0);
+      const double n = (double)cg * ds;
+      const double mean = S1 / n;
+      const double var = fmax(S2 / n - mean * mean, 0.0);
       const float rstd = (float)(1.0 / sqrt(var + (double)eps));
       const float ga = gamma != nullptr ? gamma[ch] : 1.0f;
       const float be = beta != nullptr ? beta[ch] : 0.0f;
+      const float cb = conv_bias != nullptr ? conv_bias[ch] : 0.0f;
       const float scale = rstd * ga;
       s_ab[0] = scale;
-      s_ab[1] = be - (float)mean * scale;
+      s_ab[1] = (float)((double)be + ((double)cb - mean) * (double)scale);
     }
   }
   __syncthreads();
   const float A = s_ab[0], Bc = s_ab[1];
   const float *px = x + bc * s;
-  float *py = y + bc * s;
   auto act = [](float v) { return SWISH ? v / (1.0f + expf(-v)) : v; };
-  if ((s & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0) {
-    const long long n4 = s >> 2;
-    const long long lo = (long long)blockIdx.y * tile4, hi = min(lo + tile4, n4);
-    for (long long i = lo + threadIdx.x; i < hi; i += kGnThreads) {
-      float4 v = ld_stream_f4(px + 4 * i);
-      v.x = act(fmaf(v.x, A, Bc)); v.y = act(fmaf(v.y, A, Bc)); v.z = act(fmaf(v.z, A, Bc)); v.w = act(fmaf(v.w, A, Bc));
-      *reinterpret_cast<float4 *>(py + 4 * i) = v;
+  const bool vec = (s & 3) == 0 && (reinterpret_cast<uintptr_t>(px) & 15) == 0;
+
+  if (MODE == 0) {
+    float *py = y + bc * s;
+    float local = 0.0f;
+    if (vec && (reinterpret_cast<uintptr_t>(py) & 15) == 0) {
+      const long long n4 = s >> 2;
+      const long long lo = (long long)blockIdx.y * tile4, hi = min(lo + tile4, n4);
+      for (long long i = lo + threadIdx.x; i < hi; i += kGnThreads) {
+        float4 v = ld_stream_f4(px + 4 * i);
+        v.x = act(fmaf(v.x, A, Bc)); v.y = act(fmaf(v.y, A, Bc)); v.z = act(fmaf(v.z, A, Bc)); v.w = act(fmaf(v.w, A, Bc));
+        *reinterpret_cast<float4 *>(py + 4 * i) = v;
+        local += (v.x + v.y) + (v.z + v.w);
+      }
+    } else {
+      const long long lo = (long long)blockIdx.y * tile4 * 4, hi = min(lo + (long long)tile4 * 4, s);
+      for (long long i = lo + threadIdx.x; i < hi; i += kGnThreads) {
+        const float v = act(fmaf(px[i], A, Bc));
+        py[i] = v;
+        local += v;
+      }
+    }
+    if (tile_sums != nullptr) {  // per-tile sum of the outputs (SE squeeze), fixed slot: deterministic
+#pragma unroll
+      for (int d = 16; d >= 1; d >>= 1) local += __shfl_xor_sync(0xffffffffu, local, d);
+      if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = local;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        float t = 0.0f;
+#pragma unroll
+        for (int w = 0; w < kGnThreads / 32; ++w) t += s_red[w];
+        tile_sums[bc * gridDim.y + blockIdx.y] = t;
+      }
     }
   } else {
-    const long long lo = (long long)blockIdx.y * tile4 * 4, hi = min(lo + (long long)tile4 * 4, s);
-    for (long long i = lo + threadIdx.x; i < hi; i += kGnThreads) py[i] = act(fmaf(px[i], A, Bc));
+    // u innermost values -> 1: lanes_per_row = u/4 consecutive lanes own one row (u is a power of two, 4..128)
+    const long long m = s / u;
+    float *py = y + bc * m;
+    const int lpr = u >> 2;
+    const long long n4 = s >> 2;
+    const long long lo = (long long)blockIdx.y * tile4, hi = min(lo + tile4, n4);   // tile4 is a multiple of lpr
+    for (long long i0 = lo; i0 < hi; i0 += kGnThreads) {
+      const long long i = i0 + threadIdx.x;
+      float best = -__int_as_float(0x7f800000);
+      if (i < hi) {
+        const float4 v = ld_stream_f4(px + 4 * i);
+        best = fmaxf(fmaxf(act(fmaf(v.x, A, Bc)), act(fmaf(v.y, A, Bc))), fmaxf(act(fmaf(v.z, A, Bc)), act(fmaf(v.w, A, Bc))));
+      }
+      for (int d = 1; d < lpr; d <<= 1) best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, d));
+      if (i < hi && (threadIdx.x & (lpr - 1)) == 0) py[i / lpr] = best;
+    }
   }
+}
+
+static int gn_nchunks(long long rows, long long row_len) {
+  long long n = (4LL * sm_count() + rows - 1) / rows;
+  const long long by_len = (row_len + 8191) / 8192;
+  if (n > by_len) n = by_len;
+  if (n > kGnMaxChunks) n = kGnMaxChunks;
+  return n < 1 ? 1 : (int)n;
+}
+
+static int gn_tiles(long long bc, long long n4, int align4) {
+  int tiles = 1;
+  while (bc * tiles < 8LL * sm_count() && n4 / (tiles * 2) >= 2 * kGnThreads && tiles < 16384) tiles *= 2;
+  long long tile4 = (n4 + tiles - 1) / tiles;
+  tile4 = (tile4 + align4 - 1) / align4 * align4;
+  return (int)tile4;
 }
 
 }  // namespace bdm
 
-extern "C" size_t bdm_groupnorm_workspace_bytes(long long rows) {
-  return sizeof(double2) * (size_t)(rows > 0 ? rows : 1) * bdm::kGnMaxChunks;
+extern "C" size_t bdm_groupnorm_workspace_bytes(int b, int c, long long s) {
+  if (b <= 0 || c <= 0 || s <= 0) return 16;
+  return sizeof(double2) * (size_t)b * c * bdm::gn_nchunks((long long)b * c, s);
 }
 
-extern "C" int bdm_groupnorm_act(int b, int c, long long s, int groups, float eps, int swish, const float *x,
-                                 const float *gamma, const float *beta, float *y, void *workspace,
-                                 size_t workspace_bytes, bdm_stream_t stream) {
+// number of per-(sample,channel) tile sums bdm_groupnorm_act writes when tile_sums != NULL
+extern "C" int bdm_groupnorm_tiles(int b, int c, long long s) {
+  if (b <= 0 || c <= 0 || s <= 0) return 1;
+  const long long n4 = (s + 3) >> 2;
+  const int tile4 = bdm::gn_tiles((long long)b * c, n4, 1);
+  return (int)((n4 + tile4 - 1) / tile4);
+}
+
+extern "C" int bdm_groupnorm_act(int b, int c, long long s, int groups, float eps, int swish, int max_over_u,
+                                 const float *x, const float *conv_bias, const float *gamma, const float *beta,
+                                 float *y, float *tile_sums, void *workspace, size_t workspace_bytes,
+                                 bdm_stream_t stream) {
   using namespace bdm;
   BDM_CHECK_SIZE(b >= 0 && c >= 1 && s >= 0 && groups >= 1 && c % groups == 0);
   if (b == 0 || s == 0) return BDM_OK;
   BDM_CHECK_PTR(x); BDM_CHECK_PTR(y); BDM_CHECK_PTR(workspace);
-  const long long rows = (long long)b * groups;
-  const long long row_len = (long long)(c / groups) * s;
-  if (workspace_bytes < bdm_groupnorm_workspace_bytes(rows)) return BDM_ERR_WORKSPACE_TOO_SMALL;
+  const long long rows = (long long)b * c;
+  BDM_CHECK_SIZE(rows <= 65535LL * 64);
+  if (workspace_bytes < bdm_groupnorm_workspace_bytes(b, c, s)) return BDM_ERR_WORKSPACE_TOO_SMALL;
   if ((reinterpret_cast<uintptr_t>(workspace) & 15) != 0) return BDM_ERR_MISALIGNED;
-  BDM_CHECK_SIZE(rows <= 65535);
+  if (max_over_u) {
+    // power of two in [4,128], rows of u values contiguous and 16-byte aligned
+    BDM_CHECK_SIZE(max_over_u >= 4 && max_over_u <= 128 && (max_over_u & (max_over_u - 1)) == 0 && s % max_over_u == 0);
+    if ((reinterpret_cast<uintptr_t>(x) & 15) != 0) return BDM_ERR_MISALIGNED;
+    BDM_CHECK_SIZE(tile_sums == nullptr);
+  }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  // enough CTAs to fill the machine ~4x over, at least 8 K elements per CTA
-  int nchunks = (int)((4LL * sm_count() + rows - 1) / rows);
-  const long long max_by_len = (row_len + 8191) / 8192;
-  if (nchunks > max_by_len) nchunks = (int)max_by_len;
-  if (nchunks > kGnMaxChunks) nchunks = kGnMaxChunks;
-  if (nchunks < 1) nchunks = 1;
+  const int nchunks = gn_nchunks(rows, s);
   double2 *partials = static_cast<double2 *>(workspace);
-  gn_stats_kernel<<<dim3(nchunks, (unsigned)rows), kGnThreads, 0, st>>>(row_len, nchunks, x, partials);
-  const long long bc = (long long)b * c;
+  // rows can exceed the 65535 limit of gridDim.y: fold them in slabs
+  for (long long r0 = 0; r0 < rows; r0 += 65535) {
+    const unsigned nr = (unsigned)min(65535LL, rows - r0);
+    gn_stats_kernel<<<dim3(nchunks, nr), kGnThreads, 0, st>>>(s, nchunks, x + r0 * s, partials + r0 * nchunks);
+  }
   const long long n4 = (s + 3) >> 2;
-  int tiles = 1;
-  while (bc * tiles < 8LL * sm_count() && n4 / (tiles * 2) >= 2 * kGnThreads && tiles < 65535 / 2) tiles *= 2;
-  const int tile4 = (int)((n4 + tiles - 1) / tiles);
-  BDM_CHECK_SIZE(bc <= 0x7fffffffLL);
-  const dim3 grid((unsigned)bc, (unsigned)tiles);
-  if (swish)
-    gn_apply_kernel<true><<<grid, kGnThreads, 0, st>>>(c, s, groups, nchunks, eps, tile4, x, gamma, beta, partials, y);
-  else
-    gn_apply_kernel<false><<<grid, kGnThreads, 0, st>>>(c, s, groups, nchunks, eps, tile4, x, gamma, beta, partials, y);
+  const int tile4 = gn_tiles(rows, n4, max_over_u ? max_over_u / 4 : 1);
+  const unsigned tiles = (unsigned)((n4 + tile4 - 1) / tile4);
+  BDM_CHECK_SIZE(rows <= 0x7fffffffLL && tiles <= 65535);
+  const dim3 grid((unsigned)rows, tiles);
+#define BDM_GN_LAUNCH(SW, MODE)                                                                               \
+  gn_apply_kernel<SW, MODE><<<grid, kGnThreads, 0, st>>>(c, s, groups, nchunks, eps, tile4, max_over_u, x,    \
+                                                          conv_bias, gamma, beta, partials, y, tile_sums)
+  if (max_over_u) { if (swish) BDM_GN_LAUNCH(true, 1); else BDM_GN_LAUNCH(false, 1); }
+  else            { if (swish) BDM_GN_LAUNCH(true, 0); else BDM_GN_LAUNCH(false, 0); }
+#undef BDM_GN_LAUNCH
   BDM_RETURN_LAUNCH_STATUS();
 }

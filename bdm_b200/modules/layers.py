@@ -37,21 +37,51 @@ def norm_act(norm, x, swish=True):
     return y * torch.sigmoid(y) if swish else y
 
 
-class FusedSequential(nn.Sequential):
-    """nn.Sequential (same children, same state_dict keys) that runs every GroupNorm -> Swish pair as one
-    fused kernel when the input allows it."""
+_CONVS = (nn.Conv1d, nn.Conv2d, nn.Conv3d)
 
-    def forward(self, x):
+
+class FusedSequential(nn.Sequential):
+    """nn.Sequential (same children, same state_dict keys) that, for inference on CUDA, runs
+        Conv -> GroupNorm [-> Swish] [-> SE3d | -> max over the last dim]
+    through the fused kernel: the conv is issued without its bias (folded analytically into the norm
+    statistics), norm + activation are one pass, the SE squeeze comes out of that same pass and a
+    trailing max over neighbours replaces the full-size write.  Anything else runs module by module."""
+
+    def forward(self, x, max_over_last=False):
         mods = list(self)
+        n = len(mods)
         i = 0
-        while i < len(mods):
+        reduced = False
+        while i < n:
             m = mods[i]
-            if isinstance(m, nn.GroupNorm) and i + 1 < len(mods) and isinstance(mods[i + 1], Swish) and _fusable(x):
+            fusable = _fusable(x)
+            if (fusable and isinstance(m, _CONVS) and m.bias is not None and i + 1 < n
+                    and isinstance(mods[i + 1], nn.GroupNorm)):
+                gn = mods[i + 1]
+                swish = i + 2 < n and isinstance(mods[i + 2], Swish)
+                nxt = i + (3 if swish else 2)
+                y = m._conv_forward(x, m.weight, None)
+                if nxt < n and isinstance(mods[nxt], SE3d) and swish:
+                    y, sums = _ops._B.groupnorm_act(y, gn.num_groups, gn.weight, gn.bias, gn.eps, True,
+                                                    conv_bias=m.bias, channel_sums=True)
+                    x = mods[nxt](y, channel_sums=sums)
+                    nxt += 1
+                elif (max_over_last and nxt == n and swish and y.dim() == 4
+                      and _ops._B.groupnorm_max_supported(y.shape[-1])):
+                    x = _ops._B.groupnorm_act(y, gn.num_groups, gn.weight, gn.bias, gn.eps, True,
+                                              conv_bias=m.bias, max_over_last=True)
+                    reduced = True
+                else:
+                    x = _ops._B.groupnorm_act(y, gn.num_groups, gn.weight, gn.bias, gn.eps, swish, conv_bias=m.bias)
+                i = nxt
+            elif fusable and isinstance(m, nn.GroupNorm) and i + 1 < n and isinstance(mods[i + 1], Swish):
                 x = norm_act(m, x, True)
                 i += 2
             else:
                 x = m(x)
                 i += 1
+        if max_over_last and not reduced:
+            x = x.max(dim=-1).values
         return x
 
 
@@ -79,6 +109,10 @@ class SharedMLP(nn.Module):
             return (self.layers(head), *rest)
         return self.layers(inputs)
 
+    def forward_max(self, features):
+        """`self(features).max(dim=-1).values` with the max folded into the last norm+activation pass."""
+        return self.layers(features, max_over_last=True)
+
 
 class SE3d(nn.Module):
     """Squeeze-and-excitation gate over a voxel grid; two bias-free Linears at `fc.0` / `fc.2`."""
@@ -91,9 +125,11 @@ class SE3d(nn.Module):
                                 nn.Linear(hidden, channel, bias=False),
                                 nn.Sigmoid())
 
-    def forward(self, inputs):
-        # three chained means (z, y, x) like the reference, for identical rounding
-        pooled = inputs.mean(-1).mean(-1).mean(-1)
+    def forward(self, inputs, channel_sums=None):
+        if channel_sums is not None:   # squeeze already produced by the fused norm+activation pass
+            pooled = channel_sums / float(inputs.shape[2] * inputs.shape[3] * inputs.shape[4])
+        else:                          # three chained means (z, y, x) like the reference, for identical rounding
+            pooled = inputs.mean(-1).mean(-1).mean(-1)
         return inputs * self.fc(pooled)[:, :, None, None, None]
 
 
@@ -113,8 +149,15 @@ class Attention(nn.Module):
     def forward(self, x):
         nb, nc = x.shape[:2]
         q, k, v = (proj(x).reshape(nb, nc, -1) for proj in (self.q, self.k, self.v))
-        attn = self.sm(torch.matmul(q.transpose(1, 2), k))             # [B, T, T]
-        mixed = torch.matmul(v, attn.transpose(1, 2)).reshape(x.shape)  # [B, C, ...]
+        if _fusable(x) and q.shape[-1] >= 256:
+            # softmax(q^T k) v without materialising the [B,T,T] score matrix (64 MiB per shape at
+            # T=4096): torch's fused attention with scale 1 (the reference does not scale its logits).
+            # Same math, online softmax; tolerance tests/test_dense_fused_gpu.py.
+            mixed = torch.nn.functional.scaled_dot_product_attention(
+                q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2), scale=1.0).transpose(1, 2).reshape(x.shape)
+        else:
+            attn = self.sm(torch.matmul(q.transpose(1, 2), k))              # [B, T, T]
+            mixed = torch.matmul(v, attn.transpose(1, 2)).reshape(x.shape)  # [B, C, ...]
         return norm_act(self.norm, self.out(mixed) + x, True)
 
 

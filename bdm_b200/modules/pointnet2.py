@@ -91,13 +91,17 @@ class PointNetSAModule(nn.Module):
     def forward(self, inputs):
         features, coords, temb = inputs
         centers = F.furthest_point_sample(coords, self.num_centers)
-        first = None
-        for grouper, mlp in zip(self.groupers, self.mlps):
-            # the reference rebinds `features` / `temb` inside this loop (pointnet.py:84-86) and
-            # returns the first scale only; reproduced as is
-            features, temb = mlp(grouper(coords, centers, temb, features))
-            if first is None:
-                first = features.max(dim=-1).values
+        if len(self.groupers) == 1:
+            grouped, temb = self.groupers[0](coords, centers, temb, features)
+            first = self.mlps[0].forward_max(grouped)   # == mlp(grouped).max(dim=-1).values
+        else:
+            first = None
+            for grouper, mlp in zip(self.groupers, self.mlps):
+                # the reference rebinds `features` / `temb` inside this loop (pointnet.py:84-86) and
+                # returns the first scale only; reproduced as is
+                features, temb = mlp(grouper(coords, centers, temb, features))
+                if first is None:
+                    first = features.max(dim=-1).values
         if temb.shape[1] > 0:
             # max over neighbours; when the grouped embedding is a broadcast (see F.group_time_embedding)
             # all U values are equal, so slot 0 IS the max -- and the result stays a stride-0 view, which

@@ -168,16 +168,24 @@ int bdm_surface_projection_hwc(int b, int n, int C, int H, int W, float radius, 
 int bdm_nn_f64(int b, int n, int m, int expanded, const double *src, const double *tgt,
                double *dist, int *idx, bdm_stream_t stream);
 
-/* ---- dense side: fused GroupNorm + Swish ------------------------------------
- * replaces the nn.GroupNorm(8, C) -> Swish pair that follows every conv of the point-voxel blocks
- * (modules/shared_mlp.py:25-31, modules/pvconv.py:75-88, :59-61): y = act(group_norm(x)) with biased
- * variance and eps inside the sqrt, act = x*sigmoid(x) when swish != 0, identity otherwise.
- *   x, y f32[b,c,s] (s = product of the trailing dims; y may alias x), gamma/beta f32[c] or NULL.
- * workspace: bdm_groupnorm_workspace_bytes(b*groups) bytes, 16-byte aligned. */
-size_t bdm_groupnorm_workspace_bytes(long long rows);
-int bdm_groupnorm_act(int b, int c, long long s, int groups, float eps, int swish, const float *x,
-                      const float *gamma, const float *beta, float *y, void *workspace,
-                      size_t workspace_bytes, bdm_stream_t stream);
+/* ---- dense side: fused [conv bias +] GroupNorm [+ Swish] [+ reduction] ----------
+ * replaces the bias add of the preceding conv, the nn.GroupNorm(8, C) -> Swish pair that follows every
+ * conv of the point-voxel blocks (modules/shared_mlp.py:25-31, modules/pvconv.py:75-88, :59-61) and,
+ * optionally, the reduction that consumes the result: max over the innermost U neighbours
+ * (modules/pointnet.py:86) or the per-channel sums of the squeeze-excite gate (modules/se.py:19).
+ *   y = act(group_norm(x + conv_bias[c])), biased variance, eps inside the sqrt;
+ *   act = v*sigmoid(v) when swish != 0, identity otherwise.
+ *   x f32[b,c,s] (s = product of the trailing dims), conv_bias / gamma / beta f32[c] or NULL.
+ *   max_over_u == 0: y f32[b,c,s]; tile_sums (or NULL) f32[b*c, bdm_groupnorm_tiles(b,c,s)] receives
+ *                    per-tile sums of y (sum them for the channel total).
+ *   max_over_u == U (power of two, 4..128, divides s): y f32[b,c,s/U] = max over each run of U values.
+ * workspace: bdm_groupnorm_workspace_bytes(b,c,s) bytes, 16-byte aligned. */
+size_t bdm_groupnorm_workspace_bytes(int b, int c, long long s);
+int bdm_groupnorm_tiles(int b, int c, long long s);
+int bdm_groupnorm_act(int b, int c, long long s, int groups, float eps, int swish, int max_over_u,
+                      const float *x, const float *conv_bias, const float *gamma, const float *beta,
+                      float *y, float *tile_sums, void *workspace, size_t workspace_bytes,
+                      bdm_stream_t stream);
 
 #ifdef __cplusplus
 }

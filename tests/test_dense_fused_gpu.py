@@ -5,7 +5,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 SHAPES = [(16, 32, (32, 32, 32)), (16, 64, (1024, 32)), (4, 256, (8, 8, 8)), (2, 512, (16,)), (3, 16, (5, 7)),
-          (2, 8, (1,)), (1, 128, (4096,)), (16, 64, (4096,)), (2, 24, (33,))]
+          (2, 16, (3,)), (1, 128, (4096,)), (16, 64, (4096,)), (2, 24, (33,))]
 
 
 @pytest.mark.parametrize("swish", [True, False])
@@ -62,3 +62,74 @@ def test_denoiser_fused_vs_unfused(cuda_backend):
             L.FUSED_NORM_ACT = saved
     err = (y_fused - y_plain).abs().max().item() / y_plain.abs().max().item()
     assert err <= 1e-4, err   # 60+ norm layers deep; each within 1e-5
+
+
+def test_attention_fused_vs_plain(cuda_backend):
+    import torch
+
+    import bdm_b200.modules.layers as L
+    torch.manual_seed(9)
+    att = L.Attention(64, 8, D=3).cuda().eval()
+    x = torch.randn(2, 64, 16, 16, 16, device="cuda")
+    with torch.no_grad():
+        saved = L.FUSED_NORM_ACT
+        try:
+            L.FUSED_NORM_ACT = True
+            y_fused = att(x)
+            L.FUSED_NORM_ACT = False
+            y_plain = att(x)
+        finally:
+            L.FUSED_NORM_ACT = saved
+    err = (y_fused - y_plain).abs().max().item() / y_plain.abs().max().item()
+    assert err <= 1e-5, err
+
+
+@pytest.mark.parametrize("b,c,spatial", [(16, 32, (32, 32, 32)), (4, 64, (256, 32)), (2, 512, (16, 32)), (3, 16, (9, 4))])
+def test_groupnorm_conv_bias_max_and_sums(b, c, spatial, cuda_backend):
+    """conv bias folded into the statistics; max over the last dim; per-channel sums of the output"""
+    import torch
+    import torch.nn.functional as TF
+    g = torch.Generator(device="cuda").manual_seed(c)
+    x = torch.randn((b, c) + spatial, device="cuda", generator=g) * 2.0
+    cb = torch.randn(c, device="cuda", generator=g)
+    w = torch.randn(c, device="cuda", generator=g)
+    bias = torch.randn(c, device="cuda", generator=g)
+    shape = (1, c) + (1,) * len(spatial)
+    want = TF.group_norm(x + cb.view(shape), 8, w, bias, 1e-5)
+    want = want * torch.sigmoid(want)
+    peak = want.abs().max().item()
+    got = cuda_backend.groupnorm_act(x, 8, w, bias, 1e-5, True, conv_bias=cb)
+    assert (got - want).abs().max().item() / peak <= 1e-5
+    got_y, sums = cuda_backend.groupnorm_act(x, 8, w, bias, 1e-5, True, conv_bias=cb, channel_sums=True)
+    assert torch.equal(got_y, got)
+    want_sums = want.double().flatten(2).sum(-1)
+    assert (sums.double() - want_sums).abs().max().item() <= 1e-5 * max(want_sums.abs().max().item(), 1.0)
+    if cuda_backend.groupnorm_max_supported(spatial[-1]):
+        got_max = cuda_backend.groupnorm_act(x, 8, w, bias, 1e-5, True, conv_bias=cb, max_over_last=True)
+        assert got_max.shape == want.shape[:-1]
+        assert torch.equal(got_max, got.max(dim=-1).values)
+
+
+def test_fused_sequential_matches_modules(cuda_backend):
+    """PVConv voxel stack and SA shared MLP: fused execution vs module-by-module execution"""
+    import torch
+
+    import bdm_b200.modules.layers as L
+    from bdm_b200.modules import PVConv, SharedMLP
+    torch.manual_seed(2)
+    pv = PVConv(16, 32, 3, 16, attention=False, with_se=True, with_se_relu=True).cuda().eval()
+    mlp = SharedMLP(19, (32, 64), dim=2).cuda().eval()
+    grid = torch.randn(4, 16, 16, 16, 16, device="cuda")
+    grouped = torch.randn(4, 19, 128, 32, device="cuda")
+    with torch.no_grad():
+        saved = L.FUSED_NORM_ACT
+        try:
+            L.FUSED_NORM_ACT = True
+            a1, a2 = pv.voxel_layers(grid), mlp.forward_max(grouped)
+            L.FUSED_NORM_ACT = False
+            b1, b2 = pv.voxel_layers(grid), mlp(grouped).max(dim=-1).values
+        finally:
+            L.FUSED_NORM_ACT = saved
+    for a, b in ((a1, b1), (a2, b2)):
+        assert a.shape == b.shape
+        assert (a - b).abs().max().item() / b.abs().max().item() <= 2e-5

@@ -34,21 +34,25 @@ gn_stats_kernel(long long row_len, int nchunks, const float *__restrict__ x, dou
   per = (per + 3) & ~3LL;  // chunks start on 16-byte boundaries when the row does
   const long long lo = min(chunk * per, row_len), hi = min(lo + per, row_len);
   const float *p = x + row * row_len;
+  // Sums are taken of (x - k), k = the row's first element: with a shift near the mean the fp32 partial
+  // sums of squares keep the variance even when |mean| >> std; the apply kernel undoes the shift in double.
+  const float k = __ldg(p);
   float s = 0.0f, q = 0.0f;
   double ds = 0.0, dq = 0.0;
   int since = 0;
   if ((reinterpret_cast<uintptr_t>(p + lo) & 15) == 0) {
     const long long n4 = (hi - lo) >> 2;
     for (long long i = threadIdx.x; i < n4; i += kGnThreads) {
-      const float4 v = ld_stream_f4(p + lo + 4 * i);
+      float4 v = ld_stream_f4(p + lo + 4 * i);
+      v.x -= k; v.y -= k; v.z -= k; v.w -= k;
       s += (v.x + v.y) + (v.z + v.w);
       q += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
       if (++since == 16) { ds += s; dq += q; s = q = 0.0f; since = 0; }  // bound the fp32 run length
     }
-    for (long long i = lo + (n4 << 2) + threadIdx.x; i < hi; i += kGnThreads) { const float v = p[i]; s += v; q += v * v; }
+    for (long long i = lo + (n4 << 2) + threadIdx.x; i < hi; i += kGnThreads) { const float v = p[i] - k; s += v; q += v * v; }
   } else {
     for (long long i = lo + threadIdx.x; i < hi; i += kGnThreads) {
-      const float v = p[i];
+      const float v = p[i] - k;
       s += v; q += v * v;
       if (++since == 64) { ds += s; dq += q; s = q = 0.0f; since = 0; }
     }
@@ -86,19 +90,18 @@ gn_apply_kernel(int c, long long s, int groups, int nchunks, float eps, int tile
   __shared__ float s_ab[2];
   __shared__ float s_red[kGnThreads / 32];
   if (threadIdx.x < 32) {
-    // fold (sum, sumsq) of the group's channels; a conv bias b shifts a channel's sums analytically:
-    //   sum(x+b) = sum(x) + S b,   sum((x+b)^2) = sum(x^2) + 2 b sum(x) + S b^2
+    // fold the group's per-channel partial sums of (x - k_c).  With t = k_c + conv_bias_c the channel's
+    // true sums follow analytically:  sum(x+b) = S1 + S t,   sum((x+b)^2) = S2 + 2 t S1 + S t^2
     double S1 = 0.0, S2 = 0.0;
     const double ds = (double)s;
     for (int e = threadIdx.x; e < cg * nchunks; e += 32) {
       const int cc = e / nchunks;
       const double2 v = partials[(sample * c + ch0 + cc) * nchunks + (e - cc * nchunks)];
-      S1 += v.x; S2 += v.y;
-      if (conv_bias != nullptr) {
-        const double b = (double)conv_bias[ch0 + cc];
-        S2 += 2.0 * b * v.x;
-        if (e - cc * nchunks == 0) { S1 += ds * b; S2 += ds * b * b; }
-      }
+      double t = (double)__ldg(x + (sample * c + ch0 + cc) * s);
+      if (conv_bias != nullptr) t += (double)conv_bias[ch0 + cc];
+      S1 += v.x;
+      S2 += v.y + 2.0 * t * v.x;
+      if (e - cc * nchunks == 0) { S1 += ds * t; S2 += ds * t * t; }
     }
 #pragma unroll
     for (int d = 16; d >= 1; d >>= 1) {

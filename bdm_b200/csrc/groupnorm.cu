@@ -42,14 +42,29 @@ gn_stats_kernel(long long row_len, int nchunks, const float *__restrict__ x, dou
   int since = 0;
   if ((reinterpret_cast<uintptr_t>(p + lo) & 15) == 0) {
     const long long n4 = (hi - lo) >> 2;
-    for (long long i = threadIdx.x; i < n4; i += kGnThreads) {
+    long long i = threadIdx.x;
+    // 4 independent 128-bit loads in flight per thread, 4 independent fp32 accumulator pairs
+    for (; i + 3 * kGnThreads < n4; i += 4 * kGnThreads) {
+      float4 v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = ld_stream_f4(p + lo + 4 * (i + (long long)j * kGnThreads));
+      float s4 = 0.0f, q4 = 0.0f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float a = v[j].x - k, b2 = v[j].y - k, c2 = v[j].z - k, d2 = v[j].w - k;
+        s4 += (a + b2) + (c2 + d2);
+        q4 += (a * a + b2 * b2) + (c2 * c2 + d2 * d2);
+      }
+      s += s4; q += q4;
+      if (++since == 4) { ds += s; dq += q; s = q = 0.0f; since = 0; }  // bound the fp32 run length (64 values)
+    }
+    for (; i < n4; i += kGnThreads) {
       float4 v = ld_stream_f4(p + lo + 4 * i);
       v.x -= k; v.y -= k; v.z -= k; v.w -= k;
       s += (v.x + v.y) + (v.z + v.w);
       q += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
-      if (++since == 16) { ds += s; dq += q; s = q = 0.0f; since = 0; }  // bound the fp32 run length
     }
-    for (long long i = lo + (n4 << 2) + threadIdx.x; i < hi; i += kGnThreads) { const float v = p[i] - k; s += v; q += v * v; }
+    for (long long t = lo + (n4 << 2) + threadIdx.x; t < hi; t += kGnThreads) { const float v = p[t] - k; s += v; q += v * v; }
   } else {
     for (long long i = lo + threadIdx.x; i < hi; i += kGnThreads) {
       const float v = p[i] - k;
@@ -133,7 +148,20 @@ gn_apply_kernel(int c, long long s, int groups, int nchunks, float eps, int tile
     if (vec && (reinterpret_cast<uintptr_t>(py) & 15) == 0) {
       const long long n4 = s >> 2;
       const long long lo = (long long)blockIdx.y * tile4, hi = min(lo + tile4, n4);
-      for (long long i = lo + threadIdx.x; i < hi; i += kGnThreads) {
+      long long i = lo + threadIdx.x;
+      for (; i + 3 * kGnThreads < hi; i += 4 * kGnThreads) {   // 4 loads in flight per thread
+        float4 v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = ld_stream_f4(px + 4 * (i + (long long)j * kGnThreads));
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          v[j].x = act(fmaf(v[j].x, A, Bc)); v[j].y = act(fmaf(v[j].y, A, Bc));
+          v[j].z = act(fmaf(v[j].z, A, Bc)); v[j].w = act(fmaf(v[j].w, A, Bc));
+          *reinterpret_cast<float4 *>(py + 4 * (i + (long long)j * kGnThreads)) = v[j];
+          local += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+        }
+      }
+      for (; i < hi; i += kGnThreads) {
         float4 v = ld_stream_f4(px + 4 * i);
         v.x = act(fmaf(v.x, A, Bc)); v.y = act(fmaf(v.y, A, Bc)); v.z = act(fmaf(v.z, A, Bc)); v.w = act(fmaf(v.w, A, Bc));
         *reinterpret_cast<float4 *>(py + 4 * i) = v;

@@ -71,15 +71,17 @@ vox_sort_kernel(int n, int r, const int *__restrict__ coords, int *__restrict__ 
   const int b = blockIdx.x;
   const int r2 = r * r, r3 = r2 * r;
   const int nw = L.nw;
+  const int nblk = (nw + 3) >> 2;        // 128-voxel blocks (4 words), the unit of the vectorised passes
+  const int nwp = nblk << 2;             // padded word count
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-  extern __shared__ uint32_t smem_u32[];
-  uint32_t *hist = smem_u32;             // [nw*32]   count -> (cursor<<16 | in-word exclusive prefix)
-  uint32_t *wbase = hist + nw * 32;      // [nw]      word totals -> exclusive point-offset base
-  uint32_t *obase = wbase + nw;          // [nw]      occupied-voxel rank base
-  uint32_t *wmask = obase + nw;          // [nw]      occupancy bits
-  uint16_t *perm = reinterpret_cast<uint16_t *>(wmask + nw);  // [n]  sorted position -> point
-  uint16_t *vbuf = perm + ((n + 1) & ~1);                     // [n]  point -> voxel
+  extern __shared__ __align__(16) uint32_t smem_u32[];
+  uint32_t *hist = smem_u32;             // [nwp*32]  count -> (cursor<<16 | in-word exclusive prefix)
+  uint32_t *wbase = hist + nwp * 32;     // [nwp]     word totals -> exclusive point-offset base
+  uint32_t *obase = wbase + nwp;         // [nwp]     occupied-voxel rank base
+  uint32_t *wmask = obase + nwp;         // [nwp]     occupancy bits
+  uint16_t *perm = reinterpret_cast<uint16_t *>(wmask + nwp);  // [n]  sorted position -> point
+  uint16_t *vbuf = perm + ((n + 1) & ~1);                      // [n]  point -> voxel
   __shared__ uint32_t warp_tot[32];
 
   coords += (size_t)b * 3 * n;
@@ -91,7 +93,10 @@ vox_sort_kernel(int n, int r, const int *__restrict__ coords, int *__restrict__ 
   uint16_t *g_ostart = reinterpret_cast<uint16_t *>(ws + L.ostart);
   uint16_t *g_rank = reinterpret_cast<uint16_t *>(ws + L.rank);
 
-  for (int v = tid; v < nw * 32; v += kSortThreads) hist[v] = 0;
+  {
+    uint4 *h4 = reinterpret_cast<uint4 *>(hist);
+    for (int q = tid; q < nwp * 8; q += kSortThreads) h4[q] = make_uint4(0u, 0u, 0u, 0u);
+  }
   __syncthreads();
 
   // pass 1: voxel index (vox.cu:31) + histogram
@@ -106,21 +111,40 @@ vox_sort_kernel(int n, int r, const int *__restrict__ coords, int *__restrict__ 
   }
   __syncthreads();
 
-  // pass 2: cnt out, per-word occupancy mask, in-word exclusive prefix of counts
-  for (int w = warp; w < nw; w += kSortThreads / 32) {
-    const int v = w * 32 + lane;
-    const uint32_t c = hist[v];
-    if (v < r3) cnt[v] = (int)c;
-    const uint32_t mask = __ballot_sync(0xffffffffu, c > 0);
-    uint32_t incl = c;
+  // pass 2 (one warp per 128-voxel block, 4 voxels per lane): cnt out, occupancy masks, in-word
+  // exclusive prefix of the counts
+  const bool cnt_vec = (r3 & 3) == 0 && (reinterpret_cast<uintptr_t>(cnt) & 15) == 0;
+  for (int blk = warp; blk < nblk; blk += kSortThreads / 32) {
+    const int v0 = blk * 128 + lane * 4;
+    const uint4 c4 = reinterpret_cast<const uint4 *>(hist)[blk * 32 + lane];
+    if (cnt_vec) {
+      if (v0 < r3) *reinterpret_cast<int4 *>(cnt + v0) = make_int4((int)c4.x, (int)c4.y, (int)c4.z, (int)c4.w);
+    } else {
+      if (v0 < r3) cnt[v0] = (int)c4.x;
+      if (v0 + 1 < r3) cnt[v0 + 1] = (int)c4.y;
+      if (v0 + 2 < r3) cnt[v0 + 2] = (int)c4.z;
+      if (v0 + 3 < r3) cnt[v0 + 3] = (int)c4.w;
+    }
+    const uint32_t nib = (c4.x > 0 ? 1u : 0u) | (c4.y > 0 ? 2u : 0u) | (c4.z > 0 ? 4u : 0u) | (c4.w > 0 ? 8u : 0u);
+    uint32_t mask = nib << ((lane & 7) * 4);          // OR over the 8 lanes that share one 32-voxel word
+    mask |= __shfl_xor_sync(0xffffffffu, mask, 1);
+    mask |= __shfl_xor_sync(0xffffffffu, mask, 2);
+    mask |= __shfl_xor_sync(0xffffffffu, mask, 4);
+    const uint32_t tot = c4.x + c4.y + c4.z + c4.w;
+    uint32_t incl = tot;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
       const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
       if (lane >= d) incl += t;
     }
-    hist[v] = incl - c;
-    if (lane == 31) {
-      wbase[w] = incl | ((uint32_t)__popc(mask) << 16);  // packed: points | occupied voxels
+    const uint32_t excl = incl - tot;                                            // within the 128-voxel block
+    const uint32_t wstart = __shfl_sync(0xffffffffu, excl, lane & ~7);           // ... at the word's first lane
+    const uint32_t wend = __shfl_sync(0xffffffffu, incl, lane | 7);              // ... after its last lane
+    const uint32_t e0 = excl - wstart;
+    reinterpret_cast<uint4 *>(hist)[blk * 32 + lane] = make_uint4(e0, e0 + c4.x, e0 + c4.x + c4.y, e0 + c4.x + c4.y + c4.z);
+    if ((lane & 7) == 0) {
+      const int w = blk * 4 + (lane >> 3);
+      wbase[w] = (wend - wstart) | ((uint32_t)__popc(mask) << 16);  // packed: points | occupied voxels
       wmask[w] = mask;
     }
   }
@@ -128,7 +152,7 @@ vox_sort_kernel(int n, int r, const int *__restrict__ coords, int *__restrict__ 
 
   // pass 3: block-wide exclusive scan over the (<=1024) packed word totals
   {
-    const uint32_t val = (tid < nw) ? wbase[tid] : 0u;
+    const uint32_t val = (tid < nwp) ? wbase[tid] : 0u;
     uint32_t incl = val;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -149,12 +173,14 @@ vox_sort_kernel(int n, int r, const int *__restrict__ coords, int *__restrict__ 
     }
     __syncthreads();
     const uint32_t excl = warp_tot[warp] + incl - val;
-    if (tid < nw) {
+    if (tid < nwp) {
       wbase[tid] = excl & 0xffffu;
       obase[tid] = excl >> 16;
-      g_bitmask[tid] = wmask[tid];
-      g_obase[tid] = (uint16_t)(excl >> 16);
-      if (tid == nw - 1) {
+      if (tid < nw) {
+        g_bitmask[tid] = wmask[tid];
+        g_obase[tid] = (uint16_t)(excl >> 16);
+      }
+      if (tid == nwp - 1) {
         g_ostart[(excl + val) >> 16] = (uint16_t)n;  // sentinel after the last run
         reinterpret_cast<uint32_t *>(ws + L.header)[0] = (excl + val) >> 16;
       }
@@ -170,24 +196,18 @@ vox_sort_kernel(int n, int r, const int *__restrict__ coords, int *__restrict__ 
   }
   __syncthreads();
 
-  // pass 5: stable rank = run start + number of run members with a smaller point index
+  // pass 5: stable rank = run start + number of run members with a smaller point index; the run's
+  // first point (stable rank 0) also records the run start under the voxel's occupied rank
   for (int i = tid; i < n; i += kSortThreads) {
     const int v = vbuf[i];
     const uint32_t h = hist[v];
-    const int start = wbase[v >> 5] + (h & 0xffffu);
+    const int w = v >> 5;
+    const int start = wbase[w] + (h & 0xffffu);
     const int c = h >> 16;
     int rk = 0;
     for (int q = 0; q < c; ++q) rk += (perm[start + q] < i) ? 1 : 0;
     g_rank[i] = (uint16_t)(start + rk);
-  }
-
-  // pass 6: start offset of every occupied voxel, indexed by occupied rank
-  for (int w = warp; w < nw; w += kSortThreads / 32) {
-    const uint32_t mask = wmask[w];
-    if ((mask >> lane) & 1u) {
-      const int j = obase[w] + __popc(mask & ((1u << lane) - 1u));
-      g_ostart[j] = (uint16_t)(wbase[w] + (hist[w * 32 + lane] & 0xffffu));
-    }
+    if (rk == 0) g_ostart[obase[w] + __popc(wmask[w] & ((1u << (v & 31)) - 1u))] = (uint16_t)start;
   }
 }
 
@@ -414,8 +434,8 @@ extern "C" int bdm_voxel_plan(int b, int n, int r, const int *coords, int *ind, 
     const VoxAuxLayout L = vox_aux_layout(n, r3);
     const int rc = check_workspace(L, b, workspace, workspace_bytes);
     if (rc != BDM_OK) return rc;
-    const size_t smem_sort = sizeof(uint32_t) * ((size_t)L.nw * 32 + 3 * (size_t)L.nw) +
-                             sizeof(uint16_t) * (2 * (size_t)((n + 1) & ~1));
+    const size_t nwp = ((size_t)L.nw + 3) & ~(size_t)3;
+    const size_t smem_sort = sizeof(uint32_t) * (nwp * 32 + 3 * nwp) + sizeof(uint16_t) * (2 * (size_t)((n + 1) & ~1));
     cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void *>(vox_sort_kernel), smem_sort);
     if (e != cudaSuccess) return (int)e;
     vox_sort_kernel<<<b, kSortThreads, smem_sort, st>>>(n, r, coords, ind, cnt, static_cast<unsigned char *>(workspace), L);

@@ -40,28 +40,6 @@ def norm_act(norm, x, swish=True):
 _CONVS = (nn.Conv1d, nn.Conv2d, nn.Conv3d)
 
 
-_SDPA_OK = [True]
-
-
-def _fused_attention(q, k, v, out_shape):
-    """softmax(q^T k) v without materialising the [B,T,T] score matrix (64 MiB per shape at T=4096):
-    torch's memory-efficient fused attention kernel with scale 1 (the reference does not scale its
-    logits).  Same math with an online softmax; tolerance tests/test_dense_fused_gpu.py.  Returns None when
-    that kernel is unavailable for these inputs (the caller then takes the explicit path)."""
-    if not _SDPA_OK[0]:
-        return None
-    try:
-        from torch.nn.attention import SDPBackend, sdpa_kernel
-        with sdpa_kernel(SDPBackend.EFFICIENT_ATTENTION):
-            o = torch.nn.functional.scaled_dot_product_attention(
-                q.transpose(1, 2).unsqueeze(1), k.transpose(1, 2).unsqueeze(1), v.transpose(1, 2).unsqueeze(1),
-                scale=1.0)
-        return o.squeeze(1).transpose(1, 2).reshape(out_shape)
-    except Exception:
-        _SDPA_OK[0] = False
-        return None
-
-
 class FusedSequential(nn.Sequential):
     """nn.Sequential (same children, same state_dict keys) that, for inference on CUDA, runs
         Conv -> GroupNorm [-> Swish] [-> SE3d | -> max over the last dim]
@@ -171,10 +149,8 @@ class Attention(nn.Module):
     def forward(self, x):
         nb, nc = x.shape[:2]
         q, k, v = (proj(x).reshape(nb, nc, -1) for proj in (self.q, self.k, self.v))
-        mixed = _fused_attention(q, k, v, x.shape) if (_fusable(x) and q.shape[-1] >= 256) else None
-        if mixed is None:
-            attn = self.sm(torch.matmul(q.transpose(1, 2), k))              # [B, T, T]
-            mixed = torch.matmul(v, attn.transpose(1, 2)).reshape(x.shape)  # [B, C, ...]
+        attn = self.sm(torch.matmul(q.transpose(1, 2), k))              # [B, T, T]
+        mixed = torch.matmul(v, attn.transpose(1, 2)).reshape(x.shape)  # [B, C, ...]
         return norm_act(self.norm, self.out(mixed) + x, True)
 
 

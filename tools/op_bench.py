@@ -142,6 +142,8 @@ def main():
         nbytes = B * (4 * c * n + 12 * n + 4 * c * r ** 3 + 4 * n + 4 * r ** 3)
         add("avg_voxelize", (c, n, r), nbytes,
             {k: (lambda be=be: be.avg_voxelize_forward(feat, vox, r)) for k, be in impls}, mult)
+        plan = ours.voxel_plan(vox, r)   # what the step does: one plan per (coords, R), shared by 2-3 calls
+        add("avg_voxelize_fill (plan reused)", (c, n, r), nbytes, {"ours": lambda: ours.avg_voxelize_fill(feat, plan)}, 0)
         del feat
     for (c, n, r), mult in zip(DEV, DEV_MULT):
         lvl = {4096: 0, 1024: 1, 256: 2, 64: 3}[n]
@@ -153,6 +155,9 @@ def main():
         nbytes = B * (12 * n + 4 * c * min(r ** 3, 8 * n) + 4 * c * n)
         add("trilinear_devoxelize", (c, n, r), nbytes,
             {k: (lambda be=be: be.trilinear_devoxelize_forward(r, False, nc, grid)) for k, be in impls}, mult)
+        dplan = ours.devoxelize_plan(nc, r)
+        add("trilinear_devoxelize (plan reused)", (c, n, r), nbytes,
+            {"ours": lambda: ours.trilinear_devoxelize_forward(r, False, nc, grid, dplan)}, 0)
         del grid
     for li, (n, m, rad) in enumerate(SA):
         pts, cen = levels[li], levels[li + 1]
@@ -177,7 +182,7 @@ def main():
 
     tot = {}
     for name, _ in impls:
-        tot[name] = sum(r[f"{name}_ms"] * r["calls_per_forward"] for r in rows)
+        tot[name] = sum(r[f"{name}_ms"] * r["calls_per_forward"] for r in rows if f"{name}_ms" in r)
     summary = dict(batch=B, regime=args.regime, peak_GBs=PEAK, total_ms_per_forward=tot,
                    total_MB=sum(r["MB"] * r["calls_per_forward"] for r in rows))
     print(json.dumps(summary))

@@ -18,12 +18,15 @@
 //   devox_slab_kernel     4*R^3-byte channel row: served from global memory every warp-level gather costs up
 //                         to 32 L1 wavefronts and the kernel is L1-bound at ~30 % of the HBM roofline
 //                         (measured, profiles/).  Instead: points are binned by x-slice once per call (one
-//                         small CTA per shape); then one CTA per (shape, 2 channels, slab of 8 x-slices)
-//                         bulk-loads its slab + 1 halo slice into shared memory with cp.async and serves
-//                         the slab's points from there.  HBM traffic = the grid once (+12.5 % halo) + the
-//                         output once.
+//                         small CTA per shape); then one CTA per (shape, 2 channels, slab of 3 x-slices)
+//                         bulk-loads its slab + 1 halo slice into shared memory with TMA (cp.async.bulk,
+//                         one mbarrier per slice) and serves the slab's points from there; 7 CTAs per SM
+//                         hide the load latency.  HBM traffic = the grid once + the output once (the halo
+//                         slices are L2 hits: neighbouring slabs run concurrently).
 //   devox_gather_kernel   generic path (training: also writes inds/wgts; large R or N): thread per
 //                         point, channel chunk per blockIdx.y, 8 read-only gathers per channel.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace bdm {
@@ -78,8 +81,9 @@ constexpr int kDevoxChunk = 8;  // channels per CTA in the generic path
 // fast path: x-slice binning + slice-ring gather
 // ------------------------------------------------------------------------------------------------
 constexpr int kSliceThreads = 256;
+constexpr size_t kSlabBudget = 32 * 1024;  // slab + halo per CTA: 3+1 slices x 2 channels at R=32, 7 CTAs per SM
+                                             // (swept on B200: tools/devox_sweep.sh, profiles/)
 constexpr int kSliceMaxR = 32;
-constexpr int kSliceSlots = (kSliceMaxR * kSliceMaxR) / kSliceThreads;  // yz entries per thread per slice
 constexpr int kBinThreads = 1024;
 
 struct DevoxPlanLayout {
@@ -282,7 +286,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
 // order -- gather their 8 corners from shared memory.  No per-slice pipeline: latency is hidden by the
 // three CTAs resident per SM.  Results are stored straight to global memory by original point index.
 template <int CT>
-__global__ void __launch_bounds__(kSliceThreads)
+__global__ void __launch_bounds__(1024)
 devox_slab_kernel(int c, int n, int r, int xs_per_slab, const float *__restrict__ feat,
                   const unsigned char *__restrict__ ws, DevoxPlanLayout L, float *__restrict__ outs) {
   const int b = blockIdx.z;
@@ -326,7 +330,7 @@ devox_slab_kernel(int c, int n, int r, int xs_per_slab, const float *__restrict_
   int ready = -1;  // slices [0, ready] are known to have landed
 
   while (p < p_end) {
-    const int pn = p + kSliceThreads;
+    const int pn = p + (int)blockDim.x;
     float nx = 0.f, ny = 0.f, nz = 0.f;
     int npid = 0;
     if (pn < p_end) { nx = g_sx[pn]; ny = g_sy[pn]; nz = g_sz[pn]; npid = g_spid[pn]; }
@@ -448,10 +452,10 @@ static int devox_slice_ct(int b, int c, int n, int r, int is_training) {
   if (is_training || r > kSliceMaxR || r < 1 || n < 1 || c < 1) return 0;
   if (((r * r) & 3) != 0) return 0;  // 16-byte cp.async chunks need r^2 % 4 == 0
   if (b > 65535) return 0;
-  int ct = 2;                        // 2 channels x (8+1) slices x 4 KB = 72 KB at R=32: 3 CTAs per SM
+  int ct = 2;
   if (c == 1) ct = 1;
-  if (devox_slab_width(ct, r, 72 * 1024) < 1) ct = 1;
-  if (devox_slab_width(ct, r, 72 * 1024) < 1) return 0;
+  if (devox_slab_width(ct, r, kSlabBudget) < 1) ct = 1;
+  if (devox_slab_width(ct, r, kSlabBudget) < 1) return 0;
   if (ceil_div(c, ct) > 0x7fffffff) return 0;
   return ct;
 }
@@ -484,13 +488,18 @@ static cudaError_t launch_grid(int b, int c, int n, int r, const float *coords, 
 template <int CT>
 static cudaError_t launch_slab(int b, int c, int n, int r, const float *feat, const unsigned char *ws,
                                const DevoxPlanLayout &L, float *outs, cudaStream_t st) {
-  const int width = devox_slab_width(CT, r, 72 * 1024);
+  static const char *env_t = getenv("BDM_DEVOX_THREADS");   // tuning hooks
+  static const char *env_b = getenv("BDM_DEVOX_BUDGET_KB");
+  const int threads = env_t ? atoi(env_t) : kSliceThreads;
+  const size_t budget = env_b ? (size_t)atoi(env_b) * 1024 : kSlabBudget;
+  int width = devox_slab_width(CT, r, budget);
+  if (width < 1) width = 1;
   const int nslabs = ceil_div(r, width);
   const size_t smem = sizeof(float) * (size_t)(width + 1) * CT * r * r;
   auto kern = devox_slab_kernel<CT>;
   cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void *>(kern), smem);
   if (e != cudaSuccess) return e;
-  kern<<<dim3(ceil_div(c, CT), nslabs, b), kSliceThreads, smem, st>>>(c, n, r, width, feat, ws, L, outs);
+  kern<<<dim3(ceil_div(c, CT), nslabs, b), threads, smem, st>>>(c, n, r, width, feat, ws, L, outs);
   return cudaGetLastError();
 }
 

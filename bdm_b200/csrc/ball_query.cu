@@ -21,6 +21,8 @@ namespace bdm {
 
 constexpr int kBqMaxSplits = 8;
 
+constexpr int kBqTile = 512;  // points staged per warp at a time (6 KB)
+
 template <bool VEC4>
 __global__ void __launch_bounds__(32 * kBqMaxSplits)
 ball_query_kernel(int n, int m, float r2, int u, int splits, const float *__restrict__ centers,
@@ -32,11 +34,14 @@ ball_query_kernel(int n, int m, float r2, int u, int splits, const float *__rest
   points += (size_t)b * 3 * n;
   neighbors += (size_t)b * m * u;
 
-  extern __shared__ int s_hits[];                 // [splits][32 centres][us], us = u|1 (odd stride:
-                                                  // simultaneous appends of different lanes hit different banks)
+  extern __shared__ __align__(16) int s_dyn[];    // [splits][32 centres][us] hit lists, us = u|1 (odd stride:
+                                                  // simultaneous appends of different lanes hit different
+                                                  // banks), then [splits][3][kBqTile] staged points
   __shared__ int s_cnt[kBqMaxSplits][32];
   const int us = u | 1;
+  int *s_hits = s_dyn;
   int *my = s_hits + ((size_t)split * 32 + lane) * us;
+  float *tile = reinterpret_cast<float *>(s_dyn + (((size_t)splits * 32 * us + 3) & ~(size_t)3)) + (size_t)split * 3 * kBqTile;
 
   const bool valid = j < m;
   const float cx = valid ? centers[j] : 0.0f;
@@ -52,35 +57,32 @@ ball_query_kernel(int n, int m, float r2, int u, int splits, const float *__rest
   // below it, so the hot loop needs no `cnt < u` test.
   int cnt = 0;
   float thr = valid ? r2 : -1.0f;
-  int k = k0;
-  if (VEC4 && k + 4 <= k1) {
-    // software pipeline: the next 4 points are in flight while the current 4 are tested
-    float4 X = __ldg(reinterpret_cast<const float4 *>(points + k));
-    float4 Y = __ldg(reinterpret_cast<const float4 *>(points + n + k));
-    float4 Z = __ldg(reinterpret_cast<const float4 *>(points + 2 * (size_t)n + k));
-    for (; k + 4 <= k1; k += 4) {
-      if ((k & 127) == 0 && __all_sync(0xffffffffu, thr < 0.0f)) break;
-      const int kn = (k + 8 <= k1) ? k + 4 : k;  // clamp the prefetch at the end of the range
-      const float4 Xn = __ldg(reinterpret_cast<const float4 *>(points + kn));
-      const float4 Yn = __ldg(reinterpret_cast<const float4 *>(points + n + kn));
-      const float4 Zn = __ldg(reinterpret_cast<const float4 *>(points + 2 * (size_t)n + kn));
+  for (int t0 = k0; t0 < k1; t0 += kBqTile) {
+    if (__all_sync(0xffffffffu, thr < 0.0f)) break;
+    const int tn = min(kBqTile, k1 - t0);
+    __syncwarp();
+    warp_stage_xyz<kBqTile>(points + t0, (size_t)n, tn, tile, lane, VEC4 && (tn & 3) == 0);
+    int q = 0;
+    for (; q + 4 <= tn; q += 4) {
+      const float4 X = *reinterpret_cast<const float4 *>(tile + q);
+      const float4 Y = *reinterpret_cast<const float4 *>(tile + kBqTile + q);
+      const float4 Z = *reinterpret_cast<const float4 *>(tile + 2 * kBqTile + q);
       const float d0 = sqdist_ref(__fsub_rn(cx, X.x), __fsub_rn(cy, Y.x), __fsub_rn(cz, Z.x));
       const float d1 = sqdist_ref(__fsub_rn(cx, X.y), __fsub_rn(cy, Y.y), __fsub_rn(cz, Z.y));
       const float d2 = sqdist_ref(__fsub_rn(cx, X.z), __fsub_rn(cy, Y.z), __fsub_rn(cz, Z.z));
       const float d3 = sqdist_ref(__fsub_rn(cx, X.w), __fsub_rn(cy, Y.w), __fsub_rn(cz, Z.w));
-      if (fminf(fminf(d0, d1), fminf(d2, d3)) < thr) {  // rare: balls hold a handful of points
+      if (fminf(fminf(d0, d1), fminf(d2, d3)) < thr) {  // rare when balls hold a handful of points
+        const int k = t0 + q;
         if (d0 < thr) { my[cnt++] = k;     if (cnt == u) thr = -1.0f; }
         if (d1 < thr) { my[cnt++] = k + 1; if (cnt == u) thr = -1.0f; }
         if (d2 < thr) { my[cnt++] = k + 2; if (cnt == u) thr = -1.0f; }
         if (d3 < thr) { my[cnt++] = k + 3; if (cnt == u) thr = -1.0f; }
       }
-      X = Xn; Y = Yn; Z = Zn;
     }
-  }
-  for (; k < k1; ++k) {
-    const float d = sqdist_ref(__fsub_rn(cx, __ldg(points + k)), __fsub_rn(cy, __ldg(points + n + k)),
-                               __fsub_rn(cz, __ldg(points + 2 * (size_t)n + k)));
-    if (d < thr) { my[cnt++] = k; if (cnt == u) thr = -1.0f; }
+    for (; q < tn; ++q) {
+      const float d = sqdist_ref(__fsub_rn(cx, tile[q]), __fsub_rn(cy, tile[kBqTile + q]), __fsub_rn(cz, tile[2 * kBqTile + q]));
+      if (d < thr) { my[cnt++] = t0 + q; if (cnt == u) thr = -1.0f; }
+    }
   }
   s_cnt[split][lane] = valid ? cnt : 0;
   __syncthreads();
@@ -120,9 +122,12 @@ extern "C" int bdm_ball_query(int b, int n, int m, float r2, int u, const float 
   // least 256 points per split so the per-row merge stays negligible
   const int ctas = ceil_div(m, 32) * b;
   int splits = 1;
-  while (splits < kBqMaxSplits && ctas * splits < 16 * sm_count() && n / (splits * 2) >= 256) splits *= 2;
-  size_t smem = sizeof(int) * (size_t)splits * 32 * (u | 1);
-  while (smem > 200 * 1024 && splits > 1) { splits /= 2; smem = sizeof(int) * (size_t)splits * 32 * (u | 1); }
+  while (splits < kBqMaxSplits && ctas * splits < 16 * sm_count() && n / (splits * 2) >= 64) splits *= 2;
+  auto smem_for = [&](int sp) {
+    return sizeof(int) * ((((size_t)sp * 32 * (u | 1)) + 3) & ~(size_t)3) + sizeof(float) * (size_t)sp * 3 * kBqTile;
+  };
+  size_t smem = smem_for(splits);
+  while (smem > 200 * 1024 && splits > 1) { splits /= 2; smem = smem_for(splits); }
   BDM_CHECK_SIZE(smem <= 200 * 1024);
   const bool vec4 = (n % 4 == 0) && ((reinterpret_cast<uintptr_t>(points_coords) & 15) == 0);
   auto kern = vec4 ? ball_query_kernel<true> : ball_query_kernel<false>;

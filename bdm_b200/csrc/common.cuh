@@ -89,4 +89,58 @@ __device__ __forceinline__ float ld_stream_f1(const float *p) {
   return v;
 }
 
+// TMA 1-D bulk copy (cp.async.bulk, SASS UBLKCP) completing on an mbarrier: one instruction moves a
+// whole 4 KB slice row; the issuing thread needs no registers for the data and no address loop.
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count) : "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // init visible to the async proxy
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, unsigned bytes, uint64_t *bar) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d),
+               "l"(gmem_src), "r"(bytes), "r"(a)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  unsigned done;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(a), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+
+// Warp-private staging of `count` (<= TW) consecutive coordinates of three planes (x at src, y at
+// src+stride, z at src+2*stride) into shared memory dst[3][TW]; ends with __syncwarp().  All loads of the
+// warp are issued before the first use, so the (L2) latency is paid once per tile, not once per step of
+// the scan that follows.
+template <int TW>
+__device__ __forceinline__ void warp_stage_xyz(const float *__restrict__ src, size_t stride, int count,
+                                               float *__restrict__ dst, int lane, bool vec4) {
+  if (vec4) {  // src + k*stride 16-byte aligned, count % 4 == 0
+#pragma unroll
+    for (int p = 0; p < 3; ++p)
+      for (int q = lane * 4; q < count; q += 128)
+        *reinterpret_cast<float4 *>(dst + p * TW + q) = __ldg(reinterpret_cast<const float4 *>(src + p * stride + q));
+  } else {
+#pragma unroll
+    for (int p = 0; p < 3; ++p)
+      for (int q = lane; q < count; q += 32) dst[p * TW + q] = __ldg(src + p * stride + q);
+  }
+  __syncwarp();
+}
+
 }  // namespace bdm

@@ -246,45 +246,11 @@ devox_grid_kernel(int c, int n, int r, int chunk, const float *__restrict__ coor
   }
 }
 
-// TMA 1-D bulk copy (cp.async.bulk, SASS UBLKCP) completing on an mbarrier: one instruction moves a
-// whole 4 KB slice row; the issuing thread needs no registers for the data and no address loop.
-__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
-  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count) : "memory");
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // init visible to the async proxy
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
-  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, unsigned bytes, uint64_t *bar) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d),
-               "l"(gmem_src), "r"(bytes), "r"(a)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
-  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
-  unsigned done;
-  do {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(done)
-        : "r"(a), "r"(parity)
-        : "memory");
-  } while (!done);
-}
-
 // R = 17..32 (even): one CTA per (shape, CT channels, slab of XS x-slices).  The slab plus one halo
 // slice is bulk-loaded into shared memory by TMA (cp.async.bulk: one 4 KB copy per slice row issued by
 // one thread, completion on an mbarrier, no register staging), then the slab's points -- a contiguous run of the x-sorted
 // order -- gather their 8 corners from shared memory.  No per-slice pipeline: latency is hidden by the
-// three CTAs resident per SM.  Results are stored straight to global memory by original point index.
+// several CTAs resident per SM (7 at R=32).  Results are stored straight to global memory by original point index.
 template <int CT>
 __global__ void __launch_bounds__(1024)
 devox_slab_kernel(int c, int n, int r, int xs_per_slab, const float *__restrict__ feat,

@@ -58,18 +58,34 @@ template <int CT>
 __global__ void __launch_bounds__(kGrpThreads)
 grouping_rows_kernel(int c, int n, int mu, int chunk4, const float *__restrict__ features,
                      const int *__restrict__ indices, float *__restrict__ out) {
-  extern __shared__ float rows[];  // [CT][n]
+  extern __shared__ __align__(128) float rows[];  // [CT][n]
+  __shared__ __align__(8) uint64_t mbar;
   const int b = blockIdx.z;
   const int c0 = blockIdx.y * CT;
   const int nrows = min(CT, c - c0);
   const float *f = features + ((size_t)b * c + c0) * n;
-  for (int q = threadIdx.x; q < nrows * n; q += kGrpThreads) rows[q] = ld_stream_f1(f + q);
-  __syncthreads();
+  // the CT rows are one contiguous block of nrows*n floats: a single TMA bulk copy when 16-byte aligned
+  const bool bulk = ((n & 3) == 0) && ((reinterpret_cast<uintptr_t>(f) & 15) == 0);
+  if (bulk) {
+    if (threadIdx.x == 0) mbar_init(&mbar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned bytes = (unsigned)(sizeof(float) * (size_t)nrows * n);
+      mbar_expect_tx(&mbar, bytes);
+      bulk_g2s(rows, f, bytes, &mbar);
+    }
+  } else {
+    for (int q = threadIdx.x; q < nrows * n; q += kGrpThreads) rows[q] = ld_stream_f1(f + q);
+  }
   const int4 *ix = reinterpret_cast<const int4 *>(indices + (size_t)b * mu);
   float *o = out + ((size_t)b * c + c0) * mu;
   const int g_end = min((blockIdx.x + 1) * chunk4, mu / 4);
-  for (int g = blockIdx.x * chunk4 + threadIdx.x; g < g_end; g += kGrpThreads) {
-    const int4 id = __ldg(ix + g);
+  int g = blockIdx.x * chunk4 + threadIdx.x;
+  int4 id = g < g_end ? __ldg(ix + g) : make_int4(0, 0, 0, 0);   // first indices arrive while the rows do
+  if (bulk) mbar_wait(&mbar, 0); else __syncthreads();
+  for (; g < g_end; g += kGrpThreads) {
+    const int gn = g + kGrpThreads;
+    const int4 idn = gn < g_end ? __ldg(ix + gn) : make_int4(0, 0, 0, 0);
 #pragma unroll
     for (int cc = 0; cc < CT; ++cc) {
       if (cc < nrows) {
@@ -77,6 +93,7 @@ grouping_rows_kernel(int c, int n, int mu, int chunk4, const float *__restrict__
         st_stream_f4(o + (size_t)cc * mu + 4 * (size_t)g, make_float4(r[id.x], r[id.y], r[id.z], r[id.w]));
       }
     }
+    id = idn;
   }
 }
 

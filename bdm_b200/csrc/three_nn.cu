@@ -39,6 +39,7 @@ __device__ __forceinline__ void nn3_insert(float d, int k, float &b0, float &b1,
 // order, which preserves the reference's "earlier index first on equal distance" rule because split
 // s only holds indices smaller than split s+1.
 constexpr int kNnMaxSplits = 8;
+constexpr int kNnTile = 256;  // centres staged per warp at a time (3 KB)
 
 template <bool VEC4>
 __global__ void __launch_bounds__(32 * kNnMaxSplits)
@@ -64,29 +65,36 @@ three_nn_kernel(int n, int m, int splits, const float *__restrict__ points,
   const float inf = __int_as_float(0x7f800000);
   float b0 = inf, b1 = inf, b2 = inf;
   int i0 = 0, i1 = 0, i2 = 0;
-  int k = k0;
-  if (VEC4) {
-    for (; k + 4 <= k1; k += 4) {
-      const float4 X = __ldg(reinterpret_cast<const float4 *>(centers + k));
-      const float4 Y = __ldg(reinterpret_cast<const float4 *>(centers + m + k));
-      const float4 Z = __ldg(reinterpret_cast<const float4 *>(centers + 2 * (size_t)m + k));
+  // centres of this split are staged through a warp-private shared-memory tile: the loads of a tile are
+  // all in flight together, the scan then reads broadcast 128-bit values at shared-memory latency
+  __shared__ __align__(16) float s_tile[kNnMaxSplits][3 * kNnTile];
+  float *tile = s_tile[split];
+  for (int t0 = k0; t0 < k1; t0 += kNnTile) {
+    const int tn = min(kNnTile, k1 - t0);
+    __syncwarp();
+    warp_stage_xyz<kNnTile>(centers + t0, (size_t)m, tn, tile, lane, VEC4 && (tn & 3) == 0);
+    int q = 0;
+    for (; q + 4 <= tn; q += 4) {
+      const float4 X = *reinterpret_cast<const float4 *>(tile + q);
+      const float4 Y = *reinterpret_cast<const float4 *>(tile + kNnTile + q);
+      const float4 Z = *reinterpret_cast<const float4 *>(tile + 2 * kNnTile + q);
       const float d0 = sqdist_ref(__fsub_rn(ux, X.x), __fsub_rn(uy, Y.x), __fsub_rn(uz, Z.x));
       const float d1 = sqdist_ref(__fsub_rn(ux, X.y), __fsub_rn(uy, Y.y), __fsub_rn(uz, Z.y));
       const float d2 = sqdist_ref(__fsub_rn(ux, X.z), __fsub_rn(uy, Y.z), __fsub_rn(uz, Z.z));
       const float d3 = sqdist_ref(__fsub_rn(ux, X.w), __fsub_rn(uy, Y.w), __fsub_rn(uz, Z.w));
       // none of the four can enter the top-3 unless the smallest beats the current third best
       if (fminf(fminf(d0, d1), fminf(d2, d3)) < b2) {
+        const int k = t0 + q;
         nn3_insert(d0, k, b0, b1, b2, i0, i1, i2);
         nn3_insert(d1, k + 1, b0, b1, b2, i0, i1, i2);
         nn3_insert(d2, k + 2, b0, b1, b2, i0, i1, i2);
         nn3_insert(d3, k + 3, b0, b1, b2, i0, i1, i2);
       }
     }
-  }
-  for (; k < k1; ++k) {
-    const float d = sqdist_ref(__fsub_rn(ux, __ldg(centers + k)), __fsub_rn(uy, __ldg(centers + m + k)),
-                               __fsub_rn(uz, __ldg(centers + 2 * (size_t)m + k)));
-    nn3_insert(d, k, b0, b1, b2, i0, i1, i2);
+    for (; q < tn; ++q) {
+      const float d = sqdist_ref(__fsub_rn(ux, tile[q]), __fsub_rn(uy, tile[kNnTile + q]), __fsub_rn(uz, tile[2 * kNnTile + q]));
+      nn3_insert(d, t0 + q, b0, b1, b2, i0, i1, i2);
+    }
   }
 
   // merge the per-split top-3 lists (ascending split = ascending index, strict '<' keeps ties stable)

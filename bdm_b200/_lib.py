@@ -48,6 +48,7 @@ _PROTOS = {
     "bdm_groupnorm_workspace_bytes": (_z, [_i, _i, ctypes.c_longlong]),
     "bdm_groupnorm_tiles": (_i, [_i, _i, ctypes.c_longlong]),
     "bdm_groupnorm_act": (_i, [_i, _i, ctypes.c_longlong, _i, _f, _i, _i, _p, _p, _p, _p, _p, _p, _p, _z, _p]),
+    "bdm_surface_projection_cf": (_i, [_i, _i, _i, _i, _i, _f, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p]),
     "bdm_nn_f64": (_i, [_i, _i, _i, _i, _p, _p, _p, _p, _p]),
 }
 

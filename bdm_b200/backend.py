@@ -437,6 +437,27 @@ def surface_projection(points, R, T, focal, principal, feat, radius, feat_is_hwc
 
 
 @_op(1)
+@_op(5)
+def conditioning_input(points, R, T, focal, principal, feat_hwc, radius):
+    """Fused get_input_with_conditioning: points f32[B,N,3] + feat_hwc f32[B,H,W,C] -> channel-first denoiser
+    input f32[B,3+C,N] (channels 0-2 = the coordinates, 3.. = projected features), pix int32[B,N]."""
+    for x, nm in ((points, "points"), (R, "R"), (T, "T"), (focal, "focal"), (principal, "principal"),
+                  (feat_hwc, "feat_hwc")):
+        _chk_float(x, nm)
+    b, n = points.shape[0], points.shape[1]
+    H, W, C = feat_hwc.shape[1], feat_hwc.shape[2], feat_hwc.shape[3]
+    dev = points.device
+    zbuf = torch.empty((b, H, W), dtype=torch.int64, device=dev)
+    pix = torch.empty((b, n), dtype=_I32, device=dev)
+    out = torch.empty((b, 3 + C, n), dtype=_F32, device=dev)
+    out[:, :3, :].copy_(points.transpose(1, 2))
+    with _Launch(points) as st:
+        _check(_L.bdm_surface_projection_cf(b, n, C, H, W, float(radius), points.data_ptr(), R.data_ptr(),
+                                            T.data_ptr(), focal.data_ptr(), principal.data_ptr(), feat_hwc.data_ptr(),
+                                            zbuf.data_ptr(), pix.data_ptr(), out.data_ptr(), 3 + C, 3, st))
+    return out, pix
+
+
 def nn_f64(src, tgt, expanded=False, return_index=True):
     """src f64[B,N,3], tgt f64[B,M,3] -> (min squared distance f64[B,N], argmin int32[B,N] | None)"""
     for x, nm in ((src, "src"), (tgt, "tgt")):

@@ -116,6 +116,39 @@ __global__ void proj_gather_kernel(int n, int C, int HW, int feat_is_hwc, const 
   if (lane == 0 && !won) pix[(size_t)b * n + i] = -1;
 }
 
+// Channel-first variant for the fused conditioning input: out_cf[b, ch_off + ch, i].  A CTA transposes a
+// 32-point x 32-channel tile through shared memory: reads are channel-contiguous (HWC map), writes are
+// point-contiguous.
+__global__ void __launch_bounds__(256)
+proj_gather_cf_kernel(int n, int C, int HW, int c_total, int ch_off, const float *__restrict__ feat_hwc,
+                      int *__restrict__ pix, float *__restrict__ out_cf) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int pl = warp * 4 + r, i = p0 + pl, ch = c0 + lane;
+    float v = 0.0f;
+    if (i < n && ch < C) {
+      const int q = pix[(size_t)b * n + i];
+      if (q != 0x7fffffff && q >= 0) v = __ldg(feat_hwc + ((size_t)b * HW + q) * C + ch);
+    }
+    tile[pl][lane] = v;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int cl = warp * 4 + r, ch = c0 + cl, i = p0 + lane;
+    if (i < n && ch < C) out_cf[((size_t)b * c_total + ch_off + ch) * n + i] = tile[lane][cl];
+  }
+}
+
+__global__ void proj_finalize_pix_kernel(size_t npts, int *__restrict__ pix) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < npts && pix[i] == 0x7fffffff) pix[i] = -1;
+}
+
 }  // namespace bdm
 
 static int bdm_surface_projection_impl(int b, int n, int C, int H, int W, float radius,
@@ -139,6 +172,35 @@ static int bdm_surface_projection_impl(int b, int n, int C, int H, int W, float 
                                                               zbuf);
   proj_resolve_kernel<<<dim3(ceil_div(HW, 256), b), 256, 0, st>>>(n, HW, zbuf, pix);
   proj_gather_kernel<<<dim3(ceil_div(n, 8), b), 256, 0, st>>>(n, C, HW, feat_is_hwc, feat, pix, out);
+  BDM_RETURN_LAUNCH_STATUS();
+}
+
+// Fused conditioning input: writes the projected features straight into channels [ch_off, ch_off+C) of a
+// channel-first tensor out_cf f32[b, c_total, n] (what the denoiser consumes), skipping the
+// [b,n,C] intermediate, the concat and the transpose of get_input_with_conditioning
+// (projection_model.py:179-231 + point_cloud_model.py:65).  feat_hwc f32[b,H,W,C].
+extern "C" int bdm_surface_projection_cf(int b, int n, int C, int H, int W, float radius, const float *points,
+                                         const float *R, const float *T, const float *focal,
+                                         const float *principal, const float *feat_hwc,
+                                         unsigned long long *zbuf, int *pix, float *out_cf, int c_total,
+                                         int ch_off, bdm_stream_t stream) {
+  using namespace bdm;
+  BDM_CHECK_SIZE(b >= 0 && n >= 0 && C >= 0 && H >= 1 && W >= 1 && b <= 65535 && ch_off >= 0 && ch_off + C <= c_total);
+  BDM_CHECK_SIZE((long long)H * W <= 0x7fffffffLL);
+  if (b == 0 || n == 0) return BDM_OK;
+  BDM_CHECK_PTR(points); BDM_CHECK_PTR(R); BDM_CHECK_PTR(T); BDM_CHECK_PTR(focal); BDM_CHECK_PTR(principal);
+  BDM_CHECK_PTR(zbuf); BDM_CHECK_PTR(pix);
+  if (C > 0) { BDM_CHECK_PTR(feat_hwc); BDM_CHECK_PTR(out_cf); }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int HW = H * W;
+  const size_t npix = (size_t)b * HW, npts = (size_t)b * n;
+  const size_t ninit = npix > npts ? npix : npts;
+  proj_init_kernel<<<(unsigned)((ninit + 255) / 256), 256, 0, st>>>(zbuf, npix, pix, npts);
+  proj_splat_kernel<<<dim3(ceil_div(n, 128), b), 128, 0, st>>>(n, H, W, radius, points, R, T, focal, principal, zbuf);
+  proj_resolve_kernel<<<dim3(ceil_div(HW, 256), b), 256, 0, st>>>(n, HW, zbuf, pix);
+  if (C > 0)
+    proj_gather_cf_kernel<<<dim3(ceil_div(n, 32), ceil_div(C, 32), b), 256, 0, st>>>(n, C, HW, c_total, ch_off, feat_hwc, pix, out_cf);
+  proj_finalize_pix_kernel<<<(unsigned)((npts + 255) / 256), 256, 0, st>>>(npts, pix);
   BDM_RETURN_LAUNCH_STATUS();
 }
 

@@ -257,7 +257,7 @@ class PVCNN2(nn.Module):
             if cache is not None:
                 plan_geometry_ahead(cache, self.sa_layers, self.fp_layers, coords)
             features, coords, temb, coords_per_stage, feats_per_stage = _encode(self.sa_layers, inputs, coords, temb)
-            feats_per_stage[0] = inputs[:, 3:, :].contiguous()
+            feats_per_stage[0] = inputs[:, 3:, :]   # a view: the FP stage's torch.cat copies it anyway
             if self.global_att is not None:
                 features = self.global_att(features)
             features = _decode(self.fp_layers, features, coords, temb, coords_per_stage, feats_per_stage)
@@ -293,6 +293,10 @@ class PointCloudModel(nn.Module):
 
     def forward(self, inputs, t):
         return self.model(inputs.transpose(1, 2), t).transpose(1, 2)
+
+    def forward_channel_first(self, inputs_cf, t):
+        """inputs already (B,C,N) (ProjectionConditioner.get_input_channel_first) -> (B,N,out_channels)"""
+        return self.model(inputs_cf, t).transpose(1, 2)
 
 
 class PVCNNFuse(nn.Module):

@@ -132,21 +132,27 @@ class BDMSampler:
         import torch
         b = x_example.shape[0]
         tt = torch.full((b,), 500, device=x_example.device, dtype=torch.long)
-        self._graphs[("pc2", tuple(x_example.shape))] = GraphedStep(
-            lambda x, t: self.pc2_net(self.cond.get_input_with_conditioning(x), t), x_example, tt)
+        self._graphs[("pc2", tuple(x_example.shape))] = GraphedStep(self._pc2_eps, x_example, tt)
         if self.pvd_net is not None:
             x_cf = x_example.permute(0, 2, 1).contiguous()
             self._graphs[("pvd", tuple(x_cf.shape))] = GraphedStep(lambda x, t: self.pvd_net(x, t), x_cf, tt)
+
+    def _pc2_eps(self, x_t, tt):
+        """noise prediction of the PC^2 branch: conditioning + denoiser.  With a channel-last feature map
+        and a CUDA conditioner the projected features are written directly in the denoiser's
+        channel-first layout (one pass instead of gather + concat + transpose)."""
+        fused = getattr(self.cond, "channel_last", False) and hasattr(self.cond, "get_input_channel_first") \
+            and hasattr(self.pc2_net, "forward_channel_first") and x_t.is_cuda
+        if fused:
+            return self.pc2_net.forward_channel_first(self.cond.get_input_channel_first(x_t), tt)
+        return self.pc2_net(self.cond.get_input_with_conditioning(x_t), tt)
 
     # -- one denoising step of each kind ---------------------------------------------------------
     def pc2_step(self, x_t, t):
         b = x_t.shape[0]
         tt = torch.full((b,), int(t), device=x_t.device, dtype=torch.long)
         graphed = self._graphs.get(("pc2", tuple(x_t.shape)))
-        if graphed is not None:
-            eps = graphed(x_t, tt)
-        else:
-            eps = self.pc2_net(self.cond.get_input_with_conditioning(x_t), tt)
+        eps = graphed(x_t, tt) if graphed is not None else self._pc2_eps(x_t, tt)
         self.forwards['pc2'] += 1
         return self.ddpm.step(eps, t, x_t, self.gen)
 

@@ -85,6 +85,17 @@ class ProjectionConditioner:
         return torch.cat([x_t, self.surface_projection(x_t[:, :, :3])], dim=2)
 
 
+def _channel_first_input(self, x_t):
+    """x_t f32[B,N,3] -> f32[B,3+C,N], the denoiser's channel-first input, in one pass (no [B,N,C]
+    intermediate, no concat, no transpose).  Same values as get_input_with_conditioning(x_t).transpose(1,2)."""
+    cam = self.cameras
+    out, _ = _backend.conditioning_input(x_t.contiguous(), cam.R, cam.T, cam.focal, cam.principal, self.feat, self.radius)
+    return out
+
+
+ProjectionConditioner.get_input_channel_first = _channel_first_input
+
+
 def surface_projection(points, cameras, local_features, radius=0.0075, scale_factor=1.0):
     """Functional form with the reference's argument meaning (projection_model.py:127-157)."""
     return ProjectionConditioner(local_features, cameras, radius, scale_factor, channel_last=False) \

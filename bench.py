@@ -204,6 +204,8 @@ def run_ours(args):
         raise SystemExit("bench.py (impl=ours) needs a CUDA device: bdm_b200 has no CPU fallback")
     torch.cuda.set_device(local)
     device = f"cuda:{local}"
+    if args.cudnn_benchmark:
+        torch.backends.cudnn.benchmark = True
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(device))
     B = args.batch
@@ -437,6 +439,7 @@ def main():
     ap.add_argument("--no-ref-cuda", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of one CUDA graph per step")
     ap.add_argument("--no-plan-ahead", action="store_true", help="keep the coordinate-only ops inline on one stream")
+    ap.add_argument("--cudnn-benchmark", action="store_true", help="torch.backends.cudnn.benchmark = True (experiment)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

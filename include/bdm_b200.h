@@ -159,6 +159,15 @@ int bdm_surface_projection_hwc(int b, int n, int C, int H, int W, float radius, 
                                const float *principal, const float *feat_hwc,
                                unsigned long long *zbuf, int *pix, float *out, bdm_stream_t stream);
 
+/* fused conditioning input: the projected features go straight into channels
+ * [ch_off, ch_off+C) of the channel-first tensor out_cf f32[b,c_total,n] that the denoiser consumes,
+ * skipping the [b,n,C] intermediate, the concat and the transpose of get_input_with_conditioning
+ * (projection_model.py:179-231, point_cloud_model.py:65). */
+int bdm_surface_projection_cf(int b, int n, int C, int H, int W, float radius, const float *points,
+                              const float *R, const float *T, const float *focal,
+                              const float *principal, const float *feat_hwc, unsigned long long *zbuf,
+                              int *pix, float *out_cf, int c_total, int ch_off, bdm_stream_t stream);
+
 /* ---- evaluation nearest neighbour (fp64) ----------------------------------------------------------
  * replaces pytorch3d knn (K=1) inside chamfer_distance (experiments/evaluation/evaluation_cd.py:125)
  * and compute_pc_to_pc_dist (experiments/evaluation/evaluation_f1.py:90-98).

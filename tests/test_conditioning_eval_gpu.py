@@ -153,3 +153,20 @@ def test_plan_ahead_and_graph_replay_are_bit_identical(cuda_backend):
     torch.cuda.synchronize()
     assert torch.equal(y_ahead, y_inline)
     assert torch.equal(y_ahead, y_graph) and torch.equal(y_graph, y_graph2)
+
+
+def test_fused_conditioning_input_matches_unfused(cuda_backend):
+    """one-pass channel-first conditioning input == gather + concat + transpose (bit-identical copies)"""
+    import torch
+
+    from bdm_b200.projection import ProjectionConditioner
+    torch.manual_seed(4)
+    b, n, C, H = 3, 1000, 37, 64
+    x = torch.randn(b, n, 3, device="cuda") * 0.3
+    feats = torch.randn(b, C, H, H, device="cuda")
+    cond = ProjectionConditioner(feats, _cams(b, 9).to("cuda"), radius=0.03)
+    want = cond.get_input_with_conditioning(x).transpose(1, 2)
+    got = cond.get_input_channel_first(x)
+    assert got.shape == (b, 3 + C, n) and got.is_contiguous()
+    assert torch.equal(got, want)
+    assert (got[:, 3:].abs().sum(dim=1) > 0).any() and (got[:, 3:].abs().sum(dim=1) == 0).any()

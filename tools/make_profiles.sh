@@ -3,9 +3,17 @@
 mkdir -p gpurun_out/prof
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/prof/step_launches.csv \
     python tools/step_launches.py > /dev/null 2>&1
+python tools/op_bench.py --iters 10 > gpurun_out/prof/op_bench.log 2>&1; cp gpurun_out/op_bench.json gpurun_out/prof/op_bench.json
 for op in voxelize devoxelize fps ball_query three_nn grouping; do
   ncu --set full --clock-control none --import-source on \
-      -k regex:"vox_fill|vox_sort|devox_|fps_register|ball_query_kernel|three_nn_kernel|three_interp|grouping_" \
+      -k regex:"vox_fill|vox_sort|devox_|fps_register|ball_query_kernel|three_nn_kernel|three_interp|grouping_|gn_" \
       -c 6 -o gpurun_out/prof/ncu_$op -f python tools/run_op.py $op --reps 2 > /dev/null 2>&1
 done
+ncu --set full --clock-control none --import-source on -k regex:"gn_stats|gn_apply" -c 2 -o gpurun_out/prof/ncu_groupnorm -f python -c "
+import torch, sys
+sys.path.insert(0, '.')
+from bdm_b200 import backend as B
+x = torch.randn(16, 64, 32768, device='cuda'); w = torch.randn(64, device='cuda'); b = torch.randn(64, device='cuda')
+for _ in range(2): B.groupnorm_act(x, 8, w, b, 1e-5, True, conv_bias=b)
+torch.cuda.synchronize()" > /dev/null 2>&1
 ls -la gpurun_out/prof

@@ -90,7 +90,7 @@ class ClockSampler:
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -282,10 +282,10 @@ def run_ours(args):
     # ---- timed region 1: resident inputs (value) with clocks sampled and per-op events recorded ----
     with ClockSampler(local) as clocks:
         ms_step = timed(step_resident, args.steps, final_gather=True)
-    launches = launches_per_step * args.steps   # replayed from the graph: same kernels every step
+        launches = launches_per_step * args.steps   # replayed from the graph: same kernels every step
 
-    # ---- timed region 2: host buffers through the public API (e2e) ----
-    ms_e2e = timed(step_e2e, args.steps)
+        # ---- timed region 2: host buffers through the public API (e2e) ----
+        ms_e2e = timed(step_e2e, args.steps)
 
     shapes_total = B * world
     value = shapes_total / (STEPS_PER_SHAPE * ms_step * 1e-3)

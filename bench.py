@@ -190,6 +190,55 @@ def run_reference_arm(args):
 
 
 # ---------------------------------------------------------------------------------------------------
+# one complete sampling job (BASELINE configs[2..4]): every rank samples its shard, then one all-gather of
+# the clouds and one all-reduce of the metric partials
+# ---------------------------------------------------------------------------------------------------
+def run_full_sampling(args, device, world, rank, barrier):
+    import numpy as np
+    import torch
+    from bdm_b200 import distributed as D
+    from bdm_b200 import evaluation as E
+    from bdm_b200.denoiser import PVCNN2_PVD, PVCNNFuse
+    from bdm_b200.diffusion import forward_counts
+    from tests.cases import cloud
+    mode, Bf = args.full_sampling, args.full_batch
+    x0, feats, cams = make_inputs(Bf, D.rank_seed(args.seed + 7, rank), device)
+    sampler = build_sampler(x0, feats, cams, device)
+    if mode != "vanilla":
+        torch.manual_seed(43)
+        sampler.pvd_net = PVCNN2_PVD(3, 64, True, 0.1, extra_feature_channels=0).to(device).eval()
+    if mode == "merging":
+        sampler.fuse_net = PVCNNFuse(sampler.pvd_net, sampler.pc2_net.model, extra_feature_channels=C_IMG).to(device).eval()
+    sampler.enable_cuda_graphs(x0)
+    mask_gen = torch.Generator().manual_seed(D.rank_seed(args.seed, rank))
+    barrier()
+    t0 = time.perf_counter()
+    if mode == "vanilla":
+        x = sampler.sample_vanilla(Bf, N_POINTS, device)
+    elif mode == "blending":
+        x = sampler.sample_blending(Bf, N_POINTS, device, mask_generator=mask_gen)
+    else:
+        x = sampler.sample_merging(Bf, N_POINTS, device)
+    total = Bf * world
+    clouds = D.gather_samples(x.contiguous(), total)
+    gt = torch.as_tensor(cloud(np.random.default_rng(2003 + rank), Bf, N_POINTS, "shape")).permute(0, 2, 1).to(device)
+    cd, f1 = E.evaluate(x, gt)
+    mean_cd, mean_f1, count = D.reduce_metrics(cd, f1)
+    barrier()
+    secs = torch.tensor([time.perf_counter() - t0], device=device, dtype=torch.float64)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(secs, op=dist.ReduceOp.MAX)
+    secs = float(secs.item())
+    return {"mode": mode, "schedule": "roll_step=16, milestones=[1000,968,936,872,128,64,32,0]" if mode != "vanilla" else "1000 DDPM steps",
+            "shapes_per_gpu": Bf, "shapes": total, "seconds": secs, "shapes_per_s": total / secs,
+            "forwards_per_shape": sampler.forwards, "expected_forwards": forward_counts(mode=mode) if mode != "vanilla" else {"pc2": 1000, "pvd": 0, "fuse": 0},
+            "gathered": list(clouds.shape), "finite": bool(torch.isfinite(clouds).all()),
+            "mean_cd_x1e3_vs_synthetic_gt": mean_cd, "mean_fscore_vs_synthetic_gt": mean_f1, "evaluated": count,
+            "note": "random-init weights: the metrics only exercise the evaluation path"}
+
+
+# ---------------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------------
 def run_ours(args):
@@ -287,6 +336,10 @@ def run_ours(args):
         # ---- timed region 2: host buffers through the public API (e2e) ----
         ms_e2e = timed(step_e2e, args.steps)
 
+    full = None
+    if args.full_sampling:
+        full = run_full_sampling(args, device, world, rank, barrier)
+
     shapes_total = B * world
     value = shapes_total / (STEPS_PER_SHAPE * ms_step * 1e-3)
     e2e_value = shapes_total / (STEPS_PER_SHAPE * ms_e2e * 1e-3)
@@ -343,6 +396,9 @@ def run_ours(args):
                         "share_of_step": sum(sparse_ms.values()) / ms_eager,
                         "note": "per-op CUDA events on eager launches, host gaps inside an op included"},
     }
+
+    if full is not None:
+        line["full_sampling"] = full
 
     # ---- reference CUDA kernels (recompiled for sm_100a) under the reference's call pattern ----
     if world == 1 and not args.no_ref_cuda:
@@ -440,6 +496,10 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of one CUDA graph per step")
     ap.add_argument("--no-plan-ahead", action="store_true", help="keep the coordinate-only ops inline on one stream")
     ap.add_argument("--cudnn-benchmark", action="store_true", help="torch.backends.cudnn.benchmark = True (experiment)")
+    ap.add_argument("--full-sampling", default=None, choices=["vanilla", "blending", "merging"],
+                    help="additionally run ONE complete 1000-step sampling of --full-batch shapes per GPU with the "
+                         "shipped schedule (BASELINE configs[2..4]) and report it under 'full_sampling'")
+    ap.add_argument("--full-batch", type=int, default=32, help="shapes per GPU for --full-sampling (config[4]: 32)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -156,6 +156,43 @@ def avg_voxelize_fill(features, plan):
     return out
 
 
+@_op(1)
+def avg_voxelize_compact(features, plan):
+    """features f32[B,C,N] + VoxelPlan -> f32[B,C,N]: column j = average of the j-th occupied voxel
+    (ascending voxel id), zero past the shape's occupied count."""
+    _chk_float(features, "features")
+    b, c, n = features.shape
+    _req(b == plan.b and n == plan.n, "features do not match the voxel plan")
+    out = torch.empty((b, c, n), dtype=_F32, device=features.device)
+    with _Launch(features) as st:
+        _check(_L.bdm_avg_voxelize_compact(b, c, n, plan.r, features.data_ptr(), out.data_ptr(),
+                                           plan.workspace.data_ptr(), plan.workspace.numel(), st))
+    return out
+
+
+@_op(1)
+def sparse_conv3_gather(taps, plan, bias=None):
+    """taps f32[B,N,27*Cout] (per-occupied-voxel tap products) + VoxelPlan -> the dense output
+    f32[B,Cout,R,R,R] of the zero-padded 3x3x3 convolution."""
+    _chk_float(taps, "taps")
+    b, n, k = taps.shape
+    _req(b == plan.b and n == plan.n and k % 27 == 0, "taps do not match the voxel plan")
+    cout, r = k // 27, plan.r
+    if bias is not None:
+        _chk_float(bias, "bias")
+        _req(bias.numel() == cout, "bias must hold one value per output channel")
+    out = torch.empty((b, cout, r, r, r), dtype=_F32, device=taps.device)
+    with _Launch(taps) as st:
+        _check(_L.bdm_sparse_conv3_gather(b, cout, n, r, taps.data_ptr(), bias.data_ptr() if bias is not None else None,
+                                          out.data_ptr(), plan.workspace.data_ptr(), plan.workspace.numel(), st))
+    return out
+
+
+def sparse_conv3_supported(n, resolution):
+    r = int(resolution)
+    return 1 <= r <= 32 and (r & (r - 1)) == 0 and 1 <= n <= 16384
+
+
 def avg_voxelize_forward(features, coords, resolution):
     _chk_float(features, "features")
     _chk_int(coords, "coords")

@@ -1,0 +1,161 @@
+// sparse_conv.cu -- the first 3x3x3 convolution of a PVConv block, exploiting that its input is a
+// freshly voxelized point cloud.
+//
+// The reference materialises avg_voxelize's dense grid and runs nn.Conv3d over it
+// (experiments/model/pvcnn/modules/pvconv.py:75-76,91-97: `voxel_features, voxel_coords =
+// self.voxelization(features, coords); voxel_features = self.voxel_layers(voxel_features)`).  At R=32 a
+// 4096-point cloud occupies ~5 % of the 32768 voxels, so 95 % of that convolution's multiply-adds have a
+// zero operand and the 818 MB grid of the first PC^2 layer (C=390) is written, transposed and read only
+// to carry ~1800 non-zero columns per shape.  Convolution is linear, so the same result is
+//
+//     taps[b][j][k][co] = sum_ci W[co][ci][k] * avg[b][ci][j]        j-th occupied voxel, k = (kd*3+kh)*3+kw
+//     out[b][co][v]     = sum_k taps[b][slot(v + k - 1)][k][co]      over the occupied neighbours of v
+//
+// i.e. one GEMM over the occupied voxels only (cuBLAS, issued by the host side on the output of
+// bdm_avg_voxelize_compact) followed by the gather below, which is the only pass that touches a dense
+// grid -- the convolution's OUTPUT, written once.  Taps are accumulated in ascending k for every output
+// voxel (deterministic).
+//
+// Kernel: one warp per z-row (x,y) of the output and 32 output channels.  It lists the occupied voxels of
+// the 9 neighbouring rows (occupancy bits + popcount ranks, no search); an occupied neighbour (x',y',z')
+// contributes its three kw taps -- 3 x 32 contiguous floats, lane-coalesced, four neighbours in flight at a
+// time -- to outputs z'+1, z', z'-1 of a [32 z][32 co] tile in shared memory, which is then written
+// transposed as 128-byte row segments.
+#include "common.cuh"
+#include "voxel_plan.cuh"
+
+namespace bdm {
+
+constexpr int kGatherWarps = 8;
+constexpr int kGatherCo = 32;
+constexpr int kGatherBatch = 4;   // occupied neighbours whose taps are in flight together (3 loads each)
+
+__global__ void __launch_bounds__(kGatherWarps * 32)
+sparse_conv3_gather_kernel(int n, int cout, int r, const float *__restrict__ taps,
+                           const float *__restrict__ bias, float *__restrict__ out,
+                           const unsigned char *__restrict__ ws, VoxAuxLayout L) {
+  __shared__ float tile[kGatherWarps][32][kGatherCo + 1];
+  __shared__ uint32_t entries[kGatherWarps][9 * 32];   // slot | z' << 16 | neighbour row << 24
+  const int b = blockIdx.z, co0 = blockIdx.y * kGatherCo;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * kGatherWarps + warp;  // x * r + y
+  if (row >= r * r) return;
+  const int x = row / r, y = row - x * r;
+  const int r3 = r * r * r;
+
+  ws += (size_t)b * L.stride;
+  const uint32_t *bitmask = reinterpret_cast<const uint32_t *>(ws + L.bitmask);
+  const uint16_t *obase = reinterpret_cast<const uint16_t *>(ws + L.obase);
+  const uint32_t rowmask = r >= 32 ? 0xffffffffu : ((1u << r) - 1u);
+
+  // lane j < 9 fetches the occupancy bits of neighbouring row j = (dx+1)*3 + (dy+1) and the occupied
+  // rank of that row's first voxel: one round of loads for the whole neighbourhood
+  uint32_t my_bits = 0u;
+  int my_slot = 0;
+  if (lane < 9) {
+    const int xx = x + lane / 3 - 1, yy = y + lane % 3 - 1;
+    if (xx >= 0 && xx < r && yy >= 0 && yy < r) {
+      const int bit0 = (xx * r + yy) * r;
+      const uint32_t word = __ldg(bitmask + (bit0 >> 5));
+      const int sh = bit0 & 31;
+      my_bits = (word >> sh) & rowmask;
+      my_slot = (int)__ldg(obase + (bit0 >> 5)) + __popc(word & ((1u << sh) - 1u));
+    }
+  }
+
+  float(*t)[kGatherCo + 1] = tile[warp];
+#pragma unroll
+  for (int z = 0; z < 32; ++z) t[z][lane] = 0.0f;
+
+  // the occupied neighbours as a list, row-major then z ascending (= tap index k ascending for every
+  // output voxel): lane z appends its own voxel of each row
+  uint32_t *ent = entries[warp];
+  int total = 0;
+  const uint32_t below = (1u << lane) - 1u;
+#pragma unroll
+  for (int j = 0; j < 9; ++j) {
+    const uint32_t bits = __shfl_sync(0xffffffffu, my_bits, j);
+    const int slot0 = __shfl_sync(0xffffffffu, my_slot, j);
+    if ((bits >> lane) & 1u) {
+      const int before = __popc(bits & below);
+      ent[total + before] = (uint32_t)(slot0 + before) | ((uint32_t)lane << 16) | ((uint32_t)j << 24);
+    }
+    total += __popc(bits);
+  }
+  __syncwarp();
+
+  const bool co_ok = co0 + lane < cout;
+  const float *tp = taps + (size_t)b * n * 27 * cout + co0 + lane;
+  for (int e0 = 0; e0 < total; e0 += kGatherBatch) {
+    uint32_t en[kGatherBatch];
+    float a[kGatherBatch][3];
+#pragma unroll
+    for (int u = 0; u < kGatherBatch; ++u) {
+      en[u] = e0 + u < total ? ent[e0 + u] : 0xffffffffu;
+      a[u][0] = a[u][1] = a[u][2] = 0.0f;
+      if (en[u] != 0xffffffffu && co_ok) {
+        const float *q = tp + ((size_t)(en[u] & 0xffffu) * 27 + (en[u] >> 24) * 3) * cout;
+        a[u][0] = __ldg(q);
+        a[u][1] = __ldg(q + cout);
+        a[u][2] = __ldg(q + 2 * cout);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kGatherBatch; ++u) {
+      if (en[u] != 0xffffffffu) {
+        const int zp = (en[u] >> 16) & 31;
+        // input z' = z + kw - 1  =>  tap kw lands on output z = z' + 1 - kw
+        if (zp + 1 < r) t[zp + 1][lane] += a[u][0];
+        t[zp][lane] += a[u][1];
+        if (zp >= 1) t[zp - 1][lane] += a[u][2];
+      }
+    }
+  }
+  __syncwarp();
+
+  // transposed write-out, one 4r-byte row segment per output channel
+  const int nco = min(kGatherCo, cout - co0);
+  float *orow = out + ((size_t)b * cout + co0) * r3 + (size_t)row * r;
+  if (r == 32 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+    // 8 lanes x 16 bytes cover a row; the 4 lane groups take 4 channels per store instruction
+    const int z4 = (lane & 7) * 4, cs = lane >> 3;
+    for (int co = cs; co < nco; co += 4) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (total != 0) v = make_float4(t[z4][co], t[z4 + 1][co], t[z4 + 2][co], t[z4 + 3][co]);
+      if (bias) {
+        const float bb = __ldg(bias + co0 + co);
+        v.x += bb; v.y += bb; v.z += bb; v.w += bb;
+      }
+      *reinterpret_cast<float4 *>(orow + (size_t)co * r3 + z4) = v;
+    }
+  } else if (lane < r) {
+    float *o = orow + lane;
+    for (int co = 0; co < nco; ++co) {
+      const float v = total != 0 ? t[lane][co] : 0.0f;
+      o[(size_t)co * r3] = bias ? v + __ldg(bias + co0 + co) : v;
+    }
+  }
+}
+
+}  // namespace bdm
+
+// taps f32[b][n][27][cout] (row j = the j-th occupied voxel of shape b in ascending voxel id, as produced
+// from bdm_avg_voxelize_compact; rows >= the shape's occupied count are ignored), bias f32[cout] or NULL,
+// out f32[b][cout][r^3].  workspace = the plan bdm_voxel_plan left for these (b, n, r).  r in {1,2,4,8,16,32}.
+extern "C" int bdm_sparse_conv3_gather(int b, int cout, int n, int r, const float *taps, const float *bias,
+                                       float *out, const void *workspace, size_t workspace_bytes,
+                                       bdm_stream_t stream) {
+  using namespace bdm;
+  BDM_CHECK_SIZE(b >= 0 && cout >= 0 && n >= 1 && r >= 1 && r <= 32 && (r & (r - 1)) == 0);  // rows within a word
+  const int r3 = r * r * r;
+  BDM_CHECK_SIZE(vox_fast_path(n, r3));
+  if (b == 0 || cout == 0) return BDM_OK;
+  BDM_CHECK_PTR(taps); BDM_CHECK_PTR(out);
+  const VoxAuxLayout L = vox_aux_layout(n, r3);
+  const int rc = check_workspace(L, b, workspace, workspace_bytes);
+  if (rc != BDM_OK) return rc;
+  dim3 grid(ceil_div(r * r, kGatherWarps), ceil_div(cout, kGatherCo), b);
+  sparse_conv3_gather_kernel<<<grid, kGatherWarps * 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      n, cout, r, taps, bias, out, static_cast<const unsigned char *>(workspace), L);
+  BDM_RETURN_LAUNCH_STATUS();
+}

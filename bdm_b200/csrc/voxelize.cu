@@ -31,37 +31,12 @@
 // Sizes outside the shared-memory fast path (R^3 > 32768 or N > 16384) take a generic path with
 // global atomics (memset + stats + scatter): still CUDA, still on the caller's stream.
 #include "common.cuh"
+#include "voxel_plan.cuh"
 
 namespace bdm {
 
 constexpr int kSortThreads = 1024;
 constexpr int kFillThreads = 512;
-constexpr int kFastMaxR3 = 32768;
-constexpr int kFastMaxN = 16384;
-
-struct VoxAuxLayout {
-  size_t header;   // u32[4]: [0] = number of occupied voxels
-  size_t bitmask;  // u32[nw]
-  size_t obase;    // u16[nw]
-  size_t ostart;   // u16[n+1]
-  size_t rank;     // u16[n]
-  size_t stride;   // bytes per shape
-  int nw;
-};
-
-__host__ __device__ inline VoxAuxLayout vox_aux_layout(int n, int r3) {
-  VoxAuxLayout L;
-  L.nw = (r3 + 31) / 32;
-  size_t off = 0;
-  L.header = off;  off += 16;
-  L.bitmask = off; off = align_up(off + sizeof(uint32_t) * L.nw, 16);
-  L.obase = off;   off = align_up(off + sizeof(uint16_t) * L.nw, 16);
-  L.ostart = off;  off = align_up(off + sizeof(uint16_t) * (n + 1), 16);
-  L.rank = off;    off = align_up(off + sizeof(uint16_t) * n, 16);
-  L.stride = off;
-  return L;
-}
-
 // ------------------------------------------------------------------------------------------------
 // 1. per-shape index / histogram / counting sort
 // ------------------------------------------------------------------------------------------------
@@ -214,7 +189,7 @@ vox_sort_kernel(int n, int r, const int *__restrict__ coords, int *__restrict__ 
 // ------------------------------------------------------------------------------------------------
 // 2. dense fill: one CTA per (shape, CT channels)
 // ------------------------------------------------------------------------------------------------
-template <int CT, int VEC>
+template <int CT, int VEC, bool COMPACT = false>
 __global__ void __launch_bounds__(kFillThreads)
 vox_fill_kernel(int c, int n, int r3, const float *__restrict__ feat, float *__restrict__ out,
                 const unsigned char *__restrict__ ws, VoxAuxLayout L) {
@@ -295,6 +270,18 @@ vox_fill_kernel(int c, int n, int r3, const float *__restrict__ feat, float *__r
     }
   }
   __syncthreads();
+
+  if constexpr (COMPACT) {
+    // (c') sparse consumers (sparse_conv.cu) want only the occupied voxels: out[b][c][j] = average of the
+    // j-th occupied voxel (ascending voxel id), zero-padded to n columns so the shape is static
+    float *o = out + ((size_t)b * c + c0) * n;
+    for (int j = tid; j < n; j += kFillThreads) {
+#pragma unroll
+      for (int cc = 0; cc < CT; ++cc)
+        if (c0 + cc < c) o[(size_t)cc * n + j] = j < nocc ? buf[cc * n + j] : 0.0f;
+    }
+    return;
+  }
 
   // (c) stream the dense grid
   float *o = out + ((size_t)b * c + c0) * r3;
@@ -381,26 +368,18 @@ __global__ void vox_grad_kernel(int c, int n, int s, const int *__restrict__ ind
 }
 
 
-static bool vox_fast_path(int n, int r3) { return r3 <= kFastMaxR3 && n <= kFastMaxN && n >= 1; }
 
-template <int CT, int VEC>
+template <int CT, int VEC, bool COMPACT = false>
 static cudaError_t launch_fill(int b, int c, int n, int r3, const float *feat, float *out,
                                const unsigned char *ws, const VoxAuxLayout &L, cudaStream_t st) {
   const size_t smem = sizeof(float) * (size_t)CT * n + sizeof(uint32_t) * L.nw +
                       sizeof(uint16_t) * ((L.nw + 1) & ~1);
-  auto kern = vox_fill_kernel<CT, VEC>;
+  auto kern = vox_fill_kernel<CT, VEC, COMPACT>;
   cudaError_t e0 = ensure_dynamic_smem(reinterpret_cast<const void *>(kern), smem);
   if (e0 != cudaSuccess) return e0;
   dim3 grid(ceil_div(c, CT), b);
   kern<<<grid, kFillThreads, smem, st>>>(c, n, r3, feat, out, ws, L);
   return cudaGetLastError();
-}
-
-static int check_workspace(const VoxAuxLayout &L, int b, const void *workspace, size_t workspace_bytes) {
-  if (workspace == nullptr) return BDM_ERR_NULL_POINTER;
-  if (workspace_bytes < L.stride * (size_t)b) return BDM_ERR_WORKSPACE_TOO_SMALL;
-  if ((reinterpret_cast<uintptr_t>(workspace) & 15) != 0) return BDM_ERR_MISALIGNED;
-  return BDM_OK;
 }
 
 }  // namespace bdm
@@ -493,6 +472,35 @@ extern "C" int bdm_avg_voxelize_fill(int b, int c, int n, int r, const int *ind,
   cudaMemsetAsync(out, 0, sizeof(float) * (size_t)b * c * r3, st);
   vox_scatter_generic_kernel<<<dim3(ceil_div(n, 256), ceil_div(c, 8), b), 256, 0, st>>>(c, n, r3, ind, cnt, feat, out);
   BDM_RETURN_LAUNCH_STATUS();
+}
+
+// Step 2', sparse flavour: only the occupied voxels' averages, out[b][c][j] for the j-th occupied voxel of
+// shape b in ascending voxel id, columns nocc(b)..n-1 zero.  Same arithmetic as the dense fill (the values
+// are the dense grid's non-empty entries, bit for bit).  Needs the sorted plan (fast path sizes only).
+extern "C" int bdm_avg_voxelize_compact(int b, int c, int n, int r, const float *feat, float *out,
+                                        const void *workspace, size_t workspace_bytes, bdm_stream_t stream) {
+  using namespace bdm;
+  BDM_CHECK_SIZE(b >= 0 && c >= 0 && n >= 1 && r >= 1);
+  const long long r3ll = (long long)r * r * r;
+  BDM_CHECK_SIZE(r3ll <= kFastMaxR3 && vox_fast_path(n, (int)r3ll));
+  const int r3 = (int)r3ll;
+  if (b == 0 || c == 0) return BDM_OK;
+  BDM_CHECK_PTR(feat); BDM_CHECK_PTR(out);
+  const VoxAuxLayout L = vox_aux_layout(n, r3);
+  const int rc = check_workspace(L, b, workspace, workspace_bytes);
+  if (rc != BDM_OK) return rc;
+  const unsigned char *ws = static_cast<const unsigned char *>(workspace);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int want = 2 * sm_count();
+  int ct = 4;
+  if (b * ceil_div(c, 4) < want) ct = 2;
+  if (b * ceil_div(c, 2) < want) ct = 1;
+  if (sizeof(float) * (size_t)ct * n > 160 * 1024) ct = (n > 8192) ? 1 : 2;
+  cudaError_t e;
+  if (ct == 4) e = launch_fill<4, 4, true>(b, c, n, r3, feat, out, ws, L, st);
+  else if (ct == 2) e = launch_fill<2, 4, true>(b, c, n, r3, feat, out, ws, L, st);
+  else e = launch_fill<1, 4, true>(b, c, n, r3, feat, out, ws, L, st);
+  return e == cudaSuccess ? BDM_OK : (int)e;
 }
 
 extern "C" int bdm_avg_voxelize(int b, int c, int n, int r, const int *coords, const float *feat,

@@ -47,20 +47,23 @@ class FusedSequential(nn.Sequential):
     statistics), norm + activation are one pass, the SE squeeze comes out of that same pass and a
     trailing max over neighbours replaces the full-size write.  Anything else runs module by module."""
 
-    def forward(self, x, max_over_last=False):
+    def forward(self, x, max_over_last=False, first_output=None):
+        """first_output: the bias-less output of self[0] (a conv) when the caller computed it by other
+        means (PVConv's sparse first convolution); `x` is then ignored."""
         mods = list(self)
         n = len(mods)
         i = 0
         reduced = False
         while i < n:
             m = mods[i]
-            fusable = _fusable(x)
+            pre = first_output if i == 0 else None
+            fusable = _fusable(x if pre is None else pre)
             if (fusable and isinstance(m, _CONVS) and m.bias is not None and i + 1 < n
                     and isinstance(mods[i + 1], nn.GroupNorm)):
                 gn = mods[i + 1]
                 swish = i + 2 < n and isinstance(mods[i + 2], Swish)
                 nxt = i + (3 if swish else 2)
-                y = m._conv_forward(x, m.weight, None)
+                y = pre if pre is not None else m._conv_forward(x, m.weight, None)
                 if nxt < n and isinstance(mods[nxt], SE3d) and swish:
                     y, sums = _ops._B.groupnorm_act(y, gn.num_groups, gn.weight, gn.bias, gn.eps, True,
                                                     conv_bias=m.bias, channel_sums=True)
@@ -74,6 +77,9 @@ class FusedSequential(nn.Sequential):
                 else:
                     x = _ops._B.groupnorm_act(y, gn.num_groups, gn.weight, gn.bias, gn.eps, swish, conv_bias=m.bias)
                 i = nxt
+            elif pre is not None:
+                x = pre if m.bias is None else pre + m.bias.view(1, -1, *([1] * (pre.dim() - 2)))
+                i += 1
             elif fusable and isinstance(m, nn.GroupNorm) and i + 1 < n and isinstance(mods[i + 1], Swish):
                 x = norm_act(m, x, True)
                 i += 2

@@ -2,12 +2,24 @@
 
 reference: modules/voxelization.py:9-28, modules/pvconv.py:65-137
 """
+import os
+
 import torch
 import torch.nn as nn
 
 from .. import functional as F
 from ..functional import geometry
+from ..functional import ops as _ops
 from .layers import SE3d, Attention, FusedSequential, SharedMLP, Swish
+
+# The first Conv3d of a PVConv block reads a freshly voxelized cloud: N points occupy at most N of the R^3
+# voxels (~5 % at R=32, N=4096).  When N / R^3 <= SPARSE_MAX_FILL the block skips the dense grid and the
+# dense convolution: per-occupied-voxel averages -> one GEMM against the 27 taps -> a gather that writes
+# the convolution's dense output once (csrc/sparse_conv.cu).  Same sums as the dense convolution (the
+# skipped terms are exact zeros); the GEMM runs in TF32 exactly when torch would run the Conv3d in TF32.
+# Inference on CUDA only; BDM_SPARSE_CONV=0 disables it.
+SPARSE_FIRST_CONV = os.environ.get("BDM_SPARSE_CONV", "1") != "0"
+SPARSE_MAX_FILL = float(os.environ.get("BDM_SPARSE_MAX_FILL", "0.125"))
 
 
 def normalized_voxel_coords(coords, resolution, normalize=True, eps=0):
@@ -102,10 +114,49 @@ class _PVConvBase(nn.Module):
         self.resolution = resolution
         self.voxelization = Voxelization(resolution, normalize=normalize, eps=eps)
 
+    def _sparse_eligible(self, features):
+        conv = self.voxel_layers[0]
+        vox = self.voxelization
+        return (SPARSE_FIRST_CONV and features.is_cuda and features.dtype == torch.float32
+                and not torch.is_grad_enabled() and not _ops.REFERENCE_CALL_PATTERN
+                and hasattr(_ops._B, "sparse_conv3_gather")
+                and _ops._B.sparse_conv3_supported(features.shape[2], vox.r)
+                and features.shape[2] <= SPARSE_MAX_FILL * vox.r ** 3
+                and isinstance(conv, nn.Conv3d) and conv.kernel_size == (3, 3, 3) and conv.stride == (1, 1, 1)
+                and conv.padding == (1, 1, 1) and conv.dilation == (1, 1, 1) and conv.groups == 1
+                and conv.padding_mode == 'zeros')
+
+    def _tap_matrix(self, conv):
+        """Conv3d weight [Cout,Cin,3,3,3] -> [Cin, 27*Cout] (column k*Cout+co), cached per weight version."""
+        w = conv.weight
+        key = (w.data_ptr(), w._version, w.device)
+        cached = getattr(self, "_taps", None)
+        if cached is None or cached[0] != key:
+            cached = (key, w.detach().permute(1, 2, 3, 4, 0).reshape(w.shape[1], -1).contiguous())
+            self._taps = cached
+        return cached[1]
+
+    def _sparse_first_conv(self, features, coords):
+        """-> (bias-less output of voxel_layers[0] on the voxelized features, float voxel coordinates)"""
+        vox = self.voxelization
+        norm_coords, _, plan = coordinate_plan(coords, vox.r, vox.normalize, vox.eps)
+        occupied = _ops._B.avg_voxelize_compact(features.contiguous(), plan)     # [B, Cin, N]
+        prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32    # what the Conv3d would use
+        try:
+            taps = torch.matmul(occupied.transpose(1, 2), self._tap_matrix(self.voxel_layers[0]))  # [B, N, 27*Cout]
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = prev
+        return _ops._B.sparse_conv3_gather(taps, plan), norm_coords
+
     def forward(self, inputs):
         features, coords, temb = inputs
-        grid, grid_coords = self.voxelization(features, coords)
-        grid = self.voxel_layers(grid)
+        if self._sparse_eligible(features):
+            first, grid_coords = self._sparse_first_conv(features, coords)
+            grid = self.voxel_layers(None, first_output=first)
+        else:
+            grid, grid_coords = self.voxelization(features, coords)
+            grid = self.voxel_layers(grid)
         from_voxels = F.trilinear_devoxelize(grid, grid_coords, self.resolution, self.training)
         return from_voxels + self.point_features(features), coords, temb
 

@@ -302,6 +302,11 @@ def run_ours(args):
         step_resident()
     step_e2e()
 
+    # occupied voxels of the batch at R=32 (the gather kernel's algorithmic read volume depends on it)
+    from bdm_b200.modules.point_voxel import coordinate_plan
+    with torch.no_grad():
+        occupied_r32 = int((coordinate_plan(x_dev.transpose(1, 2).contiguous(), 32)[2].cnt > 0).sum().item())
+
     # ---- per-op CUDA events on eager, single-stream launches (the roofline / sparse-path breakdown) ----
     import bdm_b200.denoiser as denoiser_mod
     plan_ahead_default = denoiser_mod.PLAN_AHEAD
@@ -349,30 +354,51 @@ def run_ours(args):
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant libbdm_b200 kernel inside the step ----
+    # ---- roofline of the dominant HBM-bound hot-path kernel inside the step ----
+    # Since the first Conv3d of the R=32 PVConv blocks went sparse (csrc/sparse_conv.cu) the step no longer
+    # materialises the 818 MB C=390 grid; the largest HBM-bound kernel of the sparse path is now the gather
+    # that writes a sparse convolution's dense output (Cout=64, R=32: three launches per step).  Algorithmic
+    # bytes per launch = the output written once + the tap rows of the occupied voxels read once
+    # (DESIGN.md section 5).  FPS, the longest single launch, is latency-bound (see sparse_path).
     peak, peak_src = measured_peak()
     sparse_ms = {k: sum(ms for ms, _ in v) / args.steps for k, v in prof.items()}
-    C, N, R = 3 + C_IMG, N_POINTS, 32
-    fill = [ms for ms, shp in prof.get("avg_voxelize_fill", []) if shp[0][1] == C]
-    plans = [ms for ms, shp in prof.get("voxel_plan", []) if shp[0][2] == N and shp[1] == R]
-    # per step the modules issue two R=32 plans (SA stage 0 and FP stage 3, different coords objects);
-    # the first one of each step belongs to the C=390 call
-    plan_first = plans[0::2] if len(plans) >= 2 * len(fill) else plans[:len(fill)]
-    vox_bytes = B * (4 * C * N + 12 * N + 4 * C * R ** 3 + 4 * N + 4 * R ** 3)
+    N, R, CO = N_POINTS, 32, 64
+    gather = [ms for ms, shp in prof.get("sparse_conv3_gather", []) if shp[0][2] == 27 * CO]
     roofline = None
-    if fill and len(plan_first) == len(fill):
-        vms = (sum(fill) + sum(plan_first)) / len(fill)
-        ach = vox_bytes / (vms * 1e-3) / 1e9
+    if gather:
+        gms = sum(gather) / len(gather)
+        gbytes = 4 * CO * (B * R ** 3 + 27 * occupied_r32)
+        ach = gbytes / (gms * 1e-3) / 1e9
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["avg_voxelize_c390_bytes"]
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["sparse_conv3_gather_co64_bytes"]
         except Exception:
             pass
-        roofline = {"bound": "hbm", "kernel": "avg_voxelize C=390 N=4096 R=32 (vox_sort_kernel + vox_fill_kernel<4,4>)",
+        roofline = {"bound": "hbm", "kernel": "sparse_conv3_gather_kernel Cout=64 N=4096 R=32",
                     "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
-                    "peak_source": peak_src, "algorithmic_bytes_per_launch": vox_bytes, "ms_per_launch": vms,
-                    "launches_timed": len(fill), "share_of_step": vms / ms_eager,
+                    "peak_source": peak_src, "algorithmic_bytes_per_launch": gbytes, "ms_per_launch": gms,
+                    "occupied_voxels_in_batch": occupied_r32,
+                    "launches_timed": len(gather), "share_of_step": gms * len(gather) / args.steps / ms_eager,
                     "timed_in": "eager single-stream pass of the same step (per-op CUDA events)"}
+    else:   # BDM_SPARSE_CONV=0: the dense route, dominated by avg_voxelize at C=390
+        C = 3 + C_IMG
+        fill = [ms for ms, shp in prof.get("avg_voxelize_fill", []) if shp[0][1] == C]
+        plans = [ms for ms, shp in prof.get("voxel_plan", []) if shp[0][2] == N and shp[1] == R]
+        plan_first = plans[0::2] if len(plans) >= 2 * len(fill) else plans[:len(fill)]
+        vox_bytes = B * (4 * C * N + 12 * N + 4 * C * R ** 3 + 4 * N + 4 * R ** 3)
+        if fill and len(plan_first) == len(fill):
+            vms = (sum(fill) + sum(plan_first)) / len(fill)
+            ach = vox_bytes / (vms * 1e-3) / 1e9
+            traffic = None
+            try:
+                traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["avg_voxelize_c390_bytes"]
+            except Exception:
+                pass
+            roofline = {"bound": "hbm", "kernel": "avg_voxelize C=390 N=4096 R=32 (vox_sort_kernel + vox_fill_kernel<4,4>)",
+                        "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+                        "peak_source": peak_src, "algorithmic_bytes_per_launch": vox_bytes, "ms_per_launch": vms,
+                        "launches_timed": len(fill), "share_of_step": vms / ms_eager,
+                        "timed_in": "eager single-stream pass of the same step (per-op CUDA events)"}
 
     line = {
         "metric": "shapes_per_sec_1000step_sampling_4096pts", "value": value, "unit": "shapes/s",
@@ -382,6 +408,8 @@ def run_ours(args):
                    "points": N_POINTS, "image_feature_map": [C_IMG, IMG, IMG], "timestep": T_MID,
                    "steps_per_shape": STEPS_PER_SHAPE, "parallelism": f"shapes sharded over {world} rank(s), no per-step collective",
                    "l2": "per-step working set (1.2 GB feature map + >2 GB activations) exceeds the 126 MB L2; no flush",
+                   "sparse_first_conv": "R=32 PVConv blocks: voxelize -> Conv3d replaced by compact averages -> cuBLAS GEMM "
+                                        "(TF32 like the Conv3d) -> sparse_conv3_gather; BDM_SPARSE_CONV=0 restores the dense route",
                    "dense_layers": "convs / attention matmuls: torch (cuDNN/cuBLAS, PyTorch default TF32 conv policy); "
                                    "conv bias + GroupNorm + Swish (+ SE squeeze, + max over neighbours): fused "
                                    "libbdm_b200 kernel, 1e-5 of the torch ops (BDM_FUSED_NORM=0 restores them)",

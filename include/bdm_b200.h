@@ -62,6 +62,22 @@ int bdm_voxel_plan(int b, int n, int r, const int *coords, int *ind, int *cnt, v
 int bdm_avg_voxelize_fill(int b, int c, int n, int r, const int *ind, const int *cnt,
                           const float *feat, float *out, const void *workspace,
                           size_t workspace_bytes, bdm_stream_t stream);
+/* Sparse consumers of a voxelization (the first Conv3d of a PVConv block, modules/pvconv.py:75-76,91-97,
+ * reads a grid that is ~95 % zeros at r=32):
+ *   bdm_avg_voxelize_compact   out f32[b,c,n]: column j = average of the j-th occupied voxel of shape b
+ *                              (ascending voxel id; bit-identical to the dense grid's entry), columns past
+ *                              the shape's occupied count are zero.  Needs the plan (r^3 <= 32768, n <= 16384).
+ *   bdm_sparse_conv3_gather    the 3x3x3 / stride 1 / zero-padded convolution's dense output from per-
+ *                              occupied-voxel tap products taps f32[b,n,27,cout]
+ *                              (taps[b,j,k,co] = sum_ci W[co,ci,kd,kh,kw] * compact[b,ci,j], k=(kd*3+kh)*3+kw,
+ *                              one GEMM on the host side): out[b,co,x,y,z] = bias[co] + sum_k taps[b,
+ *                              slot(x+kd-1,y+kh-1,z+kw-1),k,co], k ascending.  bias may be NULL.
+ *                              r must be a power of two <= 32. */
+int bdm_avg_voxelize_compact(int b, int c, int n, int r, const float *feat, float *out,
+                             const void *workspace, size_t workspace_bytes, bdm_stream_t stream);
+int bdm_sparse_conv3_gather(int b, int cout, int n, int r, const float *taps, const float *bias,
+                            float *out, const void *workspace, size_t workspace_bytes,
+                            bdm_stream_t stream);
 /* replaces avg_voxelize_grad (src/voxelization/vox.cuh:7-8): grad_y f32[b,c,s] -> grad_x f32[b,c,n] */
 int bdm_avg_voxelize_grad(int b, int c, int n, int s, const int *ind, const int *cnt,
                           const float *grad_y, float *grad_x, bdm_stream_t stream);

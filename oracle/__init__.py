@@ -294,3 +294,45 @@ def fscore(gt, pred, thr=0.01):
     precision = (d1 < thr).sum(axis=1) / float(d1.shape[1])
     recall = (d2 < thr).sum(axis=1) / float(d2.shape[1])
     return 2 * recall * precision / (recall + precision + 1e-12)
+
+
+# ------------------------------------------------------------------------------------------------
+# sparse first convolution of a PVConv block (checker for csrc/sparse_conv.cu)
+# ------------------------------------------------------------------------------------------------
+def avg_voxelize_compact(features, coords, r):
+    """The non-empty columns of avg_voxelize's grid, in ascending voxel id, zero-padded to N columns:
+    -> (compact f32[B,C,N], occupied voxel ids: list of int arrays).  The dense grid is the reference's
+    (vox.cpp:17-43); this only selects from it."""
+    dense, _, cnt = avg_voxelize_forward(features, coords, r)
+    b, c, n = np.asarray(features).shape
+    out = np.zeros((b, c, n), np.float32)
+    occupied = []
+    for i in range(b):
+        occ = np.flatnonzero(cnt[i] > 0)
+        occupied.append(occ)
+        out[i, :, :len(occ)] = dense[i][:, occ]
+    return out, occupied
+
+
+def sparse_conv3_gather(taps, occupied, r, bias=None):
+    """What `nn.Conv3d(cin, cout, 3, stride=1, padding=1)` (modules/pvconv.py:75-76, cross-correlation, zero
+    padding) yields on a grid whose only non-zero voxels are `occupied`, given the per-voxel tap products
+    taps[b, j, k, co] = sum_ci W[co, ci, kd, kh, kw] * x[b, ci, occupied[b][j]], k = (kd*3+kh)*3+kw:
+    out[b, co, x, y, z] = bias[co] + sum_k taps[b, slot(x+kd-1, y+kh-1, z+kw-1), k, co], k ascending, fp32."""
+    taps = _f32(taps)
+    b, n = taps.shape[0], taps.shape[1]
+    cout = taps.shape[2] // 27
+    taps = taps.reshape(b, n, 27, cout)
+    out = np.zeros((b, cout, r, r, r), np.float32)
+    for i in range(b):
+        occ = np.asarray(occupied[i], dtype=np.int64)
+        ox, oy, oz = occ // (r * r), (occ // r) % r, occ % r
+        for k in range(27):
+            kd, kh, kw = k // 9, (k // 3) % 3, k % 3
+            x, y, z = ox - (kd - 1), oy - (kh - 1), oz - (kw - 1)      # the output voxel this tap lands on
+            ok = (x >= 0) & (x < r) & (y >= 0) & (y < r) & (z >= 0) & (z < r)
+            # each output voxel receives at most one contribution per k, so += is an ordered fp32 add
+            out[i][:, x[ok], y[ok], z[ok]] += taps[i, np.flatnonzero(ok), k, :].T
+    if bias is not None:
+        out += _f32(bias).reshape(1, cout, 1, 1, 1)
+    return out

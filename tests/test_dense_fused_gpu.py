@@ -52,16 +52,19 @@ def test_denoiser_fused_vs_unfused(cuda_backend):
     x = torch.randn(4, 9, 2048, device="cuda")
     t = torch.tensor([500.0, 3.0, 999.0, 0.0], device="cuda")
     with torch.no_grad():
-        saved = L.FUSED_NORM_ACT
+        saved = (L.FUSED_NORM_ACT, torch.backends.cudnn.allow_tf32)
         try:
+            # TF32 convolutions round their inputs to 10 mantissa bits, which turns a 1e-7 difference in
+            # front of a conv into ~1e-3 behind it; the fused kernels are compared with fp32 convs
+            torch.backends.cudnn.allow_tf32 = False
             L.FUSED_NORM_ACT = True
             y_fused = net(x, t)
             L.FUSED_NORM_ACT = False
             y_plain = net(x, t)
         finally:
-            L.FUSED_NORM_ACT = saved
+            L.FUSED_NORM_ACT, torch.backends.cudnn.allow_tf32 = saved
     err = (y_fused - y_plain).abs().max().item() / y_plain.abs().max().item()
-    assert err <= 1e-4, err   # 60+ norm layers deep; each within 1e-5
+    assert err <= 1e-5, err   # 60+ norm layers deep
 
 
 def test_attention_fused_vs_plain(cuda_backend):

@@ -40,6 +40,43 @@ def norm_act(norm, x, swish=True):
 _CONVS = (nn.Conv1d, nn.Conv2d, nn.Conv3d)
 
 
+def _pointwise(m):
+    return (isinstance(m, (nn.Conv1d, nn.Conv2d)) and all(k == 1 for k in m.kernel_size)
+            and all(v == 1 for v in m.stride) and all(v == 0 for v in m.padding)
+            and all(v == 1 for v in m.dilation) and m.groups == 1)
+
+
+def conv_no_bias(m, x):
+    """m(x) without the bias.  A 1x1 convolution whose input width is not a multiple of 4 (390 at the first
+    PC^2 layer) makes cuDNN/cuBLAS fall back to an `align1` SIMT GEMM (~0.7 ms there); splitting the
+    reduction into an aligned head, which gets the tensor-op kernel the aligned layers get, plus a <=3-wide
+    tail costs two GEMM launches and no copy of x.  TF32 follows the conv policy (cudnn.allow_tf32), as for
+    every other convolution of the network."""
+    cin = m.in_channels
+    if not (_pointwise(m) and cin % 4 != 0 and cin >= 32 and x.is_cuda and x.is_contiguous()):
+        return m._conv_forward(x, m.weight, None)
+    w = m.weight
+    key = (w.data_ptr(), w._version, w.device)
+    cached = getattr(m, "_split_weight", None)
+    if cached is None or cached[0] != key:
+        w2 = w.detach().reshape(m.out_channels, cin)
+        head = cin & ~3
+        cached = (key, w2[:, :head].contiguous(), w2[:, head:].contiguous())
+        m._split_weight = cached
+    _, w_head, w_tail = cached
+    head = w_head.shape[1]
+    nb = x.shape[0]
+    xr = x.reshape(nb, cin, -1)
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32
+    try:
+        y = torch.matmul(w_head, xr[:, :head])
+        y.baddbmm_(w_tail.expand(nb, -1, -1), xr[:, head:])
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    return y.reshape(nb, m.out_channels, *x.shape[2:])
+
+
 class FusedSequential(nn.Sequential):
     """nn.Sequential (same children, same state_dict keys) that, for inference on CUDA, runs
         Conv -> GroupNorm [-> Swish] [-> SE3d | -> max over the last dim]
@@ -47,13 +84,16 @@ class FusedSequential(nn.Sequential):
     statistics), norm + activation are one pass, the SE squeeze comes out of that same pass and a
     trailing max over neighbours replaces the full-size write.  Anything else runs module by module."""
 
-    def forward(self, x, max_over_last=False, first_output=None):
+    def forward(self, x, max_over_last=False, first_output=None, defer_gate=False):
         """first_output: the bias-less output of self[0] (a conv) when the caller computed it by other
-        means (PVConv's sparse first convolution); `x` is then ignored."""
+        means (PVConv's sparse first convolution); `x` is then ignored.
+        defer_gate: when the stack ends in an SE3d gate, return (ungated grid, gate f32[B,C]) instead of
+        multiplying the whole grid -- the caller applies the gate after its (linear) consumer."""
         mods = list(self)
         n = len(mods)
         i = 0
         reduced = False
+        gate = None
         while i < n:
             m = mods[i]
             pre = first_output if i == 0 else None
@@ -63,11 +103,14 @@ class FusedSequential(nn.Sequential):
                 gn = mods[i + 1]
                 swish = i + 2 < n and isinstance(mods[i + 2], Swish)
                 nxt = i + (3 if swish else 2)
-                y = pre if pre is not None else m._conv_forward(x, m.weight, None)
+                y = pre if pre is not None else conv_no_bias(m, x)
                 if nxt < n and isinstance(mods[nxt], SE3d) and swish:
                     y, sums = _ops._B.groupnorm_act(y, gn.num_groups, gn.weight, gn.bias, gn.eps, True,
                                                     conv_bias=m.bias, channel_sums=True)
-                    x = mods[nxt](y, channel_sums=sums)
+                    if defer_gate and nxt == n - 1:
+                        x, gate = y, mods[nxt].gate(y, channel_sums=sums)
+                    else:
+                        x = mods[nxt](y, channel_sums=sums)
                     nxt += 1
                 elif (max_over_last and nxt == n and swish and y.dim() == 4
                       and _ops._B.groupnorm_max_supported(y.shape[-1])):
@@ -83,11 +126,16 @@ class FusedSequential(nn.Sequential):
             elif fusable and isinstance(m, nn.GroupNorm) and i + 1 < n and isinstance(mods[i + 1], Swish):
                 x = norm_act(m, x, True)
                 i += 2
+            elif defer_gate and i == n - 1 and isinstance(m, SE3d):
+                gate = m.gate(x)
+                i += 1
             else:
                 x = m(x)
                 i += 1
         if max_over_last and not reduced:
             x = x.max(dim=-1).values
+        if defer_gate:
+            return x, gate
         return x
 
 
@@ -131,12 +179,16 @@ class SE3d(nn.Module):
                                 nn.Linear(hidden, channel, bias=False),
                                 nn.Sigmoid())
 
-    def forward(self, inputs, channel_sums=None):
+    def gate(self, inputs, channel_sums=None):
+        """the per-(shape, channel) excitation f32[B,C]"""
         if channel_sums is not None:   # squeeze already produced by the fused norm+activation pass
             pooled = channel_sums / float(inputs.shape[2] * inputs.shape[3] * inputs.shape[4])
         else:                          # three chained means (z, y, x) like the reference, for identical rounding
             pooled = inputs.mean(-1).mean(-1).mean(-1)
-        return inputs * self.fc(pooled)[:, :, None, None, None]
+        return self.fc(pooled)
+
+    def forward(self, inputs, channel_sums=None):
+        return inputs * self.gate(inputs, channel_sums)[:, :, None, None, None]
 
 
 class Attention(nn.Module):

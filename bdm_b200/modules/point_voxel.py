@@ -20,6 +20,7 @@ from .layers import SE3d, Attention, FusedSequential, SharedMLP, Swish
 # Inference on CUDA only; BDM_SPARSE_CONV=0 disables it.
 SPARSE_FIRST_CONV = os.environ.get("BDM_SPARSE_CONV", "1") != "0"
 SPARSE_MAX_FILL = float(os.environ.get("BDM_SPARSE_MAX_FILL", "0.125"))
+DEFER_SE_GATE = os.environ.get("BDM_DEFER_SE_GATE", "1") != "0"
 
 
 def normalized_voxel_coords(coords, resolution, normalize=True, eps=0):
@@ -151,13 +152,24 @@ class _PVConvBase(nn.Module):
 
     def forward(self, inputs):
         features, coords, temb = inputs
+        # Inference: an SE gate at the end of the voxel stack is one scalar per (shape, channel) and
+        # devoxelization is linear in the grid, so the gate is applied to the devoxelized [B,C,N] features
+        # instead of to the [B,C,R^3] grid (one pass over the grid less).
+        defer = (DEFER_SE_GATE and features.is_cuda and not torch.is_grad_enabled()
+                 and not _ops.REFERENCE_CALL_PATTERN and hasattr(_ops._B, "groupnorm_act"))
+        first = None
         if self._sparse_eligible(features):
             first, grid_coords = self._sparse_first_conv(features, coords)
-            grid = self.voxel_layers(None, first_output=first)
+            grid = None
         else:
             grid, grid_coords = self.voxelization(features, coords)
-            grid = self.voxel_layers(grid)
+        grid = self.voxel_layers(grid, first_output=first, defer_gate=defer)
+        gate = None
+        if defer:
+            grid, gate = grid
         from_voxels = F.trilinear_devoxelize(grid, grid_coords, self.resolution, self.training)
+        if gate is not None:
+            return torch.addcmul(self.point_features(features), from_voxels, gate[:, :, None]), coords, temb
         return from_voxels + self.point_features(features), coords, temb
 
 

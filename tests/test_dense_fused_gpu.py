@@ -136,3 +136,55 @@ def test_fused_sequential_matches_modules(cuda_backend):
     for a, b in ((a1, b1), (a2, b2)):
         assert a.shape == b.shape
         assert (a - b).abs().max().item() / b.abs().max().item() <= 2e-5
+
+
+@pytest.mark.parametrize("cin,cout,spatial", [(390, 32, (4096,)), (67, 64, (256, 32)), (35, 32, (100,))])
+def test_misaligned_pointwise_conv_split(cin, cout, spatial, cuda_backend):
+    """1x1 conv with Cin % 4 != 0 as aligned head + tail GEMMs == the conv (fp32 on both sides)"""
+    import torch
+    import torch.nn as nn
+
+    import bdm_b200.modules.layers as L
+    torch.manual_seed(cin)
+    conv = (nn.Conv1d if len(spatial) == 1 else nn.Conv2d)(cin, cout, 1).cuda().eval()
+    x = torch.randn((3, cin) + spatial, device="cuda")
+    saved = torch.backends.cudnn.allow_tf32
+    try:
+        torch.backends.cudnn.allow_tf32 = False
+        with torch.no_grad():
+            got = L.conv_no_bias(conv, x)
+            want = conv._conv_forward(x, conv.weight, None)
+    finally:
+        torch.backends.cudnn.allow_tf32 = saved
+    assert got.shape == want.shape
+    assert (got - want).abs().max().item() <= 1e-5 * want.abs().max().item()
+    with torch.no_grad():   # weight edits invalidate the cached split
+        conv.weight.mul_(2.0)
+        torch.backends.cudnn.allow_tf32 = False
+        try:
+            got2 = L.conv_no_bias(conv, x)
+        finally:
+            torch.backends.cudnn.allow_tf32 = saved
+    assert (got2 - 2.0 * want).abs().max().item() <= 2e-5 * want.abs().max().item()
+
+
+def test_deferred_se_gate(cuda_backend):
+    """SE gate applied after devoxelization == gate applied to the grid (devoxelize is linear)"""
+    import torch
+
+    import bdm_b200.modules.point_voxel as PV
+    torch.manual_seed(11)
+    blk = PV.PVConv(24, 32, 3, 16, with_se=True).cuda().eval()
+    feats = torch.randn(2, 24, 700, device="cuda")
+    coords = torch.randn(2, 3, 700, device="cuda")
+    saved = (PV.DEFER_SE_GATE, torch.backends.cudnn.allow_tf32)
+    try:
+        torch.backends.cudnn.allow_tf32 = False
+        with torch.no_grad():
+            PV.DEFER_SE_GATE = True
+            y1 = blk((feats, coords, None))[0]
+            PV.DEFER_SE_GATE = False
+            y0 = blk((feats, coords, None))[0]
+    finally:
+        PV.DEFER_SE_GATE, torch.backends.cudnn.allow_tf32 = saved
+    assert (y1 - y0).abs().max().item() <= 1e-5 * y0.abs().max().item()

@@ -188,6 +188,30 @@ def sparse_conv3_gather(taps, plan, bias=None):
     return out
 
 
+def attention_supported(channels, tokens, batch=None):
+    """shapes the fused kernel takes; with `batch` given, also whether there is enough work to fill the
+    GPU (one CTA per 128 queries; below ~1 CTA per SM torch's batched GEMMs are faster)"""
+    ok = channels == 64 and tokens >= 128 and tokens % 128 == 0
+    if ok and batch is not None:
+        ok = batch * (tokens // 128) >= 128
+    return ok
+
+
+@_op(1)
+def attention(q, k, v):
+    """q, k, v f32[B,64,T] -> f32[B,64,T]: out[b,c,i] = sum_j softmax_j(q[b,:,i].k[b,:,j]) v[b,c,j]"""
+    _chk_float(q, "q")
+    _chk_float(k, "k")
+    _chk_float(v, "v")
+    b, c, t = q.shape
+    _req(k.shape == q.shape and v.shape == q.shape, "q, k, v must have one shape")
+    _req(attention_supported(c, t), "attention kernel needs 64 channels and a multiple of 128 tokens")
+    out = torch.empty_like(q)
+    with _Launch(q) as st:
+        _check(_L.bdm_attention(b, c, t, q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), st))
+    return out
+
+
 def sparse_conv3_supported(n, resolution):
     r = int(resolution)
     return 1 <= r <= 32 and (r & (r - 1)) == 0 and 1 <= n <= 16384

@@ -16,6 +16,9 @@ from ..functional import ops as _ops
 # tests/test_dense_fused_gpu.py).  BDM_FUSED_NORM=0, autograd, CPU tensors or a foreign `_backend`
 # (the reference's extension, the test oracle) fall back to nn.GroupNorm followed by Swish.
 FUSED_NORM_ACT = os.environ.get("BDM_FUSED_NORM", "1") != "0"
+# Fused online-softmax attention kernel (csrc/attention.cu) for the 64-channel attention block, inference
+# on CUDA; fp32-equivalent (3xTF32).  BDM_FUSED_ATTENTION=0 keeps torch's matmul / softmax / matmul.
+FUSED_ATTENTION = os.environ.get("BDM_FUSED_ATTENTION", "1") != "0"
 
 
 class Swish(nn.Module):
@@ -207,8 +210,12 @@ class Attention(nn.Module):
     def forward(self, x):
         nb, nc = x.shape[:2]
         q, k, v = (proj(x).reshape(nb, nc, -1) for proj in (self.q, self.k, self.v))
-        attn = self.sm(torch.matmul(q.transpose(1, 2), k))              # [B, T, T]
-        mixed = torch.matmul(v, attn.transpose(1, 2)).reshape(x.shape)  # [B, C, ...]
+        if (FUSED_ATTENTION and _fusable(x) and hasattr(_ops._B, "attention")
+                and _ops._B.attention_supported(nc, q.shape[2], nb)):
+            mixed = _ops._B.attention(q.contiguous(), k.contiguous(), v.contiguous()).reshape(x.shape)
+        else:
+            attn = self.sm(torch.matmul(q.transpose(1, 2), k))              # [B, T, T]
+            mixed = torch.matmul(v, attn.transpose(1, 2)).reshape(x.shape)  # [B, C, ...]
         return norm_act(self.norm, self.out(mixed) + x, True)
 
 

@@ -73,7 +73,7 @@ def test_attention_fused_vs_plain(cuda_backend):
     import bdm_b200.modules.layers as L
     torch.manual_seed(9)
     att = L.Attention(64, 8, D=3).cuda().eval()
-    x = torch.randn(2, 64, 16, 16, 16, device="cuda")
+    x = torch.randn(2, 64, 16, 16, 16, device="cuda")   # 64 query tiles: below the fused-attention threshold
     with torch.no_grad():
         saved = L.FUSED_NORM_ACT
         try:
@@ -187,4 +187,39 @@ def test_deferred_se_gate(cuda_backend):
             y0 = blk((feats, coords, None))[0]
     finally:
         PV.DEFER_SE_GATE, torch.backends.cudnn.allow_tf32 = saved
+    assert (y1 - y0).abs().max().item() <= 1e-5 * y0.abs().max().item()
+
+
+@pytest.mark.parametrize("b,t,scale", [(2, 512, 1.0), (3, 4096, 1.0), (1, 1024, 3.0), (2, 128, 0.2)])
+def test_fused_attention_vs_float64(b, t, scale, cuda_backend):
+    """softmax(q^T k) applied to v, un-scaled logits: at least as close to float64 as torch's fp32 route"""
+    import torch
+    g = torch.Generator(device="cuda").manual_seed(t + b)
+    q, k, v = (torch.randn(b, 64, t, device="cuda", generator=g) * scale for _ in range(3))
+    got = cuda_backend.attention(q, k, v)
+    ref = torch.matmul(v.double(), torch.softmax(torch.matmul(q.double().transpose(1, 2), k.double()), -1).transpose(1, 2))
+    f32 = torch.matmul(v, torch.softmax(torch.matmul(q.transpose(1, 2), k), -1).transpose(1, 2))
+    peak = ref.abs().max().item()
+    e_ours = (got.double() - ref).abs().max().item() / peak
+    e_torch = (f32.double() - ref).abs().max().item() / peak
+    assert e_ours <= max(3 * e_torch, 1e-5), (e_ours, e_torch)
+
+
+def test_attention_block_fused_kernel(cuda_backend):
+    import torch
+
+    import bdm_b200.modules.layers as L
+    torch.manual_seed(3)
+    blk = L.Attention(64, 8).cuda().eval()
+    x = torch.randn(4, 64, 16, 16, 16, device="cuda")
+    saved = (L.FUSED_ATTENTION, torch.backends.cudnn.allow_tf32)
+    try:
+        torch.backends.cudnn.allow_tf32 = False
+        with torch.no_grad():
+            L.FUSED_ATTENTION = True
+            y1 = blk(x)
+            L.FUSED_ATTENTION = False
+            y0 = blk(x)
+    finally:
+        L.FUSED_ATTENTION, torch.backends.cudnn.allow_tf32 = saved
     assert (y1 - y0).abs().max().item() <= 1e-5 * y0.abs().max().item()

@@ -197,7 +197,7 @@ def attention_supported(channels, tokens, batch=None):
     return ok
 
 
-@_op(1)
+@_op(3)
 def attention(q, k, v):
     """q, k, v f32[B,64,T] -> f32[B,64,T]: out[b,c,i] = sum_j softmax_j(q[b,:,i].k[b,:,j]) v[b,c,j]"""
     _chk_float(q, "q")
@@ -207,8 +207,10 @@ def attention(q, k, v):
     _req(k.shape == q.shape and v.shape == q.shape, "q, k, v must have one shape")
     _req(attention_supported(c, t), "attention kernel needs 64 channels and a multiple of 128 tokens")
     out = torch.empty_like(q)
+    ws = _workspace(16, q.device)
     with _Launch(q) as st:
-        _check(_L.bdm_attention(b, c, t, q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), st))
+        _check(_L.bdm_attention(b, c, t, q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), ws.data_ptr(),
+                                ws.numel(), st))
     return out
 
 

@@ -196,11 +196,12 @@ int bdm_nn_f64(int b, int n, int m, int expanded, const double *src, const doubl
 /* ---- fused self-attention of the PVConv attention block ------------------------------------------
  * replaces, for inference, the two torch.matmul + softmax of Attention.forward (modules/pvconv.py:36-63):
  *   out[b,c,i] = sum_j softmax_j( q[b,:,i] . k[b,:,j] ) * v[b,c,j]       q,k,v,out f32[b,c,t], un-scaled logits
- * fp32-equivalent arithmetic (3xTF32 split products, fp32 accumulation and softmax); the [t,t] logits are
- * never written.  c must be 64 and t a multiple of 128 (BDM_ERR_BAD_SIZE otherwise: the caller keeps the
- * torch route for other shapes). */
+ * fp32-equivalent arithmetic (operands split into two fp16 halves after a per-tensor power-of-two scaling,
+ * three tensor-core products per term, fp32 accumulation and softmax); the [t,t] logits are never written.
+ * c must be 64 and t a multiple of 128 (BDM_ERR_BAD_SIZE otherwise: the caller keeps the torch route for
+ * other shapes).  workspace: 16 bytes, 16-byte aligned. */
 int bdm_attention(int b, int c, int t, const float *q, const float *k, const float *v, float *out,
-                  bdm_stream_t stream);
+                  void *workspace, size_t workspace_bytes, bdm_stream_t stream);
 
 /* ---- dense side: fused [conv bias +] GroupNorm [+ Swish] [+ reduction] ----------
  * replaces the bias add of the preceding conv, the nn.GroupNorm(8, C) -> Swish pair that follows every

@@ -223,6 +223,124 @@ static int gn_tiles(long long bc, long long n4, int align4) {
   return (int)tile4;
 }
 
+// ------------------------------------------------------------------------------------------------
+// One-pass variant for small groups.  Two thirds of the step's norm layers sit on the coarse stages
+// ([16,256,8,8,8], [16,256,256], [16,128,1024] ...): 8-17 MB tensors whose (sample, group) block --
+// contiguous in memory -- is at most 32K floats.  One CTA per (sample, group) reads its block ONCE into
+// registers (up to 8 x 128-bit loads per thread, all in flight together), reduces the shifted moments
+// through shared memory in double, and normalises / activates from the registers: 1 read + 1 write and one
+// launch instead of 2 reads + 1 write and two.  Same arithmetic as the two-kernel path.
+// ------------------------------------------------------------------------------------------------
+constexpr int kOneMaxV = 8;
+
+template <int V, bool SWISH>
+__global__ void __launch_bounds__(1024)
+gn_onepass_kernel(int c, int s, int groups, float eps, int tiles, const float *__restrict__ x,
+                  const float *__restrict__ conv_bias, const float *__restrict__ gamma,
+                  const float *__restrict__ beta, float *__restrict__ y, float *__restrict__ tile_sums) {
+  const int cg = c / groups;
+  const int sample = blockIdx.x / groups, g = blockIdx.x - sample * groups;
+  const int ch0 = g * cg;
+  const size_t base = ((size_t)sample * c + ch0) * s;
+  const int n4 = (cg * s) >> 2;
+  const int nt = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  __shared__ double s_red[2][32];
+  __shared__ float s_stat[2];
+  __shared__ double s_dmean;
+  __shared__ float s_part[32 * kOneMaxV];
+
+  const float k = __ldg(x + base) + (conv_bias != nullptr ? __ldg(conv_bias + ch0) : 0.0f);
+  float4 v[V];
+  int chn[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
+    const int idx = tid + j * nt;
+    chn[j] = ch0 + min((idx * 4) / s, cg - 1);
+    v[j] = idx < n4 ? ld_stream_f4(x + base + 4 * (size_t)idx) : make_float4(k, k, k, k);
+  }
+  float s1 = 0.0f, s2 = 0.0f;
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
+    const int idx = tid + j * nt;
+    // moments of (x + conv_bias - k); padding lanes hold k with no bias and add 0
+    const float kk = (conv_bias != nullptr && idx < n4) ? k - __ldg(conv_bias + chn[j]) : k;
+    const float a = v[j].x - kk, b2 = v[j].y - kk, c2 = v[j].z - kk, d2 = v[j].w - kk;
+    s1 += (a + b2) + (c2 + d2);
+    s2 += (a * a + b2 * b2) + (c2 * c2 + d2 * d2);
+  }
+  double d1 = (double)s1, d2_ = (double)s2;
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) {
+    d1 += __shfl_xor_sync(0xffffffffu, d1, d);
+    d2_ += __shfl_xor_sync(0xffffffffu, d2_, d);
+  }
+  if (lane == 0) { s_red[0][warp] = d1; s_red[1][warp] = d2_; }
+  __syncthreads();
+  if (warp == 0) {
+    const int nw = nt >> 5;
+    double a1 = lane < nw ? s_red[0][lane] : 0.0, a2 = lane < nw ? s_red[1][lane] : 0.0;
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+      a1 += __shfl_xor_sync(0xffffffffu, a1, d);
+      a2 += __shfl_xor_sync(0xffffffffu, a2, d);
+    }
+    if (lane == 0) {
+      const double n = (double)cg * (double)s;
+      const double m = a1 / n;                       // mean of (x - k)
+      const double var = fmax(a2 / n - m * m, 0.0);
+      s_dmean = (double)k + m;
+      s_stat[1] = (float)(1.0 / sqrt(var + (double)eps));
+    }
+  }
+  __syncthreads();
+  const double mean = s_dmean;
+  const float rstd = s_stat[1];
+  auto act = [](float t) { return SWISH ? t / (1.0f + expf(-t)) : t; };
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
+    const int idx = tid + j * nt;
+    const float ga = gamma != nullptr ? __ldg(gamma + chn[j]) : 1.0f;
+    const float be = beta != nullptr ? __ldg(beta + chn[j]) : 0.0f;
+    const float cb = conv_bias != nullptr ? __ldg(conv_bias + chn[j]) : 0.0f;
+    const float A = rstd * ga;                                                       // same folding as gn_apply_kernel
+    const float Bc = (float)((double)be + ((double)cb - mean) * (double)A);
+    float4 o;
+    o.x = act(fmaf(v[j].x, A, Bc));
+    o.y = act(fmaf(v[j].y, A, Bc));
+    o.z = act(fmaf(v[j].z, A, Bc));
+    o.w = act(fmaf(v[j].w, A, Bc));
+    if (idx < n4) *reinterpret_cast<float4 *>(y + base + 4 * (size_t)idx) = o;
+    if (tile_sums != nullptr) {   // s % 128 == 0: the 32 lanes of a warp row share one channel
+      float t = idx < n4 ? (o.x + o.y) + (o.z + o.w) : 0.0f;
+#pragma unroll
+      for (int d = 16; d >= 1; d >>= 1) t += __shfl_xor_sync(0xffffffffu, t, d);
+      if (lane == 0) s_part[j * 32 + warp] = t;
+    }
+  }
+  if (tile_sums != nullptr) {
+    __syncthreads();
+    if (tid < cg) {   // fixed order: deterministic
+      float acc = 0.0f;
+      const int nw = nt >> 5;
+      for (int j = 0; j < V; ++j)
+        for (int w = 0; w < nw; ++w) {
+          const int idx = w * 32 + j * nt;
+          if (idx < n4 && (idx * 4) / s == tid) acc += s_part[j * 32 + w];
+        }
+      float *ts = tile_sums + ((size_t)sample * c + ch0 + tid) * tiles;
+      ts[0] = acc;
+      for (int q = 1; q < tiles; ++q) ts[q] = 0.0f;
+    }
+  }
+}
+
+template <int V>
+static void launch_onepass(bool swish, int ctas, int nt, cudaStream_t st, int c, int s, int groups, float eps, int tiles,
+                           const float *x, const float *cb, const float *ga, const float *be, float *y, float *ts) {
+  if (swish) gn_onepass_kernel<V, true><<<ctas, nt, 0, st>>>(c, s, groups, eps, tiles, x, cb, ga, be, y, ts);
+  else gn_onepass_kernel<V, false><<<ctas, nt, 0, st>>>(c, s, groups, eps, tiles, x, cb, ga, be, y, ts);
+}
+
 }  // namespace bdm
 
 extern "C" size_t bdm_groupnorm_workspace_bytes(int b, int c, long long s) {
@@ -257,6 +375,27 @@ extern "C" int bdm_groupnorm_act(int b, int c, long long s, int groups, float ep
     BDM_CHECK_SIZE(tile_sums == nullptr);
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  // small groups: one CTA per (sample, group), one pass
+  {
+    const long long gelems = (long long)(c / groups) * s;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
+    if (!max_over_u && aligned && s % 4 == 0 && gelems <= 4LL * 1024 * kOneMaxV && (long long)b * groups <= 0x7fffffffLL &&
+        (tile_sums == nullptr || (s % 128 == 0 && c / groups <= 1024 && c / groups <= 32 * 32))) {
+      const int n4 = (int)(gelems >> 2);
+      int v = 1;
+      while (v < kOneMaxV && (long long)v * 1024 < n4) v <<= 1;
+      int nt = (n4 + v - 1) / v;
+      nt = min(1024, max(32, (nt + 31) & ~31));
+      if (tile_sums != nullptr) nt = max(nt, min(1024, ((c / groups) + 31) & ~31));
+      const int tiles = tile_sums != nullptr ? bdm_groupnorm_tiles(b, c, s) : 1;
+      const int ctas = b * groups;
+      if (v == 1) launch_onepass<1>(swish != 0, ctas, nt, st, c, (int)s, groups, eps, tiles, x, conv_bias, gamma, beta, y, tile_sums);
+      else if (v == 2) launch_onepass<2>(swish != 0, ctas, nt, st, c, (int)s, groups, eps, tiles, x, conv_bias, gamma, beta, y, tile_sums);
+      else if (v == 4) launch_onepass<4>(swish != 0, ctas, nt, st, c, (int)s, groups, eps, tiles, x, conv_bias, gamma, beta, y, tile_sums);
+      else launch_onepass<8>(swish != 0, ctas, nt, st, c, (int)s, groups, eps, tiles, x, conv_bias, gamma, beta, y, tile_sums);
+      BDM_RETURN_LAUNCH_STATUS();
+    }
+  }
   const int nchunks = gn_nchunks(rows, s);
   double2 *partials = static_cast<double2 *>(workspace);
   // rows can exceed the 65535 limit of gridDim.y: fold them in slabs

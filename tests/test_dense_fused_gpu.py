@@ -87,7 +87,8 @@ def test_attention_fused_vs_plain(cuda_backend):
     assert err <= 1e-5, err
 
 
-@pytest.mark.parametrize("b,c,spatial", [(16, 32, (32, 32, 32)), (4, 64, (256, 32)), (2, 512, (16, 32)), (3, 16, (9, 4))])
+@pytest.mark.parametrize("b,c,spatial", [(16, 32, (32, 32, 32)), (4, 64, (256, 32)), (2, 512, (16, 32)), (3, 16, (9, 4)),
+                                         (16, 256, (8, 8, 8)), (2, 64, (16, 16, 16)), (3, 128, (128,)), (2, 256, (64,))])
 def test_groupnorm_conv_bias_max_and_sums(b, c, spatial, cuda_backend):
     """conv bias folded into the statistics; max over the last dim; per-channel sums of the output"""
     import torch
@@ -104,13 +105,14 @@ def test_groupnorm_conv_bias_max_and_sums(b, c, spatial, cuda_backend):
     got = cuda_backend.groupnorm_act(x, 8, w, bias, 1e-5, True, conv_bias=cb)
     assert (got - want).abs().max().item() / peak <= 1e-5
     got_y, sums = cuda_backend.groupnorm_act(x, 8, w, bias, 1e-5, True, conv_bias=cb, channel_sums=True)
-    assert torch.equal(got_y, got)
+    assert (got_y - got).abs().max().item() <= 2e-6 * peak   # may come from different kernels (one-pass / two-kernel)
     want_sums = want.double().flatten(2).sum(-1)
     assert (sums.double() - want_sums).abs().max().item() <= 1e-5 * max(want_sums.abs().max().item(), 1.0)
     if cuda_backend.groupnorm_max_supported(spatial[-1]):
         got_max = cuda_backend.groupnorm_act(x, 8, w, bias, 1e-5, True, conv_bias=cb, max_over_last=True)
         assert got_max.shape == want.shape[:-1]
-        assert torch.equal(got_max, got.max(dim=-1).values)
+        # (the full-size result may come from the one-pass kernel, the max from the two-kernel path)
+        assert (got_max - got.max(dim=-1).values).abs().max().item() <= 2e-6 * peak
 
 
 def test_fused_sequential_matches_modules(cuda_backend):

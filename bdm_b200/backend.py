@@ -374,6 +374,27 @@ def grouping_forward(features, indices):
 
 
 @_op(1)
+def grouping_into(features, indices, out, channel_offset, centers=None):
+    """out[:, channel_offset : channel_offset + C] = features gathered by indices (minus centers[b,c,m] when
+    given); `out` f32[B,OC,M,U] contiguous.  Lets BallQuery fill its concatenated tensor in place."""
+    _chk_float(features, "features")
+    _chk_int(indices, "indices")
+    _chk_float(out, "out")
+    b, c, n = features.shape
+    m, u = indices.shape[1], indices.shape[2]
+    _req(out.dim() == 4 and out.shape[0] == b and out.shape[2] == m and out.shape[3] == u, "out must be [B,OC,M,U]")
+    _req(0 <= channel_offset and channel_offset + c <= out.shape[1], "channel slice outside out")
+    if centers is not None:
+        _chk_float(centers, "centers")
+        _req(tuple(centers.shape) == (b, c, m), "centers must be [B,C,M]")
+    with _Launch(features) as st:
+        _check(_L.bdm_grouping_into(b, c, n, m, u, features.data_ptr(), indices.data_ptr(),
+                                    centers.data_ptr() if centers is not None else None, out.data_ptr(),
+                                    out.shape[1], channel_offset, st))
+    return out
+
+
+@_op(1)
 def grouping_backward(grad_y, indices, n):
     _chk_float(grad_y, "grad_y")
     _chk_int(indices, "indices")

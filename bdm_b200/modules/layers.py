@@ -43,6 +43,49 @@ def norm_act(norm, x, swish=True):
 _CONVS = (nn.Conv1d, nn.Conv2d, nn.Conv3d)
 
 
+def conv_no_bias_concat(m, parts):
+    """m(torch.cat(parts, dim=1)) without the bias and without materialising the concatenation, for a 1x1
+    Conv1d `m`: W @ cat(x_i) = sum_i W[:, slice_i] @ x_i, one accumulating GEMM per part (each part's
+    reduction split at a multiple of 4 like conv_no_bias).  parts: f32[B, C_i, L] with contiguous [C_i, L]
+    blocks (batch stride free).  PointNetFPModule uses it for cat([interpolated, skip]) -- at the last FP
+    stage the skip tensor alone is 100 MB."""
+    w = m.weight
+    key = (w.data_ptr(), w._version, w.device, tuple(p.shape[1] for p in parts))
+    cached = getattr(m, "_concat_weight", None)
+    if cached is None or cached[0] != key:
+        w2 = w.detach().reshape(m.out_channels, m.in_channels)
+        pieces, off = [], 0
+        for p in parts:
+            ci = p.shape[1]
+            head = ci & ~3 if ci >= 32 else ci        # aligned head (+ tail) for wide parts, whole for narrow ones
+            pieces.append((off, head, w2[:, off:off + head].contiguous()))
+            if head < ci:
+                pieces.append((off + head, ci - head, w2[:, off + head:off + ci].contiguous()))
+            off += ci
+        assert off == m.in_channels
+        cached = (key, pieces)
+        m._concat_weight = cached
+    nb = parts[0].shape[0]
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32
+    try:
+        y, off_p = None, 0
+        bounds = []
+        for p in parts:
+            bounds.append((off_p, p))
+            off_p += p.shape[1]
+        for off, width, wpiece in cached[1]:
+            src_off, src = next((o, p) for o, p in reversed(bounds) if o <= off)
+            xs = src[:, off - src_off: off - src_off + width]
+            if y is None:
+                y = torch.matmul(wpiece, xs)
+            else:
+                y.baddbmm_(wpiece.expand(nb, -1, -1), xs)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    return y
+
+
 def _pointwise(m):
     return (isinstance(m, (nn.Conv1d, nn.Conv2d)) and all(k == 1 for k in m.kernel_size)
             and all(v == 1 for v in m.stride) and all(v == 0 for v in m.padding)

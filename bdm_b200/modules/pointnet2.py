@@ -7,6 +7,7 @@ import torch.nn as nn
 
 from .. import functional as F
 from ..functional import ops as _ops
+from . import layers as _layers
 from .layers import SharedMLP
 
 
@@ -23,6 +24,17 @@ class BallQuery(nn.Module):
     def forward(self, points_coords, centers_coords, temb, points_features=None):
         pts, cen = points_coords.contiguous(), centers_coords.contiguous()
         nbr = F.ball_query(cen, pts, self.radius, self.num_neighbors)          # int32[B,M,U]
+        if (points_features is not None and self.include_coordinates and pts.is_cuda and not torch.is_grad_enabled()
+                and not _ops.REFERENCE_CALL_PATTERN and hasattr(_ops._B, "grouping_into")
+                and points_features.dtype == torch.float32):
+            # inference: both groupings write straight into the concatenated tensor, centres subtracted on
+            # the way (same values as grouping -> broadcast subtract -> cat, two full-size passes less)
+            feats = points_features.contiguous()
+            grouped = torch.empty((pts.shape[0], 3 + feats.shape[1], nbr.shape[1], nbr.shape[2]),
+                                  dtype=torch.float32, device=pts.device)
+            _ops._B.grouping_into(pts, nbr, grouped, 0, centers=cen)
+            _ops._B.grouping_into(feats, nbr, grouped, 3)
+            return grouped, F.group_time_embedding(temb, nbr)
         rel = F.grouping(pts, nbr) - cen.unsqueeze(-1)                           # f32[B,3,M,U]
         if points_features is None:
             assert self.include_coordinates, 'No Features For Grouping'
@@ -138,6 +150,13 @@ class PointNetFPModule(nn.Module):
             up = F.three_nn_interpolate(centers_features, idx, w)
             up_temb = F.three_nn_interpolate(temb, idx, w)
         if skip is not None:
+            first = self.mlp.layers[0]
+            if (_layers._fusable(up) and _layers._pointwise(first) and isinstance(first, nn.Conv1d)
+                    and skip.dtype == torch.float32 and skip.dim() == 3 and skip.stride(2) == 1
+                    and skip.stride(1) == skip.shape[2]):
+                # inference: the first 1x1 conv consumes the two tensors separately (no concatenated copy)
+                y = _layers.conv_no_bias_concat(first, [up, skip])
+                return self.mlp.layers(None, first_output=y), points_coords, up_temb
             up = torch.cat([up, skip], dim=1)
         return self.mlp(up), points_coords, up_temb
 

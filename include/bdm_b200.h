@@ -130,6 +130,14 @@ int bdm_ball_query(int b, int n, int m, float r2, int u, const float *centers_co
  *   out[b,c,m,u] = features[b,c,indices[b,m,u]] */
 int bdm_grouping(int b, int c, int n, int m, int u, const float *features, const int *indices,
                  float *out, bdm_stream_t stream);
+/* bdm_grouping writing channels [channel_offset, channel_offset + c) of a tensor out f32[b,out_channels,m,u]
+ * and, when centers f32[b,c,m] is not NULL, subtracting the centre: the reference's BallQuery.forward
+ * (modules/ball_query.py:23-33) groups coordinates and features separately, subtracts the centres with a
+ * broadcast op and concatenates the two; with this entry point both groupings fill the concatenated tensor
+ * directly (same values: one fp32 subtraction per coordinate). */
+int bdm_grouping_into(int b, int c, int n, int m, int u, const float *features, const int *indices,
+                      const float *centers, float *out, int out_channels, int channel_offset,
+                      bdm_stream_t stream);
 int bdm_grouping_grad(int b, int c, int n, int m, int u, const float *grad_y, const int *indices,
                       float *grad_x, bdm_stream_t stream);
 

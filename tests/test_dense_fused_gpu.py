@@ -225,3 +225,29 @@ def test_attention_block_fused_kernel(cuda_backend):
     finally:
         L.FUSED_ATTENTION, torch.backends.cudnn.allow_tf32 = saved
     assert (y1 - y0).abs().max().item() <= 1e-5 * y0.abs().max().item()
+
+
+def test_fp_module_without_concatenation(cuda_backend):
+    """PointNetFPModule: first conv over (interpolated, skip) separately == conv over their concatenation"""
+    import torch
+
+    import bdm_b200.modules.layers as L
+    from bdm_b200.modules import PointNetFPModule
+    torch.manual_seed(4)
+    fp = PointNetFPModule(in_channels=64 + 390, out_channels=(128, 64)).cuda().eval()
+    pts = torch.randn(2, 3, 1024, device="cuda")
+    cen = pts[:, :, :256].contiguous()
+    cen_feats = torch.randn(2, 64, 256, device="cuda")
+    full = torch.randn(2, 393, 1024, device="cuda")
+    skip = full[:, 3:, :]                      # a channel-sliced view, as in the denoiser
+    temb = torch.randn(2, 16, 256, device="cuda")
+    saved = (L.FUSED_NORM_ACT, torch.backends.cudnn.allow_tf32)
+    try:
+        torch.backends.cudnn.allow_tf32 = False
+        with torch.no_grad():
+            y1 = fp((pts, cen, cen_feats, skip, temb))[0]
+            L.FUSED_NORM_ACT = False             # module-by-module route, with torch.cat
+            y0 = fp((pts, cen, cen_feats, skip, temb))[0]
+    finally:
+        L.FUSED_NORM_ACT, torch.backends.cudnn.allow_tf32 = saved
+    assert (y1 - y0).abs().max().item() <= 1e-5 * y0.abs().max().item()

@@ -217,3 +217,23 @@ def test_input_checks_raise(cuda_backend):
         cuda_backend.grouping_forward(f, torch.zeros((1, 2, 2), dtype=torch.int64, device="cuda"))
     with pytest.raises(RuntimeError):
         cuda_backend.ball_query(f.transpose(1, 2), f, 0.1, 4)
+
+
+@pytest.mark.parametrize("b,c,n,m,u", [(2, 5, 300, 40, 8), (3, 64, 4096, 1024, 32), (1, 7, 50, 9, 3), (2, 32, 1024, 256, 32)])
+def test_grouping_into_concatenated_tensor(b, c, n, m, u, cuda_backend):
+    """BallQuery's grouping -> subtract centres -> cat, written in place: bit-exact against the oracle's
+    grouping followed by the same fp32 subtraction"""
+    import torch
+
+    import oracle
+    rng = np.random.default_rng(b * 7 + u)
+    pts = rng.normal(size=(b, 3, n)).astype(np.float32)
+    feats = rng.normal(size=(b, c, n)).astype(np.float32)
+    cen = rng.normal(size=(b, 3, m)).astype(np.float32)
+    idx = rng.integers(0, n, size=(b, m, u)).astype(np.int32)
+    want = np.concatenate([oracle.grouping_forward(pts, idx) - cen[..., None], oracle.grouping_forward(feats, idx)], axis=1)
+    out = torch.full((b, 3 + c, m, u), float("nan"), device="cuda")
+    ti = torch.from_numpy(idx).cuda()
+    cuda_backend.grouping_into(torch.from_numpy(pts).cuda(), ti, out, 0, centers=torch.from_numpy(cen).cuda())
+    cuda_backend.grouping_into(torch.from_numpy(feats).cuda(), ti, out, 3)
+    assert np.array_equal(out.cpu().numpy(), want)

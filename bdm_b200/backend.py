@@ -171,9 +171,9 @@ def avg_voxelize_compact(features, plan):
 
 
 @_op(1)
-def sparse_conv3_gather(taps, plan, bias=None):
+def sparse_conv3_gather(taps, plan, bias=None, channels_last=False):
     """taps f32[B,N,27*Cout] (per-occupied-voxel tap products) + VoxelPlan -> the dense output
-    f32[B,Cout,R,R,R] of the zero-padded 3x3x3 convolution."""
+    f32[B,Cout,R,R,R] of the zero-padded 3x3x3 convolution (f32[B,R,R,R,Cout] when channels_last)."""
     _chk_float(taps, "taps")
     b, n, k = taps.shape
     _req(b == plan.b and n == plan.n and k % 27 == 0, "taps do not match the voxel plan")
@@ -181,10 +181,24 @@ def sparse_conv3_gather(taps, plan, bias=None):
     if bias is not None:
         _chk_float(bias, "bias")
         _req(bias.numel() == cout, "bias must hold one value per output channel")
-    out = torch.empty((b, cout, r, r, r), dtype=_F32, device=taps.device)
+    out = torch.empty((b, r, r, r, cout) if channels_last else (b, cout, r, r, r), dtype=_F32, device=taps.device)
     with _Launch(taps) as st:
         _check(_L.bdm_sparse_conv3_gather(b, cout, n, r, taps.data_ptr(), bias.data_ptr() if bias is not None else None,
-                                          out.data_ptr(), plan.workspace.data_ptr(), plan.workspace.numel(), st))
+                                          out.data_ptr(), 1 if channels_last else 0, plan.workspace.data_ptr(),
+                                          plan.workspace.numel(), st))
+    return out
+
+
+@_op(1)
+def trilinear_devoxelize_cl(grid, coords, resolution):
+    """grid f32[B,R,R,R,C] (channels last) + float voxel coordinates f32[B,3,N] -> f32[B,C,N]; inference only"""
+    _chk_float(grid, "grid")
+    _chk_float(coords, "coords")
+    b, c, n, r = grid.shape[0], grid.shape[-1], coords.shape[2], int(resolution)
+    _req(grid.numel() == b * r * r * r * c, "grid does not match the resolution")
+    out = torch.empty((b, c, n), dtype=_F32, device=grid.device)
+    with _Launch(grid) as st:
+        _check(_L.bdm_trilinear_devoxelize_cl(b, c, n, r, coords.data_ptr(), grid.data_ptr(), out.data_ptr(), st))
     return out
 
 
@@ -487,6 +501,34 @@ def groupnorm_act(x, num_groups, weight, bias, eps, swish=True, conv_bias=None, 
                                     sums.data_ptr() if sums is not None else None, ws.data_ptr(), ws.numel(), st))
     if channel_sums:
         return y, sums.sum(dim=1).view(b, c)
+    return y
+
+
+def groupnorm_cl_supported(channels, num_groups):
+    return bool(_L.bdm_groupnorm_cl_supported(int(channels), int(num_groups)))
+
+
+@_op(2)
+def groupnorm_act_cl(x, num_groups, weight, bias, eps, swish=True, conv_bias=None, channel_sums=False):
+    """Channels-last flavour of groupnorm_act: x f32[B,*,C] contiguous (channel innermost) -> same layout;
+    channel_sums: also f32[B,C] sums of the output over the voxels."""
+    _chk_float(x, "x")
+    b, c = x.shape[0], x.shape[-1]
+    s = x.numel() // max(b * c, 1)
+    dev = x.device
+    y = torch.empty_like(x)
+    sums = None
+    if channel_sums:
+        sums = torch.empty((b, _L.bdm_groupnorm_cl_tiles(b, c, s), c), dtype=_F32, device=dev)
+    ws = _workspace(_L.bdm_groupnorm_cl_workspace_bytes(b, c, s), dev)
+    with _Launch(x) as st:
+        _check(_L.bdm_groupnorm_act_cl(b, c, s, int(num_groups), float(eps), 1 if swish else 0, x.data_ptr(),
+                                       conv_bias.data_ptr() if conv_bias is not None else None,
+                                       weight.data_ptr() if weight is not None else None,
+                                       bias.data_ptr() if bias is not None else None, y.data_ptr(),
+                                       sums.data_ptr() if sums is not None else None, ws.data_ptr(), ws.numel(), st))
+    if channel_sums:
+        return y, sums.sum(dim=1)
     return y
 
 

@@ -376,6 +376,52 @@ devox_gather_kernel(int c, int n, int r, int is_training, const float *__restric
   }
 }
 
+// Channels-last grid (inference): feat f32[b][r^3][c] as the channels-last voxel branch leaves it
+// (modules/point_voxel.py).  A warp takes one point: its 8 corner rows are c contiguous floats each
+// (lane = channel, fully coalesced), blended with the same weights in the same order as everywhere else
+// in this file; a [32 points][c] tile is transposed through shared memory so that outs[b][c][n] is
+// written as 128-byte row segments.
+constexpr int kDevoxClWarps = 8;
+
+__global__ void __launch_bounds__(kDevoxClWarps * 32)
+devox_cl_kernel(int c, int n, int r, const float *__restrict__ coords, const float *__restrict__ feat,
+                float *__restrict__ outs) {
+  extern __shared__ float tile[];   // [32][c + 1]
+  const int b = blockIdx.y, i0 = blockIdx.x * 32;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r2 = r * r;
+  const size_t r3 = (size_t)r2 * r;
+  const float *co = coords + (size_t)b * 3 * n;
+  const float *f = feat + (size_t)b * r3 * c;
+  const int ld = c + 1;
+  for (int p = warp; p < 32; p += kDevoxClWarps) {
+    const int i = i0 + p;
+    if (i >= n) break;
+    Corner8 k;
+    devox_corners(__ldg(co + i), __ldg(co + i + n), __ldg(co + i + n + n), r, r2, k);
+    for (int cc = lane; cc < c; cc += 32) {
+      const float f0 = __ldg(f + (size_t)k.id[0] * c + cc), f1 = __ldg(f + (size_t)k.id[1] * c + cc),
+                  f2 = __ldg(f + (size_t)k.id[2] * c + cc), f3 = __ldg(f + (size_t)k.id[3] * c + cc),
+                  f4 = __ldg(f + (size_t)k.id[4] * c + cc), f5 = __ldg(f + (size_t)k.id[5] * c + cc),
+                  f6 = __ldg(f + (size_t)k.id[6] * c + cc), f7 = __ldg(f + (size_t)k.id[7] * c + cc);
+      float acc = __fmul_rn(k.w[1], f1);
+      acc = __fmaf_rn(k.w[0], f0, acc);
+      acc = __fmaf_rn(k.w[2], f2, acc);
+      acc = __fmaf_rn(k.w[3], f3, acc);
+      acc = __fmaf_rn(k.w[4], f4, acc);
+      acc = __fmaf_rn(k.w[5], f5, acc);
+      acc = __fmaf_rn(k.w[6], f6, acc);
+      acc = __fmaf_rn(k.w[7], f7, acc);
+      tile[p * ld + cc] = acc;
+    }
+  }
+  __syncthreads();
+  const int np = min(32, n - i0);
+  float *o = outs + (size_t)b * c * n + i0;
+  for (int cc = warp; cc < c; cc += kDevoxClWarps)
+    if (lane < np) o[(size_t)cc * n + lane] = tile[lane * ld + cc];
+}
+
 // backward (trilinear_devox.cu:119-162): 8 atomic scatter-adds of fl(w*g) per (point, channel).
 __global__ void __launch_bounds__(kDevoxThreads)
 devox_grad_kernel(int c, int n, int r3, const int *__restrict__ inds, const float *__restrict__ wgts,
@@ -556,5 +602,22 @@ extern "C" int bdm_trilinear_devoxelize_grad(int b, int c, int n, int r3, const 
     devox_grad_kernel<<<dim3(ceil_div(n, kDevoxThreads), cy, b), kDevoxThreads, 0, st>>>(c, n, r3, inds, wgts,
                                                                                          grad_y, grad_x);
   }
+  BDM_RETURN_LAUNCH_STATUS();
+}
+
+// Inference devoxelization from a channels-last grid feat f32[b][r^3][c] -> outs f32[b][c][n]; same
+// arithmetic (weights, corner order, fma chain) as bdm_trilinear_devoxelize.
+extern "C" int bdm_trilinear_devoxelize_cl(int b, int c, int n, int r, const float *coords, const float *feat,
+                                           float *outs, bdm_stream_t stream) {
+  using namespace bdm;
+  BDM_CHECK_SIZE(b >= 0 && c >= 0 && n >= 0 && r >= 1 && b <= 65535);
+  BDM_CHECK_SIZE((long long)r * r * r <= 0x7fffffffLL && c <= 8192);
+  if (b == 0 || c == 0 || n == 0) return BDM_OK;
+  BDM_CHECK_PTR(coords); BDM_CHECK_PTR(feat); BDM_CHECK_PTR(outs);
+  const size_t smem = sizeof(float) * 32 * (size_t)(c + 1);
+  cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void *>(devox_cl_kernel), smem);
+  if (e != cudaSuccess) return (int)e;
+  devox_cl_kernel<<<dim3(ceil_div(n, 32), b), kDevoxClWarps * 32, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
+      c, n, r, coords, feat, outs);
   BDM_RETURN_LAUNCH_STATUS();
 }

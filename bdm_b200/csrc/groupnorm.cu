@@ -341,6 +341,154 @@ static void launch_onepass(bool swish, int ctas, int nt, cudaStream_t st, int c,
   else gn_onepass_kernel<V, false><<<ctas, nt, 0, st>>>(c, s, groups, eps, tiles, x, cb, ga, be, y, ts);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Channels-last variant, x f32[b][s][c] (the layout cuDNN's tensor-core convolutions work in; keeping the
+// voxel branch in it removes the NCDHW<->NDHWC transposes cuDNN otherwise wraps around every Conv3d).
+// A thread owns 4 consecutive channels (one 128-bit column, the same for every row it visits), so the
+// per-channel constants live in registers and a pass of 256 threads covers 256*4/c whole rows -- fully
+// contiguous 4 KB reads and writes.  Statistics are per channel (shifted by the channel's first value),
+// folded per group, with the conv bias analytically, in the apply kernel's prologue, as above.
+// Needs c in {16, 32, 64, 128, 256} (c/4 divides 256, c <= 256).
+// ------------------------------------------------------------------------------------------------
+constexpr int kClThreads = 256;
+constexpr int kClMaxChunks = 32;
+
+static inline bool gn_cl_supported(int c, int groups) {
+  return c >= 16 && c <= 256 && (c & (c - 1)) == 0 && c % groups == 0 && (c / groups) >= 1;
+}
+static inline int gn_cl_chunks(int b, long long s, int c) {
+  const int rpp = kClThreads / (c / 4);
+  long long want = (2LL * sm_count() + b - 1) / b;
+  long long maxc = (s + rpp - 1) / rpp;
+  return (int)max(1LL, min(min(want, (long long)kClMaxChunks), maxc));
+}
+static inline int gn_cl_tiles(int b, long long s, int c) {
+  const int rpp = kClThreads / (c / 4);
+  long long want = (4LL * sm_count() + b - 1) / b;
+  long long maxc = (s + 4LL * rpp - 1) / (4LL * rpp);
+  return (int)max(1LL, min(min(want, 64LL), maxc));
+}
+
+__global__ void __launch_bounds__(kClThreads)
+gn_cl_stats_kernel(int c, long long s, int nchunks, const float *__restrict__ x, double2 *__restrict__ partials) {
+  __shared__ double2 red[kClThreads * 4];   // [rows per pass][c]
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  const int c4 = c >> 2, rpp = kClThreads / c4;
+  const int q = threadIdx.x % c4, r0 = threadIdx.x / c4;
+  const float *px = x + (size_t)b * s * c;
+  long long per = (s + nchunks - 1) / nchunks;
+  const long long lo = min((long long)chunk * per, s), hi = min(lo + per, s);
+  const float4 k = __ldg(reinterpret_cast<const float4 *>(px) + q);   // the channels' values at the first voxel
+  float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+  double d1[4] = {0., 0., 0., 0.}, d2[4] = {0., 0., 0., 0.};
+  int since = 0;
+  for (long long row = lo + r0; row < hi; row += rpp) {
+    const float4 v = ld_stream_f4(px + (size_t)row * c + 4 * q);
+    const float e0 = v.x - k.x, e1 = v.y - k.y, e2 = v.z - k.z, e3 = v.w - k.w;
+    s1[0] += e0; s1[1] += e1; s1[2] += e2; s1[3] += e3;
+    s2[0] += e0 * e0; s2[1] += e1 * e1; s2[2] += e2 * e2; s2[3] += e3 * e3;
+    if (++since == 64) {   // bound the fp32 run length
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { d1[j] += s1[j]; d2[j] += s2[j]; s1[j] = s2[j] = 0.f; }
+      since = 0;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) red[r0 * c + 4 * q + j] = make_double2(d1[j] + s1[j], d2[j] + s2[j]);
+  __syncthreads();
+  if (threadIdx.x < c) {
+    double a1 = 0.0, a2 = 0.0;
+    for (int r = 0; r < rpp; ++r) { a1 += red[r * c + threadIdx.x].x; a2 += red[r * c + threadIdx.x].y; }
+    partials[((size_t)b * nchunks + chunk) * c + threadIdx.x] = make_double2(a1, a2);
+  }
+}
+
+template <bool SWISH>
+__global__ void __launch_bounds__(kClThreads)
+gn_cl_apply_kernel(int c, long long s, int groups, int nchunks, int ntiles, float eps,
+                   const float *__restrict__ x, const float *__restrict__ conv_bias,
+                   const float *__restrict__ gamma, const float *__restrict__ beta,
+                   const double2 *__restrict__ partials, float *__restrict__ y, float *__restrict__ tile_sums) {
+  __shared__ double2 chan[256];          // per-channel folded (sum, sumsq) of x + conv_bias
+  __shared__ double2 grp[256];           // per-group (mean, rstd)
+  __shared__ float2 ab[256];             // per-channel (A, B): y = act(x * A + B)
+  __shared__ float sums[kClThreads * 4]; // [rows per pass][c] for the SE squeeze
+  const int b = blockIdx.y, tile = blockIdx.x;
+  const int c4 = c >> 2, rpp = kClThreads / c4, cg = c / groups;
+  const float *px = x + (size_t)b * s * c;
+  const int t = threadIdx.x;
+  if (t < c) {
+    // true sums of (x + bias) from the shifted partials: with tt = k_c + bias_c,
+    //   sum = S1 + s*tt,  sumsq = S2 + 2*tt*S1 + s*tt^2
+    double S1 = 0.0, S2 = 0.0;
+    for (int ch = 0; ch < nchunks; ++ch) {
+      const double2 v = partials[((size_t)b * nchunks + ch) * c + t];
+      S1 += v.x; S2 += v.y;
+    }
+    double tt = (double)__ldg(px + t);
+    if (conv_bias != nullptr) tt += (double)conv_bias[t];
+    const double ds = (double)s;
+    chan[t] = make_double2(S1 + ds * tt, S2 + 2.0 * tt * S1 + ds * tt * tt);
+  }
+  __syncthreads();
+  if (t < groups) {
+    double S1 = 0.0, S2 = 0.0;
+    for (int j = 0; j < cg; ++j) { S1 += chan[t * cg + j].x; S2 += chan[t * cg + j].y; }
+    const double n = (double)cg * (double)s;
+    const double mean = S1 / n;
+    const double var = fmax(S2 / n - mean * mean, 0.0);
+    grp[t] = make_double2(mean, 1.0 / sqrt(var + (double)eps));
+  }
+  __syncthreads();
+  if (t < c) {
+    const double2 g = grp[t / cg];
+    const float ga = gamma != nullptr ? gamma[t] : 1.0f;
+    const float be = beta != nullptr ? beta[t] : 0.0f;
+    const float cb = conv_bias != nullptr ? conv_bias[t] : 0.0f;
+    const float A = (float)g.y * ga;
+    ab[t] = make_float2(A, (float)((double)be + ((double)cb - g.x) * (double)A));
+  }
+  __syncthreads();
+  const int q = t % c4, r0 = t / c4;
+  const float2 p0 = ab[4 * q], p1 = ab[4 * q + 1], p2 = ab[4 * q + 2], p3 = ab[4 * q + 3];
+  auto act = [](float v) { return SWISH ? v / (1.0f + expf(-v)) : v; };
+  long long per = (s + ntiles - 1) / ntiles;
+  per = (per + rpp - 1) / rpp * rpp;
+  const long long lo = min((long long)tile * per, s), hi = min(lo + per, s);
+  float *py = y + (size_t)b * s * c;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  long long row = lo + r0;
+  for (; row + 3LL * rpp < hi; row += 4LL * rpp) {   // 4 loads in flight per thread
+    float4 v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = ld_stream_f4(px + (size_t)(row + (long long)j * rpp) * c + 4 * q);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      v[j].x = act(fmaf(v[j].x, p0.x, p0.y)); v[j].y = act(fmaf(v[j].y, p1.x, p1.y));
+      v[j].z = act(fmaf(v[j].z, p2.x, p2.y)); v[j].w = act(fmaf(v[j].w, p3.x, p3.y));
+      *reinterpret_cast<float4 *>(py + (size_t)(row + (long long)j * rpp) * c + 4 * q) = v[j];
+      acc[0] += v[j].x; acc[1] += v[j].y; acc[2] += v[j].z; acc[3] += v[j].w;
+    }
+  }
+  for (; row < hi; row += rpp) {
+    float4 v = ld_stream_f4(px + (size_t)row * c + 4 * q);
+    v.x = act(fmaf(v.x, p0.x, p0.y)); v.y = act(fmaf(v.y, p1.x, p1.y));
+    v.z = act(fmaf(v.z, p2.x, p2.y)); v.w = act(fmaf(v.w, p3.x, p3.y));
+    *reinterpret_cast<float4 *>(py + (size_t)row * c + 4 * q) = v;
+    acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[3] += v.w;
+  }
+  if (tile_sums != nullptr) {   // per-tile, per-channel sums of y in fixed slots: deterministic
+#pragma unroll
+    for (int j = 0; j < 4; ++j) sums[r0 * c + 4 * q + j] = acc[j];
+    __syncthreads();
+    if (t < c) {
+      float a = 0.0f;
+      for (int r = 0; r < rpp; ++r) a += sums[r * c + t];
+      tile_sums[((size_t)b * ntiles + tile) * c + t] = a;
+    }
+  }
+}
+
 }  // namespace bdm
 
 extern "C" size_t bdm_groupnorm_workspace_bytes(int b, int c, long long s) {
@@ -414,5 +562,42 @@ extern "C" int bdm_groupnorm_act(int b, int c, long long s, int groups, float ep
   if (max_over_u) { if (swish) BDM_GN_LAUNCH(true, 1); else BDM_GN_LAUNCH(false, 1); }
   else            { if (swish) BDM_GN_LAUNCH(true, 0); else BDM_GN_LAUNCH(false, 0); }
 #undef BDM_GN_LAUNCH
+  BDM_RETURN_LAUNCH_STATUS();
+}
+
+// ---- channels-last entry points: x, y f32[b][s][c]; tile_sums f32[b][tiles][c] or NULL ----
+extern "C" int bdm_groupnorm_cl_supported(int c, int groups) { return bdm::gn_cl_supported(c, groups) ? 1 : 0; }
+
+extern "C" size_t bdm_groupnorm_cl_workspace_bytes(int b, int c, long long s) {
+  if (b <= 0 || c < 16 || s <= 0) return 16;
+  return sizeof(double2) * (size_t)b * bdm::gn_cl_chunks(b, s, c) * c;
+}
+
+extern "C" int bdm_groupnorm_cl_tiles(int b, int c, long long s) {
+  if (b <= 0 || c < 16 || s <= 0) return 1;
+  return bdm::gn_cl_tiles(b, s, c);
+}
+
+extern "C" int bdm_groupnorm_act_cl(int b, int c, long long s, int groups, float eps, int swish, const float *x,
+                                    const float *conv_bias, const float *gamma, const float *beta, float *y,
+                                    float *tile_sums, void *workspace, size_t workspace_bytes,
+                                    bdm_stream_t stream) {
+  using namespace bdm;
+  BDM_CHECK_SIZE(b >= 0 && s >= 0 && groups >= 1 && gn_cl_supported(c, groups) && b <= 65535);
+  if (b == 0 || s == 0) return BDM_OK;
+  BDM_CHECK_PTR(x); BDM_CHECK_PTR(y); BDM_CHECK_PTR(workspace);
+  if (workspace_bytes < bdm_groupnorm_cl_workspace_bytes(b, c, s)) return BDM_ERR_WORKSPACE_TOO_SMALL;
+  if (((reinterpret_cast<uintptr_t>(workspace) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) != 0)
+    return BDM_ERR_MISALIGNED;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int nchunks = gn_cl_chunks(b, s, c), ntiles = gn_cl_tiles(b, s, c);
+  double2 *partials = static_cast<double2 *>(workspace);
+  gn_cl_stats_kernel<<<dim3(nchunks, b), kClThreads, 0, st>>>(c, s, nchunks, x, partials);
+  if (swish)
+    gn_cl_apply_kernel<true><<<dim3(ntiles, b), kClThreads, 0, st>>>(c, s, groups, nchunks, ntiles, eps, x, conv_bias,
+                                                                   gamma, beta, partials, y, tile_sums);
+  else
+    gn_cl_apply_kernel<false><<<dim3(ntiles, b), kClThreads, 0, st>>>(c, s, groups, nchunks, ntiles, eps, x, conv_bias,
+                                                                    gamma, beta, partials, y, tile_sums);
   BDM_RETURN_LAUNCH_STATUS();
 }

@@ -31,7 +31,7 @@ constexpr int kGatherCo = 32;
 constexpr int kGatherBatch = 4;   // occupied neighbours whose taps are in flight together (3 loads each)
 
 __global__ void __launch_bounds__(kGatherWarps * 32)
-sparse_conv3_gather_kernel(int n, int cout, int r, const float *__restrict__ taps,
+sparse_conv3_gather_kernel(int n, int cout, int r, int channels_last, const float *__restrict__ taps,
                            const float *__restrict__ bias, float *__restrict__ out,
                            const unsigned char *__restrict__ ws, VoxAuxLayout L) {
   __shared__ float tile[kGatherWarps][32][kGatherCo + 1];
@@ -113,8 +113,17 @@ sparse_conv3_gather_kernel(int n, int cout, int r, const float *__restrict__ tap
   }
   __syncwarp();
 
-  // transposed write-out, one 4r-byte row segment per output channel
   const int nco = min(kGatherCo, cout - co0);
+  if (channels_last) {
+    // out[b][voxel][co]: the tile rows are already channel-contiguous; lane = channel, 128 bytes per voxel
+    if (lane < nco) {
+      float *o = out + ((size_t)b * r3 + (size_t)row * r) * cout + co0 + lane;
+      const float bb = bias ? __ldg(bias + co0 + lane) : 0.0f;
+      for (int z = 0; z < r; ++z) o[(size_t)z * cout] = (total != 0 ? t[z][lane] : 0.0f) + bb;
+    }
+    return;
+  }
+  // transposed write-out, one 4r-byte row segment per output channel
   float *orow = out + ((size_t)b * cout + co0) * r3 + (size_t)row * r;
   if (r == 32 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
     // 8 lanes x 16 bytes cover a row; the 4 lane groups take 4 channels per store instruction
@@ -141,10 +150,10 @@ sparse_conv3_gather_kernel(int n, int cout, int r, const float *__restrict__ tap
 
 // taps f32[b][n][27][cout] (row j = the j-th occupied voxel of shape b in ascending voxel id, as produced
 // from bdm_avg_voxelize_compact; rows >= the shape's occupied count are ignored), bias f32[cout] or NULL,
-// out f32[b][cout][r^3].  workspace = the plan bdm_voxel_plan left for these (b, n, r).  r in {1,2,4,8,16,32}.
+// out f32[b][cout][r^3], or f32[b][r^3][cout] when channels_last != 0.  workspace = the plan bdm_voxel_plan left for these (b, n, r).  r in {1,2,4,8,16,32}.
 extern "C" int bdm_sparse_conv3_gather(int b, int cout, int n, int r, const float *taps, const float *bias,
-                                       float *out, const void *workspace, size_t workspace_bytes,
-                                       bdm_stream_t stream) {
+                                       float *out, int channels_last, const void *workspace,
+                                       size_t workspace_bytes, bdm_stream_t stream) {
   using namespace bdm;
   BDM_CHECK_SIZE(b >= 0 && cout >= 0 && n >= 1 && r >= 1 && r <= 32 && (r & (r - 1)) == 0);  // rows within a word
   const int r3 = r * r * r;
@@ -156,6 +165,6 @@ extern "C" int bdm_sparse_conv3_gather(int b, int cout, int n, int r, const floa
   if (rc != BDM_OK) return rc;
   dim3 grid(ceil_div(r * r, kGatherWarps), ceil_div(cout, kGatherCo), b);
   sparse_conv3_gather_kernel<<<grid, kGatherWarps * 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      n, cout, r, taps, bias, out, static_cast<const unsigned char *>(workspace), L);
+      n, cout, r, channels_last, taps, bias, out, static_cast<const unsigned char *>(workspace), L);
   BDM_RETURN_LAUNCH_STATUS();
 }

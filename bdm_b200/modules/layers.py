@@ -26,16 +26,36 @@ class Swish(nn.Module):
         return x * torch.sigmoid(x)
 
 
+def is_channels_last_3d(x):
+    """a [B,C,D,H,W] tensor whose memory is [B,D,H,W,C] (and not also plain-contiguous)"""
+    return x.dim() == 5 and not x.is_contiguous() and x.is_contiguous(memory_format=torch.channels_last_3d)
+
+
 def _fusable(x):
-    return (FUSED_NORM_ACT and x.is_cuda and x.dtype == torch.float32 and x.dim() >= 3 and x.is_contiguous()
+    return (FUSED_NORM_ACT and x.is_cuda and x.dtype == torch.float32 and x.dim() >= 3
+            and (x.is_contiguous() or is_channels_last_3d(x))
             and not torch.is_grad_enabled() and not _ops.REFERENCE_CALL_PATTERN
             and hasattr(_ops._B, "groupnorm_act"))
+
+
+def _groupnorm_act(y, gn, swish, conv_bias=None, **kw):
+    """fused norm(+act) on a plain-contiguous or channels-last-3d tensor, layout preserved"""
+    if is_channels_last_3d(y):
+        if hasattr(_ops._B, "groupnorm_act_cl") and _ops._B.groupnorm_cl_supported(y.shape[1], gn.num_groups) \
+                and not kw.get("max_over_last"):
+            out = _ops._B.groupnorm_act_cl(y.permute(0, 2, 3, 4, 1), gn.num_groups, gn.weight, gn.bias, gn.eps, swish,
+                                           conv_bias=conv_bias, channel_sums=kw.get("channel_sums", False))
+            if isinstance(out, tuple):
+                return out[0].permute(0, 4, 1, 2, 3), out[1]
+            return out.permute(0, 4, 1, 2, 3)
+        y = y.contiguous()
+    return _ops._B.groupnorm_act(y, gn.num_groups, gn.weight, gn.bias, gn.eps, swish, conv_bias=conv_bias, **kw)
 
 
 def norm_act(norm, x, swish=True):
     """swish(norm(x)) for an nn.GroupNorm `norm`, through the fused kernel when possible."""
     if isinstance(norm, nn.GroupNorm) and _fusable(x):
-        return _ops._B.groupnorm_act(x, norm.num_groups, norm.weight, norm.bias, norm.eps, swish)
+        return _groupnorm_act(x, norm, swish)
     y = norm(x)
     return y * torch.sigmoid(y) if swish else y
 
@@ -99,6 +119,16 @@ def conv_no_bias(m, x):
     tail costs two GEMM launches and no copy of x.  TF32 follows the conv policy (cudnn.allow_tf32), as for
     every other convolution of the network."""
     cin = m.in_channels
+    if isinstance(m, nn.Conv3d) and is_channels_last_3d(x):
+        # channels-last activations: hand cuDNN the weight in the same format (cached), so that it neither
+        # transposes the weight on every call nor the activations around the kernel
+        w = m.weight
+        key = (w.data_ptr(), w._version, w.device)
+        cached = getattr(m, "_cl_weight", None)
+        if cached is None or cached[0] != key:
+            cached = (key, w.detach().contiguous(memory_format=torch.channels_last_3d))
+            m._cl_weight = cached
+        return m._conv_forward(x, cached[1], None)
     if not (_pointwise(m) and cin % 4 != 0 and cin >= 32 and x.is_cuda and x.is_contiguous()):
         return m._conv_forward(x, m.weight, None)
     w = m.weight
@@ -151,8 +181,7 @@ class FusedSequential(nn.Sequential):
                 nxt = i + (3 if swish else 2)
                 y = pre if pre is not None else conv_no_bias(m, x)
                 if nxt < n and isinstance(mods[nxt], SE3d) and swish:
-                    y, sums = _ops._B.groupnorm_act(y, gn.num_groups, gn.weight, gn.bias, gn.eps, True,
-                                                    conv_bias=m.bias, channel_sums=True)
+                    y, sums = _groupnorm_act(y, gn, True, conv_bias=m.bias, channel_sums=True)
                     if defer_gate and nxt == n - 1:
                         x, gate = y, mods[nxt].gate(y, channel_sums=sums)
                     else:
@@ -160,11 +189,10 @@ class FusedSequential(nn.Sequential):
                     nxt += 1
                 elif (max_over_last and nxt == n and swish and y.dim() == 4
                       and _ops._B.groupnorm_max_supported(y.shape[-1])):
-                    x = _ops._B.groupnorm_act(y, gn.num_groups, gn.weight, gn.bias, gn.eps, True,
-                                              conv_bias=m.bias, max_over_last=True)
+                    x = _groupnorm_act(y, gn, True, conv_bias=m.bias, max_over_last=True)
                     reduced = True
                 else:
-                    x = _ops._B.groupnorm_act(y, gn.num_groups, gn.weight, gn.bias, gn.eps, swish, conv_bias=m.bias)
+                    x = _groupnorm_act(y, gn, swish, conv_bias=m.bias)
                 i = nxt
             elif pre is not None:
                 x = pre if m.bias is None else pre + m.bias.view(1, -1, *([1] * (pre.dim() - 2)))

@@ -10,6 +10,7 @@ import torch.nn as nn
 from .. import functional as F
 from ..functional import geometry
 from ..functional import ops as _ops
+from . import layers as _layers
 from .layers import SE3d, Attention, FusedSequential, SharedMLP, Swish
 
 # The first Conv3d of a PVConv block reads a freshly voxelized cloud: N points occupy at most N of the R^3
@@ -21,6 +22,10 @@ from .layers import SE3d, Attention, FusedSequential, SharedMLP, Swish
 SPARSE_FIRST_CONV = os.environ.get("BDM_SPARSE_CONV", "1") != "0"
 SPARSE_MAX_FILL = float(os.environ.get("BDM_SPARSE_MAX_FILL", "0.125"))
 DEFER_SE_GATE = os.environ.get("BDM_DEFER_SE_GATE", "1") != "0"
+# Keep the voxel branch of a sparse-first-conv block in channels-last memory ([B,R,R,R,C]): the gather writes
+# it, the fused norm kernels and the devoxelization read it, and cuDNN's Conv3d (whose tensor-core kernels are
+# NDHWC inside) stops wrapping two transposes around every call.  Same values; BDM_CHANNELS_LAST=0 disables.
+CHANNELS_LAST_VOXELS = os.environ.get("BDM_CHANNELS_LAST", "1") != "0"
 
 
 def normalized_voxel_coords(coords, resolution, normalize=True, eps=0):
@@ -148,6 +153,9 @@ class _PVConvBase(nn.Module):
             taps = torch.matmul(occupied.transpose(1, 2), self._tap_matrix(self.voxel_layers[0]))  # [B, N, 27*Cout]
         finally:
             torch.backends.cuda.matmul.allow_tf32 = prev
+        if (CHANNELS_LAST_VOXELS and hasattr(_ops._B, "groupnorm_act_cl")
+                and _ops._B.groupnorm_cl_supported(self.out_channels, 8)):
+            return _ops._B.sparse_conv3_gather(taps, plan, channels_last=True).permute(0, 4, 1, 2, 3), norm_coords
         return _ops._B.sparse_conv3_gather(taps, plan), norm_coords
 
     def forward(self, inputs):
@@ -167,7 +175,11 @@ class _PVConvBase(nn.Module):
         gate = None
         if defer:
             grid, gate = grid
-        from_voxels = F.trilinear_devoxelize(grid, grid_coords, self.resolution, self.training)
+        if _layers.is_channels_last_3d(grid) and not torch.is_grad_enabled():
+            from_voxels = _ops._B.trilinear_devoxelize_cl(grid.permute(0, 2, 3, 4, 1), grid_coords.contiguous(),
+                                                          self.resolution)
+        else:
+            from_voxels = F.trilinear_devoxelize(grid, grid_coords, self.resolution, self.training)
         if gate is not None:
             return torch.addcmul(self.point_features(features), from_voxels, gate[:, :, None]), coords, temb
         return from_voxels + self.point_features(features), coords, temb

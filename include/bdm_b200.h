@@ -72,11 +72,13 @@ int bdm_avg_voxelize_fill(int b, int c, int n, int r, const int *ind, const int 
  *                              (taps[b,j,k,co] = sum_ci W[co,ci,kd,kh,kw] * compact[b,ci,j], k=(kd*3+kh)*3+kw,
  *                              one GEMM on the host side): out[b,co,x,y,z] = bias[co] + sum_k taps[b,
  *                              slot(x+kd-1,y+kh-1,z+kw-1),k,co], k ascending.  bias may be NULL.
- *                              r must be a power of two <= 32. */
+ *                              r must be a power of two <= 32.  channels_last != 0 writes out f32[b,r^3,cout]
+ *                              (NDHWC, what cuDNN's tensor-core Conv3d kernels work in) instead of
+ *                              f32[b,cout,r^3]. */
 int bdm_avg_voxelize_compact(int b, int c, int n, int r, const float *feat, float *out,
                              const void *workspace, size_t workspace_bytes, bdm_stream_t stream);
 int bdm_sparse_conv3_gather(int b, int cout, int n, int r, const float *taps, const float *bias,
-                            float *out, const void *workspace, size_t workspace_bytes,
+                            float *out, int channels_last, const void *workspace, size_t workspace_bytes,
                             bdm_stream_t stream);
 /* replaces avg_voxelize_grad (src/voxelization/vox.cuh:7-8): grad_y f32[b,c,s] -> grad_x f32[b,c,n] */
 int bdm_avg_voxelize_grad(int b, int c, int n, int s, const int *ind, const int *cnt,
@@ -99,6 +101,9 @@ int bdm_trilinear_devoxelize(int b, int c, int n, int r, int is_training, const 
                              const float *feat, int *inds, float *wgts, float *outs,
                              void *workspace, size_t workspace_bytes, int planned,
                              bdm_stream_t stream);
+/* inference devoxelization from a channels-last grid feat f32[b,r^3,c] (same arithmetic, outs f32[b,c,n]) */
+int bdm_trilinear_devoxelize_cl(int b, int c, int n, int r, const float *coords, const float *feat,
+                                float *outs, bdm_stream_t stream);
 /* replaces trilinear_devoxelize_grad (trilinear_devox.cuh:9-11): grad_x f32[b,c,r3] is zeroed here */
 int bdm_trilinear_devoxelize_grad(int b, int c, int n, int r3, const int *inds, const float *wgts,
                                   const float *grad_y, float *grad_x, bdm_stream_t stream);
@@ -229,6 +234,14 @@ int bdm_groupnorm_act(int b, int c, long long s, int groups, float eps, int swis
                       const float *x, const float *conv_bias, const float *gamma, const float *beta,
                       float *y, float *tile_sums, void *workspace, size_t workspace_bytes,
                       bdm_stream_t stream);
+/* channels-last flavour: x, y f32[b,s,c]; tile_sums f32[b,tiles,c] (tiles = bdm_groupnorm_cl_tiles) or NULL.
+ * c must be a power of two in [16,256] (bdm_groupnorm_cl_supported). */
+int bdm_groupnorm_cl_supported(int c, int groups);
+size_t bdm_groupnorm_cl_workspace_bytes(int b, int c, long long s);
+int bdm_groupnorm_cl_tiles(int b, int c, long long s);
+int bdm_groupnorm_act_cl(int b, int c, long long s, int groups, float eps, int swish, const float *x,
+                         const float *conv_bias, const float *gamma, const float *beta, float *y,
+                         float *tile_sums, void *workspace, size_t workspace_bytes, bdm_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -251,3 +251,31 @@ def test_fp_module_without_concatenation(cuda_backend):
     finally:
         L.FUSED_NORM_ACT, torch.backends.cudnn.allow_tf32 = saved
     assert (y1 - y0).abs().max().item() <= 1e-5 * y0.abs().max().item()
+
+
+@pytest.mark.parametrize("swish", [True, False])
+@pytest.mark.parametrize("b,c,spatial", [(16, 32, (32, 32, 32)), (4, 64, (16, 16, 16)), (2, 256, (8, 8, 8)), (3, 16, (5, 7, 3)),
+                                         (2, 128, (4, 4, 4))])
+def test_groupnorm_channels_last_vs_torch(b, c, spatial, swish, cuda_backend):
+    import torch
+    import torch.nn.functional as TF
+    g = torch.Generator(device="cuda").manual_seed(b + c)
+    x = torch.randn((b, c) + spatial, device="cuda", generator=g) * 2.0 + 0.3
+    cb = torch.randn(c, device="cuda", generator=g)
+    w = torch.randn(c, device="cuda", generator=g)
+    bias = torch.randn(c, device="cuda", generator=g)
+    want = TF.group_norm(x + cb.view(1, c, 1, 1, 1), 8, w, bias, 1e-5)
+    if swish:
+        want = want * torch.sigmoid(want)
+    peak = want.abs().max().item()
+    x_cl = x.permute(0, 2, 3, 4, 1).contiguous()
+    assert cuda_backend.groupnorm_cl_supported(c, 8)
+    got, sums = cuda_backend.groupnorm_act_cl(x_cl, 8, w, bias, 1e-5, swish, conv_bias=cb, channel_sums=True)
+    assert (got.permute(0, 4, 1, 2, 3) - want).abs().max().item() / peak <= 1e-5
+    want_sums = want.double().flatten(2).sum(-1)
+    assert (sums.double() - want_sums).abs().max().item() <= 1e-5 * max(want_sums.abs().max().item(), 1.0)
+    got2 = cuda_backend.groupnorm_act_cl(x_cl, 8, None, None, 1e-5, swish)
+    want2 = TF.group_norm(x, 8, None, None, 1e-5)
+    if swish:
+        want2 = want2 * torch.sigmoid(want2)
+    assert (got2.permute(0, 4, 1, 2, 3) - want2).abs().max().item() / want2.abs().max().item() <= 1e-5

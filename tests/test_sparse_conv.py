@@ -116,3 +116,33 @@ def test_pvconv_sparse_equals_dense(cin, cout, n, r, attention, cuda_backend):
         assert e_sparse <= max(3 * e_dense, 1e-5 * y_dense.abs().max().item()), (e_sparse, e_dense)
     finally:
         PV.SPARSE_FIRST_CONV, PV.SPARSE_MAX_FILL, torch.backends.cudnn.allow_tf32 = saved
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("b,cout,n,r", [(2, 32, 1000, 32), (3, 64, 4096, 32), (2, 40, 500, 16), (1, 8, 60, 8)])
+def test_gather_channels_last_is_the_same_tensor(b, cout, n, r, cuda_backend):
+    import torch
+    feats, coords = _cloud(b, 4, n, r, seed=n)
+    plan = cuda_backend.voxel_plan(torch.from_numpy(coords).cuda(), r)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    taps = torch.randn(b, n, 27 * cout, device="cuda", generator=g)
+    bias = torch.randn(cout, device="cuda", generator=g)
+    a = cuda_backend.sparse_conv3_gather(taps, plan, bias)
+    c = cuda_backend.sparse_conv3_gather(taps, plan, bias, channels_last=True)
+    assert c.shape == (b, r, r, r, cout) and c.is_contiguous()
+    assert torch.equal(c.permute(0, 4, 1, 2, 3), a)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("b,c,n,r", [(2, 64, 4096, 32), (3, 32, 1000, 32), (1, 5, 77, 8), (2, 130, 300, 16)])
+def test_devoxelize_channels_last_bit_exact(b, c, n, r, cuda_backend):
+    """same weights, corner order and fma chain as the channel-first op: bit-exact against the oracle"""
+    import torch
+    rng = np.random.default_rng(c + n)
+    grid = rng.normal(size=(b, c, r, r, r)).astype(np.float32)
+    coords = (rng.random((b, 3, n), dtype=np.float32) * (r - 1)).astype(np.float32)
+    coords[:, :, : min(n, 16)] = np.round(coords[:, :, : min(n, 16)])          # points on voxel centres / faces
+    want = oracle.trilinear_devoxelize_forward(r, False, coords, grid.reshape(b, c, -1))[0]
+    grid_cl = torch.from_numpy(grid).cuda().permute(0, 2, 3, 4, 1).contiguous()
+    got = cuda_backend.trilinear_devoxelize_cl(grid_cl, torch.from_numpy(coords).cuda(), r).cpu().numpy()
+    assert np.array_equal(got, want)

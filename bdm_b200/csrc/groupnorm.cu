@@ -382,17 +382,25 @@ gn_cl_stats_kernel(int c, long long s, int nchunks, const float *__restrict__ x,
   float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
   double d1[4] = {0., 0., 0., 0.}, d2[4] = {0., 0., 0., 0.};
   int since = 0;
-  for (long long row = lo + r0; row < hi; row += rpp) {
-    const float4 v = ld_stream_f4(px + (size_t)row * c + 4 * q);
+  auto add = [&](const float4 &v) {
     const float e0 = v.x - k.x, e1 = v.y - k.y, e2 = v.z - k.z, e3 = v.w - k.w;
     s1[0] += e0; s1[1] += e1; s1[2] += e2; s1[3] += e3;
     s2[0] += e0 * e0; s2[1] += e1 * e1; s2[2] += e2 * e2; s2[3] += e3 * e3;
-    if (++since == 64) {   // bound the fp32 run length
+  };
+  long long row = lo + r0;
+  for (; row + 3LL * rpp < hi; row += 4LL * rpp) {   // 4 loads in flight per thread
+    float4 v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = ld_stream_f4(px + (size_t)(row + (long long)j * rpp) * c + 4 * q);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) add(v[j]);
+    if (++since == 16) {   // bound the fp32 run length (64 values)
 #pragma unroll
       for (int j = 0; j < 4; ++j) { d1[j] += s1[j]; d2[j] += s2[j]; s1[j] = s2[j] = 0.f; }
       since = 0;
     }
   }
+  for (; row < hi; row += rpp) add(ld_stream_f4(px + (size_t)row * c + 4 * q));
 #pragma unroll
   for (int j = 0; j < 4; ++j) red[r0 * c + 4 * q + j] = make_double2(d1[j] + s1[j], d2[j] + s2[j]);
   __syncthreads();

@@ -1,5 +1,6 @@
 """Run one hot-path op a few times at its largest PC^2 shape (for ncu captures).
-    python tools/run_op.py voxelize|devoxelize|fps|ball_query|grouping|three_nn [--reps 3] [--batch 16]"""
+    python tools/run_op.py voxelize|devoxelize|fps|ball_query|grouping|three_nn|sparse_conv|attention|groupnorm_cl|
+                           groupnorm_small|devox_cl [--reps 3] [--batch 16]"""
 import argparse
 import os
 import sys
@@ -43,6 +44,27 @@ for _ in range(a.reps):
         c = a.channels or 64
         nb = B.ball_query(cen, co, 0.1, 32)
         B.grouping_forward(torch.randn(b, c, 4096, device="cuda"), nb)
+    elif a.op == "sparse_conv":      # compact averages -> (GEMM) -> gather, channels-last output
+        c = a.channels or 64
+        plan = B.voxel_plan(vox, 32)
+        comp = B.avg_voxelize_compact(torch.randn(b, c, 4096, device="cuda"), plan)
+        taps = torch.randn(b, 4096, 27 * 64, device="cuda")
+        B.sparse_conv3_gather(taps, plan, channels_last=True)
+    elif a.op == "attention":
+        q, k, v = (torch.randn(b, 64, 4096, device="cuda") * 0.6 for _ in range(3))
+        B.attention(q, k, v)
+    elif a.op == "groupnorm_cl":
+        c = a.channels or 64
+        x = torch.randn(b, 32, 32, 32, c, device="cuda")
+        w, bb = torch.randn(c, device="cuda"), torch.randn(c, device="cuda")
+        B.groupnorm_act_cl(x, 8, w, bb, 1e-5, True, conv_bias=bb, channel_sums=True)
+    elif a.op == "groupnorm_small":  # one-pass kernel
+        x = torch.randn(b, 256, 8, 8, 8, device="cuda")
+        w, bb = torch.randn(256, device="cuda"), torch.randn(256, device="cuda")
+        B.groupnorm_act(x, 8, w, bb, 1e-5, True, conv_bias=bb)
+    elif a.op == "devox_cl":
+        c = a.channels or 64
+        B.trilinear_devoxelize_cl(torch.randn(b, 32, 32, 32, c, device="cuda"), nc, 32)
     elif a.op == "three_nn":
         c = a.channels or 192
         B.three_nearest_neighbors_interpolate_forward(co, cen, torch.randn(b, c, 1024, device="cuda"))

@@ -31,7 +31,8 @@ _PROTOS = {
     "bdm_grouping_into": (_i, [_i, _i, _i, _i, _i, _p, _p, _p, _p, _i, _i, _p]),
     "bdm_attention": (_i, [_i, _i, _i, _p, _p, _p, _p, _p, _z, _p]),
     "bdm_sparse_conv3_gather": (_i, [_i, _i, _i, _i, _p, _p, _p, _i, _p, _z, _p]),
-    "bdm_trilinear_devoxelize_cl": (_i, [_i, _i, _i, _i, _p, _p, _p, _p]),
+    "bdm_trilinear_devoxelize_cl": (_i, [_i, _i, _i, _i, _p, _p, _p, _p, _p, _p]),
+    "bdm_se_gate": (_i, [_i, _i, _i, _i, _f, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_longlong, _p, _p, _p, _i, _p, _p]),
     "bdm_avg_voxelize_grad": (_i, [_i, _i, _i, _i, _p, _p, _p, _p, _p]),
     "bdm_trilinear_devoxelize_workspace_bytes": (_z, [_i, _i, _i]),
     "bdm_trilinear_devoxelize_plan": (_i, [_i, _i, _i, _p, _p, _z, _p]),

@@ -190,16 +190,48 @@ def sparse_conv3_gather(taps, plan, bias=None, channels_last=False):
 
 
 @_op(1)
-def trilinear_devoxelize_cl(grid, coords, resolution):
-    """grid f32[B,R,R,R,C] (channels last) + float voxel coordinates f32[B,3,N] -> f32[B,C,N]; inference only"""
+def trilinear_devoxelize_cl(grid, coords, resolution, gate=None, residual=None):
+    """grid f32[B,R,R,R,C] (channels last) + float voxel coordinates f32[B,3,N] -> f32[B,C,N]; inference only.
+    gate f32[B,C] / residual f32[B,C,N]: out = devox * gate + residual (the tail of a PVConv block)."""
     _chk_float(grid, "grid")
     _chk_float(coords, "coords")
     b, c, n, r = grid.shape[0], grid.shape[-1], coords.shape[2], int(resolution)
     _req(grid.numel() == b * r * r * r * c, "grid does not match the resolution")
+    if gate is not None:
+        _chk_float(gate, "gate")
+        _req(tuple(gate.shape) == (b, c), "gate must be [B,C]")
+    if residual is not None:
+        _chk_float(residual, "residual")
+        _req(tuple(residual.shape) == (b, c, n), "residual must be [B,C,N]")
     out = torch.empty((b, c, n), dtype=_F32, device=grid.device)
     with _Launch(grid) as st:
-        _check(_L.bdm_trilinear_devoxelize_cl(b, c, n, r, coords.data_ptr(), grid.data_ptr(), out.data_ptr(), st))
+        _check(_L.bdm_trilinear_devoxelize_cl(b, c, n, r, coords.data_ptr(), grid.data_ptr(),
+                                              gate.data_ptr() if gate is not None else None,
+                                              residual.data_ptr() if residual is not None else None,
+                                              out.data_ptr(), st))
     return out
+
+
+@_op(1)
+def se_gate(sums, count, w1, w2, use_relu):
+    """sums f32[B,C] or f32[B,tiles,C] (per-channel sums of the activations, e.g. from groupnorm_act*) ->
+    gate f32[B,C] = sigmoid(w2 @ act(w1 @ (sums / count)))"""
+    _chk_float(sums, "sums")
+    _chk_float(w1, "w1")
+    _chk_float(w2, "w2")
+    if sums.dim() == 2:
+        b, c = sums.shape
+        tiles, sb, st_, sc = 1, c, 0, 1
+    else:
+        b, tiles, c = sums.shape
+        sb, st_, sc = tiles * c, c, 1
+    hidden = w1.shape[0]
+    _req(tuple(w1.shape) == (hidden, c) and tuple(w2.shape) == (c, hidden), "SE weights do not match the channels")
+    gate = torch.empty((b, c), dtype=_F32, device=sums.device)
+    with _Launch(sums) as st:
+        _check(_L.bdm_se_gate(b, c, hidden, tiles, float(count), sb, st_, sc, sums.data_ptr(), w1.data_ptr(),
+                              w2.data_ptr(), 1 if use_relu else 0, gate.data_ptr(), st))
+    return gate
 
 
 def attention_supported(channels, tokens, batch=None):
@@ -527,6 +559,8 @@ def groupnorm_act_cl(x, num_groups, weight, bias, eps, swish=True, conv_bias=Non
                                        weight.data_ptr() if weight is not None else None,
                                        bias.data_ptr() if bias is not None else None, y.data_ptr(),
                                        sums.data_ptr() if sums is not None else None, ws.data_ptr(), ws.numel(), st))
+    if channel_sums == "tiles":     # f32[B,tiles,C], for se_gate (which folds the tiles itself)
+        return y, sums
     if channel_sums:
         return y, sums.sum(dim=1)
     return y

@@ -385,7 +385,7 @@ constexpr int kDevoxClWarps = 8;
 
 __global__ void __launch_bounds__(kDevoxClWarps * 32)
 devox_cl_kernel(int c, int n, int r, const float *__restrict__ coords, const float *__restrict__ feat,
-                float *__restrict__ outs) {
+                const float *__restrict__ gate, const float *residual, float *outs) {
   extern __shared__ float tile[];   // [32][c + 1]
   const int b = blockIdx.y, i0 = blockIdx.x * 32;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -418,8 +418,14 @@ devox_cl_kernel(int c, int n, int r, const float *__restrict__ coords, const flo
   __syncthreads();
   const int np = min(32, n - i0);
   float *o = outs + (size_t)b * c * n + i0;
+  // optional epilogue of the PVConv block (pvconv.py:97 after se.py:19): out = devox * gate[b,c] + residual
   for (int cc = warp; cc < c; cc += kDevoxClWarps)
-    if (lane < np) o[(size_t)cc * n + lane] = tile[lane * ld + cc];
+    if (lane < np) {
+      float v = tile[lane * ld + cc];
+      if (gate != nullptr) v *= __ldg(gate + (size_t)b * c + cc);
+      if (residual != nullptr) v += residual[(size_t)b * c * n + i0 + (size_t)cc * n + lane];
+      o[(size_t)cc * n + lane] = v;
+    }
 }
 
 // backward (trilinear_devox.cu:119-162): 8 atomic scatter-adds of fl(w*g) per (point, channel).
@@ -606,9 +612,11 @@ extern "C" int bdm_trilinear_devoxelize_grad(int b, int c, int n, int r3, const 
 }
 
 // Inference devoxelization from a channels-last grid feat f32[b][r^3][c] -> outs f32[b][c][n]; same
-// arithmetic (weights, corner order, fma chain) as bdm_trilinear_devoxelize.
+// arithmetic (weights, corner order, fma chain) as bdm_trilinear_devoxelize.  Optional epilogue:
+// outs = devox * gate[b][c] + residual[b][c][n] (either may be NULL; residual may alias outs).
 extern "C" int bdm_trilinear_devoxelize_cl(int b, int c, int n, int r, const float *coords, const float *feat,
-                                           float *outs, bdm_stream_t stream) {
+                                           const float *gate, const float *residual, float *outs,
+                                           bdm_stream_t stream) {
   using namespace bdm;
   BDM_CHECK_SIZE(b >= 0 && c >= 0 && n >= 0 && r >= 1 && b <= 65535);
   BDM_CHECK_SIZE((long long)r * r * r <= 0x7fffffffLL && c <= 8192);
@@ -618,6 +626,6 @@ extern "C" int bdm_trilinear_devoxelize_cl(int b, int c, int n, int r, const flo
   cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void *>(devox_cl_kernel), smem);
   if (e != cudaSuccess) return (int)e;
   devox_cl_kernel<<<dim3(ceil_div(n, 32), b), kDevoxClWarps * 32, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
-      c, n, r, coords, feat, outs);
+      c, n, r, coords, feat, gate, residual, outs);
   BDM_RETURN_LAUNCH_STATUS();
 }

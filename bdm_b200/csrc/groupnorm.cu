@@ -497,6 +497,40 @@ gn_cl_apply_kernel(int c, long long s, int groups, int nchunks, int ntiles, floa
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Squeeze-excite gate (modules/se.py:8-19) from the per-channel sums the norm kernels emit:
+//   pooled = sums / count;  gate = sigmoid(W2 . act(W1 . pooled)),  act = ReLU or Swish, no biases.
+// Through torch that is 6 tiny launches per block (sum over tiles, divide, two Linears, two activations)
+// on the critical path of every PVConv; here one CTA per sample does it.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+se_gate_kernel(int c, int hidden, int tiles, float count, long long sb, long long st_, long long sc,
+               const float *__restrict__ sums, const float *__restrict__ w1, const float *__restrict__ w2,
+               int use_relu, float *__restrict__ gate) {
+  extern __shared__ float sh[];   // pooled[c], hid[hidden]
+  float *pooled = sh, *hid = sh + c;
+  const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  for (int ch = t; ch < c; ch += 256) {
+    float a = 0.0f;
+    for (int q = 0; q < tiles; ++q) a += __ldg(sums + b * sb + q * st_ + ch * sc);
+    pooled[ch] = a / count;
+  }
+  __syncthreads();
+  for (int h = warp; h < hidden; h += 8) {
+    float a = 0.0f;
+    for (int ch = lane; ch < c; ch += 32) a = fmaf(__ldg(w1 + (size_t)h * c + ch), pooled[ch], a);
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) a += __shfl_xor_sync(0xffffffffu, a, d);
+    if (lane == 0) hid[h] = use_relu ? fmaxf(a, 0.0f) : a / (1.0f + expf(-a));
+  }
+  __syncthreads();
+  for (int ch = t; ch < c; ch += 256) {
+    float a = 0.0f;
+    for (int h = 0; h < hidden; ++h) a = fmaf(__ldg(w2 + (size_t)ch * hidden + h), hid[h], a);
+    gate[(size_t)b * c + ch] = 1.0f / (1.0f + expf(-a));
+  }
+}
+
 }  // namespace bdm
 
 extern "C" size_t bdm_groupnorm_workspace_bytes(int b, int c, long long s) {
@@ -607,5 +641,20 @@ extern "C" int bdm_groupnorm_act_cl(int b, int c, long long s, int groups, float
   else
     gn_cl_apply_kernel<false><<<dim3(ntiles, b), kClThreads, 0, st>>>(c, s, groups, nchunks, ntiles, eps, x, conv_bias,
                                                                     gamma, beta, partials, y, tile_sums);
+  BDM_RETURN_LAUNCH_STATUS();
+}
+
+// gate f32[b][c] = sigmoid(w2 . act(w1 . (sum_t sums[b,t,c] / count))); sums addressed with element strides
+// (stride_b, stride_t, stride_c) so that both the [b*c][tiles] layout of bdm_groupnorm_act and the
+// [b][tiles][c] layout of bdm_groupnorm_act_cl can be passed as they are.  w1 f32[hidden][c], w2 f32[c][hidden].
+extern "C" int bdm_se_gate(int b, int c, int hidden, int tiles, float count, long long stride_b, long long stride_t,
+                           long long stride_c, const float *sums, const float *w1, const float *w2, int use_relu,
+                           float *gate, bdm_stream_t stream) {
+  using namespace bdm;
+  BDM_CHECK_SIZE(b >= 0 && c >= 1 && hidden >= 1 && tiles >= 1 && count > 0.0f && c + hidden <= 8192);
+  if (b == 0) return BDM_OK;
+  BDM_CHECK_PTR(sums); BDM_CHECK_PTR(w1); BDM_CHECK_PTR(w2); BDM_CHECK_PTR(gate);
+  se_gate_kernel<<<b, 256, sizeof(float) * (size_t)(c + hidden), reinterpret_cast<cudaStream_t>(stream)>>>(
+      c, hidden, tiles, count, stride_b, stride_t, stride_c, sums, w1, w2, use_relu, gate);
   BDM_RETURN_LAUNCH_STATUS();
 }

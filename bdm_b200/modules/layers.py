@@ -43,8 +43,11 @@ def _groupnorm_act(y, gn, swish, conv_bias=None, **kw):
     if is_channels_last_3d(y):
         if hasattr(_ops._B, "groupnorm_act_cl") and _ops._B.groupnorm_cl_supported(y.shape[1], gn.num_groups) \
                 and not kw.get("max_over_last"):
+            want_sums = kw.get("channel_sums", False)
+            if want_sums and hasattr(_ops._B, "se_gate"):
+                want_sums = "tiles"   # raw per-tile sums: SE3d.gate folds them inside its own kernel
             out = _ops._B.groupnorm_act_cl(y.permute(0, 2, 3, 4, 1), gn.num_groups, gn.weight, gn.bias, gn.eps, swish,
-                                           conv_bias=conv_bias, channel_sums=kw.get("channel_sums", False))
+                                           conv_bias=conv_bias, channel_sums=want_sums)
             if isinstance(out, tuple):
                 return out[0].permute(0, 4, 1, 2, 3), out[1]
             return out.permute(0, 4, 1, 2, 3)
@@ -256,7 +259,14 @@ class SE3d(nn.Module):
     def gate(self, inputs, channel_sums=None):
         """the per-(shape, channel) excitation f32[B,C]"""
         if channel_sums is not None:   # squeeze already produced by the fused norm+activation pass
-            pooled = channel_sums / float(inputs.shape[2] * inputs.shape[3] * inputs.shape[4])
+            count = float(inputs.shape[2] * inputs.shape[3] * inputs.shape[4])
+            if (hasattr(_ops._B, "se_gate") and channel_sums.is_cuda and not torch.is_grad_enabled()
+                    and isinstance(self.fc[0], nn.Linear) and self.fc[0].bias is None and self.fc[2].bias is None):
+                return _ops._B.se_gate(channel_sums.contiguous(), count, self.fc[0].weight, self.fc[2].weight,
+                                       isinstance(self.fc[1], nn.ReLU))
+            if channel_sums.dim() == 3:
+                channel_sums = channel_sums.sum(dim=1)
+            pooled = channel_sums / count
         else:                          # three chained means (z, y, x) like the reference, for identical rounding
             pooled = inputs.mean(-1).mean(-1).mean(-1)
         return self.fc(pooled)

@@ -179,10 +179,11 @@ class _PVConvBase(nn.Module):
         if defer:
             grid, gate = grid
         if _layers.is_channels_last_3d(grid) and not torch.is_grad_enabled():
-            from_voxels = _ops._B.trilinear_devoxelize_cl(grid.permute(0, 2, 3, 4, 1), grid_coords.contiguous(),
-                                                          self.resolution)
-        else:
-            from_voxels = F.trilinear_devoxelize(grid, grid_coords, self.resolution, self.training)
+            # channels-last branch: devoxelize, SE gate and the residual add of the point branch in one kernel
+            fused = _ops._B.trilinear_devoxelize_cl(grid.permute(0, 2, 3, 4, 1), grid_coords.contiguous(), self.resolution,
+                                                    gate=gate, residual=self.point_features(features).contiguous())
+            return fused, coords, temb
+        from_voxels = F.trilinear_devoxelize(grid, grid_coords, self.resolution, self.training)
         if gate is not None:
             return torch.addcmul(self.point_features(features), from_voxels, gate[:, :, None]), coords, temb
         return from_voxels + self.point_features(features), coords, temb

@@ -101,9 +101,10 @@ int bdm_trilinear_devoxelize(int b, int c, int n, int r, int is_training, const 
                              const float *feat, int *inds, float *wgts, float *outs,
                              void *workspace, size_t workspace_bytes, int planned,
                              bdm_stream_t stream);
-/* inference devoxelization from a channels-last grid feat f32[b,r^3,c] (same arithmetic, outs f32[b,c,n]) */
+/* inference devoxelization from a channels-last grid feat f32[b,r^3,c] (same arithmetic, outs f32[b,c,n]);
+ * optional epilogue of the PVConv block: outs = devox * gate[b,c] + residual[b,c,n] (NULL = skip) */
 int bdm_trilinear_devoxelize_cl(int b, int c, int n, int r, const float *coords, const float *feat,
-                                float *outs, bdm_stream_t stream);
+                                const float *gate, const float *residual, float *outs, bdm_stream_t stream);
 /* replaces trilinear_devoxelize_grad (trilinear_devox.cuh:9-11): grad_x f32[b,c,r3] is zeroed here */
 int bdm_trilinear_devoxelize_grad(int b, int c, int n, int r3, const int *inds, const float *wgts,
                                   const float *grad_y, float *grad_x, bdm_stream_t stream);
@@ -236,6 +237,12 @@ int bdm_groupnorm_act(int b, int c, long long s, int groups, float eps, int swis
                       bdm_stream_t stream);
 /* channels-last flavour: x, y f32[b,s,c]; tile_sums f32[b,tiles,c] (tiles = bdm_groupnorm_cl_tiles) or NULL.
  * c must be a power of two in [16,256] (bdm_groupnorm_cl_supported). */
+/* squeeze-excite gate (modules/se.py:8-19) from the per-channel sums above:
+ * gate[b,c] = sigmoid(w2 . act(w1 . (sum_t sums / count))), act = ReLU (use_relu) or Swish; sums is addressed
+ * as sums[b*stride_b + t*stride_t + c*stride_c]. */
+int bdm_se_gate(int b, int c, int hidden, int tiles, float count, long long stride_b, long long stride_t,
+                long long stride_c, const float *sums, const float *w1, const float *w2, int use_relu,
+                float *gate, bdm_stream_t stream);
 int bdm_groupnorm_cl_supported(int c, int groups);
 size_t bdm_groupnorm_cl_workspace_bytes(int b, int c, long long s);
 int bdm_groupnorm_cl_tiles(int b, int c, long long s);

@@ -280,3 +280,33 @@ def test_groupnorm_channels_last_vs_torch(b, c, spatial, swish, cuda_backend):
     if swish:
         want2 = want2 * torch.sigmoid(want2)
     assert (got2.permute(0, 4, 1, 2, 3) - want2).abs().max().item() / want2.abs().max().item() <= 1e-5
+
+
+@pytest.mark.parametrize("c,use_relu,tiles", [(64, False, 1), (256, True, 5), (32, False, 37)])
+def test_se_gate_kernel(c, use_relu, tiles, cuda_backend):
+    import torch
+
+    import bdm_b200.modules.layers as L
+    torch.manual_seed(c)
+    se = L.SE3d(c, use_relu=use_relu).cuda().eval()
+    sums = torch.randn(3, tiles, c, device="cuda") * 50.0
+    count = 512.0
+    with torch.no_grad():
+        want = se.fc(sums.sum(dim=1) / count)
+        got = cuda_backend.se_gate(sums if tiles > 1 else sums[:, 0].contiguous(), count, se.fc[0].weight, se.fc[2].weight, use_relu)
+    assert got.shape == want.shape
+    assert (got - want).abs().max().item() <= 1e-5
+
+
+def test_devoxelize_cl_epilogue(cuda_backend):
+    import torch
+    g = torch.Generator(device="cuda").manual_seed(2)
+    b, c, n, r = 2, 32, 500, 16
+    grid = torch.randn(b, r, r, r, c, device="cuda", generator=g)
+    coords = torch.rand(b, 3, n, device="cuda", generator=g) * (r - 1)
+    gate = torch.rand(b, c, device="cuda", generator=g)
+    resid = torch.randn(b, c, n, device="cuda", generator=g)
+    plain = cuda_backend.trilinear_devoxelize_cl(grid, coords, r)
+    got = cuda_backend.trilinear_devoxelize_cl(grid, coords, r, gate=gate, residual=resid)
+    want = plain * gate[:, :, None] + resid
+    assert (got - want).abs().max().item() <= 1e-6 * want.abs().max().item()

@@ -497,6 +497,113 @@ gn_cl_apply_kernel(int c, long long s, int groups, int nchunks, int ntiles, floa
   }
 }
 
+// One-pass channels-last variant: one CTA per (sample, group).  The group's data are S segments of cg
+// contiguous channels (cg*4 bytes each, S = voxels); float4 unit idx -> voxel idx / (cg/4), quad idx % (cg/4).
+// The block size is a multiple of 32 and cg/4 divides 32, so a thread's quad -- its 4 channels -- is the same
+// for all of its units: gamma / beta / conv bias are loaded once as float4.
+template <int V, bool SWISH>
+__global__ void __launch_bounds__(1024)
+gn_onepass_cl_kernel(int c, int s, int groups, float eps, int ntiles, const float *__restrict__ x,
+                     const float *__restrict__ conv_bias, const float *__restrict__ gamma,
+                     const float *__restrict__ beta, float *__restrict__ y, float *__restrict__ tile_sums) {
+  const int cg = c / groups, q4 = cg >> 2;
+  const int sample = blockIdx.x / groups, g = blockIdx.x - sample * groups;
+  const int n4 = q4 * s;
+  const int nt = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int quad = tid % q4;
+  const int ch = g * cg + 4 * quad;                       // this thread's 4 channels
+  const size_t base = (size_t)sample * s * c + ch;        // + voxel * c
+  __shared__ double s_red[2][32];
+  __shared__ double s_dmean;
+  __shared__ float s_rstd;
+  __shared__ float s_sum[1024 * 4];
+
+  const float4 cb = conv_bias != nullptr ? __ldg(reinterpret_cast<const float4 *>(conv_bias + ch)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const float k = __ldg(x + (size_t)sample * s * c + g * cg) + (conv_bias != nullptr ? __ldg(conv_bias + g * cg) : 0.0f);
+  float4 v[V];
+  float s1 = 0.0f, s2 = 0.0f;
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
+    const int idx = tid + j * nt;
+    v[j] = idx < n4 ? ld_stream_f4(x + base + (size_t)(idx / q4) * c) : make_float4(k - cb.x, k - cb.y, k - cb.z, k - cb.w);
+  }
+#pragma unroll
+  for (int j = 0; j < V; ++j) {   // moments of (x + conv_bias - k); padding units add 0
+    const float a = v[j].x + cb.x - k, b2 = v[j].y + cb.y - k, c2 = v[j].z + cb.z - k, d2 = v[j].w + cb.w - k;
+    s1 += (a + b2) + (c2 + d2);
+    s2 += (a * a + b2 * b2) + (c2 * c2 + d2 * d2);
+  }
+  double d1 = (double)s1, d2_ = (double)s2;
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) {
+    d1 += __shfl_xor_sync(0xffffffffu, d1, d);
+    d2_ += __shfl_xor_sync(0xffffffffu, d2_, d);
+  }
+  if (lane == 0) { s_red[0][warp] = d1; s_red[1][warp] = d2_; }
+  __syncthreads();
+  if (warp == 0) {
+    const int nw = nt >> 5;
+    double a1 = lane < nw ? s_red[0][lane] : 0.0, a2 = lane < nw ? s_red[1][lane] : 0.0;
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+      a1 += __shfl_xor_sync(0xffffffffu, a1, d);
+      a2 += __shfl_xor_sync(0xffffffffu, a2, d);
+    }
+    if (lane == 0) {
+      const double n = (double)cg * (double)s;
+      const double m = a1 / n;
+      const double var = fmax(a2 / n - m * m, 0.0);
+      s_dmean = (double)k + m;
+      s_rstd = (float)(1.0 / sqrt(var + (double)eps));
+    }
+  }
+  __syncthreads();
+  const double mean = s_dmean;
+  const float rstd = s_rstd;
+  const float4 ga = gamma != nullptr ? __ldg(reinterpret_cast<const float4 *>(gamma + ch)) : make_float4(1.f, 1.f, 1.f, 1.f);
+  const float4 be = beta != nullptr ? __ldg(reinterpret_cast<const float4 *>(beta + ch)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const float A0 = rstd * ga.x, A1 = rstd * ga.y, A2 = rstd * ga.z, A3 = rstd * ga.w;    // same folding as gn_apply_kernel
+  const float B0 = (float)((double)be.x + ((double)cb.x - mean) * (double)A0);
+  const float B1 = (float)((double)be.y + ((double)cb.y - mean) * (double)A1);
+  const float B2 = (float)((double)be.z + ((double)cb.z - mean) * (double)A2);
+  const float B3 = (float)((double)be.w + ((double)cb.w - mean) * (double)A3);
+  auto act = [](float t) { return SWISH ? t / (1.0f + expf(-t)) : t; };
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
+    const int idx = tid + j * nt;
+    if (idx < n4) {
+      float4 o;
+      o.x = act(fmaf(v[j].x, A0, B0));
+      o.y = act(fmaf(v[j].y, A1, B1));
+      o.z = act(fmaf(v[j].z, A2, B2));
+      o.w = act(fmaf(v[j].w, A3, B3));
+      *reinterpret_cast<float4 *>(y + base + (size_t)(idx / q4) * c) = o;
+      acc[0] += o.x; acc[1] += o.y; acc[2] += o.z; acc[3] += o.w;
+    }
+  }
+  if (tile_sums != nullptr) {   // [b][ntiles][c]: the whole sum goes to tile 0, fixed order
+#pragma unroll
+    for (int j = 0; j < 4; ++j) s_sum[tid * 4 + j] = acc[j];
+    __syncthreads();
+    if (tid < cg) {
+      const int qd = tid >> 2, comp = tid & 3;
+      float a = 0.0f;
+      for (int t2 = qd; t2 < nt; t2 += q4) a += s_sum[t2 * 4 + comp];
+      float *ts = tile_sums + (size_t)sample * ntiles * c + g * cg + tid;
+      ts[0] = a;
+      for (int q = 1; q < ntiles; ++q) ts[(size_t)q * c] = 0.0f;
+    }
+  }
+}
+
+template <int V>
+static void launch_onepass_cl(bool swish, int ctas, int nt, cudaStream_t st, int c, int s, int groups, float eps, int ntiles,
+                              const float *x, const float *cb, const float *ga, const float *be, float *y, float *ts) {
+  if (swish) gn_onepass_cl_kernel<V, true><<<ctas, nt, 0, st>>>(c, s, groups, eps, ntiles, x, cb, ga, be, y, ts);
+  else gn_onepass_cl_kernel<V, false><<<ctas, nt, 0, st>>>(c, s, groups, eps, ntiles, x, cb, ga, be, y, ts);
+}
+
 // ------------------------------------------------------------------------------------------------
 // Squeeze-excite gate (modules/se.py:8-19) from the per-channel sums the norm kernels emit:
 //   pooled = sums / count;  gate = sigmoid(W2 . act(W1 . pooled)),  act = ReLU or Swish, no biases.
@@ -633,6 +740,25 @@ extern "C" int bdm_groupnorm_act_cl(int b, int c, long long s, int groups, float
     return BDM_ERR_MISALIGNED;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int nchunks = gn_cl_chunks(b, s, c), ntiles = gn_cl_tiles(b, s, c);
+  {   // small groups: one CTA per (sample, group), one pass
+    const int cg = c / groups;
+    const long long gelems = (long long)cg * s;
+    if (cg % 4 == 0 && cg <= 128 && (32 % (cg / 4) == 0 || (cg / 4) % 32 == 0) && gelems <= 4LL * 1024 * kOneMaxV &&
+        (long long)b * groups <= 0x7fffffffLL && s <= 0x7fffffffLL / c) {
+      const int n4 = (int)(gelems >> 2);
+      int v = 1;
+      while (v < kOneMaxV && (long long)v * 1024 < n4) v <<= 1;
+      int nt = (n4 + v - 1) / v;
+      nt = min(1024, max(32, (nt + 31) & ~31));
+      nt = max(nt, min(1024, (cg + 31) & ~31));
+      const int ctas = b * groups;
+      if (v == 1) launch_onepass_cl<1>(swish != 0, ctas, nt, st, c, (int)s, groups, eps, ntiles, x, conv_bias, gamma, beta, y, tile_sums);
+      else if (v == 2) launch_onepass_cl<2>(swish != 0, ctas, nt, st, c, (int)s, groups, eps, ntiles, x, conv_bias, gamma, beta, y, tile_sums);
+      else if (v == 4) launch_onepass_cl<4>(swish != 0, ctas, nt, st, c, (int)s, groups, eps, ntiles, x, conv_bias, gamma, beta, y, tile_sums);
+      else launch_onepass_cl<8>(swish != 0, ctas, nt, st, c, (int)s, groups, eps, ntiles, x, conv_bias, gamma, beta, y, tile_sums);
+      BDM_RETURN_LAUNCH_STATUS();
+    }
+  }
   double2 *partials = static_cast<double2 *>(workspace);
   gn_cl_stats_kernel<<<dim3(nchunks, b), kClThreads, 0, st>>>(c, s, nchunks, x, partials);
   if (swish)

@@ -30,7 +30,8 @@ _PROTOS = {
     "bdm_avg_voxelize_compact": (_i, [_i, _i, _i, _i, _p, _p, _p, _z, _p]),
     "bdm_grouping_into": (_i, [_i, _i, _i, _i, _i, _p, _p, _p, _p, _i, _i, _p]),
     "bdm_attention": (_i, [_i, _i, _i, _p, _p, _p, _p, _p, _z, _p]),
-    "bdm_sparse_conv3_gather": (_i, [_i, _i, _i, _i, _p, _p, _p, _i, _p, _z, _p]),
+    "bdm_sparse_conv3_gather": (_i, [_i, _i, _i, _i, _p, _p, _p, _i, _p, _p, _z, _p]),
+    "bdm_sparse_conv3_stats_blocks": (_i, [_i]),
     "bdm_trilinear_devoxelize_cl": (_i, [_i, _i, _i, _i, _p, _p, _p, _p, _p, _p]),
     "bdm_se_gate": (_i, [_i, _i, _i, _i, _f, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_longlong, _p, _p, _p, _i, _p, _p]),
     "bdm_avg_voxelize_grad": (_i, [_i, _i, _i, _i, _p, _p, _p, _p, _p]),
@@ -57,7 +58,7 @@ _PROTOS = {
     "bdm_groupnorm_cl_supported": (_i, [_i, _i]),
     "bdm_groupnorm_cl_workspace_bytes": (_z, [_i, _i, ctypes.c_longlong]),
     "bdm_groupnorm_cl_tiles": (_i, [_i, _i, ctypes.c_longlong]),
-    "bdm_groupnorm_act_cl": (_i, [_i, _i, ctypes.c_longlong, _i, _f, _i, _p, _p, _p, _p, _p, _p, _p, _z, _p]),
+    "bdm_groupnorm_act_cl": (_i, [_i, _i, ctypes.c_longlong, _i, _f, _i, _p, _p, _p, _p, _p, _p, _p, _z, _i, _p]),
     "bdm_surface_projection_cf": (_i, [_i, _i, _i, _i, _i, _f, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p]),
     "bdm_nn_f64": (_i, [_i, _i, _i, _i, _p, _p, _p, _p, _p]),
 }

@@ -171,9 +171,11 @@ def avg_voxelize_compact(features, plan):
 
 
 @_op(1)
-def sparse_conv3_gather(taps, plan, bias=None, channels_last=False):
+def sparse_conv3_gather(taps, plan, bias=None, channels_last=False, stats=False):
     """taps f32[B,N,27*Cout] (per-occupied-voxel tap products) + VoxelPlan -> the dense output
-    f32[B,Cout,R,R,R] of the zero-padded 3x3x3 convolution (f32[B,R,R,R,Cout] when channels_last)."""
+    f32[B,Cout,R,R,R] of the zero-padded 3x3x3 convolution (f32[B,R,R,R,Cout] when channels_last).
+    stats: also return f64[B,blocks,Cout,2], the per-channel (sum, sum of squares) of the bias-less output
+    per block of rows, which groupnorm_act_cl(..., partials=) takes instead of reading the tensor again."""
     _chk_float(taps, "taps")
     b, n, k = taps.shape
     _req(b == plan.b and n == plan.n and k % 27 == 0, "taps do not match the voxel plan")
@@ -182,11 +184,15 @@ def sparse_conv3_gather(taps, plan, bias=None, channels_last=False):
         _chk_float(bias, "bias")
         _req(bias.numel() == cout, "bias must hold one value per output channel")
     out = torch.empty((b, r, r, r, cout) if channels_last else (b, cout, r, r, r), dtype=_F32, device=taps.device)
+    part = None
+    if stats:
+        part = torch.empty((b, _L.bdm_sparse_conv3_stats_blocks(r), cout, 2), dtype=torch.float64, device=taps.device)
     with _Launch(taps) as st:
         _check(_L.bdm_sparse_conv3_gather(b, cout, n, r, taps.data_ptr(), bias.data_ptr() if bias is not None else None,
-                                          out.data_ptr(), 1 if channels_last else 0, plan.workspace.data_ptr(),
+                                          out.data_ptr(), 1 if channels_last else 0,
+                                          part.data_ptr() if part is not None else None, plan.workspace.data_ptr(),
                                           plan.workspace.numel(), st))
-    return out
+    return (out, part) if stats else out
 
 
 @_op(1)
@@ -541,9 +547,11 @@ def groupnorm_cl_supported(channels, num_groups):
 
 
 @_op(2)
-def groupnorm_act_cl(x, num_groups, weight, bias, eps, swish=True, conv_bias=None, channel_sums=False):
+def groupnorm_act_cl(x, num_groups, weight, bias, eps, swish=True, conv_bias=None, channel_sums=False, partials=None):
     """Channels-last flavour of groupnorm_act: x f32[B,*,C] contiguous (channel innermost) -> same layout;
-    channel_sums: also f32[B,C] sums of the output over the voxels."""
+    channel_sums: also f32[B,C] sums of the output over the voxels.
+    partials: f64[B,chunks,C,2] per-channel (sum, sumsq) of x over disjoint voxel blocks made by x's producer
+    (sparse_conv3_gather(stats=True)): the statistics pass is skipped."""
     _chk_float(x, "x")
     b, c = x.shape[0], x.shape[-1]
     s = x.numel() // max(b * c, 1)
@@ -552,13 +560,20 @@ def groupnorm_act_cl(x, num_groups, weight, bias, eps, swish=True, conv_bias=Non
     sums = None
     if channel_sums:
         sums = torch.empty((b, _L.bdm_groupnorm_cl_tiles(b, c, s), c), dtype=_F32, device=dev)
-    ws = _workspace(_L.bdm_groupnorm_cl_workspace_bytes(b, c, s), dev)
+    chunks = 0
+    if partials is not None:
+        _req(partials.dtype == torch.float64 and partials.is_contiguous() and partials.dim() == 4
+             and partials.shape[0] == b and partials.shape[2] == c and partials.shape[3] == 2, "partials must be f64[B,chunks,C,2]")
+        ws, chunks, ws_bytes = partials, int(partials.shape[1]), partials.numel() * 8
+    else:
+        ws = _workspace(_L.bdm_groupnorm_cl_workspace_bytes(b, c, s), dev)
+        ws_bytes = ws.numel()
     with _Launch(x) as st:
         _check(_L.bdm_groupnorm_act_cl(b, c, s, int(num_groups), float(eps), 1 if swish else 0, x.data_ptr(),
                                        conv_bias.data_ptr() if conv_bias is not None else None,
                                        weight.data_ptr() if weight is not None else None,
                                        bias.data_ptr() if bias is not None else None, y.data_ptr(),
-                                       sums.data_ptr() if sums is not None else None, ws.data_ptr(), ws.numel(), st))
+                                       sums.data_ptr() if sums is not None else None, ws.data_ptr(), ws_bytes, chunks, st))
     if channel_sums == "tiles":     # f32[B,tiles,C], for se_gate (which folds the tiles itself)
         return y, sums
     if channel_sums:

@@ -413,7 +413,7 @@ gn_cl_stats_kernel(int c, long long s, int nchunks, const float *__restrict__ x,
 
 template <bool SWISH>
 __global__ void __launch_bounds__(kClThreads)
-gn_cl_apply_kernel(int c, long long s, int groups, int nchunks, int ntiles, float eps,
+gn_cl_apply_kernel(int c, long long s, int groups, int nchunks, int ntiles, float eps, int zero_shift,
                    const float *__restrict__ x, const float *__restrict__ conv_bias,
                    const float *__restrict__ gamma, const float *__restrict__ beta,
                    const double2 *__restrict__ partials, float *__restrict__ y, float *__restrict__ tile_sums) {
@@ -433,7 +433,7 @@ gn_cl_apply_kernel(int c, long long s, int groups, int nchunks, int ntiles, floa
       const double2 v = partials[((size_t)b * nchunks + ch) * c + t];
       S1 += v.x; S2 += v.y;
     }
-    double tt = (double)__ldg(px + t);
+    double tt = zero_shift ? 0.0 : (double)__ldg(px + t);   // producer-made partials are of x itself
     if (conv_bias != nullptr) tt += (double)conv_bias[t];
     const double ds = (double)s;
     chan[t] = make_double2(S1 + ds * tt, S2 + 2.0 * tt * S1 + ds * tt * tt);
@@ -727,14 +727,32 @@ extern "C" int bdm_groupnorm_cl_tiles(int b, int c, long long s) {
   return bdm::gn_cl_tiles(b, s, c);
 }
 
+// precomputed_chunks > 0: `workspace` already holds f64[b][precomputed_chunks][c][2] = per-channel (sum, sum of
+// squares) of x over disjoint blocks of voxels, written by the producer of x (bdm_sparse_conv3_gather's
+// `stats`); the statistics pass over x is skipped.
 extern "C" int bdm_groupnorm_act_cl(int b, int c, long long s, int groups, float eps, int swish, const float *x,
                                     const float *conv_bias, const float *gamma, const float *beta, float *y,
                                     float *tile_sums, void *workspace, size_t workspace_bytes,
-                                    bdm_stream_t stream) {
+                                    int precomputed_chunks, bdm_stream_t stream) {
   using namespace bdm;
-  BDM_CHECK_SIZE(b >= 0 && s >= 0 && groups >= 1 && gn_cl_supported(c, groups) && b <= 65535);
+  BDM_CHECK_SIZE(b >= 0 && s >= 0 && groups >= 1 && gn_cl_supported(c, groups) && b <= 65535 && precomputed_chunks >= 0);
   if (b == 0 || s == 0) return BDM_OK;
   BDM_CHECK_PTR(x); BDM_CHECK_PTR(y); BDM_CHECK_PTR(workspace);
+  if (precomputed_chunks > 0) {
+    if (workspace_bytes < sizeof(double2) * (size_t)b * precomputed_chunks * c) return BDM_ERR_WORKSPACE_TOO_SMALL;
+    if (((reinterpret_cast<uintptr_t>(workspace) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) != 0)
+      return BDM_ERR_MISALIGNED;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int ntiles = gn_cl_tiles(b, s, c);
+    const double2 *partials = static_cast<const double2 *>(workspace);
+    if (swish)
+      gn_cl_apply_kernel<true><<<dim3(ntiles, b), kClThreads, 0, st>>>(c, s, groups, precomputed_chunks, ntiles, eps, 1, x,
+                                                                     conv_bias, gamma, beta, partials, y, tile_sums);
+    else
+      gn_cl_apply_kernel<false><<<dim3(ntiles, b), kClThreads, 0, st>>>(c, s, groups, precomputed_chunks, ntiles, eps, 1, x,
+                                                                      conv_bias, gamma, beta, partials, y, tile_sums);
+    BDM_RETURN_LAUNCH_STATUS();
+  }
   if (workspace_bytes < bdm_groupnorm_cl_workspace_bytes(b, c, s)) return BDM_ERR_WORKSPACE_TOO_SMALL;
   if (((reinterpret_cast<uintptr_t>(workspace) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) != 0)
     return BDM_ERR_MISALIGNED;
@@ -762,10 +780,10 @@ extern "C" int bdm_groupnorm_act_cl(int b, int c, long long s, int groups, float
   double2 *partials = static_cast<double2 *>(workspace);
   gn_cl_stats_kernel<<<dim3(nchunks, b), kClThreads, 0, st>>>(c, s, nchunks, x, partials);
   if (swish)
-    gn_cl_apply_kernel<true><<<dim3(ntiles, b), kClThreads, 0, st>>>(c, s, groups, nchunks, ntiles, eps, x, conv_bias,
+    gn_cl_apply_kernel<true><<<dim3(ntiles, b), kClThreads, 0, st>>>(c, s, groups, nchunks, ntiles, eps, 0, x, conv_bias,
                                                                    gamma, beta, partials, y, tile_sums);
   else
-    gn_cl_apply_kernel<false><<<dim3(ntiles, b), kClThreads, 0, st>>>(c, s, groups, nchunks, ntiles, eps, x, conv_bias,
+    gn_cl_apply_kernel<false><<<dim3(ntiles, b), kClThreads, 0, st>>>(c, s, groups, nchunks, ntiles, eps, 0, x, conv_bias,
                                                                     gamma, beta, partials, y, tile_sums);
   BDM_RETURN_LAUNCH_STATUS();
 }

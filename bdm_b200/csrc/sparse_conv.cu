@@ -32,14 +32,30 @@ constexpr int kGatherBatch = 4;   // occupied neighbours whose taps are in fligh
 
 __global__ void __launch_bounds__(kGatherWarps * 32)
 sparse_conv3_gather_kernel(int n, int cout, int r, int channels_last, const float *__restrict__ taps,
-                           const float *__restrict__ bias, float *__restrict__ out,
+                           const float *__restrict__ bias, float *__restrict__ out, double2 *__restrict__ stats,
                            const unsigned char *__restrict__ ws, VoxAuxLayout L) {
   __shared__ float tile[kGatherWarps][32][kGatherCo + 1];
   __shared__ uint32_t entries[kGatherWarps][9 * 32];   // slot | z' << 16 | neighbour row << 24
+  __shared__ float2 wsum[kGatherWarps][32];
   const int b = blockIdx.z, co0 = blockIdx.y * kGatherCo;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * kGatherWarps + warp;  // x * r + y
-  if (row >= r * r) return;
+  if (stats != nullptr) {
+    // per-channel (sum, sum of squares) of this CTA's rows of the (bias-less) output, for the GroupNorm that
+    // follows: stats[b][blockIdx.x][channel].  Rows beyond the grid contribute zero.
+    wsum[warp][lane] = make_float2(0.0f, 0.0f);
+  }
+  if (row >= r * r) {
+    if (stats != nullptr) {
+      __syncthreads();
+      if (warp == 0 && co0 + lane < cout) {
+        double a1 = 0.0, a2 = 0.0;
+        for (int w = 0; w < kGatherWarps; ++w) { a1 += wsum[w][lane].x; a2 += wsum[w][lane].y; }
+        stats[((size_t)b * gridDim.x + blockIdx.x) * cout + co0 + lane] = make_double2(a1, a2);
+      }
+    }
+    return;
+  }
   const int x = row / r, y = row - x * r;
   const int r3 = r * r * r;
 
@@ -114,6 +130,19 @@ sparse_conv3_gather_kernel(int n, int cout, int r, int channels_last, const floa
   __syncwarp();
 
   const int nco = min(kGatherCo, cout - co0);
+  if (stats != nullptr) {
+    if (total != 0) {
+      float a1 = 0.0f, a2 = 0.0f;
+      for (int z = 0; z < r; ++z) { const float v = t[z][lane]; a1 += v; a2 = fmaf(v, v, a2); }
+      wsum[warp][lane] = make_float2(a1, a2);
+    }
+    __syncthreads();
+    if (warp == 0 && lane < nco) {
+      double a1 = 0.0, a2 = 0.0;
+      for (int w = 0; w < kGatherWarps; ++w) { a1 += wsum[w][lane].x; a2 += wsum[w][lane].y; }
+      stats[((size_t)b * gridDim.x + blockIdx.x) * cout + co0 + lane] = make_double2(a1, a2);
+    }
+  }
   if (channels_last) {
     // out[b][voxel][co]: the tile rows are already channel-contiguous; lane = channel, 128 bytes per voxel
     if (lane < nco) {
@@ -150,9 +179,16 @@ sparse_conv3_gather_kernel(int n, int cout, int r, int channels_last, const floa
 
 // taps f32[b][n][27][cout] (row j = the j-th occupied voxel of shape b in ascending voxel id, as produced
 // from bdm_avg_voxelize_compact; rows >= the shape's occupied count are ignored), bias f32[cout] or NULL,
-// out f32[b][cout][r^3], or f32[b][r^3][cout] when channels_last != 0.  workspace = the plan bdm_voxel_plan left for these (b, n, r).  r in {1,2,4,8,16,32}.
+// out f32[b][cout][r^3], or f32[b][r^3][cout] when channels_last != 0.  stats (optional, f64[b][blocks][cout][2],
+// blocks = bdm_sparse_conv3_stats_blocks(r)): per-channel (sum, sum of squares) of the bias-less output per block of
+// rows, which bdm_groupnorm_act_cl accepts in place of its own statistics pass.  workspace = the plan bdm_voxel_plan left for these (b, n, r).  r in {1,2,4,8,16,32}.
+// Number of per-channel statistics blocks bdm_sparse_conv3_gather writes per shape when `stats` is given.
+extern "C" int bdm_sparse_conv3_stats_blocks(int r) {
+  return r >= 1 ? bdm::ceil_div(r * r, bdm::kGatherWarps) : 0;
+}
+
 extern "C" int bdm_sparse_conv3_gather(int b, int cout, int n, int r, const float *taps, const float *bias,
-                                       float *out, int channels_last, const void *workspace,
+                                       float *out, int channels_last, double *stats, const void *workspace,
                                        size_t workspace_bytes, bdm_stream_t stream) {
   using namespace bdm;
   BDM_CHECK_SIZE(b >= 0 && cout >= 0 && n >= 1 && r >= 1 && r <= 32 && (r & (r - 1)) == 0);  // rows within a word
@@ -165,6 +201,7 @@ extern "C" int bdm_sparse_conv3_gather(int b, int cout, int n, int r, const floa
   if (rc != BDM_OK) return rc;
   dim3 grid(ceil_div(r * r, kGatherWarps), ceil_div(cout, kGatherCo), b);
   sparse_conv3_gather_kernel<<<grid, kGatherWarps * 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      n, cout, r, channels_last, taps, bias, out, static_cast<const unsigned char *>(workspace), L);
+      n, cout, r, channels_last, taps, bias, out, reinterpret_cast<double2 *>(stats),
+      static_cast<const unsigned char *>(workspace), L);
   BDM_RETURN_LAUNCH_STATUS();
 }

@@ -47,11 +47,12 @@ def _groupnorm_act(y, gn, swish, conv_bias=None, **kw):
             if want_sums and hasattr(_ops._B, "se_gate"):
                 want_sums = "tiles"   # raw per-tile sums: SE3d.gate folds them inside its own kernel
             out = _ops._B.groupnorm_act_cl(y.permute(0, 2, 3, 4, 1), gn.num_groups, gn.weight, gn.bias, gn.eps, swish,
-                                           conv_bias=conv_bias, channel_sums=want_sums)
+                                           conv_bias=conv_bias, channel_sums=want_sums, partials=kw.get("partials"))
             if isinstance(out, tuple):
                 return out[0].permute(0, 4, 1, 2, 3), out[1]
             return out.permute(0, 4, 1, 2, 3)
         y = y.contiguous()
+    kw.pop("partials", None)
     return _ops._B.groupnorm_act(y, gn.num_groups, gn.weight, gn.bias, gn.eps, swish, conv_bias=conv_bias, **kw)
 
 
@@ -163,9 +164,11 @@ class FusedSequential(nn.Sequential):
     statistics), norm + activation are one pass, the SE squeeze comes out of that same pass and a
     trailing max over neighbours replaces the full-size write.  Anything else runs module by module."""
 
-    def forward(self, x, max_over_last=False, first_output=None, defer_gate=False):
+    def forward(self, x, max_over_last=False, first_output=None, defer_gate=False, first_stats=None):
         """first_output: the bias-less output of self[0] (a conv) when the caller computed it by other
         means (PVConv's sparse first convolution); `x` is then ignored.
+        first_stats: per-channel statistics of first_output made by its producer (sparse_conv3_gather), handed
+        to the norm that follows so that it does not read the tensor a second time.
         defer_gate: when the stack ends in an SE3d gate, return (ungated grid, gate f32[B,C]) instead of
         multiplying the whole grid -- the caller applies the gate after its (linear) consumer."""
         mods = list(self)
@@ -195,7 +198,7 @@ class FusedSequential(nn.Sequential):
                     x = _groupnorm_act(y, gn, True, conv_bias=m.bias, max_over_last=True)
                     reduced = True
                 else:
-                    x = _groupnorm_act(y, gn, swish, conv_bias=m.bias)
+                    x = _groupnorm_act(y, gn, swish, conv_bias=m.bias, partials=first_stats if pre is not None else None)
                 i = nxt
             elif pre is not None:
                 x = pre if m.bias is None else pre + m.bias.view(1, -1, *([1] * (pre.dim() - 2)))

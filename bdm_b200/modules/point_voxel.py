@@ -158,6 +158,12 @@ class _PVConvBase(nn.Module):
             torch.backends.cuda.matmul.allow_tf32 = prev
         if (CHANNELS_LAST_VOXELS and hasattr(_ops._B, "groupnorm_act_cl")
                 and _ops._B.groupnorm_cl_supported(self.out_channels, 8)):
+            norm = self.voxel_layers[1]
+            if (isinstance(norm, nn.GroupNorm) and _layers.FUSED_NORM_ACT
+                    and (self.out_channels // norm.num_groups) * vox.r ** 3 > 32768):
+                # group too large for the one-pass norm: the gather also emits the norm's statistics
+                out, stats = _ops._B.sparse_conv3_gather(taps, plan, channels_last=True, stats=True)
+                return (out.permute(0, 4, 1, 2, 3), stats), norm_coords
             return _ops._B.sparse_conv3_gather(taps, plan, channels_last=True).permute(0, 4, 1, 2, 3), norm_coords
         return _ops._B.sparse_conv3_gather(taps, plan), norm_coords
 
@@ -168,13 +174,15 @@ class _PVConvBase(nn.Module):
         # instead of to the [B,C,R^3] grid (one pass over the grid less).
         defer = (DEFER_SE_GATE and features.is_cuda and not torch.is_grad_enabled()
                  and not _ops.REFERENCE_CALL_PATTERN and hasattr(_ops._B, "groupnorm_act"))
-        first = None
+        first = first_stats = None
         if self._sparse_eligible(features):
             first, grid_coords = self._sparse_first_conv(features, coords)
+            if isinstance(first, tuple):
+                first, first_stats = first
             grid = None
         else:
             grid, grid_coords = self.voxelization(features, coords)
-        grid = self.voxel_layers(grid, first_output=first, defer_gate=defer)
+        grid = self.voxel_layers(grid, first_output=first, defer_gate=defer, first_stats=first_stats)
         gate = None
         if defer:
             grid, gate = grid

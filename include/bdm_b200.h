@@ -74,12 +74,15 @@ int bdm_avg_voxelize_fill(int b, int c, int n, int r, const int *ind, const int 
  *                              slot(x+kd-1,y+kh-1,z+kw-1),k,co], k ascending.  bias may be NULL.
  *                              r must be a power of two <= 32.  channels_last != 0 writes out f32[b,r^3,cout]
  *                              (NDHWC, what cuDNN's tensor-core Conv3d kernels work in) instead of
- *                              f32[b,cout,r^3]. */
+ *                              f32[b,cout,r^3].  stats (or NULL): f64[b,blocks,cout,2], blocks =
+ *                              bdm_sparse_conv3_stats_blocks(r): per-channel (sum, sum of squares) of the bias-less
+ *                              output per block of rows -- the GroupNorm statistics, made by the producer. */
 int bdm_avg_voxelize_compact(int b, int c, int n, int r, const float *feat, float *out,
                              const void *workspace, size_t workspace_bytes, bdm_stream_t stream);
+int bdm_sparse_conv3_stats_blocks(int r);
 int bdm_sparse_conv3_gather(int b, int cout, int n, int r, const float *taps, const float *bias,
-                            float *out, int channels_last, const void *workspace, size_t workspace_bytes,
-                            bdm_stream_t stream);
+                            float *out, int channels_last, double *stats, const void *workspace,
+                            size_t workspace_bytes, bdm_stream_t stream);
 /* replaces avg_voxelize_grad (src/voxelization/vox.cuh:7-8): grad_y f32[b,c,s] -> grad_x f32[b,c,n] */
 int bdm_avg_voxelize_grad(int b, int c, int n, int s, const int *ind, const int *cnt,
                           const float *grad_y, float *grad_x, bdm_stream_t stream);
@@ -248,7 +251,10 @@ size_t bdm_groupnorm_cl_workspace_bytes(int b, int c, long long s);
 int bdm_groupnorm_cl_tiles(int b, int c, long long s);
 int bdm_groupnorm_act_cl(int b, int c, long long s, int groups, float eps, int swish, const float *x,
                          const float *conv_bias, const float *gamma, const float *beta, float *y,
-                         float *tile_sums, void *workspace, size_t workspace_bytes, bdm_stream_t stream);
+                         float *tile_sums, void *workspace, size_t workspace_bytes, int precomputed_chunks,
+                         bdm_stream_t stream);
+/* precomputed_chunks > 0: workspace holds the producer's statistics f64[b,precomputed_chunks,c,2] (see
+ * bdm_sparse_conv3_gather) and the statistics pass over x is skipped. */
 
 #ifdef __cplusplus
 }

@@ -50,11 +50,11 @@ def test_argument_errors_do_not_need_a_gpu():
     assert L.bdm_attention(2, 32, 4096, None, None, None, None, None, 16, None) == -2        # 64 channels only
     assert L.bdm_attention(2, 64, 100, None, None, None, None, None, 16, None) == -2         # multiple of 128 tokens
     assert L.bdm_attention(0, 64, 4096, None, None, None, None, None, 16, None) == 0
-    assert L.bdm_sparse_conv3_gather(1, 8, 64, 12, None, None, None, 0, None, 0, None) == -2 # r must be a power of two
-    assert L.bdm_sparse_conv3_gather(1, 8, 64, 8, None, None, None, 0, None, 0, None) == -1  # NULL taps
+    assert L.bdm_sparse_conv3_gather(1, 8, 64, 12, None, None, None, 0, None, None, 0, None) == -2 # r must be a power of two
+    assert L.bdm_sparse_conv3_gather(1, 8, 64, 8, None, None, None, 0, None, None, 0, None) == -1  # NULL taps
     assert L.bdm_grouping_into(1, 4, 8, 2, 2, None, None, None, None, 3, 0, None) == -2      # slice outside the tensor
     assert L.bdm_groupnorm_cl_supported(64, 8) == 1 and L.bdm_groupnorm_cl_supported(48, 8) == 0
-    assert L.bdm_groupnorm_act_cl(2, 48, 512, 8, 1e-5, 1, None, None, None, None, None, None, None, 0, None) == -2
+    assert L.bdm_groupnorm_act_cl(2, 48, 512, 8, 1e-5, 1, None, None, None, None, None, None, None, 0, 0, None) == -2
     assert L.bdm_avg_voxelize_compact(1, 4, 64, 64, None, None, None, 0, None) == -2         # needs the sorted plan (r^3 <= 32768)
 
 

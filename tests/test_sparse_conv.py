@@ -146,3 +146,28 @@ def test_devoxelize_channels_last_bit_exact(b, c, n, r, cuda_backend):
     grid_cl = torch.from_numpy(grid).cuda().permute(0, 2, 3, 4, 1).contiguous()
     got = cuda_backend.trilinear_devoxelize_cl(grid_cl, torch.from_numpy(coords).cuda(), r).cpu().numpy()
     assert np.array_equal(got, want)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("b,cout,n,r", [(2, 64, 4096, 32), (3, 32, 900, 32), (2, 40, 300, 16), (1, 16, 5, 2)])
+def test_gather_statistics_feed_the_norm(b, cout, n, r, cuda_backend):
+    """the per-channel (sum, sumsq) blocks the gather emits equal the tensor's, and GroupNorm from them equals
+    GroupNorm with its own statistics pass"""
+    import torch
+    feats, coords = _cloud(b, 4, n, r, seed=n + 1)
+    plan = cuda_backend.voxel_plan(torch.from_numpy(coords).cuda(), r)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    taps = torch.randn(b, n, 27 * cout, device="cuda", generator=g)
+    out, stats = cuda_backend.sparse_conv3_gather(taps, plan, channels_last=True, stats=True)
+    assert torch.equal(out, cuda_backend.sparse_conv3_gather(taps, plan, channels_last=True))
+    flat = out.double().reshape(b, -1, cout)
+    tot = stats.sum(dim=1)
+    assert (tot[..., 0] - flat.sum(1)).abs().max().item() <= 1e-4 * max(flat.abs().sum(1).max().item(), 1.0)
+    assert (tot[..., 1] - (flat * flat).sum(1)).abs().max().item() <= 1e-5 * (flat * flat).sum(1).max().item()
+    if cuda_backend.groupnorm_cl_supported(cout, 8):
+        w = torch.randn(cout, device="cuda", generator=g)
+        bias = torch.randn(cout, device="cuda", generator=g)
+        cb = torch.randn(cout, device="cuda", generator=g)
+        a = cuda_backend.groupnorm_act_cl(out, 8, w, bias, 1e-5, True, conv_bias=cb)
+        c = cuda_backend.groupnorm_act_cl(out, 8, w, bias, 1e-5, True, conv_bias=cb, partials=stats)
+        assert (a - c).abs().max().item() <= 2e-6 * a.abs().max().item()

@@ -21,6 +21,8 @@
 // contributes its three kw taps -- 3 x 32 contiguous floats, lane-coalesced, four neighbours in flight at a
 // time -- to outputs z'+1, z', z'-1 of a [32 z][32 co] tile in shared memory, which is then written
 // transposed as 128-byte row segments.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "voxel_plan.cuh"
 
@@ -28,25 +30,26 @@ namespace bdm {
 
 constexpr int kGatherWarps = 8;
 constexpr int kGatherCo = 32;
-constexpr int kGatherBatch = 4;   // occupied neighbours whose taps are in flight together (3 loads each)
+constexpr int kGatherLd = kGatherCo + 1;   // tile row stride (conflict-free column and row access)
 
+// BATCH = occupied neighbours whose taps are in flight together (3 loads each)
+template <int BATCH>
 __global__ void __launch_bounds__(kGatherWarps * 32)
 sparse_conv3_gather_kernel(int n, int cout, int r, int channels_last, const float *__restrict__ taps,
                            const float *__restrict__ bias, float *__restrict__ out, double2 *__restrict__ stats,
                            const unsigned char *__restrict__ ws, VoxAuxLayout L) {
-  __shared__ float tile[kGatherWarps][32][kGatherCo + 1];
+  __shared__ __align__(16) float tile[kGatherWarps][32][kGatherLd];
   __shared__ uint32_t entries[kGatherWarps][9 * 32];   // slot | z' << 16 | neighbour row << 24
-  __shared__ float2 wsum[kGatherWarps][32];
   const int b = blockIdx.z, co0 = blockIdx.y * kGatherCo;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * kGatherWarps + warp;  // x * r + y
-  if (stats != nullptr) {
-    // per-channel (sum, sum of squares) of this CTA's rows of the (bias-less) output, for the GroupNorm that
-    // follows: stats[b][blockIdx.x][channel].  Rows beyond the grid contribute zero.
-    wsum[warp][lane] = make_float2(0.0f, 0.0f);
-  }
+  // per-channel (sum, sum of squares) of this CTA's rows of the (bias-less) output, for the GroupNorm that
+  // follows: stats[b][blockIdx.x][channel].  Rows beyond the grid contribute zero.  The per-warp partials
+  // reuse each warp's entry list (dead by then).
+  float2(*wsum)[9 * 16] = reinterpret_cast<float2(*)[9 * 16]>(entries);
   if (row >= r * r) {
     if (stats != nullptr) {
+      wsum[warp][lane] = make_float2(0.0f, 0.0f);
       __syncthreads();
       if (warp == 0 && co0 + lane < cout) {
         double a1 = 0.0, a2 = 0.0;
@@ -79,9 +82,13 @@ sparse_conv3_gather_kernel(int n, int cout, int r, int channels_last, const floa
     }
   }
 
-  float(*t)[kGatherCo + 1] = tile[warp];
+  float(*t)[kGatherLd] = tile[warp];
+  {
+    float4 *t4 = reinterpret_cast<float4 *>(&t[0][0]);
 #pragma unroll
-  for (int z = 0; z < 32; ++z) t[z][lane] = 0.0f;
+    for (int q = lane; q < 32 * kGatherLd / 4; q += 32) t4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  __syncwarp();
 
   // the occupied neighbours as a list, row-major then z ascending (= tap index k ascending for every
   // output voxel): lane z appends its own voxel of each row
@@ -102,11 +109,11 @@ sparse_conv3_gather_kernel(int n, int cout, int r, int channels_last, const floa
 
   const bool co_ok = co0 + lane < cout;
   const float *tp = taps + (size_t)b * n * 27 * cout + co0 + lane;
-  for (int e0 = 0; e0 < total; e0 += kGatherBatch) {
-    uint32_t en[kGatherBatch];
-    float a[kGatherBatch][3];
+  for (int e0 = 0; e0 < total; e0 += BATCH) {
+    uint32_t en[BATCH];
+    float a[BATCH][3];
 #pragma unroll
-    for (int u = 0; u < kGatherBatch; ++u) {
+    for (int u = 0; u < BATCH; ++u) {
       en[u] = e0 + u < total ? ent[e0 + u] : 0xffffffffu;
       a[u][0] = a[u][1] = a[u][2] = 0.0f;
       if (en[u] != 0xffffffffu && co_ok) {
@@ -117,7 +124,7 @@ sparse_conv3_gather_kernel(int n, int cout, int r, int channels_last, const floa
       }
     }
 #pragma unroll
-    for (int u = 0; u < kGatherBatch; ++u) {
+    for (int u = 0; u < BATCH; ++u) {
       if (en[u] != 0xffffffffu) {
         const int zp = (en[u] >> 16) & 31;
         // input z' = z + kw - 1  =>  tap kw lands on output z = z' + 1 - kw
@@ -131,11 +138,11 @@ sparse_conv3_gather_kernel(int n, int cout, int r, int channels_last, const floa
 
   const int nco = min(kGatherCo, cout - co0);
   if (stats != nullptr) {
-    if (total != 0) {
-      float a1 = 0.0f, a2 = 0.0f;
+    float a1 = 0.0f, a2 = 0.0f;
+    if (total != 0)
       for (int z = 0; z < r; ++z) { const float v = t[z][lane]; a1 += v; a2 = fmaf(v, v, a2); }
-      wsum[warp][lane] = make_float2(a1, a2);
-    }
+    __syncwarp();   // every lane is done reading this warp's entries
+    wsum[warp][lane] = make_float2(a1, a2);
     __syncthreads();
     if (warp == 0 && lane < nco) {
       double a1 = 0.0, a2 = 0.0;
@@ -144,11 +151,21 @@ sparse_conv3_gather_kernel(int n, int cout, int r, int channels_last, const floa
     }
   }
   if (channels_last) {
-    // out[b][voxel][co]: the tile rows are already channel-contiguous; lane = channel, 128 bytes per voxel
-    if (lane < nco) {
-      float *o = out + ((size_t)b * r3 + (size_t)row * r) * cout + co0 + lane;
+    // out[b][voxel][co]: the tile rows are already channel-contiguous
+    float *obase_ = out + ((size_t)b * r3 + (size_t)row * r) * cout + co0;
+    if (nco == kGatherCo && (cout & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+      // 8 lanes x 16 bytes cover a voxel's 32 channels; the 4 lane groups take 4 voxels per store instruction
+      const int c4 = (lane & 7) * 4, zs = lane >> 3;
+      float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (bias) bb = __ldg(reinterpret_cast<const float4 *>(bias + co0 + c4));
+      for (int z = zs; z < r; z += 4) {
+        float4 v = total != 0 ? make_float4(t[z][c4], t[z][c4 + 1], t[z][c4 + 2], t[z][c4 + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+        v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+        *reinterpret_cast<float4 *>(obase_ + (size_t)z * cout + c4) = v;
+      }
+    } else if (lane < nco) {
       const float bb = bias ? __ldg(bias + co0 + lane) : 0.0f;
-      for (int z = 0; z < r; ++z) o[(size_t)z * cout] = (total != 0 ? t[z][lane] : 0.0f) + bb;
+      for (int z = 0; z < r; ++z) obase_[(size_t)z * cout + lane] = (total != 0 ? t[z][lane] : 0.0f) + bb;
     }
     return;
   }
@@ -200,8 +217,18 @@ extern "C" int bdm_sparse_conv3_gather(int b, int cout, int n, int r, const floa
   const int rc = check_workspace(L, b, workspace, workspace_bytes);
   if (rc != BDM_OK) return rc;
   dim3 grid(ceil_div(r * r, kGatherWarps), ceil_div(cout, kGatherCo), b);
-  sparse_conv3_gather_kernel<<<grid, kGatherWarps * 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      n, cout, r, channels_last, taps, bias, out, reinterpret_cast<double2 *>(stats),
-      static_cast<const unsigned char *>(workspace), L);
+  static const int batch = [] {   // tuning hook (tools/sparse_conv_bench.py): BDM_GATHER_BATCH=4|8
+    const char *e = std::getenv("BDM_GATHER_BATCH");
+    return (e != nullptr && e[0] == '4') ? 4 : 8;
+  }();
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (batch == 4)
+    sparse_conv3_gather_kernel<4><<<grid, kGatherWarps * 32, 0, st>>>(
+        n, cout, r, channels_last, taps, bias, out, reinterpret_cast<double2 *>(stats),
+        static_cast<const unsigned char *>(workspace), L);
+  else
+    sparse_conv3_gather_kernel<8><<<grid, kGatherWarps * 32, 0, st>>>(
+        n, cout, r, channels_last, taps, bias, out, reinterpret_cast<double2 *>(stats),
+        static_cast<const unsigned char *>(workspace), L);
   BDM_RETURN_LAUNCH_STATUS();
 }

@@ -383,18 +383,22 @@ devox_gather_kernel(int c, int n, int r, int is_training, const float *__restric
 // written as 128-byte row segments.
 constexpr int kDevoxClWarps = 8;
 
+// PTS = points per CTA: 32 (128-byte output rows) when there are enough points to fill the GPU that way,
+// 8 (one point per warp) for the coarse stages, whose 64-1024 points per shape would otherwise leave most
+// SMs idle while each warp walks 4 points x C/32 dependent-latency steps.
+template <int PTS>
 __global__ void __launch_bounds__(kDevoxClWarps * 32)
 devox_cl_kernel(int c, int n, int r, const float *__restrict__ coords, const float *__restrict__ feat,
                 const float *__restrict__ gate, const float *residual, float *outs) {
-  extern __shared__ float tile[];   // [32][c + 1]
-  const int b = blockIdx.y, i0 = blockIdx.x * 32;
+  extern __shared__ float tile[];   // [PTS][c + 1]
+  const int b = blockIdx.y, i0 = blockIdx.x * PTS;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r2 = r * r;
   const size_t r3 = (size_t)r2 * r;
   const float *co = coords + (size_t)b * 3 * n;
   const float *f = feat + (size_t)b * r3 * c;
   const int ld = c + 1;
-  for (int p = warp; p < 32; p += kDevoxClWarps) {
+  for (int p = warp; p < PTS; p += kDevoxClWarps) {
     const int i = i0 + p;
     if (i >= n) break;
     Corner8 k;
@@ -416,15 +420,17 @@ devox_cl_kernel(int c, int n, int r, const float *__restrict__ coords, const flo
     }
   }
   __syncthreads();
-  const int np = min(32, n - i0);
+  const int np = min(PTS, n - i0);
   float *o = outs + (size_t)b * c * n + i0;
   // optional epilogue of the PVConv block (pvconv.py:97 after se.py:19): out = devox * gate[b,c] + residual
-  for (int cc = warp; cc < c; cc += kDevoxClWarps)
-    if (lane < np) {
-      float v = tile[lane * ld + cc];
+  constexpr int kRowsPerPass = kDevoxClWarps * 32 / PTS;   // channels written per pass of the CTA
+  const int pl = threadIdx.x % PTS, c_first = threadIdx.x / PTS;
+  for (int cc = c_first; cc < c; cc += kRowsPerPass)
+    if (pl < np) {
+      float v = tile[pl * ld + cc];
       if (gate != nullptr) v *= __ldg(gate + (size_t)b * c + cc);
-      if (residual != nullptr) v += residual[(size_t)b * c * n + i0 + (size_t)cc * n + lane];
-      o[(size_t)cc * n + lane] = v;
+      if (residual != nullptr) v += residual[(size_t)b * c * n + i0 + (size_t)cc * n + pl];
+      o[(size_t)cc * n + pl] = v;
     }
 }
 
@@ -622,10 +628,17 @@ extern "C" int bdm_trilinear_devoxelize_cl(int b, int c, int n, int r, const flo
   BDM_CHECK_SIZE((long long)r * r * r <= 0x7fffffffLL && c <= 8192);
   if (b == 0 || c == 0 || n == 0) return BDM_OK;
   BDM_CHECK_PTR(coords); BDM_CHECK_PTR(feat); BDM_CHECK_PTR(outs);
-  const size_t smem = sizeof(float) * 32 * (size_t)(c + 1);
-  cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void *>(devox_cl_kernel), smem);
-  if (e != cudaSuccess) return (int)e;
-  devox_cl_kernel<<<dim3(ceil_div(n, 32), b), kDevoxClWarps * 32, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
-      c, n, r, coords, feat, gate, residual, outs);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if ((long long)ceil_div(n, 32) * b >= 4LL * sm_count()) {
+    const size_t smem = sizeof(float) * 32 * (size_t)(c + 1);
+    cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void *>(devox_cl_kernel<32>), smem);
+    if (e != cudaSuccess) return (int)e;
+    devox_cl_kernel<32><<<dim3(ceil_div(n, 32), b), kDevoxClWarps * 32, smem, st>>>(c, n, r, coords, feat, gate, residual, outs);
+  } else {
+    const size_t smem = sizeof(float) * 8 * (size_t)(c + 1);
+    cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void *>(devox_cl_kernel<8>), smem);
+    if (e != cudaSuccess) return (int)e;
+    devox_cl_kernel<8><<<dim3(ceil_div(n, 8), b), kDevoxClWarps * 32, smem, st>>>(c, n, r, coords, feat, gate, residual, outs);
+  }
   BDM_RETURN_LAUNCH_STATUS();
 }

@@ -614,12 +614,22 @@ __global__ void __launch_bounds__(256)
 se_gate_kernel(int c, int hidden, int tiles, float count, long long sb, long long st_, long long sc,
                const float *__restrict__ sums, const float *__restrict__ w1, const float *__restrict__ w2,
                int use_relu, float *__restrict__ gate) {
-  extern __shared__ float sh[];   // pooled[c], hid[hidden]
-  float *pooled = sh, *hid = sh + c;
+  extern __shared__ float sh[];   // pooled[c], hid[hidden], w2 staged [c][hidden + 1]
+  float *pooled = sh, *hid = sh + c, *w2s = hid + hidden;
   const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  // stage W2 (coalesced) while the sums arrive; everything below is latency-bound, so loads are batched
+  for (int q = t; q < c * hidden; q += 256) w2s[(q / hidden) * (hidden + 1) + q % hidden] = __ldg(w2 + q);
   for (int ch = t; ch < c; ch += 256) {
     float a = 0.0f;
-    for (int q = 0; q < tiles; ++q) a += __ldg(sums + b * sb + q * st_ + ch * sc);
+    int q = 0;
+    for (; q + 8 <= tiles; q += 8) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = __ldg(sums + b * sb + (q + u) * st_ + ch * sc);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) a += v[u];
+    }
+    for (; q < tiles; ++q) a += __ldg(sums + b * sb + q * st_ + ch * sc);
     pooled[ch] = a / count;
   }
   __syncthreads();
@@ -633,7 +643,7 @@ se_gate_kernel(int c, int hidden, int tiles, float count, long long sb, long lon
   __syncthreads();
   for (int ch = t; ch < c; ch += 256) {
     float a = 0.0f;
-    for (int h = 0; h < hidden; ++h) a = fmaf(__ldg(w2 + (size_t)ch * hidden + h), hid[h], a);
+    for (int h = 0; h < hidden; ++h) a = fmaf(w2s[ch * (hidden + 1) + h], hid[h], a);
     gate[(size_t)b * c + ch] = 1.0f / (1.0f + expf(-a));
   }
 }
@@ -795,10 +805,14 @@ extern "C" int bdm_se_gate(int b, int c, int hidden, int tiles, float count, lon
                            long long stride_c, const float *sums, const float *w1, const float *w2, int use_relu,
                            float *gate, bdm_stream_t stream) {
   using namespace bdm;
-  BDM_CHECK_SIZE(b >= 0 && c >= 1 && hidden >= 1 && tiles >= 1 && count > 0.0f && c + hidden <= 8192);
+  BDM_CHECK_SIZE(b >= 0 && c >= 1 && hidden >= 1 && tiles >= 1 && count > 0.0f);
+  const size_t smem = sizeof(float) * ((size_t)c + hidden + (size_t)c * (hidden + 1));
+  BDM_CHECK_SIZE(smem <= 200 * 1024);
   if (b == 0) return BDM_OK;
   BDM_CHECK_PTR(sums); BDM_CHECK_PTR(w1); BDM_CHECK_PTR(w2); BDM_CHECK_PTR(gate);
-  se_gate_kernel<<<b, 256, sizeof(float) * (size_t)(c + hidden), reinterpret_cast<cudaStream_t>(stream)>>>(
+  cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void *>(se_gate_kernel), smem);
+  if (e != cudaSuccess) return (int)e;
+  se_gate_kernel<<<b, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
       c, hidden, tiles, count, stride_b, stride_t, stride_c, sums, w1, w2, use_relu, gate);
   BDM_RETURN_LAUNCH_STATUS();
 }

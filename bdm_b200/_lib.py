@@ -55,6 +55,7 @@ _PROTOS = {
     "bdm_groupnorm_workspace_bytes": (_z, [_i, _i, ctypes.c_longlong]),
     "bdm_groupnorm_tiles": (_i, [_i, _i, ctypes.c_longlong]),
     "bdm_groupnorm_act": (_i, [_i, _i, ctypes.c_longlong, _i, _f, _i, _i, _p, _p, _p, _p, _p, _p, _p, _z, _p]),
+    "bdm_groupnorm_last_launches": (_i, []),
     "bdm_groupnorm_cl_supported": (_i, [_i, _i]),
     "bdm_groupnorm_cl_workspace_bytes": (_z, [_i, _i, ctypes.c_longlong]),
     "bdm_groupnorm_cl_tiles": (_i, [_i, _i, ctypes.c_longlong]),

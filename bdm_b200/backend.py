@@ -49,6 +49,11 @@ def profile_stop():
     return {k: [(e0.elapsed_time(e1), shp) for e0, e1, shp in v] for k, v in (rec or {}).items()}
 
 
+def _count_launches(n):
+    global LAUNCHES
+    LAUNCHES += int(n)
+
+
 def _op(launches):
     """Decorator: count kernel launches; when profiling, bracket the call with CUDA events on the
     current stream of the first tensor argument's device."""
@@ -249,7 +254,7 @@ def attention_supported(channels, tokens, batch=None):
     return ok
 
 
-@_op(3)
+@_op(2)
 def attention(q, k, v):
     """q, k, v f32[B,64,T] -> f32[B,64,T]: out[b,c,i] = sum_j softmax_j(q[b,:,i].k[b,:,j]) v[b,c,j]"""
     _chk_float(q, "q")
@@ -515,7 +520,7 @@ def three_nearest_neighbors_interpolate_backward(grad_y, indices, weights, m):
 # ---------------------------------------------------------------------------------------------
 # dense side: fused GroupNorm (+ Swish)
 # ---------------------------------------------------------------------------------------------
-@_op(2)
+@_op(0)
 def groupnorm_act(x, num_groups, weight, bias, eps, swish=True, conv_bias=None, max_over_last=False,
                   channel_sums=False):
     """x f32[B,C,*] -> act(group_norm(x + conv_bias[c])), act = swish or identity.
@@ -537,6 +542,7 @@ def groupnorm_act(x, num_groups, weight, bias, eps, swish=True, conv_bias=None, 
                                     weight.data_ptr() if weight is not None else None,
                                     bias.data_ptr() if bias is not None else None, y.data_ptr(),
                                     sums.data_ptr() if sums is not None else None, ws.data_ptr(), ws.numel(), st))
+    _count_launches(_L.bdm_groupnorm_last_launches())
     if channel_sums:
         return y, sums.sum(dim=1).view(b, c)
     return y
@@ -546,7 +552,7 @@ def groupnorm_cl_supported(channels, num_groups):
     return bool(_L.bdm_groupnorm_cl_supported(int(channels), int(num_groups)))
 
 
-@_op(2)
+@_op(0)
 def groupnorm_act_cl(x, num_groups, weight, bias, eps, swish=True, conv_bias=None, channel_sums=False, partials=None):
     """Channels-last flavour of groupnorm_act: x f32[B,*,C] contiguous (channel innermost) -> same layout;
     channel_sums: also f32[B,C] sums of the output over the voxels.
@@ -574,6 +580,7 @@ def groupnorm_act_cl(x, num_groups, weight, bias, eps, swish=True, conv_bias=Non
                                        weight.data_ptr() if weight is not None else None,
                                        bias.data_ptr() if bias is not None else None, y.data_ptr(),
                                        sums.data_ptr() if sums is not None else None, ws.data_ptr(), ws_bytes, chunks, st))
+    _count_launches(_L.bdm_groupnorm_last_launches())
     if channel_sums == "tiles":     # f32[B,tiles,C], for se_gate (which folds the tiles itself)
         return y, sums
     if channel_sums:

@@ -26,6 +26,10 @@ namespace bdm {
 constexpr int kGnThreads = 256;
 constexpr int kGnMaxChunks = 32;
 
+// kernels launched by the last bdm_groupnorm_act / _cl call of this thread (1 = one-pass or apply-only,
+// 2 = statistics + apply): lets the host-side launch accounting (bench.py's gpu_launches) stay exact.
+static thread_local int g_last_launches = 0;
+
 __global__ void __launch_bounds__(kGnThreads)
 gn_stats_kernel(long long row_len, int nchunks, const float *__restrict__ x, double2 *__restrict__ partials) {
   const long long row = blockIdx.y;
@@ -700,6 +704,7 @@ extern "C" int bdm_groupnorm_act(int b, int c, long long s, int groups, float ep
       else if (v == 2) launch_onepass<2>(swish != 0, ctas, nt, st, c, (int)s, groups, eps, tiles, x, conv_bias, gamma, beta, y, tile_sums);
       else if (v == 4) launch_onepass<4>(swish != 0, ctas, nt, st, c, (int)s, groups, eps, tiles, x, conv_bias, gamma, beta, y, tile_sums);
       else launch_onepass<8>(swish != 0, ctas, nt, st, c, (int)s, groups, eps, tiles, x, conv_bias, gamma, beta, y, tile_sums);
+      g_last_launches = 1;
       BDM_RETURN_LAUNCH_STATUS();
     }
   }
@@ -721,6 +726,7 @@ extern "C" int bdm_groupnorm_act(int b, int c, long long s, int groups, float ep
   if (max_over_u) { if (swish) BDM_GN_LAUNCH(true, 1); else BDM_GN_LAUNCH(false, 1); }
   else            { if (swish) BDM_GN_LAUNCH(true, 0); else BDM_GN_LAUNCH(false, 0); }
 #undef BDM_GN_LAUNCH
+  g_last_launches = 2;
   BDM_RETURN_LAUNCH_STATUS();
 }
 
@@ -761,6 +767,7 @@ extern "C" int bdm_groupnorm_act_cl(int b, int c, long long s, int groups, float
     else
       gn_cl_apply_kernel<false><<<dim3(ntiles, b), kClThreads, 0, st>>>(c, s, groups, precomputed_chunks, ntiles, eps, 1, x,
                                                                       conv_bias, gamma, beta, partials, y, tile_sums);
+    g_last_launches = 1;
     BDM_RETURN_LAUNCH_STATUS();
   }
   if (workspace_bytes < bdm_groupnorm_cl_workspace_bytes(b, c, s)) return BDM_ERR_WORKSPACE_TOO_SMALL;
@@ -784,6 +791,7 @@ extern "C" int bdm_groupnorm_act_cl(int b, int c, long long s, int groups, float
       else if (v == 2) launch_onepass_cl<2>(swish != 0, ctas, nt, st, c, (int)s, groups, eps, ntiles, x, conv_bias, gamma, beta, y, tile_sums);
       else if (v == 4) launch_onepass_cl<4>(swish != 0, ctas, nt, st, c, (int)s, groups, eps, ntiles, x, conv_bias, gamma, beta, y, tile_sums);
       else launch_onepass_cl<8>(swish != 0, ctas, nt, st, c, (int)s, groups, eps, ntiles, x, conv_bias, gamma, beta, y, tile_sums);
+      g_last_launches = 1;
       BDM_RETURN_LAUNCH_STATUS();
     }
   }
@@ -795,6 +803,7 @@ extern "C" int bdm_groupnorm_act_cl(int b, int c, long long s, int groups, float
   else
     gn_cl_apply_kernel<false><<<dim3(ntiles, b), kClThreads, 0, st>>>(c, s, groups, nchunks, ntiles, eps, 0, x, conv_bias,
                                                                     gamma, beta, partials, y, tile_sums);
+  g_last_launches = 2;
   BDM_RETURN_LAUNCH_STATUS();
 }
 
@@ -816,3 +825,5 @@ extern "C" int bdm_se_gate(int b, int c, int hidden, int tiles, float count, lon
       c, hidden, tiles, count, stride_b, stride_t, stride_c, sums, w1, w2, use_relu, gate);
   BDM_RETURN_LAUNCH_STATUS();
 }
+
+extern "C" int bdm_groupnorm_last_launches(void) { return bdm::g_last_launches; }

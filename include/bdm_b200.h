@@ -240,6 +240,8 @@ int bdm_groupnorm_act(int b, int c, long long s, int groups, float eps, int swis
                       bdm_stream_t stream);
 /* channels-last flavour: x, y f32[b,s,c]; tile_sums f32[b,tiles,c] (tiles = bdm_groupnorm_cl_tiles) or NULL.
  * c must be a power of two in [16,256] (bdm_groupnorm_cl_supported). */
+/* kernels launched by this thread's last bdm_groupnorm_act / bdm_groupnorm_act_cl call (1 or 2) */
+int bdm_groupnorm_last_launches(void);
 /* squeeze-excite gate (modules/se.py:8-19) from the per-channel sums above:
  * gate[b,c] = sigmoid(w2 . act(w1 . (sum_t sums / count))), act = ReLU (use_relu) or Swish; sums is addressed
  * as sums[b*stride_b + t*stride_t + c*stride_c]. */

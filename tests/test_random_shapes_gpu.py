@@ -92,3 +92,63 @@ def test_empty_inputs(cuda_backend):
     assert cuda_backend.ball_query(z(1, 3, 0), z(1, 3, 4), 0.1, 3).shape == (1, 0, 3)
     nb = cuda_backend.ball_query(z(1, 3, 2) + 50.0, z(1, 3, 4), 0.1, 3)
     assert (nb == 0).all()
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_sparse_conv_route_random(seed, cuda_backend):
+    """compact averages -> gather (both layouts, with / without bias and statistics) and the channels-last
+    devoxelize on odd sizes: against the oracle"""
+    import torch
+
+    import oracle as O
+    rng = _rng(100 + seed)
+    b, c, n = int(rng.integers(1, 4)), int(rng.integers(1, 40)), int(rng.integers(1, 2500))
+    r = int(rng.choice([1, 2, 4, 8, 16, 32]))
+    cout = int(rng.choice([1, 3, 8, 32, 33, 64, 70]))
+    nc = (rng.random((b, 3, n)) * (r - 1)).astype(np.float32)
+    vox = np.round(nc).astype(np.int32)
+    feat = rng.standard_normal((b, c, n)).astype(np.float32)
+    plan = cuda_backend.voxel_plan(torch.as_tensor(vox).cuda(), r)
+    comp = cuda_backend.avg_voxelize_compact(torch.as_tensor(feat).cuda(), plan).cpu().numpy()
+    want_comp, occupied = O.avg_voxelize_compact(feat, vox, r)
+    assert np.abs(comp - want_comp).max() <= 1e-4 * max(np.abs(want_comp).max(), 1e-30)
+    taps = rng.standard_normal((b, n, 27 * cout)).astype(np.float32)
+    bias = rng.standard_normal((cout,)).astype(np.float32)
+    tt = torch.as_tensor(taps).cuda()
+    want = O.sparse_conv3_gather(taps, occupied, r, bias)
+    got = cuda_backend.sparse_conv3_gather(tt, plan, torch.as_tensor(bias).cuda()).cpu().numpy()
+    assert np.array_equal(got, want)
+    got_cl, stats = cuda_backend.sparse_conv3_gather(tt, plan, torch.as_tensor(bias).cuda(), channels_last=True, stats=True)
+    assert np.array_equal(got_cl.permute(0, 4, 1, 2, 3).cpu().numpy(), want)
+    nobias = O.sparse_conv3_gather(taps, occupied, r, None).astype(np.float64).reshape(b, cout, -1)
+    assert np.abs(stats.sum(1)[..., 0].cpu().numpy() - nobias.sum(-1)).max() <= 1e-4 * max(np.abs(nobias).sum(-1).max(), 1.0)
+    grid = rng.standard_normal((b, cout, r, r, r)).astype(np.float32)
+    want_dev = O.trilinear_devoxelize_forward(r, False, nc, grid.reshape(b, cout, -1))[0]
+    grid_cl = torch.as_tensor(grid).cuda().permute(0, 2, 3, 4, 1).contiguous()
+    got_dev = cuda_backend.trilinear_devoxelize_cl(grid_cl, torch.as_tensor(nc).cuda(), r).cpu().numpy()
+    assert np.array_equal(got_dev, want_dev)
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_groupnorm_variants_random(seed, cuda_backend):
+    """channel-first / channels-last, one-pass / two-pass selection on random shapes: against torch fp32"""
+    import torch
+    import torch.nn.functional as TF
+    rng = _rng(200 + seed)
+    b = int(rng.integers(1, 5))
+    c = int(rng.choice([8, 16, 24, 32, 64, 128, 256]))
+    spatial = tuple(int(v) for v in rng.integers(1, 13, size=3))
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    x = torch.randn((b, c) + spatial, device="cuda", generator=g) * 1.7 + 0.4
+    w, bias, cb = (torch.randn(c, device="cuda", generator=g) for _ in range(3))
+    want = TF.group_norm(x + cb.view(1, c, 1, 1, 1), 8, w, bias, 1e-5)
+    want = want * torch.sigmoid(want)
+    peak = want.abs().max().item()
+    got = cuda_backend.groupnorm_act(x, 8, w, bias, 1e-5, True, conv_bias=cb)
+    assert (got - want).abs().max().item() <= 1e-5 * peak
+    if cuda_backend.groupnorm_cl_supported(c, 8):
+        x_cl = x.permute(0, 2, 3, 4, 1).contiguous()
+        got_cl, sums = cuda_backend.groupnorm_act_cl(x_cl, 8, w, bias, 1e-5, True, conv_bias=cb, channel_sums=True)
+        assert (got_cl.permute(0, 4, 1, 2, 3) - want).abs().max().item() <= 1e-5 * peak
+        want_sums = want.double().flatten(2).sum(-1)
+        assert (sums.double() - want_sums).abs().max().item() <= 1e-5 * max(want_sums.abs().max().item(), 1.0)

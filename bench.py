@@ -385,7 +385,8 @@ def run_ours(args):
                     "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                     "peak_source": peak_src, "algorithmic_bytes_per_launch": gbytes, "ms_per_launch": gms,
                     "occupied_voxels_in_batch": occupied_r32,
-                    "launches_timed": len(gather), "share_of_step": gms * len(gather) / args.steps / ms_eager,
+                    "launches_timed": len(gather), "launches_per_step": len(gather) // args.steps,
+                    "share_of_step": gms * len(gather) / args.steps / ms_step,
                     "timed_in": "eager single-stream pass of the same step (per-op CUDA events)"}
     else:   # BDM_SPARSE_CONV=0: the dense route, dominated by avg_voxelize at C=390
         C = 3 + C_IMG

@@ -43,7 +43,7 @@ def build(force=False, verbose=False):
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed building libbdm_b200.so")
-    subprocess.check_call([nvcc, "-shared", "-cudart", "static", "-o", SO] + objs)
+    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-cudart", "static", "-o", SO] + objs)
     return SO
 
 

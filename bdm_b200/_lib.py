@@ -58,7 +58,7 @@ _PROTOS = {
     "bdm_groupnorm_last_launches": (_i, []),
     "bdm_groupnorm_cl_supported": (_i, [_i, _i]),
     "bdm_groupnorm_cl_workspace_bytes": (_z, [_i, _i, ctypes.c_longlong]),
-    "bdm_groupnorm_cl_tiles": (_i, [_i, _i, ctypes.c_longlong]),
+    "bdm_groupnorm_cl_tiles": (_i, [_i, _i, ctypes.c_longlong, _i]),
     "bdm_groupnorm_act_cl": (_i, [_i, _i, ctypes.c_longlong, _i, _f, _i, _p, _p, _p, _p, _p, _p, _p, _z, _i, _p]),
     "bdm_surface_projection_cf": (_i, [_i, _i, _i, _i, _i, _f, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p]),
     "bdm_nn_f64": (_i, [_i, _i, _i, _i, _p, _p, _p, _p, _p]),

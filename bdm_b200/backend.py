@@ -565,7 +565,7 @@ def groupnorm_act_cl(x, num_groups, weight, bias, eps, swish=True, conv_bias=Non
     y = torch.empty_like(x)
     sums = None
     if channel_sums:
-        sums = torch.empty((b, _L.bdm_groupnorm_cl_tiles(b, c, s), c), dtype=_F32, device=dev)
+        sums = torch.empty((b, _L.bdm_groupnorm_cl_tiles(b, c, s, int(num_groups)), c), dtype=_F32, device=dev)
     chunks = 0
     if partials is not None:
         _req(partials.dtype == torch.float64 and partials.is_contiguous() and partials.dim() == 4

@@ -366,6 +366,12 @@ static inline int gn_cl_chunks(int b, long long s, int c) {
   long long maxc = (s + rpp - 1) / rpp;
   return (int)max(1LL, min(min(want, (long long)kClMaxChunks), maxc));
 }
+static inline bool gn_cl_onepass(int b, int c, long long s, int groups) {
+  const int cg = c / groups;
+  const long long gelems = (long long)cg * s;
+  return cg % 4 == 0 && cg <= 128 && (32 % (cg / 4) == 0 || (cg / 4) % 32 == 0) && gelems <= 4LL * 1024 * 8 &&
+         (long long)b * groups <= 0x7fffffffLL && s <= 0x7fffffffLL / c;
+}
 static inline int gn_cl_tiles(int b, long long s, int c) {
   const int rpp = kClThreads / (c / 4);
   long long want = (4LL * sm_count() + b - 1) / b;
@@ -618,23 +624,38 @@ __global__ void __launch_bounds__(256)
 se_gate_kernel(int c, int hidden, int tiles, float count, long long sb, long long st_, long long sc,
                const float *__restrict__ sums, const float *__restrict__ w1, const float *__restrict__ w2,
                int use_relu, float *__restrict__ gate) {
-  extern __shared__ float sh[];   // pooled[c], hid[hidden], w2 staged [c][hidden + 1]
-  float *pooled = sh, *hid = sh + c, *w2s = hid + hidden;
+  extern __shared__ float sh[];   // pooled[c], hid[hidden], part[256]
+  float *pooled = sh, *hid = sh + c, *part = hid + hidden;
   const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  // stage W2 (coalesced) while the sums arrive; everything below is latency-bound, so loads are batched
-  for (int q = t; q < c * hidden; q += 256) w2s[(q / hidden) * (hidden + 1) + q % hidden] = __ldg(w2 + q);
-  for (int ch = t; ch < c; ch += 256) {
+  // everything here is latency-bound: independent loads are issued together, and the sum over tiles is
+  // split over 256 / c thread groups (fixed assignment and order: deterministic)
+  if (c <= 256) {
+    const int groups = 256 / c, ch = t % c, grp = t / c;
     float a = 0.0f;
-    int q = 0;
-    for (; q + 8 <= tiles; q += 8) {
-      float v[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) v[u] = __ldg(sums + b * sb + (q + u) * st_ + ch * sc);
-#pragma unroll
-      for (int u = 0; u < 8; ++u) a += v[u];
+    if (grp < groups) {
+      int q = grp;
+      for (; q + 3 * groups < tiles; q += 4 * groups) {
+        const float v0 = __ldg(sums + b * sb + (long long)q * st_ + ch * sc);
+        const float v1 = __ldg(sums + b * sb + (long long)(q + groups) * st_ + ch * sc);
+        const float v2 = __ldg(sums + b * sb + (long long)(q + 2 * groups) * st_ + ch * sc);
+        const float v3 = __ldg(sums + b * sb + (long long)(q + 3 * groups) * st_ + ch * sc);
+        a += (v0 + v1) + (v2 + v3);
+      }
+      for (; q < tiles; q += groups) a += __ldg(sums + b * sb + (long long)q * st_ + ch * sc);
     }
-    for (; q < tiles; ++q) a += __ldg(sums + b * sb + q * st_ + ch * sc);
-    pooled[ch] = a / count;
+    part[t] = a;
+    __syncthreads();
+    if (t < c) {
+      float tot = 0.0f;
+      for (int g2 = 0; g2 < groups; ++g2) tot += part[g2 * c + t];
+      pooled[t] = tot / count;
+    }
+  } else {
+    for (int ch = t; ch < c; ch += 256) {
+      float a = 0.0f;
+      for (int q = 0; q < tiles; ++q) a += __ldg(sums + b * sb + (long long)q * st_ + ch * sc);
+      pooled[ch] = a / count;
+    }
   }
   __syncthreads();
   for (int h = warp; h < hidden; h += 8) {
@@ -645,9 +666,22 @@ se_gate_kernel(int c, int hidden, int tiles, float count, long long sb, long lon
     if (lane == 0) hid[h] = use_relu ? fmaxf(a, 0.0f) : a / (1.0f + expf(-a));
   }
   __syncthreads();
+  const bool vec = (hidden & 3) == 0 && (reinterpret_cast<uintptr_t>(w2) & 15) == 0;
   for (int ch = t; ch < c; ch += 256) {
     float a = 0.0f;
-    for (int h = 0; h < hidden; ++h) a = fmaf(w2s[ch * (hidden + 1) + h], hid[h], a);
+    if (vec) {   // the row's loads are independent: one latency, not `hidden` of them
+      const float4 *wr = reinterpret_cast<const float4 *>(w2 + (size_t)ch * hidden);
+#pragma unroll 8
+      for (int h4 = 0; h4 < hidden / 4; ++h4) {
+        const float4 w = __ldg(wr + h4);
+        a = fmaf(w.x, hid[4 * h4], a);
+        a = fmaf(w.y, hid[4 * h4 + 1], a);
+        a = fmaf(w.z, hid[4 * h4 + 2], a);
+        a = fmaf(w.w, hid[4 * h4 + 3], a);
+      }
+    } else {
+      for (int h = 0; h < hidden; ++h) a = fmaf(__ldg(w2 + (size_t)ch * hidden + h), hid[h], a);
+    }
     gate[(size_t)b * c + ch] = 1.0f / (1.0f + expf(-a));
   }
 }
@@ -738,8 +772,9 @@ extern "C" size_t bdm_groupnorm_cl_workspace_bytes(int b, int c, long long s) {
   return sizeof(double2) * (size_t)b * bdm::gn_cl_chunks(b, s, c) * c;
 }
 
-extern "C" int bdm_groupnorm_cl_tiles(int b, int c, long long s) {
-  if (b <= 0 || c < 16 || s <= 0) return 1;
+extern "C" int bdm_groupnorm_cl_tiles(int b, int c, long long s, int groups) {
+  if (b <= 0 || c < 16 || s <= 0 || groups < 1 || c % groups != 0) return 1;
+  if (bdm::gn_cl_onepass(b, c, s, groups)) return 1;   // the one-pass kernel emits whole sums
   return bdm::gn_cl_tiles(b, s, c);
 }
 
@@ -754,12 +789,14 @@ extern "C" int bdm_groupnorm_act_cl(int b, int c, long long s, int groups, float
   BDM_CHECK_SIZE(b >= 0 && s >= 0 && groups >= 1 && gn_cl_supported(c, groups) && b <= 65535 && precomputed_chunks >= 0);
   if (b == 0 || s == 0) return BDM_OK;
   BDM_CHECK_PTR(x); BDM_CHECK_PTR(y); BDM_CHECK_PTR(workspace);
-  if (precomputed_chunks > 0) {
+  // (a group small enough for the one-pass kernel ignores producer statistics: one read either way, and the
+  // tile count reported by bdm_groupnorm_cl_tiles stays consistent)
+  if (precomputed_chunks > 0 && !gn_cl_onepass(b, c, s, groups)) {
     if (workspace_bytes < sizeof(double2) * (size_t)b * precomputed_chunks * c) return BDM_ERR_WORKSPACE_TOO_SMALL;
     if (((reinterpret_cast<uintptr_t>(workspace) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) != 0)
       return BDM_ERR_MISALIGNED;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    const int ntiles = gn_cl_tiles(b, s, c);
+    const int ntiles = gn_cl_tiles(b, s, c);   // precomputed statistics: always the two-kernel apply
     const double2 *partials = static_cast<const double2 *>(workspace);
     if (swish)
       gn_cl_apply_kernel<true><<<dim3(ntiles, b), kClThreads, 0, st>>>(c, s, groups, precomputed_chunks, ntiles, eps, 1, x,
@@ -770,16 +807,16 @@ extern "C" int bdm_groupnorm_act_cl(int b, int c, long long s, int groups, float
     g_last_launches = 1;
     BDM_RETURN_LAUNCH_STATUS();
   }
-  if (workspace_bytes < bdm_groupnorm_cl_workspace_bytes(b, c, s)) return BDM_ERR_WORKSPACE_TOO_SMALL;
+  if (!gn_cl_onepass(b, c, s, groups) && workspace_bytes < bdm_groupnorm_cl_workspace_bytes(b, c, s))
+    return BDM_ERR_WORKSPACE_TOO_SMALL;
   if (((reinterpret_cast<uintptr_t>(workspace) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) != 0)
     return BDM_ERR_MISALIGNED;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const int nchunks = gn_cl_chunks(b, s, c), ntiles = gn_cl_tiles(b, s, c);
+  const int nchunks = gn_cl_chunks(b, s, c), ntiles = bdm_groupnorm_cl_tiles(b, c, s, groups);
   {   // small groups: one CTA per (sample, group), one pass
     const int cg = c / groups;
     const long long gelems = (long long)cg * s;
-    if (cg % 4 == 0 && cg <= 128 && (32 % (cg / 4) == 0 || (cg / 4) % 32 == 0) && gelems <= 4LL * 1024 * kOneMaxV &&
-        (long long)b * groups <= 0x7fffffffLL && s <= 0x7fffffffLL / c) {
+    if (gn_cl_onepass(b, c, s, groups)) {
       const int n4 = (int)(gelems >> 2);
       int v = 1;
       while (v < kOneMaxV && (long long)v * 1024 < n4) v <<= 1;
@@ -815,7 +852,7 @@ extern "C" int bdm_se_gate(int b, int c, int hidden, int tiles, float count, lon
                            float *gate, bdm_stream_t stream) {
   using namespace bdm;
   BDM_CHECK_SIZE(b >= 0 && c >= 1 && hidden >= 1 && tiles >= 1 && count > 0.0f);
-  const size_t smem = sizeof(float) * ((size_t)c + hidden + (size_t)c * (hidden + 1));
+  const size_t smem = sizeof(float) * ((size_t)c + hidden + 256);
   BDM_CHECK_SIZE(smem <= 200 * 1024);
   if (b == 0) return BDM_OK;
   BDM_CHECK_PTR(sums); BDM_CHECK_PTR(w1); BDM_CHECK_PTR(w2); BDM_CHECK_PTR(gate);

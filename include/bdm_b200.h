@@ -250,7 +250,7 @@ int bdm_se_gate(int b, int c, int hidden, int tiles, float count, long long stri
                 float *gate, bdm_stream_t stream);
 int bdm_groupnorm_cl_supported(int c, int groups);
 size_t bdm_groupnorm_cl_workspace_bytes(int b, int c, long long s);
-int bdm_groupnorm_cl_tiles(int b, int c, long long s);
+int bdm_groupnorm_cl_tiles(int b, int c, long long s, int groups);
 int bdm_groupnorm_act_cl(int b, int c, long long s, int groups, float eps, int swish, const float *x,
                          const float *conv_bias, const float *gamma, const float *beta, float *y,
                          float *tile_sums, void *workspace, size_t workspace_bytes, int precomputed_chunks,

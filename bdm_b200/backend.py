@@ -92,6 +92,14 @@ def _chk_int(x, name):
     _req(x.dtype == _I32, f"{name} must be an int tensor")
 
 
+def _chk_channel_vector(t, name, c):
+    """optional per-channel f32 parameter (GroupNorm affine, conv bias): CUDA, contiguous, float32, C values"""
+    if t is None:
+        return
+    _chk_float(t, name)
+    _req(t.numel() == c, f"{name} must hold one value per channel ({c})")
+
+
 class _Launch:
     """Device guard + current stream of the device that owns `ref`."""
     __slots__ = ("dev", "prev", "stream")
@@ -528,6 +536,8 @@ def groupnorm_act(x, num_groups, weight, bias, eps, swish=True, conv_bias=None, 
     channel_sums:  also return f32[B,C] sums of the output over the trailing dims (SE squeeze)."""
     _chk_float(x, "x")
     b, c = x.shape[0], x.shape[1]
+    for t_, nm in ((weight, "weight"), (bias, "bias"), (conv_bias, "conv_bias")):
+        _chk_channel_vector(t_, nm, c)
     s = x.numel() // max(b * c, 1)
     dev = x.device
     u = int(x.shape[-1]) if max_over_last else 0
@@ -560,6 +570,8 @@ def groupnorm_act_cl(x, num_groups, weight, bias, eps, swish=True, conv_bias=Non
     (sparse_conv3_gather(stats=True)): the statistics pass is skipped."""
     _chk_float(x, "x")
     b, c = x.shape[0], x.shape[-1]
+    for t_, nm in ((weight, "weight"), (bias, "bias"), (conv_bias, "conv_bias")):
+        _chk_channel_vector(t_, nm, c)
     s = x.numel() // max(b * c, 1)
     dev = x.device
     y = torch.empty_like(x)
@@ -638,6 +650,31 @@ def conditioning_input(points, R, T, focal, principal, feat_hwc, radius):
                                             T.data_ptr(), focal.data_ptr(), principal.data_ptr(), feat_hwc.data_ptr(),
                                             zbuf.data_ptr(), pix.data_ptr(), out.data_ptr(), 3 + C, 3, st))
     return out, pix
+
+
+
+# ---------------------------------------------------------------------------------------------
+# reverse-diffusion update (model.py:182-194 via diffusers DDPMScheduler.step; pvd/__init__.py:136-224)
+# ---------------------------------------------------------------------------------------------
+@_op(1)
+def sampler_update(x, eps, noise, table, t_dev, mode, out=None):
+    """out = posterior sample from (x_t, predicted noise, fresh noise) with the coefficients of row *t_dev of
+    `table` f32[T,8]; mode 0 = DDPM (PC^2 side), 1 = PVD.  x, eps, noise: same-shaped contiguous f32 tensors;
+    t_dev int32[1] on the device (nothing is read back).  out may be x (in place)."""
+    for t_, nm in ((x, "x"), (eps, "eps"), (noise, "noise"), (table, "table")):
+        _chk_float(t_, nm)
+    _chk_int(t_dev, "t_dev")
+    _req(eps.shape == x.shape and noise.shape == x.shape, "x, eps and noise must have one shape")
+    _req(table.dim() == 2 and table.shape[1] == 8, "table must be f32[T,8]")
+    if out is None:
+        out = torch.empty_like(x)
+    else:
+        _chk_float(out, "out")
+        _req(out.shape == x.shape, "out must be shaped like x")
+    with _Launch(x) as st:
+        _check(_L.bdm_sampler_update(x.numel(), int(mode), x.data_ptr(), eps.data_ptr(), noise.data_ptr(),
+                                     table.data_ptr(), table.shape[0], t_dev.data_ptr(), out.data_ptr(), st))
+    return out
 
 
 def nn_f64(src, tgt, expanded=False, return_index=True):

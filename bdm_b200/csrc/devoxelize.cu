@@ -59,6 +59,13 @@ __device__ __forceinline__ void devox_corners(float x, float y, float z, int r, 
   k.id[7] = k.id[6] + zo;
 }
 
+// Corner indices of a coordinate outside [0, r-1] would address outside the grid (the reference has no
+// check either: trilinear_devox.cu:64-75); loads go through this clamp, results on valid input are unchanged.
+__device__ __forceinline__ void devox_clamp_ids(Corner8 &k, int r3) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q) k.id[q] = min(max(k.id[q], 0), r3 - 1);
+}
+
 __device__ __forceinline__ float devox_blend(const float *__restrict__ f, const Corner8 &k) {
   const float f0 = __ldg(f + k.id[0]), f1 = __ldg(f + k.id[1]), f2 = __ldg(f + k.id[2]),
               f3 = __ldg(f + k.id[3]), f4 = __ldg(f + k.id[4]), f5 = __ldg(f + k.id[5]),
@@ -357,6 +364,7 @@ devox_gather_kernel(int c, int n, int r, int is_training, const float *__restric
       in[i + (size_t)n * q] = k.id[q];
     }
   }
+  devox_clamp_ids(k, (int)r3);
   const int c0 = blockIdx.y * kDevoxChunk;
   const int c1 = min(c0 + kDevoxChunk, c);
   const float *f = feat + ((size_t)b * c + c0) * r3;
@@ -403,6 +411,7 @@ devox_cl_kernel(int c, int n, int r, const float *__restrict__ coords, const flo
     if (i >= n) break;
     Corner8 k;
     devox_corners(__ldg(co + i), __ldg(co + i + n), __ldg(co + i + n + n), r, r2, k);
+    devox_clamp_ids(k, (int)r3);
     for (int cc = lane; cc < c; cc += 32) {
       const float f0 = __ldg(f + (size_t)k.id[0] * c + cc), f1 = __ldg(f + (size_t)k.id[1] * c + cc),
                   f2 = __ldg(f + (size_t)k.id[2] * c + cc), f3 = __ldg(f + (size_t)k.id[3] * c + cc),

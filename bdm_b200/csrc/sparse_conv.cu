@@ -47,18 +47,9 @@ sparse_conv3_gather_kernel(int n, int cout, int r, int channels_last, const floa
   // follows: stats[b][blockIdx.x][channel].  Rows beyond the grid contribute zero.  The per-warp partials
   // reuse each warp's entry list (dead by then).
   float2(*wsum)[9 * 16] = reinterpret_cast<float2(*)[9 * 16]>(entries);
-  if (row >= r * r) {
-    if (stats != nullptr) {
-      wsum[warp][lane] = make_float2(0.0f, 0.0f);
-      __syncthreads();
-      if (warp == 0 && co0 + lane < cout) {
-        double a1 = 0.0, a2 = 0.0;
-        for (int w = 0; w < kGatherWarps; ++w) { a1 += wsum[w][lane].x; a2 += wsum[w][lane].y; }
-        stats[((size_t)b * gridDim.x + blockIdx.x) * cout + co0 + lane] = make_double2(a1, a2);
-      }
-    }
-    return;
-  }
+  // rows beyond the grid exist only when r*r is not a multiple of the warps per CTA (r = 1, 2); the launcher
+  // refuses `stats` there, so no warp of a CTA that takes the __syncthreads() below can have left early
+  if (row >= r * r) return;
   const int x = row / r, y = row - x * r;
   const int r3 = r * r * r;
 
@@ -197,7 +188,7 @@ sparse_conv3_gather_kernel(int n, int cout, int r, int channels_last, const floa
 // taps f32[b][n][27][cout] (row j = the j-th occupied voxel of shape b in ascending voxel id, as produced
 // from bdm_avg_voxelize_compact; rows >= the shape's occupied count are ignored), bias f32[cout] or NULL,
 // out f32[b][cout][r^3], or f32[b][r^3][cout] when channels_last != 0.  stats (optional, f64[b][blocks][cout][2],
-// blocks = bdm_sparse_conv3_stats_blocks(r)): per-channel (sum, sum of squares) of the bias-less output per block of
+// blocks = bdm_sparse_conv3_stats_blocks(r); r >= 4 only): per-channel (sum, sum of squares) of the bias-less output per block of
 // rows, which bdm_groupnorm_act_cl accepts in place of its own statistics pass.  workspace = the plan bdm_voxel_plan left for these (b, n, r).  r in {1,2,4,8,16,32}.
 // Number of per-channel statistics blocks bdm_sparse_conv3_gather writes per shape when `stats` is given.
 extern "C" int bdm_sparse_conv3_stats_blocks(int r) {
@@ -211,6 +202,7 @@ extern "C" int bdm_sparse_conv3_gather(int b, int cout, int n, int r, const floa
   BDM_CHECK_SIZE(b >= 0 && cout >= 0 && n >= 1 && r >= 1 && r <= 32 && (r & (r - 1)) == 0);  // rows within a word
   const int r3 = r * r * r;
   BDM_CHECK_SIZE(vox_fast_path(n, r3));
+  BDM_CHECK_SIZE(stats == nullptr || (r * r) % kGatherWarps == 0);   // whole CTAs only (block-wide barrier)
   if (b == 0 || cout == 0) return BDM_OK;
   BDM_CHECK_PTR(taps); BDM_CHECK_PTR(out);
   const VoxAuxLayout L = vox_aux_layout(n, r3);

@@ -168,6 +168,15 @@ def _stage_parts(stage):
     return list(stage) if isinstance(stage, nn.Sequential) else [stage]
 
 
+def _plan_block(block, pts):
+    """coordinate-only work of one PVConv block: the voxel plan always; the x-slice binning of the plain
+    devoxelization only when the block will not take the channels-last route (which has no use for it)"""
+    v = block.voxelization
+    norm_coords = coordinate_plan(pts, v.r, v.normalize, v.eps)[0]
+    if not block.devoxelizes_channels_last(pts.shape[2]):
+        F.devoxelize_plan(norm_coords, v.r)
+
+
 def plan_geometry_ahead(cache, sa_layers, fp_layers, coords):
     """Issue every coordinate-only op of the forward on the cache's side stream, in dependency order:
     voxel plans of the first stage first (the main stream needs them immediately), then the FPS /
@@ -178,8 +187,7 @@ def plan_geometry_ahead(cache, sa_layers, fp_layers, coords):
             pts = levels[-1]
             for part in _stage_parts(stage):
                 if isinstance(part, PVConv):
-                    v = part.voxelization
-                    F.devoxelize_plan(coordinate_plan(pts, v.r, v.normalize, v.eps)[0], v.r)
+                    _plan_block(part, pts)
                 elif isinstance(part, PointNetSAModule):
                     cen = F.furthest_point_sample(pts, part.num_centers)
                     for grouper in part.groupers:
@@ -193,8 +201,7 @@ def plan_geometry_ahead(cache, sa_layers, fp_layers, coords):
                     if isinstance(part, PointNetFPModule):
                         F.three_nn_search(pts, cen)
                     elif isinstance(part, PVConv):
-                        v = part.voxelization
-                        F.devoxelize_plan(coordinate_plan(pts, v.r, v.normalize, v.eps)[0], v.r)
+                        _plan_block(part, pts)
                 cen = pts
 
 

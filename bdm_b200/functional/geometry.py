@@ -22,8 +22,15 @@ def active():
     return _active
 
 
+def tensor_version(t):
+    """In-place edit counter of a tensor; inference tensors (torch.inference_mode) do not track one -- they
+    cannot be edited in place outside inference mode either, and the memo holds a reference to the tensor
+    object itself, so identity alone is a sound key there."""
+    return 0 if t.is_inference() else t._version
+
+
 def _tensor_key(t):
-    return (t.data_ptr(), t._version, tuple(t.shape), tuple(t.stride()))
+    return (t.data_ptr(), tensor_version(t), tuple(t.shape), tuple(t.stride()))
 
 
 class _Entry:

@@ -5,7 +5,6 @@ Each class states which reference wrapper it mirrors (paths under
 (`.int()`, `.contiguous()`), what is saved for backward and which inputs receive gradients are the
 reference's; the implementation underneath is bdm_b200.backend.
 """
-import numpy as np
 import torch
 import torch.nn.functional as tnf
 from torch.autograd import Function
@@ -239,21 +238,6 @@ def huber_loss(error, delta):
 
 
 def logits_mask(coords, logits, num_points_per_object):
-    """Foreground selection by logits, host-side index choice, then `gather`."""
-    nb, _, npts = coords.shape
-    fg = logits[:, 0, :] < logits[:, 1, :]
-    count = fg.sum(dim=-1, keepdim=True)
-    masked = coords * fg.view(nb, 1, npts)
-    centroid = masked.sum(dim=-1) / torch.max(count, torch.ones_like(count)).float()
-    picked = torch.zeros((nb, num_points_per_object), device=coords.device, dtype=torch.int32)
-    for i in range(nb):
-        cand = fg[i].nonzero().view(-1)
-        k = cand.numel()
-        if k >= num_points_per_object:
-            picked[i] = cand[np.random.choice(k, num_points_per_object, replace=False)]
-        elif k > 0:
-            sel = np.concatenate([np.arange(k).repeat(num_points_per_object // k),
-                                  np.random.choice(k, num_points_per_object % k, replace=False)])
-            np.random.shuffle(sel)
-            picked[i] = cand[sel]
-    return gather(masked - centroid.view(nb, -1, 1), picked), centroid, fg
+    """Frustum-PointNet leftover of upstream PVCNN (reference functional/sampling.py:51-88).  No BDM driver
+    reaches it (SURVEY.md section 2.1 #21): the name stays importable, the routine is out of scope."""
+    raise NotImplementedError("logits_mask is not part of the BDM hot path (reference functional/sampling.py:51-88)")

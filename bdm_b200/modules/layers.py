@@ -4,12 +4,15 @@ names, parameter names, layer order -- matches the reference's and its checkpoin
 
 reference: modules/shared_mlp.py:10-37, modules/se.py:8-19, modules/pvconv.py:12-63, modules/loss.py:8-10
 """
+import contextlib
 import os
+import threading
 
 import torch
 import torch.nn as nn
 
 from .. import functional as F
+from ..functional import geometry
 from ..functional import ops as _ops
 
 # Fused GroupNorm+Swish kernel of libbdm_b200 for inference on CUDA (tolerance 1e-5 vs the torch pair,
@@ -19,6 +22,28 @@ FUSED_NORM_ACT = os.environ.get("BDM_FUSED_NORM", "1") != "0"
 # Fused online-softmax attention kernel (csrc/attention.cu) for the 64-channel attention block, inference
 # on CUDA; fp32-equivalent (3xTF32).  BDM_FUSED_ATTENTION=0 keeps torch's matmul / softmax / matmul.
 FUSED_ATTENTION = os.environ.get("BDM_FUSED_ATTENTION", "1") != "0"
+
+
+_TF32_LOCK = threading.RLock()
+
+
+@contextlib.contextmanager
+def matmul_precision_of_convs():
+    """Run the enclosed torch.matmul calls with the TF32 policy torch applies to convolutions
+    (torch.backends.cudnn.allow_tf32): they stand in for 1x1 / 3x3x3 convolutions of the reference network.
+    The matmul switch is process-global, so the (rare) flip is serialised behind a lock and always restored;
+    when both policies already agree nothing is touched."""
+    want = bool(torch.backends.cudnn.allow_tf32)
+    with _TF32_LOCK:
+        prev = bool(torch.backends.cuda.matmul.allow_tf32)
+        if prev == want:
+            yield
+            return
+        torch.backends.cuda.matmul.allow_tf32 = want
+        try:
+            yield
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = prev
 
 
 class Swish(nn.Module):
@@ -74,7 +99,7 @@ def conv_no_bias_concat(m, parts):
     blocks (batch stride free).  PointNetFPModule uses it for cat([interpolated, skip]) -- at the last FP
     stage the skip tensor alone is 100 MB."""
     w = m.weight
-    key = (w.data_ptr(), w._version, w.device, tuple(p.shape[1] for p in parts))
+    key = (w.data_ptr(), geometry.tensor_version(w), w.device, tuple(p.shape[1] for p in parts))
     cached = getattr(m, "_concat_weight", None)
     if cached is None or cached[0] != key:
         w2 = w.detach().reshape(m.out_channels, m.in_channels)
@@ -90,9 +115,7 @@ def conv_no_bias_concat(m, parts):
         cached = (key, pieces)
         m._concat_weight = cached
     nb = parts[0].shape[0]
-    prev = torch.backends.cuda.matmul.allow_tf32
-    torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32
-    try:
+    with matmul_precision_of_convs():
         y, off_p = None, 0
         bounds = []
         for p in parts:
@@ -105,8 +128,6 @@ def conv_no_bias_concat(m, parts):
                 y = torch.matmul(wpiece, xs)
             else:
                 y.baddbmm_(wpiece.expand(nb, -1, -1), xs)
-    finally:
-        torch.backends.cuda.matmul.allow_tf32 = prev
     return y
 
 
@@ -127,7 +148,7 @@ def conv_no_bias(m, x):
         # channels-last activations: hand cuDNN the weight in the same format (cached), so that it neither
         # transposes the weight on every call nor the activations around the kernel
         w = m.weight
-        key = (w.data_ptr(), w._version, w.device)
+        key = (w.data_ptr(), geometry.tensor_version(w), w.device)
         cached = getattr(m, "_cl_weight", None)
         if cached is None or cached[0] != key:
             cached = (key, w.detach().contiguous(memory_format=torch.channels_last_3d))
@@ -136,7 +157,7 @@ def conv_no_bias(m, x):
     if not (_pointwise(m) and cin % 4 != 0 and cin >= 32 and x.is_cuda and x.is_contiguous()):
         return m._conv_forward(x, m.weight, None)
     w = m.weight
-    key = (w.data_ptr(), w._version, w.device)
+    key = (w.data_ptr(), geometry.tensor_version(w), w.device)
     cached = getattr(m, "_split_weight", None)
     if cached is None or cached[0] != key:
         w2 = w.detach().reshape(m.out_channels, cin)
@@ -147,13 +168,9 @@ def conv_no_bias(m, x):
     head = w_head.shape[1]
     nb = x.shape[0]
     xr = x.reshape(nb, cin, -1)
-    prev = torch.backends.cuda.matmul.allow_tf32
-    torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32
-    try:
+    with matmul_precision_of_convs():
         y = torch.matmul(w_head, xr[:, :head])
         y.baddbmm_(w_tail.expand(nb, -1, -1), xr[:, head:])
-    finally:
-        torch.backends.cuda.matmul.allow_tf32 = prev
     return y.reshape(nb, m.out_channels, *x.shape[2:])
 
 

@@ -64,7 +64,7 @@ class _LastPlan:
         self.key = self.coords = self.value = None
 
     def lookup(self, coords, r, normalize, eps):
-        key = (coords.data_ptr(), coords._version, tuple(coords.shape), coords.device, r, normalize, eps)
+        key = (coords.data_ptr(), geometry.tensor_version(coords), tuple(coords.shape), coords.device, r, normalize, eps)
         if self.coords is coords and self.key == key:
             return self.value
         self.key, self.coords = key, coords
@@ -135,10 +135,24 @@ class _PVConvBase(nn.Module):
                 and conv.padding == (1, 1, 1) and conv.dilation == (1, 1, 1) and conv.groups == 1
                 and conv.padding_mode == 'zeros')
 
+    def devoxelizes_channels_last(self, num_points):
+        """True when an inference forward over `num_points` CUDA fp32 points keeps the voxel branch in
+        channels-last memory and devoxelizes through trilinear_devoxelize_cl, which needs no x-slice plan
+        (denoiser.plan_geometry_ahead then skips the binning kernel)."""
+        conv = self.voxel_layers[0]
+        vox = self.voxelization
+        return (SPARSE_FIRST_CONV and CHANNELS_LAST_VOXELS and not _ops.REFERENCE_CALL_PATTERN
+                and hasattr(_ops._B, "sparse_conv3_gather") and hasattr(_ops._B, "groupnorm_act_cl")
+                and _ops._B.sparse_conv3_supported(num_points, vox.r) and num_points <= SPARSE_MAX_FILL * vox.r ** 3
+                and _ops._B.groupnorm_cl_supported(self.out_channels, 8)
+                and isinstance(conv, nn.Conv3d) and conv.kernel_size == (3, 3, 3) and conv.stride == (1, 1, 1)
+                and conv.padding == (1, 1, 1) and conv.dilation == (1, 1, 1) and conv.groups == 1
+                and conv.padding_mode == 'zeros')
+
     def _tap_matrix(self, conv):
         """Conv3d weight [Cout,Cin,3,3,3] -> [Cin, 27*Cout] (column k*Cout+co), cached per weight version."""
         w = conv.weight
-        key = (w.data_ptr(), w._version, w.device)
+        key = (w.data_ptr(), geometry.tensor_version(w), w.device)
         cached = getattr(self, "_taps", None)
         if cached is None or cached[0] != key:
             cached = (key, w.detach().permute(1, 2, 3, 4, 0).reshape(w.shape[1], -1).contiguous())
@@ -150,12 +164,8 @@ class _PVConvBase(nn.Module):
         vox = self.voxelization
         norm_coords, _, plan = coordinate_plan(coords, vox.r, vox.normalize, vox.eps)
         occupied = _ops._B.avg_voxelize_compact(features.contiguous(), plan)     # [B, Cin, N]
-        prev = torch.backends.cuda.matmul.allow_tf32
-        torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32    # what the Conv3d would use
-        try:
+        with _layers.matmul_precision_of_convs():     # TF32 exactly when the Conv3d it replaces would use it
             taps = torch.matmul(occupied.transpose(1, 2), self._tap_matrix(self.voxel_layers[0]))  # [B, N, 27*Cout]
-        finally:
-            torch.backends.cuda.matmul.allow_tf32 = prev
         if (CHANNELS_LAST_VOXELS and hasattr(_ops._B, "groupnorm_act_cl")
                 and _ops._B.groupnorm_cl_supported(self.out_channels, 8)):
             norm = self.voxel_layers[1]

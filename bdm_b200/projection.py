@@ -66,12 +66,35 @@ class ProjectionConditioner:
     reads C contiguous floats."""
 
     def __init__(self, local_features, cameras, radius=0.0075, scale_factor=1.0, channel_last=True):
-        self.cameras = Cameras(cameras.R.contiguous(), (cameras.T * scale_factor).contiguous(),  # :136-137
-                               cameras.focal.contiguous(), cameras.principal.contiguous())
+        self.cameras = Cameras(cameras.R.clone().contiguous(), (cameras.T * scale_factor).contiguous(),  # :136-137
+                               cameras.focal.clone().contiguous(), cameras.principal.clone().contiguous())
         self.radius = float(radius)
+        self.scale_factor = float(scale_factor)
         self.channel_last = channel_last
         self.C = local_features.shape[1]
         self.feat = local_features.permute(0, 2, 3, 1).contiguous() if channel_last else local_features.contiguous()
+
+    def load(self, local_features, cameras):
+        """Refill this conditioner IN PLACE with the feature maps and cameras of another batch of the same
+        shape (device tensors, or pinned host tensors: the copies are stream-ordered).  CUDA graphs captured
+        over this conditioner (BDMSampler.enable_cuda_graphs) keep pointing at valid, current data; the
+        channel-last transposition happens inside the copy."""
+        assert tuple(local_features.shape) == (self.feat.shape[0], self.C) + tuple(
+            self.feat.shape[1:3] if self.channel_last else self.feat.shape[2:4]), "batch shape changed"
+        if self.channel_last:
+            if local_features.device != self.feat.device:      # host -> device first, then transpose on the device
+                local_features = local_features.to(self.feat.device, non_blocking=True)
+            self.feat.copy_(local_features.permute(0, 2, 3, 1))
+        else:
+            self.feat.copy_(local_features, non_blocking=True)
+        cam = self.cameras
+        cam.R.copy_(cameras.R, non_blocking=True)
+        cam.T.copy_(cameras.T, non_blocking=True)
+        if self.scale_factor != 1.0:
+            cam.T.mul_(self.scale_factor)
+        cam.focal.copy_(cameras.focal, non_blocking=True)
+        cam.principal.copy_(cameras.principal, non_blocking=True)
+        return self
 
     def surface_projection(self, points):
         """points f32[B,N,3] -> f32[B,N,C]: each visible point gets the feature vector of its pixel."""

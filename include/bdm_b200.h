@@ -210,6 +210,18 @@ int bdm_surface_projection_cf(int b, int n, int C, int H, int W, float radius, c
 int bdm_nn_f64(int b, int n, int m, int expanded, const double *src, const double *tgt,
                double *dist, int *idx, bdm_stream_t stream);
 
+/* ---- reverse-diffusion update of one sampling step ---------------------------
+ * replaces the eager torch ops of diffusers' DDPMScheduler.step as driven by experiments/model/model.py:182-194
+ * (mode 0; published algorithm, parity unpinned) and of GaussianDiffusion.p_sample,
+ * experiments/pvd/__init__.py:136-224 (mode 1), elementwise over n floats:
+ *   mode 0:  x0 = (x - c0*eps) * c1        mode 1:  x0 = c0*x - c1*eps
+ *   out = c2*x0 + c3*x  (+ c4*noise when t > 0),   (c0..c4) = table[t][0..4],   t = *t_dev clamped to [0,rows-1]
+ * table f32[rows][8] lives on the device and so does the timestep: a CUDA graph holding this kernel walks the
+ * schedule by itself.  Products and sums are rounded one by one (bit-identical to the torch sequence).
+ * out may alias x; all four arrays 16-byte aligned. */
+int bdm_sampler_update(long long n, int mode, const float *x, const float *eps, const float *noise,
+                       const float *table, int rows, const int *t_dev, float *out, bdm_stream_t stream);
+
 /* ---- fused self-attention of the PVConv attention block ------------------------------------------
  * replaces, for inference, the two torch.matmul + softmax of Attention.forward (modules/pvconv.py:36-63):
  *   out[b,c,i] = sum_j softmax_j( q[b,:,i] . k[b,:,j] ) * v[b,c,j]       q,k,v,out f32[b,c,t], un-scaled logits

@@ -336,3 +336,70 @@ def sparse_conv3_gather(taps, occupied, r, bias=None):
     if bias is not None:
         out += _f32(bias).reshape(1, cout, 1, 1, 1)
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# reverse-diffusion updates around the path (checker for csrc/sampler.cu and bdm_b200.diffusion)
+# ------------------------------------------------------------------------------------------------
+def pvd_coefficients(b_start=1e-4, b_end=0.02, time_num=1000):
+    """GaussianDiffusion.__init__, pvd/__init__.py:18-68, with the betas of :477 (linear, float64 -> float32
+    exactly where the reference casts).  -> dict of float32 arrays indexed by timestep."""
+    import torch
+    betas = np.linspace(b_start, b_end, time_num).astype(np.float64)
+    alphas = 1.0 - betas
+    ac = torch.from_numpy(np.cumprod(alphas, axis=0)).float()
+    ac_prev = torch.from_numpy(np.append(1.0, ac[:-1])).float()
+    b32, a32 = torch.from_numpy(betas).float(), torch.from_numpy(alphas).float()
+    post_var = b32 * (1.0 - ac_prev) / (1.0 - ac)
+    post_log_var = torch.log(torch.max(post_var, 1e-20 * torch.ones_like(post_var)))
+    return dict(sqrt_recip_ac=torch.sqrt(1.0 / ac).numpy(), sqrt_recipm1_ac=torch.sqrt(1.0 / ac - 1).numpy(),
+                coef1=(b32 * torch.sqrt(ac_prev) / (1.0 - ac)).numpy(),
+                coef2=((1.0 - ac_prev) * torch.sqrt(a32) / (1.0 - ac)).numpy(),
+                sigma=torch.exp(0.5 * post_log_var).numpy())
+
+
+def pvd_p_sample(x_t, eps, noise, t, coef=None):
+    """GaussianDiffusion.p_sample, pvd/__init__.py:196-224 with model_mean_type='eps' (:184-193),
+    model_var_type='fixedsmall', clip_denoised=False: every product / sum a separate fp32 rounding."""
+    c = coef if coef is not None else pvd_coefficients()
+    x_t, eps, noise = _f32(x_t), _f32(eps), _f32(noise)
+    f = np.float32
+    x0 = f(c["sqrt_recip_ac"][t]) * x_t - f(c["sqrt_recipm1_ac"][t]) * eps
+    mean = f(c["coef1"][t]) * x0 + f(c["coef2"][t]) * x_t
+    if t == 0:
+        return mean
+    return mean + f(c["sigma"][t]) * noise
+
+
+def ddpm_coefficients(beta_start=1e-5, beta_end=8e-3, steps=1000):
+    """diffusers 0.21.0 DDPMScheduler(beta_schedule='linear', variance_type='fixed_small', clip_sample=False,
+    prediction_type='epsilon') as configured by model/model.py:51-62 and config/structured.py:105-107.
+    diffusers is not vendored in the reference: PARITY UNPINNED (restated from the published algorithm)."""
+    import torch
+    betas = torch.linspace(beta_start, beta_end, steps, dtype=torch.float32)
+    ac = torch.cumprod(1.0 - betas, dim=0)
+    rows = np.zeros((steps, 5), np.float32)
+    for t in range(steps):
+        a_t = ac[t]
+        a_prev = ac[t - 1] if t > 0 else torch.tensor(1.0)
+        cur_alpha = a_t / a_prev
+        cur_beta = 1 - cur_alpha
+        coef_x0 = (a_prev ** 0.5 * cur_beta) / (1 - a_t)
+        coef_xt = cur_alpha ** 0.5 * (1 - a_prev) / (1 - a_t)
+        var = torch.clamp((1 - a_prev) / (1 - a_t) * cur_beta, min=1e-20)
+        sigma = float(var ** 0.5) if t > 0 else 0.0
+        rows[t] = [float((1 - a_t) ** 0.5), 1.0 / float(a_t ** 0.5), float(coef_x0), float(coef_xt), sigma]
+    return rows
+
+
+def ddpm_step(x_t, eps, noise, t, rows=None):
+    """prev_sample of DDPMScheduler.step: x0 = (x_t - sqrt(1-abar) eps) / sqrt(abar) -- evaluated, as torch's
+    CUDA kernel for `tensor / host scalar` does, as a product with the reciprocal rounded to float --,
+    mean = coef_x0 x0 + coef_xt x_t, plus sigma * noise for t > 0."""
+    r = (rows if rows is not None else ddpm_coefficients())[t]
+    x_t, eps, noise = _f32(x_t), _f32(eps), _f32(noise)
+    x0 = (x_t - r[0] * eps) * r[1]
+    prev = r[2] * x0 + r[3] * x_t
+    if t > 0:
+        prev = prev + r[4] * noise
+    return prev

@@ -158,3 +158,37 @@ def test_ddpm_schedule_properties():
     assert torch.allclose(p.step(torch.zeros(2, 3, 8), 0, x.transpose(1, 2)),
                           float(p.coef1[0]) * float(p.sqrt_recip_ac[0]) * x.transpose(1, 2)
                           + float(p.coef2[0]) * x.transpose(1, 2))
+
+
+def test_modules_run_under_inference_mode(oracle_backend):
+    """Activation tensors made under torch.inference_mode() carry no version counter; the plan / geometry
+    memos must not ask for one (the reference's modules run under inference_mode)."""
+    from bdm_b200.denoiser import PVCNN2_PC2
+    from bdm_b200.modules import PVConv
+    torch.manual_seed(2)
+    block = PVConv(8, 16, kernel_size=3, resolution=8, with_se=True).eval()
+    net = PVCNN2_PC2(num_classes=3, embed_dim=64, extra_feature_channels=5).eval()
+    x, t = _small_inputs(seed=6)
+    with torch.no_grad():
+        want_block = block((x[:, :8].contiguous(), x[:, :3].contiguous(), None))[0]
+        want = net(x, t)
+    with torch.inference_mode():
+        feats, coords = x[:, :8].contiguous(), x[:, :3].contiguous()
+        got_block = block((feats, coords, None))[0]
+        got_block2 = block((feats, coords, None))[0]          # second call hits the one-entry plan memo
+        got = net(x.clone(), t)
+    assert torch.equal(got_block, want_block) and torch.equal(got_block2, want_block)
+    assert torch.equal(got, want)
+
+
+def test_sampler_drops_graphs_on_reassignment():
+    from bdm_b200.diffusion import BDMSampler
+    s = BDMSampler(object(), object())
+    s._graphs["x"] = 1
+    s.cond = s.cond
+    assert s._graphs
+    s.cond = object()
+    assert not s._graphs
+    s._graphs["x"] = 1
+    s.pc2_net = object()
+    assert not s._graphs

@@ -66,6 +66,8 @@ def _op(launches):
             if _PROFILE is None:
                 return fn(*args, **kwargs)
             shapes = tuple(tuple(a.shape) if isinstance(a, torch.Tensor) else a for a in args)
+            if kwargs:   # keyword arguments as one trailing dict (tensor -> shape, None / scalars as they are)
+                shapes += ({k: (tuple(v.shape) if isinstance(v, torch.Tensor) else v) for k, v in kwargs.items()},)
             e0 = torch.cuda.Event(enable_timing=True)
             e1 = torch.cuda.Event(enable_timing=True)
             e0.record()

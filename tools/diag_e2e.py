@@ -4,7 +4,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import bench
 x, feats, cams = bench.make_inputs(16, 1234, "cuda:0")
-sampler = bench.build_sampler(x, feats, cams, "cuda:0")
+sampler = bench.build_sampler(feats, cams, "cuda:0", mode="vanilla")
 x_host = x.cpu().pin_memory(); out_host = torch.empty_like(x_host).pin_memory()
 with torch.no_grad():
     for _ in range(3): sampler.pc2_step(x, 500)

@@ -6,8 +6,8 @@ import bench
 import bdm_b200.denoiser as D
 from bdm_b200 import backend
 D.PLAN_AHEAD = False
-x, feats, cams = bench.make_inputs(16, 1234, "cuda:0")
-sampler = bench.build_sampler(x, feats, cams, "cuda:0")
+x, feats, cams = bench.make_inputs(int(os.environ.get("BDM_BATCH", "32")), 1234, "cuda:0")
+sampler = bench.build_sampler(feats, cams, "cuda:0", mode="vanilla")
 with torch.no_grad():
     sampler.pc2_step(x, 500)
     torch.cuda.synchronize()

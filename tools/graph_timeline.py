@@ -12,7 +12,7 @@ sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 
 x, feats, cams = bench.make_inputs(16, 1234, "cuda:0")
-sampler = bench.build_sampler(x, feats, cams, "cuda:0")
+sampler = bench.build_sampler(feats, cams, "cuda:0", mode="vanilla")
 with torch.no_grad():
     for _ in range(3):
         sampler.pc2_step(x, 500)

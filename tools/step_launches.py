@@ -11,9 +11,9 @@ import bench  # noqa: E402
 import bdm_b200.denoiser as D  # noqa: E402
 
 D.PLAN_AHEAD = False
-x, feats, cams = bench.make_inputs(16, 1234, "cuda:0")
-sampler = bench.build_sampler(x, feats, cams, "cuda:0")
+x, feats, cams = bench.make_inputs(int(os.environ.get("BDM_BATCH", "32")), 1234, "cuda:0")
+sampler = bench.build_sampler(feats, cams, "cuda:0", mode="vanilla")
 for _ in range(2):
     with torch.no_grad():
-        sampler.pc2_step(x, 500)
+        sampler._pc2_eps(x, torch.full((x.shape[0],), 500, device=x.device, dtype=torch.long))
     torch.cuda.synchronize()

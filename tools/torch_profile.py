@@ -8,8 +8,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 
-x, feats, cams = bench.make_inputs(16, 1234, "cuda:0")
-sampler = bench.build_sampler(x, feats, cams, "cuda:0")
+x, feats, cams = bench.make_inputs(int(os.environ.get("BDM_BATCH", "32")), 1234, "cuda:0")
+sampler = bench.build_sampler(feats, cams, "cuda:0", mode="vanilla")
 for _ in range(3):
     with torch.no_grad():
         sampler.pc2_step(x, 500)

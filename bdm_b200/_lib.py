@@ -29,6 +29,7 @@ _PROTOS = {
     "bdm_avg_voxelize_fill": (_i, [_i, _i, _i, _i, _p, _p, _p, _p, _p, _z, _p]),
     "bdm_avg_voxelize_compact": (_i, [_i, _i, _i, _i, _p, _p, _p, _z, _p]),
     "bdm_grouping_into": (_i, [_i, _i, _i, _i, _i, _p, _p, _p, _p, _i, _i, _p]),
+    "bdm_attention_workspace_bytes": (_z, [_i, _i, _i]),
     "bdm_attention": (_i, [_i, _i, _i, _p, _p, _p, _p, _p, _z, _p]),
     "bdm_sparse_conv3_gather": (_i, [_i, _i, _i, _i, _p, _p, _p, _i, _p, _p, _z, _p]),
     "bdm_sparse_conv3_stats_blocks": (_i, [_i]),

@@ -264,7 +264,7 @@ def attention_supported(channels, tokens, batch=None):
     return ok
 
 
-@_op(2)
+@_op(3)
 def attention(q, k, v):
     """q, k, v f32[B,64,T] -> f32[B,64,T]: out[b,c,i] = sum_j softmax_j(q[b,:,i].k[b,:,j]) v[b,c,j]"""
     _chk_float(q, "q")
@@ -274,7 +274,7 @@ def attention(q, k, v):
     _req(k.shape == q.shape and v.shape == q.shape, "q, k, v must have one shape")
     _req(attention_supported(c, t), "attention kernel needs 64 channels and a multiple of 128 tokens")
     out = torch.empty_like(q)
-    ws = _workspace(16, q.device)
+    ws = _workspace(_L.bdm_attention_workspace_bytes(b, c, t), q.device)
     with _Launch(q) as st:
         _check(_L.bdm_attention(b, c, t, q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), ws.data_ptr(),
                                 ws.numel(), st))
@@ -632,8 +632,7 @@ def surface_projection(points, R, T, focal, principal, feat, radius, feat_is_hwc
     return out, pix
 
 
-@_op(1)
-@_op(5)
+@_op(6)
 def conditioning_input(points, R, T, focal, principal, feat_hwc, radius):
     """Fused get_input_with_conditioning: points f32[B,N,3] + feat_hwc f32[B,H,W,C] -> channel-first denoiser
     input f32[B,3+C,N] (channels 0-2 = the coordinates, 3.. = projected features), pix int32[B,N]."""

@@ -313,8 +313,10 @@ attention_hd64_f16_kernel(int T, const float *__restrict__ q, const float *__res
 // q, k, v, out: f32[b][64][t] (channel-first, as the 1x1 convolutions of the block produce them);
 // out[b][c][i] = sum_j softmax_j(q[b][:,i] . k[b][:,j]) * v[b][c][j].  c must be 64, t a multiple of 128.
 // workspace: 16 bytes (the three max|.|).
-extern "C" int bdm_attention(int b, int c, int t, const float *q, const float *k, const float *v, float *out,
-                             void *workspace, size_t workspace_bytes, bdm_stream_t stream) {
+// Not part of the public header: the entry point is bdm_attention (attention_tc05.cu), which routes here when
+// BDM_ATTENTION=mma is set (A/B timing of the legacy tensor path against the tcgen05 kernel).
+extern "C" int bdm_attention_mma(int b, int c, int t, const float *q, const float *k, const float *v, float *out,
+                                 void *workspace, size_t workspace_bytes, bdm_stream_t stream) {
   using namespace bdm;
   BDM_CHECK_SIZE(b >= 0 && c == kHD && t >= kBM && t % kBM == 0);
   if (b == 0) return BDM_OK;

@@ -47,9 +47,11 @@ sparse_conv3_gather_kernel(int n, int cout, int r, int channels_last, const floa
   // follows: stats[b][blockIdx.x][channel].  Rows beyond the grid contribute zero.  The per-warp partials
   // reuse each warp's entry list (dead by then).
   float2(*wsum)[9 * 16] = reinterpret_cast<float2(*)[9 * 16]>(entries);
-  // rows beyond the grid exist only when r*r is not a multiple of the warps per CTA (r = 1, 2); the launcher
-  // refuses `stats` there, so no warp of a CTA that takes the __syncthreads() below can have left early
-  if (row >= r * r) return;
+  // rows beyond the grid exist only when r*r is not a multiple of the warps per CTA (r = 1, 2).  Without
+  // `stats` such a warp may leave at once; with it, it stays (as a row without neighbours: zero sums) until
+  // the block-wide barrier of the statistics reduction, so that every warp of the CTA reaches that barrier.
+  const bool valid = row < r * r;
+  if (!valid && stats == nullptr) return;
   const int x = row / r, y = row - x * r;
   const int r3 = r * r * r;
 
@@ -62,7 +64,7 @@ sparse_conv3_gather_kernel(int n, int cout, int r, int channels_last, const floa
   // rank of that row's first voxel: one round of loads for the whole neighbourhood
   uint32_t my_bits = 0u;
   int my_slot = 0;
-  if (lane < 9) {
+  if (lane < 9 && valid) {
     const int xx = x + lane / 3 - 1, yy = y + lane % 3 - 1;
     if (xx >= 0 && xx < r && yy >= 0 && yy < r) {
       const int bit0 = (xx * r + yy) * r;
@@ -141,6 +143,7 @@ sparse_conv3_gather_kernel(int n, int cout, int r, int channels_last, const floa
       stats[((size_t)b * gridDim.x + blockIdx.x) * cout + co0 + lane] = make_double2(a1, a2);
     }
   }
+  if (!valid) return;
   if (channels_last) {
     // out[b][voxel][co]: the tile rows are already channel-contiguous
     float *obase_ = out + ((size_t)b * r3 + (size_t)row * r) * cout + co0;
@@ -188,7 +191,7 @@ sparse_conv3_gather_kernel(int n, int cout, int r, int channels_last, const floa
 // taps f32[b][n][27][cout] (row j = the j-th occupied voxel of shape b in ascending voxel id, as produced
 // from bdm_avg_voxelize_compact; rows >= the shape's occupied count are ignored), bias f32[cout] or NULL,
 // out f32[b][cout][r^3], or f32[b][r^3][cout] when channels_last != 0.  stats (optional, f64[b][blocks][cout][2],
-// blocks = bdm_sparse_conv3_stats_blocks(r); r >= 4 only): per-channel (sum, sum of squares) of the bias-less output per block of
+// blocks = bdm_sparse_conv3_stats_blocks(r)): per-channel (sum, sum of squares) of the bias-less output per block of
 // rows, which bdm_groupnorm_act_cl accepts in place of its own statistics pass.  workspace = the plan bdm_voxel_plan left for these (b, n, r).  r in {1,2,4,8,16,32}.
 // Number of per-channel statistics blocks bdm_sparse_conv3_gather writes per shape when `stats` is given.
 extern "C" int bdm_sparse_conv3_stats_blocks(int r) {
@@ -202,7 +205,6 @@ extern "C" int bdm_sparse_conv3_gather(int b, int cout, int n, int r, const floa
   BDM_CHECK_SIZE(b >= 0 && cout >= 0 && n >= 1 && r >= 1 && r <= 32 && (r & (r - 1)) == 0);  // rows within a word
   const int r3 = r * r * r;
   BDM_CHECK_SIZE(vox_fast_path(n, r3));
-  BDM_CHECK_SIZE(stats == nullptr || (r * r) % kGatherWarps == 0);   // whole CTAs only (block-wide barrier)
   if (b == 0 || cout == 0) return BDM_OK;
   BDM_CHECK_PTR(taps); BDM_CHECK_PTR(out);
   const VoxAuxLayout L = vox_aux_layout(n, r3);

@@ -404,8 +404,8 @@ def standalone_rooflines(device, batch, peaks):
         b * (12 * n + 24 * IMG * IMG + 4 * n * (C_IMG + 3)) + 4 * C_IMG * winners, ms,
         note=f"{winners} of {b * n} points win a pixel")
     # a11: evaluation nearest neighbour, fp64
-    gt = torch.as_tensor(cases.cloud(rng, 8, n, "shape").transpose(0, 2, 1).astype(np.float64)).to(device)
-    pred = gt[:, torch.randperm(n, device=device)] + 0.05 * torch.randn(gt.shape, device=device, dtype=torch.float64)
+    gt = torch.as_tensor(np.ascontiguousarray(cases.cloud(rng, 8, n, "shape").transpose(0, 2, 1).astype(np.float64))).to(device)
+    pred = (gt[:, torch.randperm(n, device=device)] + 0.05 * torch.randn(gt.shape, device=device, dtype=torch.float64)).contiguous()
     ms = timeit(lambda: B.nn_f64(pred, gt, expanded=False, return_index=False))
     out.append({"kernel": f"nn_f64 8 pairs x {n} x {n} (direct form)", "bound": "fp64 issue", "achieved": 8.0 * n * n / (ms * 1e-3) / 1e12,
                 "unit": "T pair-tests/s (8 fp64 flops each)", "peak": None, "frac": None, "ms_per_launch": ms})

@@ -227,8 +227,11 @@ int bdm_sampler_update(long long n, int mode, const float *x, const float *eps, 
  *   out[b,c,i] = sum_j softmax_j( q[b,:,i] . k[b,:,j] ) * v[b,c,j]       q,k,v,out f32[b,c,t], un-scaled logits
  * fp32-equivalent arithmetic (operands split into two fp16 halves after a per-tensor power-of-two scaling,
  * three tensor-core products per term, fp32 accumulation and softmax); the [t,t] logits are never written.
+ * Runs on the 5th-generation tensor cores (tcgen05.mma, accumulators in tensor memory, operands by TMA bulk
+ * copy); a pre-pass writes the fp16 operand planes into the workspace.
  * c must be 64 and t a multiple of 128 (BDM_ERR_BAD_SIZE otherwise: the caller keeps the torch route for
- * other shapes).  workspace: 16 bytes, 16-byte aligned. */
+ * other shapes).  workspace: bdm_attention_workspace_bytes(b,c,t) bytes, 256-byte aligned. */
+size_t bdm_attention_workspace_bytes(int b, int c, int t);
 int bdm_attention(int b, int c, int t, const float *q, const float *k, const float *v, float *out,
                   void *workspace, size_t workspace_bytes, bdm_stream_t stream);
 

@@ -28,7 +28,7 @@ for name, us in half:
     a[1] += us
 total = sum(a[1] for a in agg.values())
 ours = sum(a[1] for k, a in agg.items() if k.startswith("bdm::"))
-print(f"# One PC^2 step (B=16, N=4096), eager, serialised under ncu: {len(half)} launches, {total / 1e3:.2f} ms of kernel time")
+print(f"# One PC^2 iteration (B={__import__('os').environ.get('BDM_BATCH', '32')}, N=4096), eager, serialised under ncu: {len(half)} launches, {total / 1e3:.2f} ms of kernel time")
 print(f"# libbdm_b200 kernels: {ours / 1e3:.3f} ms = {ours / total * 100:.1f} % of the step's kernel time")
 print("| kernel | launches | total us | share % |")
 print("|---|---|---|---|")

@@ -1,6 +1,6 @@
 // attention_tc05.cu -- the PVConv attention block (reference: experiments/model/pvcnn/modules/pvconv.py:36-63,
 // class Attention: softmax(q^T k) applied to v, un-scaled logits, fp32) on Blackwell's 5th-generation tensor
-// cores: tcgen05.mma with the accumulators in tensor memory (TMEM), operands fetched by TMA bulk copies.
+// cores: tcgen05.mma with accumulators AND the A operands in tensor memory (TMEM), B operands fetched by TMA.
 //
 // Arithmetic is the one csrc/attention.cu established (and tests/test_dense_fused_gpu.py checks against
 // float64): every fp32 operand is split into two fp16 numbers after a per-tensor power-of-two scaling
@@ -8,20 +8,25 @@
 // the softmax is online (running max / sum per query, fp32), and the P.V product of every key tile starts
 // from zero and is merged into the running output with one rounded FMA.
 //
-// Two kernels:
-//   attention_prep_kernel   q, k, v f32[B,64,T] -> fp16 hi/lo planes laid out tile by tile exactly as the MMA
-//                           reads them from shared memory (8x8 "core matrices", no swizzle), so that a tile
+// Kernels:
+//   attention_prep_kernel   k, v f32[B,64,T] -> fp16 hi/lo planes laid out tile by tile exactly as the MMA reads
+//                           its B operand from shared memory (8x8 "core matrices", no swizzle), so that a tile
 //                           arrives in shared memory with ONE 1-D bulk copy (cp.async.bulk + mbarrier).
 //   attention_tc05_kernel   CTA = NQ tiles of 128 queries x all keys in tiles of 64.
-//       warps 0..4NQ-1  softmax: warp-group w owns query tile w, thread = one query row (TMEM lane); reads its
-//                       S row with tcgen05.ld, exponentiates, writes P (fp16 hi/lo) to shared memory for the
-//                       second GEMM, keeps the output row O[64] and the running max / sum in registers
-//       warp 4NQ        one thread: TMA producer (Q once; K and V rings of 3 stages)
-//       warp 4NQ+1      TMEM allocation; one thread: issues every tcgen05.mma and commits them to mbarriers
-//   S = Q K^T  : M=128 queries, N=64 keys, K=64 channels; A = Q (MN-major), B = K (MN-major): as stored
-//   O_tile = P V: M=128 queries, N=64 channels, K=64 keys; A = P (K-major), B = V (K-major): as stored
-//   TMEM per query tile: S double-buffered (2 x 64 columns) + O_tile double-buffered (2 x 64 columns).
-// Descriptor conventions were verified on the device with tools/probe/tc05_probe.cu.
+//       warps 0..4NQ-1      softmax: warp-group w owns query tile w, thread = one query row = one TMEM lane.
+//                           Stores its Q row (fp16 hi/lo) into TMEM once; per key tile reads its S row with
+//                           tcgen05.ld, exponentiates, stores P (fp16 hi/lo) back into TMEM with tcgen05.st as
+//                           the A operand of the second GEMM; keeps the output row O[64] and the running
+//                           max / sum in registers.
+//       warp 4NQ            one thread: TMA producer (K ring and V ring of kStages tiles)
+//       warps 4NQ+1+w       one thread each: issues the tcgen05.mma of query tile w and commits them to mbarriers
+//   S = Q K^T   : M=128 queries, N=64 keys, K=64 channels; A = Q in TMEM, B = K tile in smem (MN-major, as stored)
+//   O_tile = P V: M=128 queries, N=64 channels, K=64 keys; A = P in TMEM, B = V tile in smem (K-major, as stored)
+//   TMEM per query tile (256 columns): S 64 | O_tile 64 | Q hi 32 | Q lo 32 | P hi 32 | P lo 32.
+// Why the A operands live in TMEM: with both operands in shared memory an M=128, N=64, K=16 MMA reads 6 KB per 32
+// tensor-pipe cycles -- 192 B/clk against a 128 B/clk shared-memory port; that version (still correct) ran at
+// 341 us for B=16, T=4096.  With A in TMEM only the 2 KB B slice comes from shared memory.
+// Operand layouts / descriptor conventions were verified on the device with tools/probe/tc05_probe.cu.
 #include <cuda_fp16.h>
 
 #include <cstdlib>
@@ -34,10 +39,8 @@ namespace tc05 {
 constexpr int kD = 64;            // channels
 constexpr int kQT = 128;          // queries per tile (UMMA M)
 constexpr int kKT = 64;           // keys per tile (UMMA N of S, K of P.V)
-constexpr int kStages = 3;        // K ring and V ring depth
-constexpr int kQTileBytes = 2 * kQT * kD * 2;   // hi + lo planes of one query tile (32 KB)
+constexpr int kStages = 4;        // K ring and V ring depth
 constexpr int kKTileBytes = 2 * kKT * kD * 2;   // hi + lo planes of one key tile (16 KB), same for V
-constexpr int kPTileBytes = 2 * kQT * kKT * 2;  // hi + lo planes of one P tile (32 KB)
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -98,6 +101,34 @@ __host__ __device__ constexpr uint32_t instr_desc(uint32_t a_mn, uint32_t b_mn) 
         "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])     \
       : "r"(taddr))
 
+#define BDM_TMEM_ST32(taddr, r)                                                                                    \
+  asm volatile(                                                                                                    \
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "                                                              \
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "                                   \
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"                           \
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),        \
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),              \
+        "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),            \
+        "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])             \
+      : "memory")
+
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// D[tmem] (+)= A[tmem] . B[smem]
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+// (hi, lo) fp16 pairs of two fp32 values: hi = rn(x), lo = rn(x - hi)
+__device__ __forceinline__ void split2(float a, float b, uint32_t &hi, uint32_t &lo) {
+  const __half2 hh = __floats2half2_rn(a, b);
+  const float2 hf = __half22float2(hh);
+  const __half2 ll = __floats2half2_rn(a - hf.x, b - hf.y);
+  hi = *reinterpret_cast<const uint32_t *>(&hh);
+  lo = *reinterpret_cast<const uint32_t *>(&ll);
+}
+
 __device__ __forceinline__ float fast_exp2(float x) {   // one MUFU.EX2; ex2(-inf) = +0
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -150,23 +181,20 @@ __global__ void attention_tc05_amax_kernel(size_t n4, const float4 *__restrict__
   }
 }
 
-// Workspace (bytes): [0,16) amax | Q planes | K planes | V planes, each b * t * 64 * 2 (hi, lo) * 2 bytes.
-//   Q tile (128 queries): plane hi then lo; element (query i, channel d) of a plane at half index
-//       ((d/8) * 16 + i/8) * 64 + (d%8) * 8 + i%8            MN-major core matrices (8 channels x 8 queries)
-//   K tile (64 keys):     ((d/8) * 8 + j/8) * 64 + (d%8) * 8 + j%8          MN-major (8 channels x 8 keys)
+// Workspace (bytes): [0,16) amax | [256, ...) K planes | V planes, each b * t * 64 * 2 (hi, lo) * 2 bytes.
+//   K tile (64 keys): plane hi then lo; element (key j, channel d) of a plane at half index
+//       ((d/8) * 8 + j/8) * 64 + (d%8) * 8 + j%8          MN-major core matrices (8 channels x 8 keys)
 //   V tile (64 keys):     ((j/8) * 8 + d/8) * 64 + (d%8) * 8 + j%8          K-major  (8 channels x 8 keys)
 // Block = 256 threads = 64 channels x 4 runs of 8 consecutive tokens; 8 lanes with consecutive channels write one
 // contiguous 128-byte core matrix, and read 8 x 32-byte sectors.
 __global__ void __launch_bounds__(256)
-attention_prep_kernel(int T, const float *__restrict__ q, const float *__restrict__ k, const float *__restrict__ v,
-                      const unsigned *__restrict__ amax, __half *__restrict__ qp, __half *__restrict__ kp,
-                      __half *__restrict__ vp) {
+attention_prep_kernel(int T, const float *__restrict__ k, const float *__restrict__ v,
+                      const unsigned *__restrict__ amax, __half *__restrict__ kp, __half *__restrict__ vp) {
   const int b = blockIdx.y;
   const int tid = threadIdx.x;
   const int d = (tid >> 5) * 8 + (tid & 7);
   const int t0 = blockIdx.x * 32 + ((tid >> 3) & 3) * 8;
   float inv;
-  const float sq = pow2_scale(__uint_as_float(__ldg(amax + 0)), &inv);
   const float sk = pow2_scale(__uint_as_float(__ldg(amax + 1)), &inv);
   const float sv = pow2_scale(__uint_as_float(__ldg(amax + 2)), &inv);
   const size_t src = ((size_t)b * kD + d) * T + t0;
@@ -177,14 +205,6 @@ attention_prep_kernel(int T, const float *__restrict__ q, const float *__restric
     x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = c.x; x[5] = c.y; x[6] = c.z; x[7] = c.w;
   };
   const int dg = d >> 3, dr = d & 7;
-  {   // Q
-    load8(q);
-    split8(x, sq, hi, lo);
-    const int tile = t0 / kQT, i = t0 % kQT;
-    __half *base = qp + ((size_t)b * (T / kQT) + tile) * (2 * kQT * kD) + ((dg * 16 + i / 8) * 64 + dr * 8);
-    *reinterpret_cast<uint4 *>(base) = hi;
-    *reinterpret_cast<uint4 *>(base + kQT * kD) = lo;
-  }
   const int tile = t0 / kKT, j = t0 % kKT;
   {   // K
     load8(k);
@@ -202,53 +222,55 @@ attention_prep_kernel(int T, const float *__restrict__ q, const float *__restric
   }
 }
 
+// TMEM columns of one query tile
+constexpr uint32_t kColS = 0, kColO = 64, kColQhi = 128, kColQlo = 160, kColPhi = 192, kColPlo = 224, kColsPerTile = 256;
+
 template <int NQ>
 struct Smem {
-  static constexpr int kQ = 0;
-  static constexpr int kK = kQ + NQ * kQTileBytes;
+  static constexpr int kK = 0;
   static constexpr int kV = kK + kStages * kKTileBytes;
-  static constexpr int kP = kV + kStages * kKTileBytes;
-  static constexpr int kBars = kP + NQ * kPTileBytes;
-  // barriers: q_full | k_full[3] k_empty[3] v_full[3] v_empty[3] | per w: s_full[2] s_empty[2] p_full o_full[2] o_empty[2]
-  static constexpr int kNumBars = 1 + 4 * kStages + NQ * 9;
+  static constexpr int kBars = kV + kStages * kKTileBytes;
+  // barriers: k_full[S] k_empty[S] v_full[S] v_empty[S] | per w: q_ready s_full s_empty p_full o_full
+  static constexpr int kPerTile = 5;
+  static constexpr int kNumBars = 4 * kStages + NQ * kPerTile;
   static constexpr int kTmemSlot = kBars + kNumBars * 8;
   static constexpr int kBytes = kTmemSlot + 16;
 };
 
 template <int NQ>
-__global__ void __launch_bounds__((4 * NQ + 2) * 32, 1)
-attention_tc05_kernel(int T, const __half *__restrict__ qp, const __half *__restrict__ kp, const __half *__restrict__ vp,
+__global__ void __launch_bounds__((5 * NQ + 1) * 32, 1)
+attention_tc05_kernel(int T, const float *__restrict__ q, const __half *__restrict__ kp, const __half *__restrict__ vp,
                       const unsigned *__restrict__ amax, float *__restrict__ out) {
   extern __shared__ __align__(1024) unsigned char smem[];
   using L = Smem<NQ>;
+  constexpr uint32_t kTmemCols = NQ * kColsPerTile;
   const int b = blockIdx.y;
   const int qtile0 = blockIdx.x * NQ;          // first 128-query tile of this CTA
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int J = T / kKT;
 
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L::kBars);
-  uint64_t *q_full = bars;
-  uint64_t *k_full = bars + 1, *k_empty = k_full + kStages, *v_full = k_empty + kStages, *v_empty = v_full + kStages;
-  uint64_t *wbars = v_empty + kStages;           // + w * 9
+  uint64_t *k_full = bars, *k_empty = k_full + kStages, *v_full = k_empty + kStages, *v_empty = v_full + kStages;
+  uint64_t *wbars = v_empty + kStages;           // + w * kPerTile: q_ready, s_full, s_empty, p_full, o_full
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + L::kTmemSlot);
 
   if (threadIdx.x == 0) {
-    mbar_init(q_full, 1);
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(k_full + s, 1); mbar_init(k_empty + s, 1); mbar_init(v_full + s, 1); mbar_init(v_empty + s, 1);
+      mbar_init(k_full + s, 1); mbar_init(v_full + s, 1);          // TMA producer (expect_tx)
+      mbar_init(k_empty + s, NQ); mbar_init(v_empty + s, NQ);      // one tcgen05.commit per MMA thread
     }
     for (int w = 0; w < NQ; ++w) {
-      uint64_t *wb = wbars + w * 9;
-      mbar_init(wb + 0, 1); mbar_init(wb + 1, 1);          // s_full[2]   (tcgen05.commit)
-      mbar_init(wb + 2, kQT); mbar_init(wb + 3, kQT);      // s_empty[2]  (every softmax thread)
-      mbar_init(wb + 4, kQT);                              // p_full
-      mbar_init(wb + 5, 1); mbar_init(wb + 6, 1);          // o_full[2]   (tcgen05.commit)
-      mbar_init(wb + 7, kQT); mbar_init(wb + 8, kQT);      // o_empty[2]
+      uint64_t *wb = wbars + w * L::kPerTile;
+      mbar_init(wb + 0, kQT);     // q_ready: every softmax thread has stored its Q row into TMEM
+      mbar_init(wb + 1, 1);       // s_full   (tcgen05.commit)
+      mbar_init(wb + 2, kQT);     // s_empty: every softmax thread has its S row in registers
+      mbar_init(wb + 3, kQT);     // p_full:  every softmax thread has stored its P row into TMEM
+      mbar_init(wb + 4, 1);       // o_full   (tcgen05.commit)
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 4 * NQ + 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(NQ * 256));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   tc_fence_before();
@@ -259,10 +281,6 @@ attention_tc05_kernel(int T, const __half *__restrict__ qp, const __half *__rest
   if (warp == 4 * NQ) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      const __half *qsrc = qp + ((size_t)b * (T / kQT) + qtile0) * (2 * kQT * kD);
-      mbar_expect_tx(q_full, NQ * kQTileBytes);
-      for (int w = 0; w < NQ; ++w)
-        tma_load(smem + L::kQ + w * kQTileBytes, qsrc + (size_t)w * (2 * kQT * kD), kQTileBytes, q_full);
       const __half *ksrc = kp + (size_t)b * J * (2 * kKT * kD);
       const __half *vsrc = vp + (size_t)b * J * (2 * kKT * kD);
       for (int j = 0; j < J; ++j) {
@@ -276,66 +294,51 @@ attention_tc05_kernel(int T, const __half *__restrict__ qp, const __half *__rest
         tma_load(smem + L::kV + s * kKTileBytes, vsrc + (size_t)j * (2 * kKT * kD), kKTileBytes, v_full + s);
       }
     }
-  } else if (warp == 4 * NQ + 1) {
-    // ===================== MMA issuer =====================
+  } else if (warp > 4 * NQ) {
+    // ===================== MMA issuer of query tile w =====================
+    const int w = warp - (4 * NQ + 1);
     if (lane == 0) {
-      constexpr uint32_t idesc_s = instr_desc(1, 1);     // A = Q (MN-major), B = K (MN-major)
-      constexpr uint32_t idesc_o = instr_desc(0, 0);     // A = P (K-major),  B = V (K-major)
-      const uint32_t q_base = smem_u32(smem + L::kQ), k_base = smem_u32(smem + L::kK), v_base = smem_u32(smem + L::kV),
-                     p_base = smem_u32(smem + L::kP);
-      mbar_wait(q_full, 0);
+      constexpr uint32_t idesc_s = instr_desc(0, 1);     // A = Q (TMEM), B = K (MN-major)
+      constexpr uint32_t idesc_o = instr_desc(0, 0);     // A = P (TMEM), B = V (K-major)
+      const uint32_t k_base = smem_u32(smem + L::kK), v_base = smem_u32(smem + L::kV);
+      uint64_t *wb = wbars + w * L::kPerTile;
+      const uint32_t tw = tmem + w * kColsPerTile;
+      mbar_wait(wb + 0, 0);                        // Q is in TMEM
+      tc_fence_after();
       for (int j = 0; j <= J; ++j) {
         if (j < J) {
           const int s = j % kStages;
           mbar_wait(k_full + s, (j / kStages) & 1);
+          mbar_wait(wb + 2, (j & 1) ^ 1);          // the softmax threads have taken S_{j-1} out of TMEM
           tc_fence_after();
           const uint32_t kb = k_base + s * kKTileBytes;
+          // terms in ascending magnitude: lo*hi, hi*lo, hi*hi; 4 k-steps of 16 channels (8 TMEM columns of A)
 #pragma unroll
-          for (int w = 0; w < NQ; ++w) {
-            uint64_t *wb = wbars + w * 9;
-            const int buf = j & 1;
-            mbar_wait(wb + 2 + buf, ((j >> 1) & 1) ^ 1);           // softmax has taken S_{j-2} out of this buffer
-            tc_fence_after();
-            const uint32_t d_s = tmem + w * 256 + buf * 64;
-            const uint32_t qb = q_base + w * kQTileBytes;
-            // terms in ascending magnitude: lo*hi, hi*lo, hi*hi; 4 k-steps of 16 channels each
+          for (int term = 0; term < 3; ++term) {
+            const uint32_t qa = tw + (term == 0 ? kColQlo : kColQhi);
+            const uint32_t ka = kb + (term == 1 ? kKT * kD * 2 : 0);            // K lo plane for term 1
 #pragma unroll
-            for (int term = 0; term < 3; ++term) {
-              const uint32_t qa = qb + (term == 0 ? kQT * kD * 2 : 0);          // Q lo plane for term 0
-              const uint32_t ka = kb + (term == 1 ? kKT * kD * 2 : 0);          // K lo plane for term 1
-#pragma unroll
-              for (int kk = 0; kk < 4; ++kk)
-                umma_f16(d_s, smem_desc(qa + kk * 4096, 2048, 128), smem_desc(ka + kk * 2048, 1024, 128), idesc_s,
-                         (term | kk) != 0);
-            }
-            umma_commit(wb + 0 + buf);                             // s_full
+            for (int kk = 0; kk < 4; ++kk)
+              umma_f16_ts(tw + kColS, qa + kk * 8, smem_desc(ka + kk * 2048, 1024, 128), idesc_s, (term | kk) != 0);
           }
+          umma_commit(wb + 1);                     // s_full
           umma_commit(k_empty + s);
         }
         if (j >= 1) {
           const int jj = j - 1, s = jj % kStages;
           mbar_wait(v_full + s, (jj / kStages) & 1);
+          mbar_wait(wb + 3, jj & 1);               // P_jj is in TMEM (and O_tile_{jj-1} has been taken out)
+          tc_fence_after();
           const uint32_t vb = v_base + s * kKTileBytes;
 #pragma unroll
-          for (int w = 0; w < NQ; ++w) {
-            uint64_t *wb = wbars + w * 9;
-            const int buf = jj & 1;
-            mbar_wait(wb + 4, jj & 1);                             // P_jj is in shared memory
-            mbar_wait(wb + 7 + buf, ((jj >> 1) & 1) ^ 1);          // softmax has taken O_tile_{jj-2} out of this buffer
-            tc_fence_after();
-            const uint32_t d_o = tmem + w * 256 + 128 + buf * 64;
-            const uint32_t pb = p_base + w * kPTileBytes;
+          for (int term = 0; term < 3; ++term) {
+            const uint32_t pa = tw + (term == 0 ? kColPlo : kColPhi);
+            const uint32_t va = vb + (term == 1 ? kKT * kD * 2 : 0);            // V lo plane for term 1
 #pragma unroll
-            for (int term = 0; term < 3; ++term) {
-              const uint32_t pa = pb + (term == 0 ? kQT * kKT * 2 : 0);         // P lo plane for term 0
-              const uint32_t va = vb + (term == 1 ? kKT * kD * 2 : 0);          // V lo plane for term 1
-#pragma unroll
-              for (int kk = 0; kk < 4; ++kk)
-                umma_f16(d_o, smem_desc(pa + kk * 4096, 2048, 128), smem_desc(va + kk * 2048, 1024, 128), idesc_o,
-                         (term | kk) != 0);
-            }
-            umma_commit(wb + 5 + buf);                             // o_full
+            for (int kk = 0; kk < 4; ++kk)
+              umma_f16_ts(tw + kColO, pa + kk * 8, smem_desc(va + kk * 2048, 1024, 128), idesc_o, (term | kk) != 0);
           }
+          umma_commit(wb + 4);                     // o_full
           umma_commit(v_empty + s);
         }
       }
@@ -344,15 +347,26 @@ attention_tc05_kernel(int T, const __half *__restrict__ qp, const __half *__rest
     // ===================== softmax warp-groups =====================
     const int w = warp >> 2;                        // query tile of this warp-group
     const int row = (warp & 3) * 32 + lane;         // query row inside the tile == TMEM lane
-    uint64_t *wb = wbars + w * 9;
-    const uint32_t t_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16) + w * 256;
+    uint64_t *wb = wbars + w * L::kPerTile;
+    const uint32_t t_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16) + w * kColsPerTile;
     float inv_sq, inv_sk, inv_sv;
-    pow2_scale(__uint_as_float(__ldg(amax + 0)), &inv_sq);
+    const float sq = pow2_scale(__uint_as_float(__ldg(amax + 0)), &inv_sq);
     pow2_scale(__uint_as_float(__ldg(amax + 1)), &inv_sk);
     pow2_scale(__uint_as_float(__ldg(amax + 2)), &inv_sv);
     const float c = inv_sq * inv_sk * 1.4426950408889634f;     // raw logit -> log2 units
-    unsigned char *p_hi = smem + L::kP + w * kPTileBytes + (row >> 3) * 128 + (row & 7) * 16;
-    unsigned char *p_lo = p_hi + kQT * kKT * 2;
+
+    {   // this thread's query row -> fp16 hi / lo pairs -> TMEM (A operand of S = Q K^T): column = channel pair
+      const float *qrow = q + (size_t)b * kD * T + (size_t)(qtile0 + w) * kQT + row;
+      uint32_t qh[32], ql[32];
+#pragma unroll
+      for (int c2 = 0; c2 < 32; ++c2)
+        split2(__ldg(qrow + (size_t)(2 * c2) * T) * sq, __ldg(qrow + (size_t)(2 * c2 + 1) * T) * sq, qh[c2], ql[c2]);
+      BDM_TMEM_ST32(t_lane + kColQhi, qh);
+      BDM_TMEM_ST32(t_lane + kColQlo, ql);
+      tmem_wait_st();
+      tc_fence_before();
+      mbar_arrive(wb + 0);                         // q_ready
+    }
 
     float o[kD];
 #pragma unroll
@@ -360,71 +374,64 @@ attention_tc05_kernel(int T, const __half *__restrict__ qp, const __half *__rest
     float m_run = -INFINITY, l_run = 0.0f, alpha_prev = 0.0f;
 
     for (int j = 0; j < J; ++j) {
-      const int buf = j & 1;
       uint32_t sr[kKT];
-      mbar_wait(wb + 0 + buf, (j >> 1) & 1);       // S_j is in TMEM
+      mbar_wait(wb + 1, j & 1);                    // S_j is in TMEM
       tc_fence_after();
-      BDM_TMEM_LD32(sr, t_lane + buf * 64);
+      BDM_TMEM_LD32(sr, t_lane + kColS);
       {
         uint32_t(&hi32)[32] = *reinterpret_cast<uint32_t(*)[32]>(&sr[32]);
-        BDM_TMEM_LD32(hi32, t_lane + buf * 64 + 32);
+        BDM_TMEM_LD32(hi32, t_lane + kColS + 32);
       }
       tmem_wait_ld();
       tc_fence_before();
-      mbar_arrive(wb + 2 + buf);                   // S buffer may be overwritten
-      float mx = m_run;
+      mbar_arrive(wb + 2);                         // s_empty: S_{j+1} may be written
+      float mx4[4] = {m_run, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-      for (int i = 0; i < kKT; ++i) mx = fmaxf(mx, __uint_as_float(sr[i]));
+      for (int i = 0; i < kKT; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(sr[i]));
+      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
       const float alpha = fast_exp2((m_run - mx) * c);
       m_run = mx;
-      float sum = 0.0f;
+      float sum4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
       for (int i = 0; i < kKT; ++i) {
         const float p = fast_exp2((__uint_as_float(sr[i]) - mx) * c);
         sr[i] = __float_as_uint(p);
-        sum += p;
+        sum4[i & 3] += p;
       }
-      l_run = fmaf(l_run, alpha, sum);
+      l_run = fmaf(l_run, alpha, (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]));
       if (j > 0) {
         // O_{j-1} = O_{j-2} * alpha_{j-1} + P_{j-1} V_{j-1}: one rounded FMA per element
-        const int pbuf = (j - 1) & 1;
-        mbar_wait(wb + 5 + pbuf, ((j - 1) >> 1) & 1);
+        mbar_wait(wb + 4, (j - 1) & 1);            // o_full: P_{j-1} V_{j-1} is in TMEM (and P_{j-1} has been read)
         tc_fence_after();
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           uint32_t ot[32];
-          BDM_TMEM_LD32(ot, t_lane + 128 + pbuf * 64 + h * 32);
+          BDM_TMEM_LD32(ot, t_lane + kColO + h * 32);
           tmem_wait_ld();
 #pragma unroll
           for (int i = 0; i < 32; ++i) o[h * 32 + i] = fmaf(o[h * 32 + i], alpha_prev, __uint_as_float(ot[i]));
         }
-        tc_fence_before();
-        mbar_arrive(wb + 7 + pbuf);                // O_tile buffer may be overwritten
       }
       alpha_prev = alpha;
-      // P_j -> shared memory as fp16 hi / lo planes (K-major core matrices: 8 rows x 8 keys = 128 bytes).
-      // The previous P.V product has completed (o_full above), so the buffer is free.
+      // P_j -> TMEM as fp16 hi / lo pairs (A operand of O_tile = P V): column = key pair
+      {
+        uint32_t ph[32], pl[32];
 #pragma unroll
-      for (int kc = 0; kc < kKT / 8; ++kc) {
-        float x[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) x[i] = __uint_as_float(sr[kc * 8 + i]);
-        uint4 hi, lo;
-        split8(x, 1.0f, hi, lo);
-        *reinterpret_cast<uint4 *>(p_hi + kc * 2048) = hi;
-        *reinterpret_cast<uint4 *>(p_lo + kc * 2048) = lo;
+        for (int c2 = 0; c2 < 32; ++c2) split2(__uint_as_float(sr[2 * c2]), __uint_as_float(sr[2 * c2 + 1]), ph[c2], pl[c2]);
+        BDM_TMEM_ST32(t_lane + kColPhi, ph);
+        BDM_TMEM_ST32(t_lane + kColPlo, pl);
       }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA
-      mbar_arrive(wb + 4);                         // p_full
+      tmem_wait_st();
+      tc_fence_before();
+      mbar_arrive(wb + 3);                         // p_full
     }
     {
-      const int pbuf = (J - 1) & 1;
-      mbar_wait(wb + 5 + pbuf, ((J - 1) >> 1) & 1);
+      mbar_wait(wb + 4, (J - 1) & 1);
       tc_fence_after();
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         uint32_t ot[32];
-        BDM_TMEM_LD32(ot, t_lane + 128 + pbuf * 64 + h * 32);
+        BDM_TMEM_LD32(ot, t_lane + kColO + h * 32);
         tmem_wait_ld();
 #pragma unroll
         for (int i = 0; i < 32; ++i) o[h * 32 + i] = fmaf(o[h * 32 + i], alpha_prev, __uint_as_float(ot[i]));
@@ -441,7 +448,7 @@ attention_tc05_kernel(int T, const __half *__restrict__ qp, const __half *__rest
   __syncthreads();
   if (warp == 4 * NQ + 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(NQ * 256));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols));
   }
 }
 
@@ -450,7 +457,7 @@ attention_tc05_kernel(int T, const __half *__restrict__ qp, const __half *__rest
 
 extern "C" size_t bdm_attention_workspace_bytes(int b, int c, int t) {
   if (b <= 0 || c <= 0 || t <= 0) return 16;
-  return 256 + (size_t)3 * b * t * c * 2 * 2;
+  return 256 + (size_t)2 * b * t * c * 2 * 2;
 }
 
 // defined in attention.cu: the mma.sync (legacy tensor path) version, kept for A/B comparison (BDM_ATTENTION=mma)
@@ -481,24 +488,24 @@ extern "C" int bdm_attention(int b, int c, int t, const float *q, const float *k
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   unsigned *amax = static_cast<unsigned *>(workspace);
   const size_t plane = (size_t)b * t * kD * 2;   // halves per tensor (hi + lo)
-  __half *qp = reinterpret_cast<__half *>(static_cast<unsigned char *>(workspace) + 256);
-  __half *kp = qp + plane, *vp = kp + plane;
+  __half *kp = reinterpret_cast<__half *>(static_cast<unsigned char *>(workspace) + 256);
+  __half *vp = kp + plane;
   cudaMemsetAsync(amax, 0, 16, st);
   const size_t n4 = (size_t)b * kD * t / 4;
   attention_tc05_amax_kernel<<<2 * sm_count(), 512, 0, st>>>(n4, reinterpret_cast<const float4 *>(q),
                                                            reinterpret_cast<const float4 *>(k),
                                                            reinterpret_cast<const float4 *>(v), amax);
-  attention_prep_kernel<<<dim3(t / 32, b), 256, 0, st>>>(t, q, k, v, amax, qp, kp, vp);
+  attention_prep_kernel<<<dim3(t / 32, b), 256, 0, st>>>(t, k, v, amax, kp, vp);
   const int nq = (variant == 2 && t % (2 * kQT) == 0) ? 2 : 1;
   cudaError_t e;
   if (nq == 2) {
     e = ensure_dynamic_smem(reinterpret_cast<const void *>(attention_tc05_kernel<2>), Smem<2>::kBytes);
     if (e != cudaSuccess) return (int)e;
-    attention_tc05_kernel<2><<<dim3(t / (2 * kQT), b), (4 * 2 + 2) * 32, Smem<2>::kBytes, st>>>(t, qp, kp, vp, amax, out);
+    attention_tc05_kernel<2><<<dim3(t / (2 * kQT), b), (5 * 2 + 1) * 32, Smem<2>::kBytes, st>>>(t, q, kp, vp, amax, out);
   } else {
     e = ensure_dynamic_smem(reinterpret_cast<const void *>(attention_tc05_kernel<1>), Smem<1>::kBytes);
     if (e != cudaSuccess) return (int)e;
-    attention_tc05_kernel<1><<<dim3(t / kQT, b), (4 * 1 + 2) * 32, Smem<1>::kBytes, st>>>(t, qp, kp, vp, amax, out);
+    attention_tc05_kernel<1><<<dim3(t / kQT, b), (5 * 1 + 1) * 32, Smem<1>::kBytes, st>>>(t, q, kp, vp, amax, out);
   }
   BDM_RETURN_LAUNCH_STATUS();
 }

@@ -27,7 +27,7 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo, uint3
 
 // a_mn / b_mn: 1 = MN-major operand, 0 = K-major.  swap: exchange the two byte offsets in the descriptors.
 __global__ void __launch_bounds__(128, 1)
-probe_kernel(const __half *A, const __half *B, float *D, int a_mn, int b_mn, int swap) {
+probe_kernel(const __half *A, const __half *B, float *D, int a_mn, int b_mn, int swap, int a_tmem) {
   __shared__ __align__(1024) unsigned char sA[M * K * 2];
   __shared__ __align__(1024) unsigned char sB[N * K * 2];
   __shared__ __align__(8) uint64_t bar;
@@ -53,7 +53,7 @@ probe_kernel(const __half *A, const __half *B, float *D, int a_mn, int b_mn, int
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base)), "r"(64));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base)), "r"(128));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> visible to the MMA (async proxy)
@@ -62,6 +62,29 @@ probe_kernel(const __half *A, const __half *B, float *D, int a_mn, int b_mn, int
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = tmem_base;
 
+  if (a_tmem) {
+    // A operand in tensor memory: lane = row, 32-bit column c = (A[row][2c], A[row][2c+1]); columns 64..95
+    uint32_t ar[32];
+    const int row = warp * 32 + lane;
+    for (int c2 = 0; c2 < 32; ++c2) {
+      const __half2 h = __halves2half2(A[row * K + 2 * c2], A[row * K + 2 * c2 + 1]);
+      ar[c2] = *reinterpret_cast<const uint32_t *>(&h);
+    }
+    const uint32_t ta = tmem + ((uint32_t)(warp * 32) << 16) + 64;
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(ta), "r"(ar[0]), "r"(ar[1]), "r"(ar[2]), "r"(ar[3]), "r"(ar[4]), "r"(ar[5]), "r"(ar[6]), "r"(ar[7]),
+          "r"(ar[8]), "r"(ar[9]), "r"(ar[10]), "r"(ar[11]), "r"(ar[12]), "r"(ar[13]), "r"(ar[14]), "r"(ar[15]),
+          "r"(ar[16]), "r"(ar[17]), "r"(ar[18]), "r"(ar[19]), "r"(ar[20]), "r"(ar[21]), "r"(ar[22]), "r"(ar[23]),
+          "r"(ar[24]), "r"(ar[25]), "r"(ar[26]), "r"(ar[27]), "r"(ar[28]), "r"(ar[29]), "r"(ar[30]), "r"(ar[31])
+        : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  }
   if (warp == 0 && lane == 0) {
     // byte offset between core matrices adjacent in K (k8 -> k8+1) and adjacent in MN (mn8 -> mn8+1)
     const uint32_t a_kstride = (M / 8) * 128, a_mnstride = 128;
@@ -75,6 +98,13 @@ probe_kernel(const __half *A, const __half *B, float *D, int a_mn, int b_mn, int
       const uint64_t da = make_desc(smem_u32(sA) + 2 * j * a_kstride, a_lbo, a_sbo);
       const uint64_t db = make_desc(smem_u32(sB) + 2 * j * b_kstride, b_lbo, b_sbo);
       const uint32_t acc = j > 0;
+      if (a_tmem) {
+        const uint32_t ta = tmem + 64 + j * 8;     // 16 fp16 of K = 8 columns
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+            ::"r"(tmem), "r"(ta), "l"(db), "r"(idesc), "r"(acc) : "memory");
+      } else
       asm volatile(
           "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
           "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
@@ -114,11 +144,11 @@ probe_kernel(const __half *A, const __half *B, float *D, int a_mn, int b_mn, int
   for (int c = 0; c < N; ++c) D[row * N + c] = __uint_as_float(r[c]);
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(64));
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128));
 }
 
 int main(int argc, char **argv) {
-  const int only = argc > 1 ? atoi(argv[1]) : -1;   // variant id = a_mn*4 + b_mn*2 + swap (one per process: a fault is sticky)
+  const int only = argc > 1 ? atoi(argv[1]) : -1;   // variant id = a_tmem*8 + a_mn*4 + b_mn*2 + swap (one per process: a fault is sticky)
   std::vector<__half> hA(M * K), hB(N * K);
   std::vector<float> fA(M * K), fB(N * K), ref(M * N), got(M * N);
   srand(7);
@@ -135,12 +165,14 @@ int main(int argc, char **argv) {
   cudaMemcpy(dA, hA.data(), M * K * 2, cudaMemcpyHostToDevice);
   cudaMemcpy(dB, hB.data(), N * K * 2, cudaMemcpyHostToDevice);
   int ok_any = 0;
+  for (int a_tmem = 0; a_tmem < 2; ++a_tmem)
   for (int a_mn = 0; a_mn < 2; ++a_mn)
     for (int b_mn = 0; b_mn < 2; ++b_mn)
       for (int swap = 0; swap < 2; ++swap) {
-        if (only >= 0 && only != a_mn * 4 + b_mn * 2 + swap) continue;
+        if (only >= 0 && only != a_tmem * 8 + a_mn * 4 + b_mn * 2 + swap) continue;
+        if (a_tmem && (a_mn || swap)) continue;
         cudaMemset(dD, 0xff, M * N * 4);
-        probe_kernel<<<1, 128>>>(dA, dB, dD, a_mn, b_mn, swap);
+        probe_kernel<<<1, 128>>>(dA, dB, dD, a_mn, b_mn, swap, a_tmem);
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) { printf("a_mn=%d b_mn=%d swap=%d: CUDA error %s\n", a_mn, b_mn, swap, cudaGetErrorString(e)); return 1; }
         cudaMemcpy(got.data(), dD, M * N * 4, cudaMemcpyDeviceToHost);
@@ -151,7 +183,7 @@ int main(int argc, char **argv) {
           if (d > maxerr) maxerr = d;
           if (d > 1e-2) ++bad;
         }
-        printf("a_mn=%d b_mn=%d swap=%d: max_err=%.3e mismatches=%d/%d %s\n", a_mn, b_mn, swap, maxerr, bad, M * N,
+        printf("a_tmem=%d a_mn=%d b_mn=%d swap=%d: max_err=%.3e mismatches=%d/%d %s\n", a_tmem, a_mn, b_mn, swap, maxerr, bad, M * N,
                bad == 0 ? "OK" : "WRONG");
         if (bad == 0) ok_any = 1;
       }

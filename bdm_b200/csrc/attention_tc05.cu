@@ -238,7 +238,7 @@ struct Smem {
 };
 
 template <int NQ>
-__global__ void __launch_bounds__((5 * NQ + 1) * 32, 1)
+__global__ void __launch_bounds__((4 * NQ + 4) * 32, 1)
 attention_tc05_kernel(int T, const float *__restrict__ q, const __half *__restrict__ kp, const __half *__restrict__ vp,
                       const unsigned *__restrict__ amax, float *__restrict__ out) {
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -278,8 +278,14 @@ attention_tc05_kernel(int T, const float *__restrict__ q, const __half *__restri
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
+  // Register budget: the kernel is compiled for (4NQ+4) warps sharing the register file evenly; the control
+  // warp-group (TMA producer, MMA issuers, one idle warp) hands most of its share to the softmax warp-groups,
+  // whose threads hold a 64-value output row and a 64-value S row each.
+  // (NQ == 2: 12 warps x 168 registers at launch -> control warp-group 4 x 80, softmax warp-groups 8 x 208;
+  // each setmaxnreg sits at the top of the branch whose code it governs)
   if (warp == 4 * NQ) {
     // ===================== TMA producer =====================
+    if (NQ == 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
     if (lane == 0) {
       const __half *ksrc = kp + (size_t)b * J * (2 * kKT * kD);
       const __half *vsrc = vp + (size_t)b * J * (2 * kKT * kD);
@@ -297,7 +303,8 @@ attention_tc05_kernel(int T, const float *__restrict__ q, const __half *__restri
   } else if (warp > 4 * NQ) {
     // ===================== MMA issuer of query tile w =====================
     const int w = warp - (4 * NQ + 1);
-    if (lane == 0) {
+    if (NQ == 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
+    if (lane == 0 && w < NQ) {
       constexpr uint32_t idesc_s = instr_desc(0, 1);     // A = Q (TMEM), B = K (MN-major)
       constexpr uint32_t idesc_o = instr_desc(0, 0);     // A = P (TMEM), B = V (K-major)
       const uint32_t k_base = smem_u32(smem + L::kK), v_base = smem_u32(smem + L::kV);
@@ -345,6 +352,7 @@ attention_tc05_kernel(int T, const float *__restrict__ q, const __half *__restri
     }
   } else {
     // ===================== softmax warp-groups =====================
+    if (NQ == 2) asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
     const int w = warp >> 2;                        // query tile of this warp-group
     const int row = (warp & 3) * 32 + lane;         // query row inside the tile == TMEM lane
     uint64_t *wb = wbars + w * L::kPerTile;
@@ -389,6 +397,8 @@ attention_tc05_kernel(int T, const float *__restrict__ q, const __half *__restri
 #pragma unroll
       for (int i = 0; i < kKT; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(sr[i]));
       const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+      // exp(s - max) = 2^((s - max) * c): the difference first -- it is exact or nearly so for the entries that
+      // matter -- then the scale.  (Folding it into one FFMA with a pre-rounded max*c costs 5x in accuracy.)
       const float alpha = fast_exp2((m_run - mx) * c);
       m_run = mx;
       float sum4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
@@ -501,11 +511,11 @@ extern "C" int bdm_attention(int b, int c, int t, const float *q, const float *k
   if (nq == 2) {
     e = ensure_dynamic_smem(reinterpret_cast<const void *>(attention_tc05_kernel<2>), Smem<2>::kBytes);
     if (e != cudaSuccess) return (int)e;
-    attention_tc05_kernel<2><<<dim3(t / (2 * kQT), b), (5 * 2 + 1) * 32, Smem<2>::kBytes, st>>>(t, q, kp, vp, amax, out);
+    attention_tc05_kernel<2><<<dim3(t / (2 * kQT), b), (4 * 2 + 4) * 32, Smem<2>::kBytes, st>>>(t, q, kp, vp, amax, out);
   } else {
     e = ensure_dynamic_smem(reinterpret_cast<const void *>(attention_tc05_kernel<1>), Smem<1>::kBytes);
     if (e != cudaSuccess) return (int)e;
-    attention_tc05_kernel<1><<<dim3(t / kQT, b), (5 * 1 + 1) * 32, Smem<1>::kBytes, st>>>(t, q, kp, vp, amax, out);
+    attention_tc05_kernel<1><<<dim3(t / kQT, b), (4 * 1 + 4) * 32, Smem<1>::kBytes, st>>>(t, q, kp, vp, amax, out);
   }
   BDM_RETURN_LAUNCH_STATUS();
 }

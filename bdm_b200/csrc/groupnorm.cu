@@ -19,7 +19,10 @@
 //                     instead of writing them all, or emits per-tile sums of y for the SE squeeze.
 // Tolerance against torch (conv bias add, F.group_norm, x*sigmoid(x), max / mean): 1e-5 relative to the
 // output's peak (tests/test_dense_fused_gpu.py); biased variance, eps inside the sqrt, like torch.
+#include <cstdlib>
+
 #include "common.cuh"
+#include "groupnorm_cluster.cuh"
 
 namespace bdm {
 
@@ -143,7 +146,7 @@ gn_apply_kernel(int c, long long s, int groups, int nchunks, float eps, int tile
   __syncthreads();
   const float A = s_ab[0], Bc = s_ab[1];
   const float *px = x + bc * s;
-  auto act = [](float v) { return SWISH ? v / (1.0f + expf(-v)) : v; };
+  auto act = [](float v) { return SWISH ? gnc::swish_fast(v) : v; };
   const bool vec = (s & 3) == 0 && (reinterpret_cast<uintptr_t>(px) & 15) == 0;
 
   if (MODE == 0) {
@@ -153,16 +156,33 @@ gn_apply_kernel(int c, long long s, int groups, int nchunks, float eps, int tile
       const long long n4 = s >> 2;
       const long long lo = (long long)blockIdx.y * tile4, hi = min(lo + tile4, n4);
       long long i = lo + threadIdx.x;
-      for (; i + 3 * kGnThreads < hi; i += 4 * kGnThreads) {   // 4 loads in flight per thread
-        float4 v[4];
+      {   // software-pipelined: the next 4 loads are in flight while the current 4 values are activated and stored
+        float4 v[4], w[4];
+        bool have = i + 3 * kGnThreads < hi;
+        if (have) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) v[j] = ld_stream_f4(px + 4 * (i + (long long)j * kGnThreads));
+          for (int j = 0; j < 4; ++j) v[j] = ld_stream_f4(px + 4 * (i + (long long)j * kGnThreads));
+        }
+        while (have) {
+          const long long ni = i + 4 * kGnThreads;
+          const bool more = ni + 3 * kGnThreads < hi;
+          if (more) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          v[j].x = act(fmaf(v[j].x, A, Bc)); v[j].y = act(fmaf(v[j].y, A, Bc));
-          v[j].z = act(fmaf(v[j].z, A, Bc)); v[j].w = act(fmaf(v[j].w, A, Bc));
-          *reinterpret_cast<float4 *>(py + 4 * (i + (long long)j * kGnThreads)) = v[j];
-          local += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+            for (int j = 0; j < 4; ++j) w[j] = ld_stream_f4(px + 4 * (ni + (long long)j * kGnThreads));
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            v[j].x = act(fmaf(v[j].x, A, Bc)); v[j].y = act(fmaf(v[j].y, A, Bc));
+            v[j].z = act(fmaf(v[j].z, A, Bc)); v[j].w = act(fmaf(v[j].w, A, Bc));
+            *reinterpret_cast<float4 *>(py + 4 * (i + (long long)j * kGnThreads)) = v[j];
+            local += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+          }
+          if (more) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] = w[j];
+          }
+          i = ni;
+          have = more;
         }
       }
       for (; i < hi; i += kGnThreads) {
@@ -198,15 +218,23 @@ gn_apply_kernel(int c, long long s, int groups, int nchunks, float eps, int tile
     const int lpr = u >> 2;
     const long long n4 = s >> 2;
     const long long lo = (long long)blockIdx.y * tile4, hi = min(lo + tile4, n4);   // tile4 is a multiple of lpr
-    for (long long i0 = lo; i0 < hi; i0 += kGnThreads) {
-      const long long i = i0 + threadIdx.x;
-      float best = -__int_as_float(0x7f800000);
-      if (i < hi) {
-        const float4 v = ld_stream_f4(px + 4 * i);
-        best = fmaxf(fmaxf(act(fmaf(v.x, A, Bc)), act(fmaf(v.y, A, Bc))), fmaxf(act(fmaf(v.z, A, Bc)), act(fmaf(v.w, A, Bc))));
+    const float ninf = -__int_as_float(0x7f800000);
+    for (long long i0 = lo; i0 < hi; i0 += 4LL * kGnThreads) {   // 4 loads in flight per thread
+      float4 v[4];
+      long long idx[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        idx[j] = i0 + (long long)j * kGnThreads + threadIdx.x;
+        if (idx[j] < hi) v[j] = ld_stream_f4(px + 4 * idx[j]);
       }
-      for (int d = 1; d < lpr; d <<= 1) best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, d));
-      if (i < hi && (threadIdx.x & (lpr - 1)) == 0) py[i / lpr] = best;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float best = ninf;
+        if (idx[j] < hi)
+          best = fmaxf(fmaxf(act(fmaf(v[j].x, A, Bc)), act(fmaf(v[j].y, A, Bc))), fmaxf(act(fmaf(v[j].z, A, Bc)), act(fmaf(v[j].w, A, Bc))));
+        for (int d = 1; d < lpr; d <<= 1) best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, d));
+        if (idx[j] < hi && (threadIdx.x & (lpr - 1)) == 0) py[idx[j] / lpr] = best;
+      }
     }
   }
 }
@@ -299,7 +327,7 @@ gn_onepass_kernel(int c, int s, int groups, float eps, int tiles, const float *_
   __syncthreads();
   const double mean = s_dmean;
   const float rstd = s_stat[1];
-  auto act = [](float t) { return SWISH ? t / (1.0f + expf(-t)) : t; };
+  auto act = [](float t) { return SWISH ? gnc::swish_fast(t) : t; };
 #pragma unroll
   for (int j = 0; j < V; ++j) {
     const int idx = tid + j * nt;
@@ -372,9 +400,14 @@ static inline bool gn_cl_onepass(int b, int c, long long s, int groups) {
   return cg % 4 == 0 && cg <= 128 && (32 % (cg / 4) == 0 || (cg / 4) % 32 == 0) && gelems <= 4LL * 1024 * 8 &&
          (long long)b * groups <= 0x7fffffffLL && s <= 0x7fffffffLL / c;
 }
+static inline int gn_tune(const char *name, int dflt) {   // tuning hooks (tools/gn_bench.py)
+  const char *e = std::getenv(name);
+  return e != nullptr ? atoi(e) : dflt;
+}
 static inline int gn_cl_tiles(int b, long long s, int c) {
+  static const int per_sm = gn_tune("BDM_GN_CL_CTAS_PER_SM", 8);
   const int rpp = kClThreads / (c / 4);
-  long long want = (4LL * sm_count() + b - 1) / b;
+  long long want = ((long long)per_sm * sm_count() + b - 1) / b;
   long long maxc = (s + 4LL * rpp - 1) / (4LL * rpp);
   return (int)max(1LL, min(min(want, 64LL), maxc));
 }
@@ -421,9 +454,9 @@ gn_cl_stats_kernel(int c, long long s, int nchunks, const float *__restrict__ x,
   }
 }
 
-template <bool SWISH>
+template <bool SWISH, int UNR>
 __global__ void __launch_bounds__(kClThreads)
-gn_cl_apply_kernel(int c, long long s, int groups, int nchunks, int ntiles, float eps, int zero_shift,
+gn_cl_apply_kernel(int c, long long s, int groups, int nchunks, int pstride, int ntiles, float eps, int zero_shift,
                    const float *__restrict__ x, const float *__restrict__ conv_bias,
                    const float *__restrict__ gamma, const float *__restrict__ beta,
                    const double2 *__restrict__ partials, float *__restrict__ y, float *__restrict__ tile_sums) {
@@ -435,14 +468,24 @@ gn_cl_apply_kernel(int c, long long s, int groups, int nchunks, int ntiles, floa
   const int c4 = c >> 2, rpp = kClThreads / c4, cg = c / groups;
   const float *px = x + (size_t)b * s * c;
   const int t = threadIdx.x;
+  {
+    // the sample's partial moments, folded by all 256 threads: thread (channel t % c, slice t / c) sums every
+    // (256/c)-th block, the slices are combined in order below (producer-made statistics come in up to 128 blocks;
+    // with c threads alone this prologue cost every CTA several microseconds)
+    const int nsl = kClThreads / c, tc = t % c, sl = t / c;
+    double S1 = 0.0, S2 = 0.0;
+    for (int ch = sl; ch < nchunks; ch += nsl) {
+      const double2 v = partials[((size_t)b * pstride + ch) * c + tc];   // pstride = blocks per sample in memory
+      S1 += v.x; S2 += v.y;
+    }
+    grp[t] = make_double2(S1, S2);          // grp doubles as the slice buffer until the group fold below
+  }
+  __syncthreads();
   if (t < c) {
     // true sums of (x + bias) from the shifted partials: with tt = k_c + bias_c,
     //   sum = S1 + s*tt,  sumsq = S2 + 2*tt*S1 + s*tt^2
     double S1 = 0.0, S2 = 0.0;
-    for (int ch = 0; ch < nchunks; ++ch) {
-      const double2 v = partials[((size_t)b * nchunks + ch) * c + t];
-      S1 += v.x; S2 += v.y;
-    }
+    for (int sl = 0; sl < kClThreads / c; ++sl) { S1 += grp[sl * c + t].x; S2 += grp[sl * c + t].y; }
     double tt = zero_shift ? 0.0 : (double)__ldg(px + t);   // producer-made partials are of x itself
     if (conv_bias != nullptr) tt += (double)conv_bias[t];
     const double ds = (double)s;
@@ -469,23 +512,44 @@ gn_cl_apply_kernel(int c, long long s, int groups, int nchunks, int ntiles, floa
   __syncthreads();
   const int q = t % c4, r0 = t / c4;
   const float2 p0 = ab[4 * q], p1 = ab[4 * q + 1], p2 = ab[4 * q + 2], p3 = ab[4 * q + 3];
-  auto act = [](float v) { return SWISH ? v / (1.0f + expf(-v)) : v; };
+  auto act = [](float v) { return SWISH ? gnc::swish_fast(v) : v; };
   long long per = (s + ntiles - 1) / ntiles;
   per = (per + rpp - 1) / rpp * rpp;
   const long long lo = min((long long)tile * per, s), hi = min(lo + per, s);
   float *py = y + (size_t)b * s * c;
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
   long long row = lo + r0;
-  for (; row + 3LL * rpp < hi; row += 4LL * rpp) {   // 4 loads in flight per thread
-    float4 v[4];
+  // software-pipelined: the next UNR loads are issued before the current UNR values are activated and stored, so a
+  // thread always has loads in flight (a plain load -> compute -> store loop left HBM idle during the compute phase:
+  // 4.1 TB/s against 6.5 TB/s for a copy of the same tensor)
+  {
+    const long long step = (long long)UNR * rpp;
+    float4 v[UNR], w[UNR];
+    bool have = row + (long long)(UNR - 1) * rpp < hi;
+    if (have) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) v[j] = ld_stream_f4(px + (size_t)(row + (long long)j * rpp) * c + 4 * q);
+      for (int j = 0; j < UNR; ++j) v[j] = ld_stream_f4(px + (size_t)(row + (long long)j * rpp) * c + 4 * q);
+    }
+    while (have) {
+      const long long nrow = row + step;
+      const bool more = nrow + (long long)(UNR - 1) * rpp < hi;
+      if (more) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      v[j].x = act(fmaf(v[j].x, p0.x, p0.y)); v[j].y = act(fmaf(v[j].y, p1.x, p1.y));
-      v[j].z = act(fmaf(v[j].z, p2.x, p2.y)); v[j].w = act(fmaf(v[j].w, p3.x, p3.y));
-      *reinterpret_cast<float4 *>(py + (size_t)(row + (long long)j * rpp) * c + 4 * q) = v[j];
-      acc[0] += v[j].x; acc[1] += v[j].y; acc[2] += v[j].z; acc[3] += v[j].w;
+        for (int j = 0; j < UNR; ++j) w[j] = ld_stream_f4(px + (size_t)(nrow + (long long)j * rpp) * c + 4 * q);
+      }
+#pragma unroll
+      for (int j = 0; j < UNR; ++j) {
+        v[j].x = act(fmaf(v[j].x, p0.x, p0.y)); v[j].y = act(fmaf(v[j].y, p1.x, p1.y));
+        v[j].z = act(fmaf(v[j].z, p2.x, p2.y)); v[j].w = act(fmaf(v[j].w, p3.x, p3.y));
+        *reinterpret_cast<float4 *>(py + (size_t)(row + (long long)j * rpp) * c + 4 * q) = v[j];
+        acc[0] += v[j].x; acc[1] += v[j].y; acc[2] += v[j].z; acc[3] += v[j].w;
+      }
+      if (more) {
+#pragma unroll
+        for (int j = 0; j < UNR; ++j) v[j] = w[j];
+      }
+      row = nrow;
+      have = more;
     }
   }
   for (; row < hi; row += rpp) {
@@ -577,7 +641,7 @@ gn_onepass_cl_kernel(int c, int s, int groups, float eps, int ntiles, const floa
   const float B1 = (float)((double)be.y + ((double)cb.y - mean) * (double)A1);
   const float B2 = (float)((double)be.z + ((double)cb.z - mean) * (double)A2);
   const float B3 = (float)((double)be.w + ((double)cb.w - mean) * (double)A3);
-  auto act = [](float t) { return SWISH ? t / (1.0f + expf(-t)) : t; };
+  auto act = [](float t) { return SWISH ? gnc::swish_fast(t) : t; };
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
   for (int j = 0; j < V; ++j) {
@@ -686,6 +750,51 @@ se_gate_kernel(int c, int hidden, int tiles, float count, long long sb, long lon
   }
 }
 
+
+// ---- thread-block-cluster launches (groupnorm_cluster.cuh) ----
+// Whether a cluster of `cl` CTAs of `func` with `smem` dynamic bytes can be co-scheduled on this device; the answer
+// (and the one-time function attributes it needs) is cached per (function, cluster size).
+static bool cluster_launchable(const void *func, int cl, int threads, size_t smem) {
+  static std::mutex mu;
+  static std::map<std::pair<const void *, int>, int> cache;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lock(mu);
+  int &state = cache[std::make_pair(func, cl * 64 + dev)];
+  if (state != 0) return state > 0;
+  state = -1;
+  if (cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return false; }
+  if (cl > 8 && cudaFuncSetAttribute(func, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) { cudaGetLastError(); return false; }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(cl, 1, 1);
+  cfg.blockDim = dim3(threads, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int nclusters = 0;
+  if (cudaOccupancyMaxActiveClusters(&nclusters, func, &cfg) != cudaSuccess) { cudaGetLastError(); return false; }
+  if (nclusters >= 1) state = 1;
+  return state > 0;
+}
+
+template <typename... Args>
+static cudaError_t launch_cluster(void (*kernel)(Args...), dim3 grid, int threads, size_t smem, int cl, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(threads, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
 }  // namespace bdm
 
 extern "C" size_t bdm_groupnorm_workspace_bytes(int b, int c, long long s) {
@@ -740,6 +849,40 @@ extern "C" int bdm_groupnorm_act(int b, int c, long long s, int groups, float ep
       else launch_onepass<8>(swish != 0, ctas, nt, st, c, (int)s, groups, eps, tiles, x, conv_bias, gamma, beta, y, tile_sums);
       g_last_launches = 1;
       BDM_RETURN_LAUNCH_STATUS();
+    }
+  }
+  // mid-sized groups (64 KB .. 256 KB; any size up to that when the max over neighbours is wanted): a cluster of up to 4
+  // CTAs per (sample, group), one pass.  (Measured on B200, 32 shapes: [32,512,16,32]+max 103 -> 33 us, [32,256,64,32]+max
+  // 71 -> 53 us; clusters of 8 / 16 for 0.5 - 1 MB groups were SLOWER than the two-kernel path -- 192 vs 146 us for
+  // [32,64,1024,32] -- and are not used.)
+  {
+    const int cg = c / groups;
+    const long long gelems = (long long)cg * s;
+    const int cl = gnc::cf_cluster_size(gelems);
+    const bool aligned = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
+    static const bool enabled = [] { const char *e = std::getenv("BDM_GN_CLUSTER"); return e == nullptr || e[0] != '0'; }();
+    if (enabled && cl > 0 && cl <= 4 && tile_sums == nullptr && aligned && s % 4 == 0 && cg <= gnc::kCfMaxCg && s <= 0x7fffffffLL / 4 &&
+        (long long)b * groups <= 65535) {
+      const int n4 = (int)(gelems >> 2);
+      const int lpr = max_over_u ? max_over_u / 4 : 1;
+      int per4 = (n4 + cl - 1) / cl;
+      per4 = (per4 + lpr - 1) / lpr * lpr;
+      const size_t smem = (size_t)per4 * 16;
+      const dim3 grid(cl, (unsigned)(b * groups));
+#define BDM_GNC_LAUNCH(SW, MODE)                                                                                   \
+      do {                                                                                                         \
+        auto kfn = gnc::gn_cluster_kernel<SW, MODE>;                                                               \
+        if (cluster_launchable(reinterpret_cast<const void *>(kfn), cl, gnc::kCfThreads, (size_t)gnc::kCfSliceFloats * 4)) { \
+          cudaError_t e = launch_cluster(kfn, grid, gnc::kCfThreads, smem, cl, st, c, (int)s, groups, eps, max_over_u, per4, x, \
+                                         conv_bias, gamma, beta, y);                                             \
+          if (e != cudaSuccess) return (int)e;                                                                     \
+          g_last_launches = 1;                                                                                     \
+          BDM_RETURN_LAUNCH_STATUS();                                                                              \
+        }                                                                                                          \
+      } while (0)
+      if (max_over_u) { if (swish) BDM_GNC_LAUNCH(true, 1); else BDM_GNC_LAUNCH(false, 1); }
+      else            { if (swish) BDM_GNC_LAUNCH(true, 0); else BDM_GNC_LAUNCH(false, 0); }
+#undef BDM_GNC_LAUNCH
     }
   }
   const int nchunks = gn_nchunks(rows, s);
@@ -798,13 +941,14 @@ extern "C" int bdm_groupnorm_act_cl(int b, int c, long long s, int groups, float
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int ntiles = gn_cl_tiles(b, s, c);   // precomputed statistics: always the two-kernel apply
     const double2 *partials = static_cast<const double2 *>(workspace);
+    const int use_chunks = precomputed_chunks;
+    g_last_launches = 1;
     if (swish)
-      gn_cl_apply_kernel<true><<<dim3(ntiles, b), kClThreads, 0, st>>>(c, s, groups, precomputed_chunks, ntiles, eps, 1, x,
+      gn_cl_apply_kernel<true, 4><<<dim3(ntiles, b), kClThreads, 0, st>>>(c, s, groups, use_chunks, precomputed_chunks, ntiles, eps, 1, x,
                                                                      conv_bias, gamma, beta, partials, y, tile_sums);
     else
-      gn_cl_apply_kernel<false><<<dim3(ntiles, b), kClThreads, 0, st>>>(c, s, groups, precomputed_chunks, ntiles, eps, 1, x,
+      gn_cl_apply_kernel<false, 4><<<dim3(ntiles, b), kClThreads, 0, st>>>(c, s, groups, use_chunks, precomputed_chunks, ntiles, eps, 1, x,
                                                                       conv_bias, gamma, beta, partials, y, tile_sums);
-    g_last_launches = 1;
     BDM_RETURN_LAUNCH_STATUS();
   }
   if (!gn_cl_onepass(b, c, s, groups) && workspace_bytes < bdm_groupnorm_cl_workspace_bytes(b, c, s))
@@ -835,10 +979,10 @@ extern "C" int bdm_groupnorm_act_cl(int b, int c, long long s, int groups, float
   double2 *partials = static_cast<double2 *>(workspace);
   gn_cl_stats_kernel<<<dim3(nchunks, b), kClThreads, 0, st>>>(c, s, nchunks, x, partials);
   if (swish)
-    gn_cl_apply_kernel<true><<<dim3(ntiles, b), kClThreads, 0, st>>>(c, s, groups, nchunks, ntiles, eps, 0, x, conv_bias,
+    gn_cl_apply_kernel<true, 4><<<dim3(ntiles, b), kClThreads, 0, st>>>(c, s, groups, nchunks, nchunks, ntiles, eps, 0, x, conv_bias,
                                                                    gamma, beta, partials, y, tile_sums);
   else
-    gn_cl_apply_kernel<false><<<dim3(ntiles, b), kClThreads, 0, st>>>(c, s, groups, nchunks, ntiles, eps, 0, x, conv_bias,
+    gn_cl_apply_kernel<false, 4><<<dim3(ntiles, b), kClThreads, 0, st>>>(c, s, groups, nchunks, nchunks, ntiles, eps, 0, x, conv_bias,
                                                                     gamma, beta, partials, y, tile_sums);
   g_last_launches = 2;
   BDM_RETURN_LAUNCH_STATUS();

@@ -342,3 +342,58 @@ def test_whole_denoiser_all_fused_routes_vs_plain_torch(cuda_backend):
     assert torch.isfinite(y_fused).all()
     err = (y_fused - y_plain).abs().max().item() / y_plain.abs().max().item()
     assert err <= 5e-5, err   # ~70 layers deep, each route within 1e-5 of the ops it replaces
+
+
+@pytest.mark.parametrize("b,c,spatial,u", [(2, 64, (1024, 32), 32), (3, 32, (1024, 32), 0), (2, 128, (256, 32), 32),
+                                           (2, 128, (4096,), 0), (2, 512, (16, 32), 32), (1, 24, (40, 4), 4)])
+def test_groupnorm_cluster_kernel_channel_first(b, c, spatial, u, cuda_backend):
+    """Groups of 64 KB .. 256 KB (and every max-over-neighbours call up to that size) take the thread-block
+    cluster kernel -- slices in shared memory by TMA, moments exchanged through DSMEM, one read of the tensor --;
+    the 0.5 and 1 MB groups here take the two-kernel path.  Against torch, with and without the conv bias."""
+    import torch
+    import torch.nn.functional as TF
+    g = torch.Generator(device="cuda").manual_seed(c + u)
+    x = torch.randn((b, c) + spatial, device="cuda", generator=g) * 1.5 - 0.4
+    cb = torch.randn(c, device="cuda", generator=g)
+    w = torch.randn(c, device="cuda", generator=g)
+    bias = torch.randn(c, device="cuda", generator=g)
+    shape = (1, c) + (1,) * len(spatial)
+    for conv_bias in (cb, None):
+        want = TF.group_norm(x + (conv_bias.view(shape) if conv_bias is not None else 0.0), 8, w, bias, 1e-5)
+        want = want * torch.sigmoid(want)
+        if u:
+            want = want.max(dim=-1).values
+        got = cuda_backend.groupnorm_act(x, 8, w, bias, 1e-5, True, conv_bias=conv_bias, max_over_last=bool(u))
+        assert got.shape == want.shape
+        assert (got - want).abs().max().item() <= 1e-5 * want.abs().max().item()
+        again = cuda_backend.groupnorm_act(x, 8, w, bias, 1e-5, True, conv_bias=conv_bias, max_over_last=bool(u))
+        assert torch.equal(got, again)            # fixed reduction order: deterministic
+
+
+@pytest.mark.parametrize("b,c,r,swish", [(2, 64, 32, True), (3, 32, 32, True), (2, 128, 16, False), (1, 16, 32, True)])
+def test_groupnorm_channels_last_large_samples(b, c, r, swish, cuda_backend):
+    """Samples of 1 MB and more in channels-last memory (the R = 32 / R = 16 voxel grids of the step): statistics +
+    software-pipelined apply, conv bias folded in, per-tile channel sums for the SE gate."""
+    import torch
+    import torch.nn.functional as TF
+    g = torch.Generator(device="cuda").manual_seed(c + r)
+    x = torch.randn(b, c, r, r, r, device="cuda", generator=g) * 2.0 + 0.3
+    cb = torch.randn(c, device="cuda", generator=g)
+    w = torch.randn(c, device="cuda", generator=g)
+    bias = torch.randn(c, device="cuda", generator=g)
+    want = TF.group_norm(x + cb.view(1, c, 1, 1, 1), 8, w, bias, 1e-5)
+    if swish:
+        want = want * torch.sigmoid(want)
+    peak = want.abs().max().item()
+    x_cl = x.permute(0, 2, 3, 4, 1).contiguous()
+    got, sums = cuda_backend.groupnorm_act_cl(x_cl, 8, w, bias, 1e-5, swish, conv_bias=cb, channel_sums=True)
+    assert (got.permute(0, 4, 1, 2, 3) - want).abs().max().item() / peak <= 1e-5
+    want_sums = want.double().flatten(2).sum(-1)
+    assert (sums.double() - want_sums).abs().max().item() <= 1e-5 * max(want_sums.abs().max().item(), 1.0)
+    got2, tiles = cuda_backend.groupnorm_act_cl(x_cl, 8, w, bias, 1e-5, swish, conv_bias=cb, channel_sums="tiles")
+    assert torch.equal(got2, got) and tiles.dim() == 3 and torch.allclose(tiles.sum(dim=1), sums)
+    plain = cuda_backend.groupnorm_act_cl(x_cl, 8, None, None, 1e-5, swish)
+    want2 = TF.group_norm(x, 8, None, None, 1e-5)
+    if swish:
+        want2 = want2 * torch.sigmoid(want2)
+    assert (plain.permute(0, 4, 1, 2, 3) - want2).abs().max().item() / want2.abs().max().item() <= 1e-5

@@ -26,11 +26,13 @@ _PROTOS = {
     "bdm_avg_voxelize_workspace_bytes": (_z, [_i, _i, _i]),
     "bdm_avg_voxelize": (_i, [_i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _z, _p]),
     "bdm_voxel_plan": (_i, [_i, _i, _i, _p, _p, _p, _p, _z, _p]),
+    "bdm_voxelize_coords": (_i, [_i, _i, _i, _i, _f, _p, _p, _p, _p]),
     "bdm_avg_voxelize_fill": (_i, [_i, _i, _i, _i, _p, _p, _p, _p, _p, _z, _p]),
     "bdm_avg_voxelize_compact": (_i, [_i, _i, _i, _i, _p, _p, _p, _z, _p]),
     "bdm_grouping_into": (_i, [_i, _i, _i, _i, _i, _p, _p, _p, _p, _i, _i, _p]),
     "bdm_attention_workspace_bytes": (_z, [_i, _i, _i]),
     "bdm_attention": (_i, [_i, _i, _i, _p, _p, _p, _p, _p, _z, _p]),
+    "bdm_attention_qkv": (_i, [_i, _i, _i, _p, _i, _p, _p, _p, _z, _p]),
     "bdm_sparse_conv3_gather": (_i, [_i, _i, _i, _i, _p, _p, _p, _i, _p, _p, _z, _p]),
     "bdm_sparse_conv3_stats_blocks": (_i, [_i]),
     "bdm_trilinear_devoxelize_cl": (_i, [_i, _i, _i, _i, _p, _p, _p, _p, _p, _p]),

@@ -142,6 +142,21 @@ class VoxelPlan:
 
 
 @_op(1)
+def voxelize_coords(coords, resolution, normalize=True, eps=0.0):
+    """coords f32[B,3,N] -> (float voxel coordinates f32[B,3,N] in [0, R-1], int32[B,3,N] = their round-half-even):
+    the torch op sequence of Voxelization.forward (modules/voxelization.py:17-24) as one kernel"""
+    _chk_float(coords, "coords")
+    _req(coords.dim() == 3 and coords.shape[1] == 3, "coords must be [B,3,N]")
+    b, n = coords.shape[0], coords.shape[2]
+    norm = torch.empty_like(coords)
+    vox = torch.empty((b, 3, n), dtype=_I32, device=coords.device)
+    with _Launch(coords) as st:
+        _check(_L.bdm_voxelize_coords(b, n, int(resolution), 1 if normalize else 0, float(eps), coords.data_ptr(),
+                                      norm.data_ptr(), vox.data_ptr(), st))
+    return norm, vox
+
+
+@_op(1)
 def voxel_plan(coords, resolution):
     """coords int32[B,3,N] (voxel coordinates in [0,R)) -> VoxelPlan"""
     _chk_int(coords, "coords")
@@ -278,6 +293,25 @@ def attention(q, k, v):
     with _Launch(q) as st:
         _check(_L.bdm_attention(b, c, t, q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), ws.data_ptr(),
                                 ws.numel(), st))
+    return out
+
+
+@_op(3)
+def attention_qkv(qkv, bias=None):
+    """qkv f32[B,T,3*64] (q | k | v per token: one fused projection of channels-last activations) + bias f32[192]
+    -> f32[B,T,64] token-major: softmax(q.k) applied to v, the biases added on the way in"""
+    _chk_float(qkv, "qkv")
+    b, t, ld = qkv.shape
+    c = ld // 3
+    _req(ld == 3 * c and attention_supported(c, t), "attention kernel needs 3 x 64 columns and a multiple of 128 tokens")
+    if bias is not None:
+        _chk_float(bias, "bias")
+        _req(bias.numel() == ld, "bias must hold 3*64 values")
+    out = torch.empty((b, t, c), dtype=_F32, device=qkv.device)
+    ws = _workspace(_L.bdm_attention_workspace_bytes(b, c, t), qkv.device)
+    with _Launch(qkv) as st:
+        _check(_L.bdm_attention_qkv(b, c, t, qkv.data_ptr(), ld, bias.data_ptr() if bias is not None else None,
+                                    out.data_ptr(), ws.data_ptr(), ws.numel(), st))
     return out
 
 

@@ -181,14 +181,43 @@ __global__ void attention_tc05_amax_kernel(size_t n4, const float4 *__restrict__
   }
 }
 
+// the same for the fused projection layout qkv f32[rows][ld] (q | k | v in columns [0,c) [c,2c) [2c,3c), + bias)
+__global__ void attention_tc05_amax_qkv_kernel(size_t rows, int ld, const float *__restrict__ qkv,
+                                               const float *__restrict__ bias, unsigned *__restrict__ amax) {
+  float m[3] = {0.0f, 0.0f, 0.0f};
+  const int c4 = 3 * kD / 4;   // float4 units per row that belong to q, k, v
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < rows * c4; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = i / c4;
+    const int col = (int)(i - r * c4) * 4;
+    float4 x = __ldg(reinterpret_cast<const float4 *>(qkv + r * ld + col));
+    if (bias != nullptr) {
+      const float4 bb = __ldg(reinterpret_cast<const float4 *>(bias + col));
+      x.x += bb.x; x.y += bb.y; x.z += bb.z; x.w += bb.w;
+    }
+    const float a = fmaxf(fmaxf(fabsf(x.x), fabsf(x.y)), fmaxf(fabsf(x.z), fabsf(x.w)));
+    const int w = col / kD;
+    if (w == 0) m[0] = fmaxf(m[0], a); else if (w == 1) m[1] = fmaxf(m[1], a); else m[2] = fmaxf(m[2], a);
+  }
+#pragma unroll
+  for (int w = 0; w < 3; ++w) {
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) m[w] = fmaxf(m[w], __shfl_xor_sync(0xffffffffu, m[w], d));
+    if ((threadIdx.x & 31) == 0) atomicMax(amax + w, __float_as_uint(m[w]));
+  }
+}
+
 // Workspace (bytes): [0,16) amax | [256, ...) K planes | V planes, each b * t * 64 * 2 (hi, lo) * 2 bytes.
 //   K tile (64 keys): plane hi then lo; element (key j, channel d) of a plane at half index
 //       ((d/8) * 8 + j/8) * 64 + (d%8) * 8 + j%8          MN-major core matrices (8 channels x 8 keys)
 //   V tile (64 keys):     ((j/8) * 8 + d/8) * 64 + (d%8) * 8 + j%8          K-major  (8 channels x 8 keys)
 // Block = 256 threads = 64 channels x 4 runs of 8 consecutive tokens; 8 lanes with consecutive channels write one
 // contiguous 128-byte core matrix, and read 8 x 32-byte sectors.
+// TM (token-major): k, v point at the first k / v column of the fused projection qkv f32[b][T][ld] and `kbias` /
+// `vbias` (or NULL) are added on the way; otherwise k, v are f32[b][64][T] (ld, biases unused).
+template <bool TM>
 __global__ void __launch_bounds__(256)
-attention_prep_kernel(int T, const float *__restrict__ k, const float *__restrict__ v,
+attention_prep_kernel(int T, int ld, const float *__restrict__ k, const float *__restrict__ v,
+                      const float *__restrict__ kbias, const float *__restrict__ vbias,
                       const unsigned *__restrict__ amax, __half *__restrict__ kp, __half *__restrict__ vp) {
   const int b = blockIdx.y;
   const int tid = threadIdx.x;
@@ -197,24 +226,30 @@ attention_prep_kernel(int T, const float *__restrict__ k, const float *__restric
   float inv;
   const float sk = pow2_scale(__uint_as_float(__ldg(amax + 1)), &inv);
   const float sv = pow2_scale(__uint_as_float(__ldg(amax + 2)), &inv);
-  const size_t src = ((size_t)b * kD + d) * T + t0;
+  const size_t src = TM ? ((size_t)b * T + t0) * ld + d : ((size_t)b * kD + d) * T + t0;
   float x[8];
   uint4 hi, lo;
-  auto load8 = [&](const float *p) {
-    const float4 a = __ldg(reinterpret_cast<const float4 *>(p + src)), c = __ldg(reinterpret_cast<const float4 *>(p + src + 4));
-    x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = c.x; x[5] = c.y; x[6] = c.z; x[7] = c.w;
+  auto load8 = [&](const float *p, const float *bias) {
+    if (TM) {   // 8 tokens of one channel: 8 lanes with consecutive channels share a 32-byte sector per token
+      const float bb = bias != nullptr ? __ldg(bias + d) : 0.0f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x[i] = __ldg(p + src + (size_t)i * ld) + bb;
+    } else {
+      const float4 a = __ldg(reinterpret_cast<const float4 *>(p + src)), c = __ldg(reinterpret_cast<const float4 *>(p + src + 4));
+      x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = c.x; x[5] = c.y; x[6] = c.z; x[7] = c.w;
+    }
   };
   const int dg = d >> 3, dr = d & 7;
   const int tile = t0 / kKT, j = t0 % kKT;
   {   // K
-    load8(k);
+    load8(k, kbias);
     split8(x, sk, hi, lo);
     __half *base = kp + ((size_t)b * (T / kKT) + tile) * (2 * kKT * kD) + ((dg * 8 + j / 8) * 64 + dr * 8);
     *reinterpret_cast<uint4 *>(base) = hi;
     *reinterpret_cast<uint4 *>(base + kKT * kD) = lo;
   }
   {   // V
-    load8(v);
+    load8(v, vbias);
     split8(x, sv, hi, lo);
     __half *base = vp + ((size_t)b * (T / kKT) + tile) * (2 * kKT * kD) + (((j / 8) * 8 + dg) * 64 + dr * 8);
     *reinterpret_cast<uint4 *>(base) = hi;
@@ -237,9 +272,12 @@ struct Smem {
   static constexpr int kBytes = kTmemSlot + 16;
 };
 
-template <int NQ>
+// TM (token-major): q = fused projection f32[b][T][ld] (q in columns [0,64), + qbias), out f32[b][T][64];
+// otherwise q, out f32[b][64][T].
+template <int NQ, bool TM>
 __global__ void __launch_bounds__((4 * NQ + 4) * 32, 1)
-attention_tc05_kernel(int T, const float *__restrict__ q, const __half *__restrict__ kp, const __half *__restrict__ vp,
+attention_tc05_kernel(int T, int ld, const float *__restrict__ q, const float *__restrict__ qbias,
+                      const __half *__restrict__ kp, const __half *__restrict__ vp,
                       const unsigned *__restrict__ amax, float *__restrict__ out) {
   extern __shared__ __align__(1024) unsigned char smem[];
   using L = Smem<NQ>;
@@ -364,11 +402,25 @@ attention_tc05_kernel(int T, const float *__restrict__ q, const __half *__restri
     const float c = inv_sq * inv_sk * 1.4426950408889634f;     // raw logit -> log2 units
 
     {   // this thread's query row -> fp16 hi / lo pairs -> TMEM (A operand of S = Q K^T): column = channel pair
-      const float *qrow = q + (size_t)b * kD * T + (size_t)(qtile0 + w) * kQT + row;
       uint32_t qh[32], ql[32];
+      if (TM) {
+        const float *qrow = q + ((size_t)b * T + (size_t)(qtile0 + w) * kQT + row) * ld;
 #pragma unroll
-      for (int c2 = 0; c2 < 32; ++c2)
-        split2(__ldg(qrow + (size_t)(2 * c2) * T) * sq, __ldg(qrow + (size_t)(2 * c2 + 1) * T) * sq, qh[c2], ql[c2]);
+        for (int c4 = 0; c4 < 16; ++c4) {
+          float4 v = __ldg(reinterpret_cast<const float4 *>(qrow) + c4);
+          if (qbias != nullptr) {
+            const float4 bb = __ldg(reinterpret_cast<const float4 *>(qbias) + c4);
+            v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+          }
+          split2(v.x * sq, v.y * sq, qh[2 * c4], ql[2 * c4]);
+          split2(v.z * sq, v.w * sq, qh[2 * c4 + 1], ql[2 * c4 + 1]);
+        }
+      } else {
+        const float *qrow = q + (size_t)b * kD * T + (size_t)(qtile0 + w) * kQT + row;
+#pragma unroll
+        for (int c2 = 0; c2 < 32; ++c2)
+          split2(__ldg(qrow + (size_t)(2 * c2) * T) * sq, __ldg(qrow + (size_t)(2 * c2 + 1) * T) * sq, qh[c2], ql[c2]);
+      }
       BDM_TMEM_ST32(t_lane + kColQhi, qh);
       BDM_TMEM_ST32(t_lane + kColQlo, ql);
       tmem_wait_st();
@@ -449,9 +501,16 @@ attention_tc05_kernel(int T, const float *__restrict__ q, const __half *__restri
       tc_fence_before();
     }
     const float scale = inv_sv / l_run;
-    float *ob = out + (size_t)b * kD * T + (size_t)(qtile0 + w) * kQT + row;
+    if (TM) {   // the thread's 64 channels are one 256-byte row of out[b][T][64]
+      float4 *ob = reinterpret_cast<float4 *>(out + ((size_t)b * T + (size_t)(qtile0 + w) * kQT + row) * kD);
 #pragma unroll
-    for (int ch = 0; ch < kD; ++ch) ob[(size_t)ch * T] = o[ch] * scale;   // 32 lanes = 128 contiguous bytes per channel
+      for (int c4 = 0; c4 < 16; ++c4)
+        ob[c4] = make_float4(o[4 * c4] * scale, o[4 * c4 + 1] * scale, o[4 * c4 + 2] * scale, o[4 * c4 + 3] * scale);
+    } else {
+      float *ob = out + (size_t)b * kD * T + (size_t)(qtile0 + w) * kQT + row;
+#pragma unroll
+      for (int ch = 0; ch < kD; ++ch) ob[(size_t)ch * T] = o[ch] * scale;   // 32 lanes = 128 contiguous bytes per channel
+    }
   }
 
   tc_fence_before();
@@ -474,6 +533,45 @@ extern "C" size_t bdm_attention_workspace_bytes(int b, int c, int t) {
 extern "C" int bdm_attention_mma(int b, int c, int t, const float *q, const float *k, const float *v, float *out,
                                  void *workspace, size_t workspace_bytes, bdm_stream_t stream);
 
+namespace bdm {
+namespace tc05 {
+
+// common tail of the two entry points: statistics are in amax, planes in the workspace
+template <bool TM>
+static int launch_attention(int b, int t, int ld, const float *q, const float *qbias, const float *k, const float *v,
+                            const float *kbias, const float *vbias, float *out, void *workspace, int variant, cudaStream_t st) {
+  unsigned *amax = static_cast<unsigned *>(workspace);
+  const size_t plane = (size_t)b * t * kD * 2;   // halves per tensor (hi + lo)
+  __half *kp = reinterpret_cast<__half *>(static_cast<unsigned char *>(workspace) + 256);
+  __half *vp = kp + plane;
+  attention_prep_kernel<TM><<<dim3(t / 32, b), 256, 0, st>>>(t, ld, k, v, kbias, vbias, amax, kp, vp);
+  const int nq = (variant == 2 && t % (2 * kQT) == 0) ? 2 : 1;
+  cudaError_t e;
+  if (nq == 2) {
+    e = ensure_dynamic_smem(reinterpret_cast<const void *>(attention_tc05_kernel<2, TM>), Smem<2>::kBytes);
+    if (e != cudaSuccess) return (int)e;
+    attention_tc05_kernel<2, TM><<<dim3(t / (2 * kQT), b), (4 * 2 + 4) * 32, Smem<2>::kBytes, st>>>(t, ld, q, qbias, kp, vp, amax, out);
+  } else {
+    e = ensure_dynamic_smem(reinterpret_cast<const void *>(attention_tc05_kernel<1, TM>), Smem<1>::kBytes);
+    if (e != cudaSuccess) return (int)e;
+    attention_tc05_kernel<1, TM><<<dim3(t / kQT, b), (4 * 1 + 4) * 32, Smem<1>::kBytes, st>>>(t, ld, q, qbias, kp, vp, amax, out);
+  }
+  BDM_RETURN_LAUNCH_STATUS();
+}
+
+static int attention_variant() {   // A/B hook: BDM_ATTENTION=mma | tc05x1 | tc05x2 (default: tc05x2 when t % 256 == 0)
+  static const int variant = [] {
+    const char *e = std::getenv("BDM_ATTENTION");
+    if (e == nullptr) return 2;
+    if (e[0] == 'm') return 0;
+    return (e[0] == 't' && e[1] == 'c' && e[2] == '0' && e[3] == '5' && e[4] == 'x' && e[5] == '1') ? 1 : 2;
+  }();
+  return variant;
+}
+
+}  // namespace tc05
+}  // namespace bdm
+
 // q, k, v, out: f32[b][64][t] (channel-first, as the 1x1 convolutions of the block produce them);
 // out[b][c][i] = sum_j softmax_j(q[b][:,i] . k[b][:,j]) * v[b][c][j].  c must be 64, t a multiple of 128 (256
 // for the two-tile CTA).  workspace: bdm_attention_workspace_bytes(b, c, t) bytes, 256-byte aligned.
@@ -487,35 +585,40 @@ extern "C" int bdm_attention(int b, int c, int t, const float *q, const float *k
   if (((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) |
         reinterpret_cast<uintptr_t>(out)) & 15) != 0 || (reinterpret_cast<uintptr_t>(workspace) & 255) != 0)
     return BDM_ERR_MISALIGNED;
-  static const int variant = [] {   // A/B hook: BDM_ATTENTION=mma | tc05x1 | tc05x2 (default: tc05x2 when t % 256 == 0)
-    const char *e = std::getenv("BDM_ATTENTION");
-    if (e == nullptr) return 2;
-    if (e[0] == 'm') return 0;
-    return (e[0] == 't' && e[1] == 'c' && e[2] == '0' && e[3] == '5' && e[4] == 'x' && e[5] == '1') ? 1 : 2;
-  }();
+  const int variant = attention_variant();
   if (variant == 0) return bdm_attention_mma(b, c, t, q, k, v, out, workspace, workspace_bytes, stream);
   if (workspace_bytes < bdm_attention_workspace_bytes(b, c, t)) return BDM_ERR_WORKSPACE_TOO_SMALL;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   unsigned *amax = static_cast<unsigned *>(workspace);
-  const size_t plane = (size_t)b * t * kD * 2;   // halves per tensor (hi + lo)
-  __half *kp = reinterpret_cast<__half *>(static_cast<unsigned char *>(workspace) + 256);
-  __half *vp = kp + plane;
   cudaMemsetAsync(amax, 0, 16, st);
   const size_t n4 = (size_t)b * kD * t / 4;
   attention_tc05_amax_kernel<<<2 * sm_count(), 512, 0, st>>>(n4, reinterpret_cast<const float4 *>(q),
                                                            reinterpret_cast<const float4 *>(k),
                                                            reinterpret_cast<const float4 *>(v), amax);
-  attention_prep_kernel<<<dim3(t / 32, b), 256, 0, st>>>(t, k, v, amax, kp, vp);
-  const int nq = (variant == 2 && t % (2 * kQT) == 0) ? 2 : 1;
-  cudaError_t e;
-  if (nq == 2) {
-    e = ensure_dynamic_smem(reinterpret_cast<const void *>(attention_tc05_kernel<2>), Smem<2>::kBytes);
-    if (e != cudaSuccess) return (int)e;
-    attention_tc05_kernel<2><<<dim3(t / (2 * kQT), b), (4 * 2 + 4) * 32, Smem<2>::kBytes, st>>>(t, q, kp, vp, amax, out);
-  } else {
-    e = ensure_dynamic_smem(reinterpret_cast<const void *>(attention_tc05_kernel<1>), Smem<1>::kBytes);
-    if (e != cudaSuccess) return (int)e;
-    attention_tc05_kernel<1><<<dim3(t / kQT, b), (4 * 1 + 4) * 32, Smem<1>::kBytes, st>>>(t, q, kp, vp, amax, out);
-  }
-  BDM_RETURN_LAUNCH_STATUS();
+  return launch_attention<false>(b, t, 0, q, nullptr, k, v, nullptr, nullptr, out, workspace, variant, st);
+}
+
+// The same attention fed by ONE fused projection: qkv f32[b][t][ld] holds q | k | v of a token in columns [0,c),
+// [c,2c), [2c,3c) (what x[b][t][:] @ [Wq;Wk;Wv]^T yields for channels-last activations), bias f32[3c] (or NULL) is
+// added on the way in (the three 1x1 convolutions' biases), and the result is written token-major, out f32[b][t][c]:
+// no bias-add kernels, no layout copies around the kernel (modules/pvconv.py:40-57).  ld >= 3c, ld % 4 == 0.
+extern "C" int bdm_attention_qkv(int b, int c, int t, const float *qkv, int ld, const float *bias, float *out,
+                                 void *workspace, size_t workspace_bytes, bdm_stream_t stream) {
+  using namespace bdm;
+  using namespace bdm::tc05;
+  BDM_CHECK_SIZE(b >= 0 && c == kD && t >= kQT && t % kQT == 0 && ld >= 3 * c && ld % 4 == 0);
+  if (b == 0) return BDM_OK;
+  BDM_CHECK_PTR(qkv); BDM_CHECK_PTR(out); BDM_CHECK_PTR(workspace);
+  if (((reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(bias)) & 15) != 0 ||
+      (reinterpret_cast<uintptr_t>(workspace) & 255) != 0)
+    return BDM_ERR_MISALIGNED;
+  if (workspace_bytes < bdm_attention_workspace_bytes(b, c, t)) return BDM_ERR_WORKSPACE_TOO_SMALL;
+  int variant = attention_variant();
+  if (variant == 0) variant = 2;   // the mma.sync kernel has no token-major form
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  unsigned *amax = static_cast<unsigned *>(workspace);
+  cudaMemsetAsync(amax, 0, 16, st);
+  attention_tc05_amax_qkv_kernel<<<2 * sm_count(), 512, 0, st>>>((size_t)b * t, ld, qkv, bias, amax);
+  return launch_attention<true>(b, t, ld, qkv, bias, qkv + c, qkv + 2 * c, bias != nullptr ? bias + c : nullptr,
+                                bias != nullptr ? bias + 2 * c : nullptr, out, workspace, variant, st);
 }

@@ -223,6 +223,15 @@ class FusedSequential(nn.Sequential):
             elif fusable and isinstance(m, nn.GroupNorm) and i + 1 < n and isinstance(mods[i + 1], Swish):
                 x = norm_act(m, x, True)
                 i += 2
+            elif (isinstance(m, Attention) and i + 1 < n and isinstance(mods[i + 1], SE3d) and pre is None
+                  and m.fused_applicable(x)):
+                # the attention block hands the SE squeeze its per-channel sums (no three chained means over the grid)
+                y, sums = m.forward_fused(x, channel_sums=True)
+                if defer_gate and i + 1 == n - 1:
+                    x, gate = y, mods[i + 1].gate(y, channel_sums=sums)
+                else:
+                    x = mods[i + 1](y, channel_sums=sums)
+                i += 2
             elif defer_gate and i == n - 1 and isinstance(m, SE3d):
                 gate = m.gate(x)
                 i += 1
@@ -308,7 +317,59 @@ class Attention(nn.Module):
         self.nonlin = Swish()
         self.sm = nn.Softmax(-1)
 
+    # -- inference on CUDA over a channels-last voxel grid: the whole block in five launches ------------------
+    def fused_applicable(self, x):
+        """x f32[B,64,D,H,W] in channels-last-3d memory, enough query tiles to fill the GPU, 1x1 Conv3d projections"""
+        if not (FUSED_ATTENTION and _fusable(x) and is_channels_last_3d(x) and hasattr(_ops._B, "attention_qkv")
+                and hasattr(_ops._B, "groupnorm_act_cl")):
+            return False
+        nb, nc = x.shape[:2]
+        tokens = x.shape[2] * x.shape[3] * x.shape[4]
+        return (all(isinstance(m, nn.Conv3d) and m.kernel_size == (1, 1, 1) and m.bias is not None
+                    for m in (self.q, self.k, self.v, self.out))
+                and isinstance(self.norm, nn.GroupNorm) and _ops._B.attention_supported(nc, tokens, nb)
+                and _ops._B.groupnorm_cl_supported(nc, self.norm.num_groups))
+
+    def _fused_weights(self):
+        """[Wq;Wk;Wv]^T f32[C,3C], their biases f32[3C], Wo^T f32[C,C]; cached per weight version"""
+        params = (self.q.weight, self.k.weight, self.v.weight, self.out.weight, self.q.bias, self.k.bias, self.v.bias)
+        key = tuple((p.data_ptr(), geometry.tensor_version(p), p.device) for p in params)
+        cached = getattr(self, "_fused", None)
+        if cached is None or cached[0] != key:
+            c = self.q.weight.shape[0]
+            wqkv = torch.cat([m.weight.detach().reshape(c, c) for m in (self.q, self.k, self.v)], dim=0).t().contiguous()
+            bqkv = torch.cat([m.bias.detach() for m in (self.q, self.k, self.v)]).contiguous()
+            cached = (key, wqkv, bqkv, self.out.weight.detach().reshape(c, c).t().contiguous())
+            self._fused = cached
+        return cached[1:]
+
+    def forward_fused(self, x, channel_sums=False):
+        """The block on a channels-last grid (memory [B,T,C], T = voxels) without a single layout copy or bias kernel:
+        one GEMM for q | k | v, the attention kernel (biases added as it reads, token-major output), one GEMM that
+        adds the residual (x + mixed @ Wo^T), and the norm kernel (out-conv bias folded in, + Swish, + the SE squeeze
+        sums when asked).  The reference runs 4 convolutions, 4 bias adds, a residual add, 2 matmuls, a softmax and
+        3 layout copies here (modules/pvconv.py:40-63).  -> y (same shape / memory format as x) [, sums]"""
+        nb, nc = x.shape[:2]
+        spatial = tuple(x.shape[2:])
+        x_cl = x.permute(0, 2, 3, 4, 1).reshape(nb, -1, nc)                 # a view of the channels-last memory
+        wqkv, bqkv, wo = self._fused_weights()
+        with matmul_precision_of_convs():                                   # they stand in for 1x1 convolutions
+            qkv = torch.matmul(x_cl, wqkv)                                  # [B,T,3C]
+            mixed = _ops._B.attention_qkv(qkv, bqkv)                        # [B,T,C]
+            y = torch.baddbmm(x_cl, mixed, wo.expand(nb, -1, -1))           # residual + out projection (bias: below)
+        gn = self.norm
+        want = channel_sums
+        if want and hasattr(_ops._B, "se_gate"):
+            want = "tiles"
+        out = _ops._B.groupnorm_act_cl(y, gn.num_groups, gn.weight, gn.bias, gn.eps, True, conv_bias=self.out.bias,
+                                       channel_sums=want)
+        if isinstance(out, tuple):
+            return out[0].view((nb,) + spatial + (nc,)).permute(0, 4, 1, 2, 3), out[1]
+        return out.view((nb,) + spatial + (nc,)).permute(0, 4, 1, 2, 3)
+
     def forward(self, x):
+        if self.fused_applicable(x):
+            return self.forward_fused(x)
         nb, nc = x.shape[:2]
         q, k, v = (proj(x).reshape(nb, nc, -1) for proj in (self.q, self.k, self.v))
         if (FUSED_ATTENTION and _fusable(x) and hasattr(_ops._B, "attention")

@@ -46,10 +46,20 @@ def normalized_voxel_coords(coords, resolution, normalize=True, eps=0):
     return torch.clamp(unit * resolution, 0, resolution - 1)
 
 
+# One kernel instead of the eight torch launches of normalized_voxel_coords + round (inference on CUDA, fp32).
+# BDM_FUSED_VOXEL_COORDS=0 restores the torch sequence.
+FUSED_VOXEL_COORDS = os.environ.get("BDM_FUSED_VOXEL_COORDS", "1") != "0"
+
+
 def _coordinate_plan(coords, r, normalize, eps):
     """(float voxel coords, int voxel coords, voxel plan) for one (coords tensor, resolution)."""
-    norm_coords = normalized_voxel_coords(coords.detach(), r, normalize, eps)
-    vox_coords = torch.round(norm_coords).to(torch.int32)  # half-to-even, like the reference
+    coords = coords.detach()
+    if (FUSED_VOXEL_COORDS and coords.is_cuda and coords.dtype == torch.float32 and not _ops.REFERENCE_CALL_PATTERN
+            and hasattr(_ops._B, "voxelize_coords")):
+        norm_coords, vox_coords = _ops._B.voxelize_coords(coords.contiguous(), r, normalize, eps)
+    else:
+        norm_coords = normalized_voxel_coords(coords, r, normalize, eps)
+        vox_coords = torch.round(norm_coords).to(torch.int32)  # half-to-even, like the reference
     return norm_coords, vox_coords, F.voxel_plan(vox_coords, r)
 
 

@@ -52,6 +52,12 @@ size_t bdm_avg_voxelize_workspace_bytes(int b, int n, int r);
 int bdm_avg_voxelize(int b, int c, int n, int r, const int *coords, const float *feat, int *ind,
                      int *cnt, float *out, void *workspace, size_t workspace_bytes,
                      bdm_stream_t stream);
+/* The coordinate half of Voxelization.forward (modules/voxelization.py:17-24) in one kernel: per shape, centre on the
+ * mean, scale by twice the largest point norm (+ eps) when `normalize` (else (c + 1) / 2), shift, stretch to the grid,
+ * clamp to [0, r-1] -> norm_coords f32[b,3,n]; vox_coords i32[b,3,n] = round-half-even of it.  Each elementwise step
+ * is the torch op's fp32 arithmetic; the mean is the correctly rounded one (double accumulation). */
+int bdm_voxelize_coords(int b, int n, int r, int normalize, float eps, const float *coords,
+                        float *norm_coords, int *vox_coords, bdm_stream_t stream);
 /* The two halves of bdm_avg_voxelize, for callers that voxelize several feature tensors over the
  * same coordinates (consecutive PVConv blocks of one stage do: modules/pvconv.py:91-97 is called 2-3
  * times per stage with unchanged coords).  bdm_voxel_plan does everything that depends only on the
@@ -234,6 +240,12 @@ int bdm_sampler_update(long long n, int mode, const float *x, const float *eps, 
 size_t bdm_attention_workspace_bytes(int b, int c, int t);
 int bdm_attention(int b, int c, int t, const float *q, const float *k, const float *v, float *out,
                   void *workspace, size_t workspace_bytes, bdm_stream_t stream);
+/* The same attention fed by one fused projection (the q, k, v 1x1 convolutions of modules/pvconv.py:40-50 as a single
+ * GEMM over channels-last activations): qkv f32[b,t,ld] holds q | k | v of a token in columns [0,c) [c,2c) [2c,3c),
+ * bias f32[3c] (or NULL: the convolutions' biases, added on the way in), out f32[b,t,c] token-major.
+ * ld >= 3c, ld % 4 == 0; same size rules and workspace as bdm_attention. */
+int bdm_attention_qkv(int b, int c, int t, const float *qkv, int ld, const float *bias, float *out,
+                      void *workspace, size_t workspace_bytes, bdm_stream_t stream);
 
 /* ---- dense side: fused [conv bias +] GroupNorm [+ Swish] [+ reduction] ----------
  * replaces the bias add of the preceding conv, the nn.GroupNorm(8, C) -> Swish pair that follows every

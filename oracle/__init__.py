@@ -403,3 +403,21 @@ def ddpm_step(x_t, eps, noise, t, rows=None):
     if t > 0:
         prev = prev + r[4] * noise
     return prev
+
+
+def voxelization_coords_rounded_mean(coords, r, normalize=True, eps=0.0):
+    """modules/voxelization.py:16-25 with every elementwise step in fp32, exactly as torch evaluates it, and the mean
+    taken as the CORRECTLY ROUNDED fp32 mean (double accumulation) instead of in a particular fp32 summation order
+    -- the arithmetic of csrc/voxel_coords.cu.  -> (vox int32[B,3,N], norm_coords f32[B,3,N])"""
+    x = np.asarray(coords, dtype=np.float32)
+    f = np.float32
+    mean = (x.astype(np.float64).sum(axis=2, keepdims=True) / x.shape[2]).astype(np.float32)
+    c = x - mean
+    if normalize:
+        sq = (c[:, 0] * c[:, 0] + c[:, 1] * c[:, 1]) + c[:, 2] * c[:, 2]          # three rounded squares, summed left to right
+        extent = (np.sqrt(sq).max(axis=1) * f(2.0) + f(eps)).astype(np.float32).reshape(-1, 1, 1)
+        u = c / extent + f(0.5)
+    else:
+        u = (c + f(1.0)) / f(2.0)
+    nc = np.clip(u * f(r), f(0.0), f(r - 1)).astype(np.float32)
+    return np.rint(nc).astype(np.int32), nc

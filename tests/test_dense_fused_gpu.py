@@ -397,3 +397,51 @@ def test_groupnorm_channels_last_large_samples(b, c, r, swish, cuda_backend):
     if swish:
         want2 = want2 * torch.sigmoid(want2)
     assert (plain.permute(0, 4, 1, 2, 3) - want2).abs().max().item() / want2.abs().max().item() <= 1e-5
+
+
+@pytest.mark.parametrize("b,t,scale", [(2, 512, 1.0), (3, 4096, 1.0), (1, 1024, 3.0), (2, 128, 0.2)])
+def test_attention_from_fused_projection_vs_float64(b, t, scale, cuda_backend):
+    """bdm_attention_qkv: q | k | v of a token side by side (one projection GEMM), biases added as the kernel reads,
+    token-major output -- as close to float64 as torch's fp32 route, like the channel-first entry point"""
+    import torch
+    g = torch.Generator(device="cuda").manual_seed(t + b)
+    qkv = torch.randn(b, t, 192, device="cuda", generator=g) * scale
+    bias = torch.randn(192, device="cuda", generator=g) * 0.3
+    got = cuda_backend.attention_qkv(qkv, bias)                                   # [B,T,64]
+    q, k, v = ((qkv + bias)[..., i * 64:(i + 1) * 64] for i in range(3))           # [B,T,64] each
+    ref = torch.matmul(torch.softmax(torch.matmul(q.double(), k.double().transpose(1, 2)), -1), v.double())
+    f32 = torch.matmul(torch.softmax(torch.matmul(q, k.transpose(1, 2)), -1), v)
+    peak = ref.abs().max().item()
+    e_ours = (got.double() - ref).abs().max().item() / peak
+    e_torch = (f32.double() - ref).abs().max().item() / peak
+    assert e_ours <= max(3 * e_torch, 1e-5), (e_ours, e_torch)
+    assert torch.equal(cuda_backend.attention_qkv(qkv, None), cuda_backend.attention_qkv(qkv, torch.zeros_like(bias)))
+
+
+def test_attention_block_on_channels_last_grid(cuda_backend):
+    """The attention block of the R=16 PVConv stage on a channels-last grid: fused route (one projection GEMM, the
+    tcgen05 attention kernel, residual GEMM, norm kernel with the out-conv bias folded in and the SE sums) against
+    the module-by-module torch route; and inside a voxel stack, where the SE gate takes the block's sums."""
+    import torch
+
+    import bdm_b200.modules.layers as L
+    torch.manual_seed(5)
+    blk = L.Attention(64, 8).cuda().eval()
+    x = torch.randn(4, 64, 16, 16, 16, device="cuda").contiguous(memory_format=torch.channels_last_3d)
+    saved = (L.FUSED_ATTENTION, torch.backends.cudnn.allow_tf32)
+    try:
+        torch.backends.cudnn.allow_tf32 = False            # fp32 projections on both sides
+        with torch.no_grad():
+            L.FUSED_ATTENTION = True
+            assert blk.fused_applicable(x)
+            y1 = blk(x)
+            y1s, sums = blk.forward_fused(x, channel_sums=True)
+            L.FUSED_ATTENTION = False
+            y0 = blk(x)
+    finally:
+        L.FUSED_ATTENTION, torch.backends.cudnn.allow_tf32 = saved
+    assert y1.shape == y0.shape and L.is_channels_last_3d(y1)
+    assert (y1 - y0).abs().max().item() <= 1e-5 * y0.abs().max().item()
+    assert torch.equal(y1s, y1)
+    want_sums = y0.double().flatten(2).sum(-1)
+    assert (sums.sum(dim=1).double() - want_sums).abs().max().item() <= 1e-5 * want_sums.abs().max().item()

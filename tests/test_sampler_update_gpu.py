@@ -138,3 +138,29 @@ def test_voxelization_module_matches_oracle(cuda_backend):
             assert np.array_equal(plan.ind.cpu().numpy(), ind_want) and np.array_equal(plan.cnt.cpu().numpy(), cnt_want)
             runners.assert_close(f"{label}.norm_coords", nc.cpu().numpy(), nc_want, 1e-5)
             runners.assert_close(f"{label}.grid", grid.reshape(4, 7, -1).cpu().numpy(), grid_want, 1e-4)
+
+
+@pytest.mark.parametrize("normalize", [True, False])
+def test_fused_voxel_coordinates(cuda_backend, normalize):
+    """csrc/voxel_coords.cu (one kernel for the eight torch launches of Voxelization.forward's coordinate half):
+    bit-exact -- floats and integers -- against the oracle's statement of the same arithmetic, and the same integer
+    voxel coordinates as the torch op sequence on the GPU (whose mean differs in summation order only)."""
+    import torch
+    import oracle as O
+    from bdm_b200.modules.point_voxel import normalized_voxel_coords
+    from . import cases, runners
+    rng = np.random.default_rng(77)
+    for regime in ("noise", "shape"):
+        for r, n in ((32, 4096), (16, 1024), (8, 256), (8, 64), (16, 1000), (4, 7)):
+            co = cases.cloud(rng, 3, n, regime) * (1.0 if normalize else 0.3)
+            eps = 0.0 if n != 1000 else 1e-3
+            vox_want, nc_want = O.voxelization_coords_rounded_mean(co, r, normalize, eps)
+            co_t = torch.from_numpy(co).cuda()
+            nc, vox = cuda_backend.voxelize_coords(co_t, r, normalize, eps)
+            label = f"voxel_coords[{regime},r={r},n={n},normalize={normalize}]"
+            assert np.array_equal(vox.cpu().numpy(), vox_want), f"{label}: integer coordinates differ from the oracle"
+            assert np.array_equal(nc.cpu().numpy(), nc_want), f"{label}: float coordinates differ from the oracle"
+            nc_torch = normalized_voxel_coords(co_t, r, normalize, eps)
+            vox_torch = torch.round(nc_torch).to(torch.int32)
+            assert torch.equal(vox, vox_torch), f"{label}: integer coordinates differ from the torch op sequence"
+            runners.assert_close(f"{label} vs torch", nc.cpu().numpy(), nc_torch.cpu().numpy(), 2e-6)

@@ -65,6 +65,8 @@ _PROTOS = {
     "bdm_groupnorm_act_cl": (_i, [_i, _i, ctypes.c_longlong, _i, _f, _i, _p, _p, _p, _p, _p, _p, _p, _z, _i, _p]),
     "bdm_surface_projection_cf": (_i, [_i, _i, _i, _i, _i, _f, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p]),
     "bdm_nn_f64": (_i, [_i, _i, _i, _i, _p, _p, _p, _p, _p]),
+    "bdm_nn_f64_reduce_blocks": (_i, [_i, _i]),
+    "bdm_nn_f64_reduce": (_i, [_i, _i, _i, _i, ctypes.c_double, _p, _p, _p, _p, _p]),
     "bdm_sampler_update": (_i, [ctypes.c_longlong, _i, _p, _p, _p, _p, _i, _p, _p, _p]),
 }
 

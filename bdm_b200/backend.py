@@ -726,3 +726,22 @@ def nn_f64(src, tgt, expanded=False, return_index=True):
         _check(_L.bdm_nn_f64(b, n, m, 1 if expanded else 0, src.data_ptr(), tgt.data_ptr(), dist.data_ptr(),
                              idx.data_ptr() if idx is not None else None, st))
     return dist, idx
+
+
+@_op(1)
+def nn_f64_reduce(src, tgt, expanded=False, thr=0.01):
+    """src f64[B,N,3], tgt f64[B,M,3] -> (sum over i of min_j |s_i - t_j|^2  f64[B],  #{i: that minimum < thr} int64[B]):
+    the nearest-neighbour search with the Chamfer / F-score reductions fused in (per-block partials, summed here)"""
+    for x, nm in ((src, "src"), (tgt, "tgt")):
+        _req(x.is_cuda, f"{nm} must be a CUDA tensor")
+        _req(x.is_contiguous(), f"{nm} must be a contiguous tensor")
+        _req(x.dtype == torch.float64, f"{nm} must be a double tensor")
+    b, n = src.shape[0], src.shape[1]
+    m = tgt.shape[1]
+    blocks = max(int(_L.bdm_nn_f64_reduce_blocks(b, n)), 1)
+    psum = torch.zeros((b, blocks), dtype=torch.float64, device=src.device)
+    pcnt = torch.zeros((b, blocks), dtype=torch.int32, device=src.device)
+    with _Launch(src) as st:
+        _check(_L.bdm_nn_f64_reduce(b, n, m, 1 if expanded else 0, float(thr), src.data_ptr(), tgt.data_ptr(),
+                                    psum.data_ptr(), pcnt.data_ptr(), st))
+    return psum.sum(dim=1), pcnt.sum(dim=1, dtype=torch.int64)

@@ -24,9 +24,9 @@ def chamfer_distance(pred, gt):
     """pred f64[B,N,3], gt f64[B,M,3] -> per-pair CD f64[B] = mean_i min_j |p_i-g_j|^2 + mean_j min_i |.|^2
     (pytorch3d defaults: squared L2, point_reduction='mean'; the caller averages over pairs)."""
     pred, gt = _as_batch(pred), _as_batch(gt)
-    d_pg, _ = _backend.nn_f64(pred, gt, expanded=False, return_index=False)
-    d_gp, _ = _backend.nn_f64(gt, pred, expanded=False, return_index=False)
-    return d_pg.mean(dim=1) + d_gp.mean(dim=1)
+    s_pg, _ = _backend.nn_f64_reduce(pred, gt, expanded=False)
+    s_gp, _ = _backend.nn_f64_reduce(gt, pred, expanded=False)
+    return s_pg / pred.shape[1] + s_gp / gt.shape[1]
 
 
 def compute_pc_to_pc_dist(src, tgt):
@@ -37,10 +37,11 @@ def compute_pc_to_pc_dist(src, tgt):
 
 def fscore(gt, pred, thr=0.01):
     """evaluation_f1.py:101-110 -> per-pair F f64[B]"""
-    d1 = compute_pc_to_pc_dist(gt, pred)
-    d2 = compute_pc_to_pc_dist(pred, gt)
-    precision = (d1 < thr).sum(dim=1).double() / d1.shape[1]
-    recall = (d2 < thr).sum(dim=1).double() / d2.shape[1]
+    gt, pred = _as_batch(gt), _as_batch(pred)
+    _, c1 = _backend.nn_f64_reduce(gt, pred, expanded=True, thr=thr)      # d1 = compute_pc_to_pc_dist(gt, pred)
+    _, c2 = _backend.nn_f64_reduce(pred, gt, expanded=True, thr=thr)      # d2 = compute_pc_to_pc_dist(pred, gt)
+    precision = c1.double() / gt.shape[1]
+    recall = c2.double() / pred.shape[1]
     return 2 * recall * precision / (recall + precision + 1e-12)
 
 

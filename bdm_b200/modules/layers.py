@@ -46,6 +46,13 @@ def matmul_precision_of_convs():
             torch.backends.cuda.matmul.allow_tf32 = prev
 
 
+# A 1x1 convolution whose input width is not a multiple of 4 runs on cuBLAS's fp32 SIMT kernels.  Splitting the
+# reduction into an aligned head (tensor-op kernel) and a <= 3-wide tail pays only when the SIMT kernel is compute
+# bound: the tail is a read-modify-write pass over the whole output.  Measured on B200 at 32 shapes
+# (tools/gemm_probe.py): Cin=35 plain 123 us / split 214 us, Cin=67 71 / 114, Cin=131 64 / 51, Cin=390 86 / 54.
+SPLIT_MIN_CHANNELS = 128
+
+
 class Swish(nn.Module):
     def forward(self, x):
         return x * torch.sigmoid(x)
@@ -106,7 +113,7 @@ def conv_no_bias_concat(m, parts):
         pieces, off = [], 0
         for p in parts:
             ci = p.shape[1]
-            head = ci & ~3 if ci >= 32 else ci        # aligned head (+ tail) for wide parts, whole for narrow ones
+            head = ci & ~3 if ci >= SPLIT_MIN_CHANNELS else ci   # aligned head (+ tail) for wide parts, whole for narrow ones
             pieces.append((off, head, w2[:, off:off + head].contiguous()))
             if head < ci:
                 pieces.append((off + head, ci - head, w2[:, off + head:off + ci].contiguous()))
@@ -154,7 +161,7 @@ def conv_no_bias(m, x):
             cached = (key, w.detach().contiguous(memory_format=torch.channels_last_3d))
             m._cl_weight = cached
         return m._conv_forward(x, cached[1], None)
-    if not (_pointwise(m) and cin % 4 != 0 and cin >= 32 and x.is_cuda and x.is_contiguous()):
+    if not (_pointwise(m) and cin % 4 != 0 and cin >= SPLIT_MIN_CHANNELS and x.is_cuda and x.is_contiguous()):
         return m._conv_forward(x, m.weight, None)
     w = m.weight
     key = (w.data_ptr(), geometry.tensor_version(w), w.device)

@@ -215,6 +215,12 @@ int bdm_surface_projection_cf(int b, int n, int C, int H, int W, float radius, c
  *   dist f64[b,n] (min squared distance), idx i32[b,n] (argmin, lowest index on ties; may be NULL). */
 int bdm_nn_f64(int b, int n, int m, int expanded, const double *src, const double *tgt,
                double *dist, int *idx, bdm_stream_t stream);
+/* The same search with the metrics' reductions fused in (evaluation_cd.py:125 mean of the minima; evaluation_f1.py:104-106
+ * fraction of minima below thr): part_sum f64[b,blocks] / part_cnt i32[b,blocks] receive, per block of source
+ * points, the sum of the minima and the number below thr; blocks = bdm_nn_f64_reduce_blocks(b, n). */
+int bdm_nn_f64_reduce_blocks(int b, int n);
+int bdm_nn_f64_reduce(int b, int n, int m, int expanded, double thr, const double *src, const double *tgt,
+                      double *part_sum, int *part_cnt, bdm_stream_t stream);
 
 /* ---- reverse-diffusion update of one sampling step ---------------------------
  * replaces the eager torch ops of diffusers' DDPMScheduler.step as driven by experiments/model/model.py:182-194

@@ -76,6 +76,25 @@ def test_nn_f64_vs_oracle(n, m, cuda_backend):
     assert np.array_equal(de.cpu().numpy(), O.nn_expanded(src, gt))
 
 
+@pytest.mark.parametrize("n,m", [(4096, 4096), (1000, 777), (5, 3)])
+def test_nn_f64_fused_reductions(n, m, cuda_backend):
+    """bdm_nn_f64_reduce: the sum of the minima equals the sum of bdm_nn_f64's minima (to fp64 summation order) and
+    the count below the threshold equals the count over them exactly, in both distance forms."""
+    import torch
+    rng = np.random.default_rng(77)
+    b = 3
+    gt = rng.standard_normal((b, m, 3)) * 0.2
+    src = gt[:, rng.integers(0, m, n)] + 0.05 * rng.standard_normal((b, n, 3))
+    s_t, g_t = torch.as_tensor(src).cuda(), torch.as_tensor(gt).cuda()
+    for expanded in (False, True):
+        d, _ = cuda_backend.nn_f64(s_t, g_t, expanded=expanded, return_index=False)
+        total, count = cuda_backend.nn_f64_reduce(s_t, g_t, expanded=expanded, thr=0.01)
+        assert torch.equal(count, (d < 0.01).sum(dim=1))
+        assert torch.allclose(total, d.sum(dim=1), rtol=1e-13, atol=0)
+        again, _ = cuda_backend.nn_f64_reduce(s_t, g_t, expanded=expanded, thr=0.01)
+        assert torch.equal(total, again)                    # fixed reduction order
+
+
 def test_chamfer_fscore_config1(cuda_backend):
     """BASELINE.json configs[0]: CD + F-score@0.01 on 8 synthetic 4096-point pairs."""
     import torch

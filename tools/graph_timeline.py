@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 
-x, feats, cams = bench.make_inputs(16, 1234, "cuda:0")
+x, feats, cams = bench.make_inputs(int(os.environ.get("BDM_BATCH", "32")), 1234, "cuda:0")
 sampler = bench.build_sampler(feats, cams, "cuda:0", mode="vanilla")
 with torch.no_grad():
     for _ in range(3):
@@ -38,6 +38,8 @@ for sid, es in sorted(streams.items(), key=lambda kv: -sum(e["dur"] for e in kv[
     print(f"stream {sid}: {len(es)} activities, busy {sum(e['dur'] for e in es) / 1e3:.3f} ms")
 main = max(streams.values(), key=lambda es: sum(e["dur"] for e in es))
 gaps = []
+small = sum(max(0, b["ts"] - (a["ts"] + a["dur"])) for a, b in zip(main, main[1:]))
+print(f"main stream: total idle between consecutive activities {small / 1e3:.3f} ms")
 for a, b in zip(main, main[1:]):
     g = b["ts"] - (a["ts"] + a["dur"])
     if g > 8:

@@ -265,6 +265,9 @@ def algorithmic_work(op, shp):
     if op == "attention":                                   # q [B,C,T]: 2 GEMMs of 2*T*T*C flops per shape
         b, c, t = shp[0]
         return "tensor", 4.0 * b * t * t * c, "flop"
+    if op == "attention_qkv":                               # qkv [B,T,3C]
+        b, t, c3 = shp[0]
+        return "tensor", 4.0 * b * t * t * (c3 // 3), "flop"
     if op == "groupnorm_act":
         x = shp[0]
         n = _numel(x)
@@ -322,8 +325,14 @@ def pick_roofline(prof, steps, ms_step, occupied, peaks):
             ach, peak, u = units / (ms * 1e-3) / 1e12, peaks["bf16_tflops_sustained"], "TFLOP/s"
         shown = [list(s) if isinstance(s, tuple) else (s if isinstance(s, (int, float, str, bool, dict, type(None))) else type(s).__name__)
                  for s in shp]
+        extra = {}
+        if op in ("attention", "attention_qkv"):
+            # every fp32 product is three fp16 tensor-core products (lo*hi + hi*lo + hi*hi): the tensor pipe executes 3x
+            extra = {"executed_tflops": 3.0 * ach, "frac_executed": 3.0 * ach / peak,
+                     "note": "algorithmic flops = the fp32 attention (4*B*T*T*C); executed = 3x (fp16 hi/lo split). The launch "
+                             "group is amax + operand prep + the tcgen05 kernel."}
         return {"bound": bound, "kernel": f"{op} {json.dumps(shown)}", "achieved": ach, "peak": peak, "unit": u,
-                "frac": ach / peak, "traffic": None, "peak_source": peaks["source"],
+                "frac": ach / peak, "traffic": None, "peak_source": peaks["source"], **extra,
                 "algorithmic_%ss_per_launch" % unit: units, "ms_per_launch": ms,
                 "launches_timed": len(g["ms"]), "launches_per_iteration": len(g["ms"]) // max(steps, 1),
                 "share_of_iteration": sum(g["ms"]) / max(steps, 1) / ms_step,

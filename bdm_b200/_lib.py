@@ -6,7 +6,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libbdm_b200.so")
+SO_PATH = os.environ.get("BDM_LIB_PATH") or os.path.join(_HERE, "libbdm_b200.so")   # BDM_LIB_PATH: A/B builds (tools/)
 
 if not os.path.exists(SO_PATH):
     raise ImportError(

@@ -745,3 +745,84 @@ def nn_f64_reduce(src, tgt, expanded=False, thr=0.01):
         _check(_L.bdm_nn_f64_reduce(b, n, m, 1 if expanded else 0, float(thr), src.data_ptr(), tgt.data_ptr(),
                                     psum.data_ptr(), pcnt.data_ptr(), st))
     return psum.sum(dim=1), pcnt.sum(dim=1, dtype=torch.int64)
+
+
+# ---------------------------------------------------------------------------------------------
+# tcgen05 3x3x3 convolution of the voxel branch (csrc/conv3_tc05.cu; reference: modules/pvconv.py:75-88)
+# ---------------------------------------------------------------------------------------------
+def conv3_tc05_supported(c_in, c_out, resolution):
+    return bool(_L.bdm_conv3_tc05_supported(int(c_in), int(c_out), int(resolution)))
+
+
+class HalfPlanes:
+    """fp16 chunk planes [C/8, rows, 8] of the flat padded grid for (batch, resolution): the convolution's operand.
+    Zero-filled at creation; producers write real voxels only, so pad rows stay zero for the buffer's lifetime."""
+    __slots__ = ("b", "c", "r", "rows", "data")
+
+    def __init__(self, b, c, r, device):
+        self.b, self.c, self.r = int(b), int(c), int(r)
+        self.rows = int(_L.bdm_conv3_tc05_plane_rows(self.b, self.r))
+        self.data = torch.zeros((self.c // 8, self.rows, 8), dtype=torch.float16, device=device)
+
+
+@_op(2)
+def conv3_tc05_prepare(weight, gamma, beta, group_elems):
+    """Conv3d weight f32[Cout,Cin,3,3,3] (+ the affine of the GroupNorm that produces the conv's input and the
+    element count of one of its groups) -> the prepared weight buffer (scales + fp16 stage images)."""
+    _chk_float(weight, "weight")
+    c_out, c_in = weight.shape[:2]
+    _req(tuple(weight.shape[2:]) == (3, 3, 3), "weight must be [Cout,Cin,3,3,3]")
+    for t_, nm in ((gamma, "gamma"), (beta, "beta")):
+        _chk_channel_vector(t_, nm, c_in)
+    nbytes = int(_L.bdm_conv3_tc05_weight_bytes(c_in, c_out))
+    prepared = torch.empty((nbytes,), dtype=torch.uint8, device=weight.device)
+    with _Launch(weight) as st:
+        _check(_L.bdm_conv3_tc05_prepare(c_in, c_out, weight.data_ptr(), gamma.data_ptr() if gamma is not None else None,
+                                         beta.data_ptr() if beta is not None else None, int(group_elems),
+                                         prepared.data_ptr(), nbytes, st))
+    return prepared
+
+
+@_op(1)
+def groupnorm_swish_half_planar(x, num_groups, weight, bias, eps, swish, conv_bias, partials, prepared, planes):
+    """x f32[B,R,R,R,C] channels-last + producer statistics f64[B,chunks,C,2] -> act(group_norm(x + conv_bias)) written
+    into `planes` (HalfPlanes) in the scaling `prepared` prescribes."""
+    _chk_float(x, "x")
+    b, r, c = x.shape[0], x.shape[1], x.shape[-1]
+    _req(x.dim() == 5 and x.shape[2] == r and x.shape[3] == r, "x must be [B,R,R,R,C]")
+    _req(planes.b == b and planes.c == c and planes.r == r and planes.data.device == x.device, "planes do not match x")
+    for t_, nm in ((weight, "weight"), (bias, "bias"), (conv_bias, "conv_bias")):
+        _chk_channel_vector(t_, nm, c)
+    _req(partials.dtype == torch.float64 and partials.is_contiguous() and partials.dim() == 4 and partials.shape[0] == b
+         and partials.shape[2] == c and partials.shape[3] == 2, "partials must be f64[B,chunks,C,2]")
+    with _Launch(x) as st:
+        _check(_L.bdm_groupnorm_swish_half_planar(b, c, r, int(num_groups), float(eps), 1 if swish else 0, x.data_ptr(),
+                                                  conv_bias.data_ptr() if conv_bias is not None else None,
+                                                  weight.data_ptr() if weight is not None else None,
+                                                  bias.data_ptr() if bias is not None else None, partials.data_ptr(),
+                                                  int(partials.shape[1]), prepared.data_ptr(), planes.data.data_ptr(),
+                                                  planes.rows, st))
+    return planes
+
+
+@_op(1)
+def conv3_tc05(planes, prepared, c_out, bias=None, stats=False):
+    """HalfPlanes + prepared weights -> f32[B,R,R,R,Cout] channels-last (= conv + bias) and, with stats, the result's
+    GroupNorm(8) statistics f64[B,1,Cout,2] for groupnorm_act_cl(partials=)."""
+    b, r, c_in = planes.b, planes.r, planes.c
+    dev = planes.data.device
+    _chk_channel_vector(bias, "bias", c_out)
+    out = torch.empty((b, r, r, r, c_out), dtype=_F32, device=dev)
+    part = ws = None
+    ws_bytes = 0
+    if stats:
+        part = torch.empty((b, 1, c_out, 2), dtype=torch.float64, device=dev)
+        ws_bytes = int(_L.bdm_conv3_tc05_workspace_bytes(b, r))
+        ws = _workspace(ws_bytes, dev)
+        _count_launches(1)
+    with _Launch(planes.data) as st:
+        _check(_L.bdm_conv3_tc05(b, c_in, int(c_out), r, planes.data.data_ptr(), planes.rows, prepared.data_ptr(),
+                                 bias.data_ptr() if bias is not None else None, out.data_ptr(),
+                                 part.data_ptr() if part is not None else None, ws.data_ptr() if ws is not None else None,
+                                 ws_bytes, st))
+    return (out, part) if stats else out

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libbdm_b200.so")
 SOURCES = ["abi.cu", "voxelize.cu", "voxel_coords.cu", "devoxelize.cu", "sampling.cu", "ball_query.cu", "grouping.cu",
-           "three_nn.cu", "projection.cu", "knn_eval.cu", "groupnorm.cu", "sparse_conv.cu", "attention.cu", "attention_tc05.cu", "sampler.cu"]
+           "three_nn.cu", "projection.cu", "knn_eval.cu", "groupnorm.cu", "sparse_conv.cu", "attention.cu", "attention_tc05.cu", "conv3_tc05.cu", "sampler.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo",
               "-Xcompiler", "-fPIC", "-cudart", "static"]
 

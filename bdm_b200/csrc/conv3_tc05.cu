@@ -1,0 +1,654 @@
+// conv3_tc05.cu -- the dense 3x3x3 / stride 1 / zero-padded convolution of a PVConv block (reference:
+// experiments/model/pvcnn/modules/pvconv.py:75-88, the second nn.Conv3d of `voxel_layers`, run by cuDNN in TF32 under
+// torch's default conv policy) as an implicit GEMM on Blackwell's 5th-generation tensor cores: tcgen05.mma with the
+// accumulators in tensor memory, both operands fetched by 1-D TMA bulk copies, a persistent warp-specialised CTA per SM.
+//
+// Precision.  cuDNN's TF32 kernels keep 11 significant bits of every operand and accumulate in fp32.  Here the
+// operands are fp16 -- also 11 significant bits -- after a power-of-two scaling that rules out overflow (weights:
+// max|w| -> [512, 1024); activations: a bound derived from the GroupNorm affine that produced them), products are
+// exact and accumulation is fp32 in TMEM.  tests/test_conv3_tc05_gpu.py checks the result against float64 and
+// requires an error no larger than cuDNN's TF32 result has.
+//
+// The flat padded grid.  A voxel (x, y, z) of an R^3 grid sits at flat position p = (x*Q + y)*Q + z, Q = R + 1, of a
+// (R+1)^3 volume whose extra plane / row / column hold zeros: the +1 neighbour of the last voxel of a row and the -1
+// neighbour of the first voxel of the next row are the SAME zero position.  A tap (dx, dy, dz) is then the constant
+// row offset dx*Q^2 + dy*Q + dz for every output position, so the A operand of one tap is simply a window of 128
+// consecutive rows of the activation array, shifted.  Activations live in global memory as fp16 "chunk planes"
+// xh[C/8][rows][8]: for each group of 8 channels a flat array of 16-byte rows.  A slab of consecutive rows of one plane
+// is contiguous (one bulk copy) and lands in shared memory as the tensor core's canonical K-major no-swizzle
+// layout: a core matrix = 8 consecutive rows x 16 bytes, SBO = 128, LBO = slab rows * 16; shifting the window by one
+// row is +16 bytes on the descriptor's start address (verified on the device: tools/probe/tc05_probe_shift.cu).
+// The price is (R+1)^2/R^2 - 1 padded output rows that are computed and dropped (6 % at R=32, 13 % at R=16).
+//
+// Rows of sample b: [guard G zeros][(R+1)^3 positions]...; sample stride S, see conv3_geometry().  Pad positions and
+// guards are zero because the buffer is zero-filled when it is created and producers only ever write real voxels.
+//
+// Kernel.  A unit = 256 consecutive flat positions (two M=128 accumulators) x all N = Cout channels.
+//   warp 0     one thread: A producer.  Per (dx, 64-channel chunk): the slab of 256 + 2Q + 2 rows that covers the 9
+//              (dy, dz) windows, KC/8 bulk copies into a 3-stage ring.
+//   warp 1     one thread: W producer.  Weights are pre-arranged (conv3_tc05_prep) as the exact shared-memory image of
+//              each (dx, chunk, tap group) stage; one bulk copy per stage into a ring.
+//   warp 2     one thread: issues the MMAs (2 tiles x taps x K/16 per stage), commits stages back to the producers.
+//   warp 3     TMEM allocation.
+//   warps 4-11 epilogue: thread = output row = TMEM lane; scale, + bias, GroupNorm statistics of the result
+//              (per-group sum / sum of squares, reduced per unit, no atomics), channels-last fp32 store of the real
+//              voxels.  Accumulators are double-buffered (2 x 2 x N TMEM columns), so the epilogue of unit i overlaps
+//              the MMAs of unit i+1.
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+
+namespace bdm {
+namespace cv3 {
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void bar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bar_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t done = 0;
+  const uint32_t a = smem_u32(bar);
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(a), "r"(parity) : "memory");
+  }
+}
+__device__ __forceinline__ void tma_load(uint32_t dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// shared-memory operand descriptor, no swizzle, K-major: lbo = bytes between core matrices adjacent along K,
+// sbo = along M / N
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46);
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+// kind::f16, fp16 operands (both K-major), fp32 accumulate, M = 128
+__host__ __device__ constexpr uint32_t instr_desc(int n) {
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+#define BDM_CV3_TMEM_LD32(r, taddr)                                                                                \
+  asm volatile(                                                                                                    \
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                                    \
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "                                    \
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"                    \
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),            \
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),      \
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),    \
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])     \
+      : "r"(taddr))
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ float swish_fast(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
+
+constexpr int kUnitRows = 256;        // output positions per unit (2 accumulators of 128)
+constexpr int kHeaderBytes = 256;     // prepared-weight header: float out_scale, float act_scale
+constexpr int kAStages = 3;
+constexpr int kThreads = 384;         // 12 warps
+constexpr int kEpiThreads = 256;
+
+struct Geometry {
+  int r, q, p;                // resolution, Q = r+1, P = Q^2
+  int guard;                  // zero rows in front of every sample (>= P + Q + 1, multiple of 8)
+  int units;                  // units per sample
+  long long sample_rows;      // row stride between samples
+  long long total_rows;       // rows of one chunk plane
+  int slab_rows;              // rows of an A stage: 256 + 2Q + 2
+};
+__host__ __device__ inline Geometry conv3_geometry(int b, int r) {
+  Geometry g;
+  g.r = r; g.q = r + 1; g.p = g.q * g.q;
+  g.guard = (g.p + g.q + 1 + 7) / 8 * 8;
+  const int last_valid = ((r - 1) * g.q + (r - 1)) * g.q + (r - 1);
+  g.units = (last_valid + 1 + kUnitRows - 1) / kUnitRows;
+  g.sample_rows = ((long long)g.guard + (long long)g.q * g.p + 7) / 8 * 8;
+  g.slab_rows = kUnitRows + 2 * g.q + 2;
+  // the last unit of the last sample reads up to units*256 + P + Q + 1 rows past its sample's first position
+  g.total_rows = (long long)g.guard + (long long)b * g.sample_rows + (long long)g.units * kUnitRows + g.guard + 8;
+  return g;
+}
+
+// -------------------------------------------------------------------------------------------------------------
+// weights: f32[cout][cin][27] -> header + fp16 stage images.  Stage s = ((dx*NKC + kc)*NG + grp); inside a stage:
+// [tap j of the group][chunk c of KC/8][row n of cout][8 halves] = w[n][kc*KC + 8c + e][dx*9 + grp*TG + j] * wscale
+// -------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float pow2_scale_to(float amax, float target_exp, float *inv) {   // amax * s in [2^t, 2^(t+1))
+  int e = (int)target_exp;
+  if (amax > 0.0f && amax < INFINITY) e = (int)((__float_as_uint(amax) >> 23) & 255u) - 127;
+  const int se = min(max((int)target_exp - e, -60), 60);
+  *inv = __uint_as_float((uint32_t)(127 - se) << 23);
+  return __uint_as_float((uint32_t)(127 + se) << 23);
+}
+
+// one CTA: max|w|, and the activation scale from the GroupNorm affine that produces the conv's input:
+// |swish(gn(x))| <= max|gamma| * sqrt(group elements) + max|beta|  (sum of squared normalised values = count).
+__global__ void __launch_bounds__(1024)
+conv3_prep_header_kernel(size_t nw, const float *__restrict__ w, int c_in, const float *__restrict__ gamma,
+                         const float *__restrict__ beta, float group_elems, float *__restrict__ header) {
+  __shared__ float red[3][32];
+  float mw = 0.0f, mg = 0.0f, mb = 0.0f;
+  for (size_t i = threadIdx.x; i < nw; i += blockDim.x) mw = fmaxf(mw, fabsf(__ldg(w + i)));
+  for (int i = threadIdx.x; i < c_in; i += blockDim.x) {
+    mg = fmaxf(mg, gamma != nullptr ? fabsf(gamma[i]) : 1.0f);
+    mb = fmaxf(mb, beta != nullptr ? fabsf(beta[i]) : 0.0f);
+  }
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) {
+    mw = fmaxf(mw, __shfl_xor_sync(0xffffffffu, mw, d));
+    mg = fmaxf(mg, __shfl_xor_sync(0xffffffffu, mg, d));
+    mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, d));
+  }
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = mw; red[1][threadIdx.x >> 5] = mg; red[2][threadIdx.x >> 5] = mb; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < (int)(blockDim.x >> 5); ++i) {
+      mw = fmaxf(mw, red[0][i]); mg = fmaxf(mg, red[1][i]); mb = fmaxf(mb, red[2][i]);
+    }
+    float inv_w, inv_a = 1.0f, sa = 1.0f;
+    const float sw = pow2_scale_to(mw, 9.0f, &inv_w);
+    const float bound = mg * sqrtf(group_elems) + mb;
+    if (bound > 32768.0f && bound < INFINITY) {          // scale down by a power of two so that bound * sa <= 32768
+      const int e = (int)((__float_as_uint(bound) >> 23) & 255u) - 127;   // bound in [2^e, 2^(e+1))
+      const int se = min(e + 1 - 15, 60);
+      sa = __uint_as_float((uint32_t)(127 - se) << 23);
+      inv_a = __uint_as_float((uint32_t)(127 + se) << 23);
+    }
+    header[0] = inv_w * inv_a;   // out_scale: accumulator -> convolution result
+    header[1] = sa;              // act_scale: applied by the producer of xh
+    header[2] = sw;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+conv3_prep_weights_kernel(int c_in, int c_out, int kc_size, int tg, const float *__restrict__ w,
+                          const float *__restrict__ header, __half *__restrict__ out) {
+  const float sw = header[2];
+  const int nkc = c_in / kc_size, ng = 9 / tg, chunks = kc_size / 8;
+  const size_t total = (size_t)27 * c_in * c_out;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    size_t rest = i;
+    const int e = (int)(rest % 8); rest /= 8;
+    const int n = (int)(rest % c_out); rest /= c_out;
+    const int c = (int)(rest % chunks); rest /= chunks;
+    const int j = (int)(rest % tg); rest /= tg;
+    const int grp = (int)(rest % ng); rest /= ng;
+    const int kc = (int)(rest % nkc); rest /= nkc;
+    const int dx = (int)rest;
+    const int ci = kc * kc_size + c * 8 + e;
+    const int tap = dx * 9 + grp * tg + j;
+    out[i] = __float2half_rn(__ldg(w + ((size_t)n * c_in + ci) * 27 + tap) * sw);
+  }
+}
+
+// -------------------------------------------------------------------------------------------------------------
+// GroupNorm(+conv bias)+Swish of a channels-last grid x f32[b][r^3][c] with producer-made statistics, written as
+// the fp16 chunk planes the convolution reads.  Thread = 8 channels of one voxel (two 128-bit loads, one 128-bit
+// store); a warp reads 1 KB of consecutive voxels.
+// -------------------------------------------------------------------------------------------------------------
+constexpr int kApplyThreads = 256;
+__global__ void __launch_bounds__(kApplyThreads)
+gn_apply_half_planar_kernel(int c, int r, int groups, int nchunks, int ntiles, float eps, int swish,
+                            const float *__restrict__ x, const float *__restrict__ conv_bias,
+                            const float *__restrict__ gamma, const float *__restrict__ beta,
+                            const double2 *__restrict__ partials, const float *__restrict__ header,
+                            __half *__restrict__ xh, int guard, long long sample_rows, long long total_rows) {
+  __shared__ double2 slice[kApplyThreads];
+  __shared__ double2 chan[256];
+  __shared__ double2 grp[32];
+  __shared__ float2 ab[256];
+  const int b = blockIdx.y, tile = blockIdx.x, t = threadIdx.x;
+  const int cg = c / groups;
+  const long long s = (long long)r * r * r;
+  {
+    const int nsl = kApplyThreads / c, tc = t % c, sl = t / c;
+    double S1 = 0.0, S2 = 0.0;
+    for (int ch = sl; ch < nchunks; ch += nsl) {
+      const double2 v = partials[((size_t)b * nchunks + ch) * c + tc];
+      S1 += v.x; S2 += v.y;
+    }
+    slice[t] = make_double2(S1, S2);
+  }
+  __syncthreads();
+  if (t < c) {
+    double S1 = 0.0, S2 = 0.0;
+    for (int sl = 0; sl < kApplyThreads / c; ++sl) { S1 += slice[sl * c + t].x; S2 += slice[sl * c + t].y; }
+    const double tt = conv_bias != nullptr ? (double)conv_bias[t] : 0.0;   // statistics are of the bias-less tensor
+    const double ds = (double)s;
+    chan[t] = make_double2(S1 + ds * tt, S2 + 2.0 * tt * S1 + ds * tt * tt);
+  }
+  __syncthreads();
+  if (t < groups) {
+    double S1 = 0.0, S2 = 0.0;
+    for (int j = 0; j < cg; ++j) { S1 += chan[t * cg + j].x; S2 += chan[t * cg + j].y; }
+    const double n = (double)cg * (double)s;
+    const double mean = S1 / n;
+    const double var = fmax(S2 / n - mean * mean, 0.0);
+    grp[t] = make_double2(mean, 1.0 / sqrt(var + (double)eps));
+  }
+  __syncthreads();
+  if (t < c) {
+    const double2 g = grp[t / cg];
+    const float ga = gamma != nullptr ? gamma[t] : 1.0f;
+    const float be = beta != nullptr ? beta[t] : 0.0f;
+    const float cb = conv_bias != nullptr ? conv_bias[t] : 0.0f;
+    const float A = (float)g.y * ga;
+    ab[t] = make_float2(A, (float)((double)be + ((double)cb - g.x) * (double)A));
+  }
+  __syncthreads();
+  const float act_scale = __ldg(header + 1);
+  const int c8 = c >> 3, rpp = kApplyThreads / c8;
+  const int j = t % c8, r0 = t / c8;
+  float2 co[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) co[i] = ab[8 * j + i];
+  const int q = r + 1;
+  const int sh = 31 - __clz(r);                 // r is a power of two
+  long long per = (s + ntiles - 1) / ntiles;
+  per = (per + rpp - 1) / rpp * rpp;
+  const long long lo = min((long long)tile * per, s), hi = min(lo + per, s);
+  const float *px = x + (size_t)b * s * c + 8 * j;
+  __half *plane = xh + ((size_t)j * total_rows + (size_t)guard + (size_t)b * sample_rows) * 8;
+  auto emit = [&](long long row, const float4 &u, const float4 &w) {
+    float v[8] = {u.x, u.y, u.z, u.w, w.x, w.y, w.z, w.w};
+    uint32_t h[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float a0 = fmaf(v[2 * i], co[2 * i].x, co[2 * i].y), a1 = fmaf(v[2 * i + 1], co[2 * i + 1].x, co[2 * i + 1].y);
+      if (swish) { a0 = swish_fast(a0); a1 = swish_fast(a1); }
+      const __half2 hh = __floats2half2_rn(a0 * act_scale, a1 * act_scale);
+      h[i] = *reinterpret_cast<const uint32_t *>(&hh);
+    }
+    const int vz = (int)row & (r - 1), vy = ((int)row >> sh) & (r - 1), vx = (int)row >> (2 * sh);
+    const long long p = ((long long)vx * q + vy) * q + vz;
+    *reinterpret_cast<uint4 *>(plane + (size_t)p * 8) = make_uint4(h[0], h[1], h[2], h[3]);
+  };
+  constexpr int UNR = 4;
+  long long row = lo + r0;
+  for (; row + (long long)(UNR - 1) * rpp < hi; row += (long long)UNR * rpp) {
+    float4 u[UNR], w[UNR];
+#pragma unroll
+    for (int k = 0; k < UNR; ++k) {
+      u[k] = ld_stream_f4(px + (size_t)(row + (long long)k * rpp) * c);
+      w[k] = ld_stream_f4(px + (size_t)(row + (long long)k * rpp) * c + 4);
+    }
+#pragma unroll
+    for (int k = 0; k < UNR; ++k) emit(row + (long long)k * rpp, u[k], w[k]);
+  }
+  for (; row < hi; row += rpp) emit(row, ld_stream_f4(px + (size_t)row * c), ld_stream_f4(px + (size_t)row * c + 4));
+}
+
+// -------------------------------------------------------------------------------------------------------------
+// the convolution
+// -------------------------------------------------------------------------------------------------------------
+template <int N, int KC, int TG>
+struct Cfg {
+  static constexpr int kChunks = KC / 8;
+  static constexpr int kK16 = KC / 16;
+  static constexpr int kNG = 9 / TG;
+  static constexpr int kTapBytes = N * KC * 2;
+  static constexpr int kWStageBytes = TG * kTapBytes;
+  static constexpr int kWStages = kWStageBytes <= 16 * 1024 ? 4 : 3;
+  static constexpr int kTmemCols = 4 * N;          // 2 buffers x 2 tiles x N
+  static constexpr int kNumBars = 2 * kAStages + 2 * kWStages + 4;
+};
+
+template <int N, int KC, int TG>
+__global__ void __launch_bounds__(kThreads, 1)
+conv3_tc05_kernel(int b, int c_in, Geometry geo, int a_stage_bytes, const __half *__restrict__ xh,
+                  const unsigned char *__restrict__ wprep, const float *__restrict__ bias,
+                  float *__restrict__ out, double *__restrict__ unit_stats) {
+  using C = Cfg<N, KC, TG>;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nkc = c_in / KC;
+  const int total_units = b * geo.units;
+  const int slab_rows = geo.slab_rows;
+
+  unsigned char *a_smem = smem;
+  unsigned char *w_smem = smem + kAStages * a_stage_bytes;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(w_smem + C::kWStages * C::kWStageBytes);
+  uint64_t *a_full = bars, *a_empty = a_full + kAStages, *w_full = a_empty + kAStages, *w_empty = w_full + C::kWStages;
+  uint64_t *t_full = w_empty + C::kWStages, *t_empty = t_full + 2;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + C::kNumBars);
+  float *red = reinterpret_cast<float *>(tmem_slot + 4);        // [2][8 warps][16]
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kAStages; ++s) { bar_init(a_full + s, 1); bar_init(a_empty + s, 1); }
+    for (int s = 0; s < C::kWStages; ++s) { bar_init(w_full + s, 1); bar_init(w_empty + s, 1); }
+    for (int s = 0; s < 2; ++s) { bar_init(t_full + s, 1); bar_init(t_empty + s, kEpiThreads); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 3) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(C::kTmemCols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== A producer =====================
+    if (lane == 0) {
+      int sa = 0; uint32_t pa = 0;
+      const uint32_t slab_bytes = (uint32_t)slab_rows * 16u;
+      for (int g = blockIdx.x; g < total_units; g += gridDim.x) {
+        const int smp = g / geo.units, u = g - smp * geo.units;
+        const long long row_base = (long long)geo.guard + (long long)smp * geo.sample_rows + (long long)u * kUnitRows;
+        for (int dx = 0; dx < 3; ++dx) {
+          const long long src_row = row_base + (long long)(dx - 1) * geo.p - geo.q - 1;
+          for (int kc = 0; kc < nkc; ++kc) {
+            bar_wait(a_empty + sa, pa ^ 1);
+            bar_expect_tx(a_full + sa, C::kChunks * slab_bytes);
+            const uint32_t dst = smem_u32(a_smem + sa * a_stage_bytes);
+#pragma unroll
+            for (int j = 0; j < C::kChunks; ++j)
+              tma_load(dst + j * slab_bytes, xh + ((size_t)(kc * C::kChunks + j) * geo.total_rows + (size_t)src_row) * 8,
+                       slab_bytes, a_full + sa);
+            if (++sa == kAStages) { sa = 0; pa ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== W producer =====================
+    if (lane == 0) {
+      int sw = 0; uint32_t pw = 0;
+      const int stages_per_unit = 3 * nkc * C::kNG;
+      const unsigned char *wsrc = wprep + kHeaderBytes;
+      for (int g = blockIdx.x; g < total_units; g += gridDim.x) {
+        for (int s = 0; s < stages_per_unit; ++s) {
+          bar_wait(w_empty + sw, pw ^ 1);
+          bar_expect_tx(w_full + sw, C::kWStageBytes);
+          tma_load(smem_u32(w_smem + sw * C::kWStageBytes), wsrc + (size_t)s * C::kWStageBytes, C::kWStageBytes, w_full + sw);
+          if (++sw == C::kWStages) { sw = 0; pw ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = instr_desc(N);
+      int sa = 0, sw = 0; uint32_t pa = 0, pw = 0;
+      const uint32_t a_lbo = (uint32_t)slab_rows * 16u, b_lbo = N * 16u;
+      int it = 0;
+      for (int g = blockIdx.x; g < total_units; g += gridDim.x, ++it) {
+        const int buf = it & 1;
+        bar_wait(t_empty + buf, ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d0 = tmem + buf * 2 * N;
+        uint32_t acc = 0;
+        for (int dx = 0; dx < 3; ++dx) {
+          for (int kc = 0; kc < nkc; ++kc) {
+            bar_wait(a_full + sa, pa);
+            tc_fence_after();
+            const uint32_t ab = smem_u32(a_smem + sa * a_stage_bytes);
+            for (int grp = 0; grp < C::kNG; ++grp) {
+              bar_wait(w_full + sw, pw);
+              tc_fence_after();
+              const uint32_t wb = smem_u32(w_smem + sw * C::kWStageBytes);
+#pragma unroll
+              for (int j = 0; j < TG; ++j) {
+                const int tap = grp * TG + j;
+                const int dy = tap / 3, dz = tap - dy * 3;
+                const uint32_t a_row = (uint32_t)(dy * geo.q + dz) * 16u;
+#pragma unroll
+                for (int t = 0; t < 2; ++t) {
+#pragma unroll
+                  for (int k = 0; k < C::kK16; ++k) {
+                    const uint64_t da = smem_desc(ab + a_row + t * 128 * 16 + k * 2 * a_lbo, a_lbo, 128);
+                    const uint64_t db = smem_desc(wb + j * C::kTapBytes + k * 2 * b_lbo, b_lbo, 128);
+                    umma_f16(d0 + t * N, da, db, idesc, acc | (uint32_t)k);
+                  }
+                }
+                acc = 1;
+              }
+              umma_commit(w_empty + sw);
+              if (++sw == C::kWStages) { sw = 0; pw ^= 1; }
+            }
+            umma_commit(a_empty + sa);
+            if (++sa == kAStages) { sa = 0; pa ^= 1; }
+          }
+        }
+        umma_commit(t_full + buf);
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int e = warp - 4, t = e >> 2, qd = e & 3;    // tile, TMEM lane quarter (== warp % 4)
+    const float out_scale = __ldg(reinterpret_cast<const float *>(wprep));
+    const int r = geo.r, q = geo.q;
+    const size_t s3 = (size_t)r * r * r;
+    constexpr int CG = N / 8;                           // channels per GroupNorm group (8 groups)
+    int it = 0;
+    for (int g = blockIdx.x; g < total_units; g += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const int smp = g / geo.units, u = g - smp * geo.units;
+      const int m = t * 128 + qd * 32 + lane;
+      const int p = u * kUnitRows + m;
+      const int z = p % q, xy = p / q, y = xy % q, x = xy / q;
+      const bool valid = x < r && y < r && z < r;
+      float *dst = out + ((size_t)smp * s3 + ((size_t)x * r + y) * r + z) * N;
+      float gs1[8], gs2[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) gs1[i] = gs2[i] = 0.0f;
+      bar_wait(t_full + buf, (it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem + ((uint32_t)(qd * 32) << 16) + buf * 2 * N + t * N;
+#pragma unroll
+      for (int c0 = 0; c0 < N; c0 += 32) {
+        uint32_t rr[32];
+        BDM_CV3_TMEM_LD32(rr, taddr + c0);
+        tmem_wait_ld();
+        float f[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          f[i] = fmaf(__uint_as_float(rr[i]), out_scale, bias != nullptr ? __ldg(bias + c0 + i) : 0.0f);
+          const float fv = valid ? f[i] : 0.0f;
+          gs1[(c0 + i) / CG] += fv;
+          gs2[(c0 + i) / CG] = fmaf(fv, fv, gs2[(c0 + i) / CG]);
+        }
+        if (valid) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            *reinterpret_cast<float4 *>(dst + c0 + 4 * i) = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+        }
+      }
+      tc_fence_before();
+      bar_arrive(t_empty + buf);
+      if (unit_stats != nullptr) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+#pragma unroll
+          for (int d = 16; d >= 1; d >>= 1) {
+            gs1[i] += __shfl_xor_sync(0xffffffffu, gs1[i], d);
+            gs2[i] += __shfl_xor_sync(0xffffffffu, gs2[i], d);
+          }
+        }
+        float *rb = red + (buf * 8 + e) * 16;
+        if (lane == 0) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { rb[2 * i] = gs1[i]; rb[2 * i + 1] = gs2[i]; }
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (e == 0 && lane < 16) {
+          double a = 0.0;
+#pragma unroll
+          for (int w = 0; w < 8; ++w) a += (double)red[(buf * 8 + w) * 16 + lane];
+          unit_stats[(size_t)g * 16 + lane] = a;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 3) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(C::kTmemCols));
+  }
+}
+
+// unit partials f64[b][units][8 groups][2] -> the GroupNorm kernels' producer-statistics format f64[b][1][c][2]:
+// the group's sums sit in its first channel's slot, the other channels hold zeros (the consumer adds the
+// channels of a group).  Fixed summation order: deterministic.
+__global__ void conv3_stats_fold_kernel(int units, int c, const double *__restrict__ unit_stats, double2 *__restrict__ stats) {
+  const int b = blockIdx.x, ch = threadIdx.x;
+  if (ch >= c) return;
+  const int cg = c / 8;
+  double s1 = 0.0, s2 = 0.0;
+  if (ch % cg == 0) {
+    const int grp = ch / cg;
+    for (int u = 0; u < units; ++u) {
+      s1 += unit_stats[((size_t)b * units + u) * 16 + 2 * grp];
+      s2 += unit_stats[((size_t)b * units + u) * 16 + 2 * grp + 1];
+    }
+  }
+  stats[(size_t)b * c + ch] = make_double2(s1, s2);
+}
+
+static inline bool supported(int c_in, int c_out, int r) {
+  const bool pow2 = r >= 4 && r <= 64 && (r & (r - 1)) == 0;
+  return pow2 && (c_out == 32 || c_out == 64 || c_out == 128) && (c_in == 32 || (c_in >= 64 && c_in % 64 == 0 && c_in <= 512));
+}
+static inline int kc_of(int c_in) { return c_in == 32 ? 32 : 64; }
+static inline int tg_of(int c_in, int c_out) {      // taps per weight stage: keep a stage between 8 and 24 KB
+  const int tap_bytes = c_out * kc_of(c_in) * 2;
+  return tap_bytes <= 2048 ? 9 : (tap_bytes <= 8192 ? 3 : 1);
+}
+
+template <int N, int KC, int TG>
+static int launch_conv(int b, int c_in, const Geometry &geo, const __half *xh, const unsigned char *wprep, const float *bias,
+                       float *out, double *unit_stats, cudaStream_t st) {
+  using C = Cfg<N, KC, TG>;
+  const int a_stage_bytes = (int)align_up((size_t)C::kChunks * geo.slab_rows * 16, 128);
+  const size_t smem_bytes = (size_t)kAStages * a_stage_bytes + (size_t)C::kWStages * C::kWStageBytes + C::kNumBars * 8 + 16 +
+                            2 * 8 * 16 * sizeof(float);
+  if (smem_bytes > 227 * 1024) return BDM_ERR_BAD_SIZE;
+  cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void *>(conv3_tc05_kernel<N, KC, TG>), smem_bytes);
+  if (e != cudaSuccess) return (int)e;
+  const int total_units = b * geo.units;
+  const int grid = total_units < sm_count() ? total_units : sm_count();
+  conv3_tc05_kernel<N, KC, TG><<<grid, kThreads, smem_bytes, st>>>(b, c_in, geo, a_stage_bytes, xh, wprep, bias, out, unit_stats);
+  BDM_RETURN_LAUNCH_STATUS();
+}
+
+}  // namespace cv3
+}  // namespace bdm
+
+using namespace bdm;
+
+extern "C" int bdm_conv3_tc05_supported(int c_in, int c_out, int r) { return cv3::supported(c_in, c_out, r) ? 1 : 0; }
+
+/* rows of one fp16 chunk plane of the padded activation array for b samples at resolution r */
+extern "C" long long bdm_conv3_tc05_plane_rows(int b, int r) {
+  if (b <= 0 || r <= 0) return 0;
+  return cv3::conv3_geometry(b, r).total_rows;
+}
+extern "C" int bdm_conv3_tc05_units(int r) {
+  if (r <= 0) return 0;
+  return cv3::conv3_geometry(1, r).units;
+}
+extern "C" size_t bdm_conv3_tc05_weight_bytes(int c_in, int c_out) {
+  if (c_in <= 0 || c_out <= 0) return 0;
+  return cv3::kHeaderBytes + (size_t)27 * c_in * c_out * 2;
+}
+
+extern "C" int bdm_conv3_tc05_prepare(int c_in, int c_out, const float *weight, const float *gamma, const float *beta,
+                                      long long group_elems, void *prepared, size_t prepared_bytes, bdm_stream_t stream) {
+  BDM_CHECK_SIZE(c_in > 0 && c_out > 0 && group_elems > 0);
+  BDM_CHECK_SIZE(c_in == 32 || c_in % 64 == 0);
+  BDM_CHECK_PTR(weight); BDM_CHECK_PTR(prepared);
+  if (prepared_bytes < bdm_conv3_tc05_weight_bytes(c_in, c_out)) return BDM_ERR_WORKSPACE_TOO_SMALL;
+  if ((reinterpret_cast<uintptr_t>(prepared) & 255) != 0) return BDM_ERR_MISALIGNED;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  float *header = static_cast<float *>(prepared);
+  cv3::conv3_prep_header_kernel<<<1, 1024, 0, st>>>((size_t)27 * c_in * c_out, weight, c_in, gamma, beta, (float)group_elems, header);
+  const size_t total = (size_t)27 * c_in * c_out;
+  const int blocks = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
+  cv3::conv3_prep_weights_kernel<<<blocks, 256, 0, st>>>(
+      c_in, c_out, cv3::kc_of(c_in), cv3::tg_of(c_in, c_out), weight, header,
+      reinterpret_cast<__half *>(static_cast<unsigned char *>(prepared) + cv3::kHeaderBytes));
+  BDM_RETURN_LAUNCH_STATUS();
+}
+
+extern "C" int bdm_groupnorm_swish_half_planar(int b, int c, int r, int groups, float eps, int swish, const float *x,
+                                               const float *conv_bias, const float *gamma, const float *beta,
+                                               const double *partials, int chunks, const void *prepared, void *xh,
+                                               long long plane_rows, bdm_stream_t stream) {
+  BDM_CHECK_SIZE(b >= 0 && b <= 65535 && c >= 8 && c % 8 == 0 && c <= 256 && 256 % c == 0 && groups >= 1 && groups <= 32 &&
+                 c % groups == 0 && chunks >= 1 && r >= 2 && r <= 64 && (r & (r - 1)) == 0);
+  if (b == 0) return BDM_OK;
+  BDM_CHECK_PTR(x); BDM_CHECK_PTR(partials); BDM_CHECK_PTR(prepared); BDM_CHECK_PTR(xh);
+  const cv3::Geometry geo = cv3::conv3_geometry(b, r);
+  BDM_CHECK_SIZE(plane_rows == geo.total_rows);
+  if (((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(xh)) & 15) != 0) return BDM_ERR_MISALIGNED;
+  const long long s = (long long)r * r * r;
+  const int rpp = cv3::kApplyThreads / (c / 8);
+  long long want = ((long long)8 * sm_count() + b - 1) / b;
+  long long maxt = (s + 4LL * rpp - 1) / (4LL * rpp);
+  const int ntiles = (int)(want < maxt ? (want < 1 ? 1 : want) : (maxt < 1 ? 1 : maxt));
+  cv3::gn_apply_half_planar_kernel<<<dim3(ntiles, b), cv3::kApplyThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      c, r, groups, chunks, ntiles, eps, swish, x, conv_bias, gamma, beta, reinterpret_cast<const double2 *>(partials),
+      static_cast<const float *>(prepared), static_cast<__half *>(xh), geo.guard, geo.sample_rows, geo.total_rows);
+  BDM_RETURN_LAUNCH_STATUS();
+}
+
+/* out f32[b][r^3][c_out] (channels last) = conv3x3x3(xh) + bias; stats (or NULL) f64[b][1][c_out][2] receives the
+ * per-group (sum, sum of squares) of the result in the layout bdm_groupnorm_act_cl(precomputed_chunks = 1) takes
+ * (8 groups); workspace: b * units * 16 doubles when stats != NULL. */
+extern "C" size_t bdm_conv3_tc05_workspace_bytes(int b, int r) {
+  if (b <= 0 || r <= 0) return 16;
+  return (size_t)b * cv3::conv3_geometry(b, r).units * 16 * sizeof(double);
+}
+extern "C" int bdm_conv3_tc05(int b, int c_in, int c_out, int r, const void *xh, long long plane_rows, const void *prepared,
+                              const float *bias, float *out, double *stats, void *workspace, size_t workspace_bytes,
+                              bdm_stream_t stream) {
+  BDM_CHECK_SIZE(b >= 0 && cv3::supported(c_in, c_out, r));
+  if (b == 0) return BDM_OK;
+  BDM_CHECK_PTR(xh); BDM_CHECK_PTR(prepared); BDM_CHECK_PTR(out);
+  const cv3::Geometry geo = cv3::conv3_geometry(b, r);
+  BDM_CHECK_SIZE(plane_rows == geo.total_rows && (long long)b * geo.units < 0x7fffffffLL);
+  if (((reinterpret_cast<uintptr_t>(xh) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(prepared)) & 15) != 0)
+    return BDM_ERR_MISALIGNED;
+  double *unit_stats = nullptr;
+  if (stats != nullptr) {
+    BDM_CHECK_PTR(workspace);
+    if (workspace_bytes < bdm_conv3_tc05_workspace_bytes(b, r)) return BDM_ERR_WORKSPACE_TOO_SMALL;
+    unit_stats = static_cast<double *>(workspace);
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const __half *x = static_cast<const __half *>(xh);
+  const unsigned char *wp = static_cast<const unsigned char *>(prepared);
+  int rc;
+  const int kc = cv3::kc_of(c_in);
+  if (c_out == 32 && kc == 32) rc = cv3::launch_conv<32, 32, 9>(b, c_in, geo, x, wp, bias, out, unit_stats, st);
+  else if (c_out == 32) rc = cv3::launch_conv<32, 64, 3>(b, c_in, geo, x, wp, bias, out, unit_stats, st);
+  else if (c_out == 64 && kc == 32) rc = cv3::launch_conv<64, 32, 3>(b, c_in, geo, x, wp, bias, out, unit_stats, st);
+  else if (c_out == 64) rc = cv3::launch_conv<64, 64, 3>(b, c_in, geo, x, wp, bias, out, unit_stats, st);
+  else if (kc == 32) rc = cv3::launch_conv<128, 32, 3>(b, c_in, geo, x, wp, bias, out, unit_stats, st);
+  else rc = cv3::launch_conv<128, 64, 1>(b, c_in, geo, x, wp, bias, out, unit_stats, st);
+  if (rc != BDM_OK) return rc;
+  if (stats != nullptr) {
+    cv3::conv3_stats_fold_kernel<<<b, c_out, 0, st>>>(geo.units, c_out, unit_stats, reinterpret_cast<double2 *>(stats));
+    BDM_RETURN_LAUNCH_STATUS();
+  }
+  return BDM_OK;
+}

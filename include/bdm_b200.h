@@ -291,6 +291,40 @@ int bdm_groupnorm_act_cl(int b, int c, long long s, int groups, float eps, int s
 /* precomputed_chunks > 0: workspace holds the producer's statistics f64[b,precomputed_chunks,c,2] (see
  * bdm_sparse_conv3_gather) and the statistics pass over x is skipped. */
 
+/* ---- dense side: the 3x3x3 convolution of the voxel branch on the 5th-generation tensor cores -------------------
+ * replaces the second nn.Conv3d(c, c, 3, padding=1) of a PVConv block's voxel_layers (modules/pvconv.py:75-88), which
+ * torch hands to cuDNN (TF32 under the default conv policy), together with the GroupNorm+Swish pass in front of it
+ * (which now writes the convolution's fp16 operand directly) and the statistics pass of the GroupNorm behind it.
+ * Precision: operands rounded to fp16 after a power-of-two scaling (11 significant bits, as TF32 keeps), exact
+ * products, fp32 accumulation in tensor memory.
+ *   activations xh: fp16 "chunk planes" [c_in/8][plane_rows][8] of the flat padded grid (position of voxel (x,y,z) of
+ *       sample i: guard + i*sample_rows + (x*(r+1)+y)*(r+1)+z, see csrc/conv3_tc05.cu); the buffer must be zero-filled
+ *       once by the caller (pad positions are never written), plane_rows = bdm_conv3_tc05_plane_rows(b, r).
+ *   bdm_conv3_tc05_prepare   weight f32[c_out][c_in][3][3][3] -> `prepared` (bdm_conv3_tc05_weight_bytes, 256-byte
+ *       aligned): scales + the per-stage shared-memory images of the weights.  gamma / beta f32[c_in] (or NULL) and
+ *       group_elems (elements of one normalisation group) are those of the GroupNorm that produces xh: they bound
+ *       the activations for the fp16 scaling.  Once per weight version.
+ *   bdm_groupnorm_swish_half_planar   x f32[b][r^3][c] channels-last + its producer's statistics partials
+ *       f64[b][chunks][c][2] (of the bias-less tensor) -> act(group_norm(x + conv_bias)) * act_scale as xh.
+ *   bdm_conv3_tc05   out f32[b][r^3][c_out] = conv(xh) + bias; stats (or NULL): f64[b][1][c_out][2], the result's
+ *       GroupNorm(8) statistics in the layout bdm_groupnorm_act_cl(precomputed_chunks = 1) takes; workspace:
+ *       bdm_conv3_tc05_workspace_bytes(b, r) bytes when stats != NULL.
+ * c_out in {32, 64, 128}, c_in = 32 or a multiple of 64, r a power of two (bdm_conv3_tc05_supported). */
+int bdm_conv3_tc05_supported(int c_in, int c_out, int r);
+long long bdm_conv3_tc05_plane_rows(int b, int r);
+int bdm_conv3_tc05_units(int r);
+size_t bdm_conv3_tc05_weight_bytes(int c_in, int c_out);
+size_t bdm_conv3_tc05_workspace_bytes(int b, int r);
+int bdm_conv3_tc05_prepare(int c_in, int c_out, const float *weight, const float *gamma, const float *beta,
+                           long long group_elems, void *prepared, size_t prepared_bytes, bdm_stream_t stream);
+int bdm_groupnorm_swish_half_planar(int b, int c, int r, int groups, float eps, int swish, const float *x,
+                                    const float *conv_bias, const float *gamma, const float *beta,
+                                    const double *partials, int chunks, const void *prepared, void *xh,
+                                    long long plane_rows, bdm_stream_t stream);
+int bdm_conv3_tc05(int b, int c_in, int c_out, int r, const void *xh, long long plane_rows, const void *prepared,
+                   const float *bias, float *out, double *stats, void *workspace, size_t workspace_bytes,
+                   bdm_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -384,10 +384,18 @@ conv3_tc05_kernel(int b, int c_in, Geometry geo, int a_stage_bytes, const __half
     }
   } else if (warp == 2) {
     // ===================== MMA issuer =====================
+    // One thread issues every MMA of the CTA, so the instructions per MMA matter (a first version that rebuilt both
+    // 64-bit descriptors from scratch spent ~87 clocks per MMA whatever its shape).  A descriptor's upper word is
+    // constant; its lower word is (address >> 4) | (LBO >> 4) << 16, and since an activation row is 16 bytes a window
+    // shift of n rows is simply +n on that word.  Taps and k-steps are unrolled: their offsets are immediates or one
+    // of a few registers.
     if (lane == 0) {
       constexpr uint32_t idesc = instr_desc(N);
+      constexpr uint32_t desc_hi = (128u >> 4) | (1u << 14);           // SBO = 128 bytes, descriptor version 1
       int sa = 0, sw = 0; uint32_t pa = 0, pw = 0;
-      const uint32_t a_lbo = (uint32_t)slab_rows * 16u, b_lbo = N * 16u;
+      const uint32_t a_lbo16 = (uint32_t)slab_rows, b_lbo16 = (uint32_t)N;      // LBO in 16-byte units
+      const uint32_t kstep = 2u * a_lbo16;                               // rows (16-byte units) per K=16 step
+      const uint32_t q1 = (uint32_t)geo.q, q2 = 2u * (uint32_t)geo.q;
       int it = 0;
       for (int g = blockIdx.x; g < total_units; g += gridDim.x, ++it) {
         const int buf = it & 1;
@@ -399,30 +407,36 @@ conv3_tc05_kernel(int b, int c_in, Geometry geo, int a_stage_bytes, const __half
           for (int kc = 0; kc < nkc; ++kc) {
             bar_wait(a_full + sa, pa);
             tc_fence_after();
-            const uint32_t ab = smem_u32(a_smem + sa * a_stage_bytes);
+            const uint32_t a_lo = (smem_u32(a_smem + sa * a_stage_bytes) >> 4) | (a_lbo16 << 16);
+#pragma unroll
             for (int grp = 0; grp < C::kNG; ++grp) {
               bar_wait(w_full + sw, pw);
               tc_fence_after();
-              const uint32_t wb = smem_u32(w_smem + sw * C::kWStageBytes);
+              const uint32_t b_lo = (smem_u32(w_smem + sw * C::kWStageBytes) >> 4) | (b_lbo16 << 16);
 #pragma unroll
               for (int j = 0; j < TG; ++j) {
                 const int tap = grp * TG + j;
                 const int dy = tap / 3, dz = tap - dy * 3;
-                const uint32_t a_row = (uint32_t)(dy * geo.q + dz) * 16u;
+                const uint32_t a_tap = a_lo + (dy == 0 ? 0u : (dy == 1 ? q1 : q2)) + (uint32_t)dz;
 #pragma unroll
                 for (int t = 0; t < 2; ++t) {
 #pragma unroll
                   for (int k = 0; k < C::kK16; ++k) {
-                    const uint64_t da = smem_desc(ab + a_row + t * 128 * 16 + k * 2 * a_lbo, a_lbo, 128);
-                    const uint64_t db = smem_desc(wb + j * C::kTapBytes + k * 2 * b_lbo, b_lbo, 128);
-                    umma_f16(d0 + t * N, da, db, idesc, acc | (uint32_t)k);
+                    const uint32_t da_lo = a_tap + (uint32_t)(t * 128) + (uint32_t)k * kstep;
+                    const uint32_t db_lo = b_lo + (uint32_t)(j * (C::kTapBytes >> 4) + k * 2 * N);
+                    const uint32_t accumulate = (tap == 0 && k == 0) ? acc : 1u;
+                    asm volatile(
+                        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %5, 0;\n\t"
+                        "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %2};\n\t"
+                        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
+                        ::"r"(d0 + t * N), "r"(da_lo), "r"(desc_hi), "r"(db_lo), "r"(idesc), "r"(accumulate) : "memory");
                   }
                 }
-                acc = 1;
               }
               umma_commit(w_empty + sw);
               if (++sw == C::kWStages) { sw = 0; pw ^= 1; }
             }
+            acc = 1;
             umma_commit(a_empty + sa);
             if (++sa == kAStages) { sa = 0; pa ^= 1; }
           }

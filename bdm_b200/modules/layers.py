@@ -22,6 +22,13 @@ FUSED_NORM_ACT = os.environ.get("BDM_FUSED_NORM", "1") != "0"
 # Fused online-softmax attention kernel (csrc/attention.cu) for the 64-channel attention block, inference
 # on CUDA; fp32-equivalent (3xTF32).  BDM_FUSED_ATTENTION=0 keeps torch's matmul / softmax / matmul.
 FUSED_ATTENTION = os.environ.get("BDM_FUSED_ATTENTION", "1") != "0"
+# The dense second 3x3x3 convolution of a voxel stack on the tcgen05 tensor cores (csrc/conv3_tc05.cu) instead of
+# cuDNN's TF32 kernels: the GroupNorm+Swish in front of it writes the convolution's fp16 operand, the convolution
+# adds its bias and emits the statistics of the GroupNorm behind it.  Taken only when torch itself would run the
+# convolution in TF32 (torch.backends.cudnn.allow_tf32), on grids of at least CONV3_TC05_MIN_R^3 voxels (cuDNN is
+# faster on the 8^3 grids: too few 128-row tiles for 148 SMs).  BDM_CONV3_TC05=0 disables.
+CONV3_TC05 = os.environ.get("BDM_CONV3_TC05", "1") != "0"
+CONV3_TC05_MIN_R = int(os.environ.get("BDM_CONV3_TC05_MIN_R", "16"))
 
 
 _TF32_LOCK = threading.RLock()
@@ -97,6 +104,45 @@ def norm_act(norm, x, swish=True):
 
 
 _CONVS = (nn.Conv1d, nn.Conv2d, nn.Conv3d)
+
+
+def _plain_conv3(m):
+    return (isinstance(m, nn.Conv3d) and m.kernel_size == (3, 3, 3) and m.stride == (1, 1, 1) and m.padding == (1, 1, 1)
+            and m.dilation == (1, 1, 1) and m.groups == 1 and m.padding_mode == 'zeros')
+
+
+def conv3_tc05_applicable(conv, gn_before, channels, resolution):
+    """Can `conv` (fed by GroupNorm `gn_before` + Swish over a channels-last [B,R,R,R,C] grid) take the tcgen05 route?"""
+    return (CONV3_TC05 and hasattr(_ops._B, "conv3_tc05") and bool(torch.backends.cudnn.allow_tf32)
+            and _plain_conv3(conv) and conv.in_channels == channels and isinstance(gn_before, nn.GroupNorm)
+            and channels % gn_before.num_groups == 0 and 256 % channels == 0 and channels >= 8
+            and resolution >= CONV3_TC05_MIN_R
+            and _ops._B.conv3_tc05_supported(conv.in_channels, conv.out_channels, resolution))
+
+
+_HALF_PLANES = {}     # (B, C, R, device) -> backend.HalfPlanes: scratch between a norm and its convolution, shared by
+                      # every block of that shape (pad rows are zero once and for all; stream order serialises reuse)
+
+
+def _half_planes(b, c, r, device):
+    key = (int(b), int(c), int(r), str(device))
+    planes = _HALF_PLANES.get(key)
+    if planes is None:
+        planes = _HALF_PLANES[key] = _ops._B.HalfPlanes(b, c, r, device)
+    return planes
+
+
+def _conv3_prepared(conv, gn, group_elems):
+    """scales + fp16 weight stages of `conv` (whose input GroupNorm `gn` produces), cached per parameter version"""
+    params = (conv.weight, gn.weight, gn.bias)
+    key = tuple((p.data_ptr(), geometry.tensor_version(p), p.device) if p is not None else None for p in params) + (int(group_elems),)
+    cached = getattr(conv, "_tc05_prepared", None)
+    if cached is None or cached[0] != key:
+        cached = (key, _ops._B.conv3_tc05_prepare(conv.weight.detach().contiguous(),
+                                                 gn.weight.detach() if gn.weight is not None else None,
+                                                 gn.bias.detach() if gn.bias is not None else None, group_elems))
+        conv._tc05_prepared = cached
+    return cached[1]
 
 
 def conv_no_bias_concat(m, parts):
@@ -200,9 +246,9 @@ class FusedSequential(nn.Sequential):
         i = 0
         reduced = False
         gate = None
+        pre, pre_stats, pre_biased = first_output, first_stats, False   # output of mods[i] made by other means
         while i < n:
             m = mods[i]
-            pre = first_output if i == 0 else None
             fusable = _fusable(x if pre is None else pre)
             if (fusable and isinstance(m, _CONVS) and m.bias is not None and i + 1 < n
                     and isinstance(mods[i + 1], nn.GroupNorm)):
@@ -210,8 +256,28 @@ class FusedSequential(nn.Sequential):
                 swish = i + 2 < n and isinstance(mods[i + 2], Swish)
                 nxt = i + (3 if swish else 2)
                 y = pre if pre is not None else conv_no_bias(m, x)
+                cbias = None if (pre is not None and pre_biased) else m.bias
+                stats = pre_stats if pre is not None else None
+                pre = pre_stats = None
+                pre_biased = False
+                # conv -> norm -> Swish [-> Dropout (inference: identity)] -> 3x3x3 conv: tcgen05 route for the second conv
+                j = nxt
+                if j < n and isinstance(mods[j], nn.Dropout) and not mods[j].training:
+                    j += 1
+                if (swish and stats is not None and j < n and is_channels_last_3d(y) and y.shape[2] == y.shape[3] == y.shape[4]
+                        and conv3_tc05_applicable(mods[j], gn, y.shape[1], y.shape[2])):
+                    conv2 = mods[j]
+                    nb, nc, r = y.shape[0], y.shape[1], y.shape[2]
+                    prepared = _conv3_prepared(conv2, gn, (nc // gn.num_groups) * r ** 3)
+                    planes = _half_planes(nb, nc, r, y.device)
+                    _ops._B.groupnorm_swish_half_planar(y.permute(0, 2, 3, 4, 1), gn.num_groups, gn.weight, gn.bias, gn.eps,
+                                                        True, cbias, stats, prepared, planes)
+                    out2, pre_stats = _ops._B.conv3_tc05(planes, prepared, conv2.out_channels, bias=conv2.bias, stats=True)
+                    pre, pre_biased = out2.permute(0, 4, 1, 2, 3), True
+                    i = j
+                    continue
                 if nxt < n and isinstance(mods[nxt], SE3d) and swish:
-                    y, sums = _groupnorm_act(y, gn, True, conv_bias=m.bias, channel_sums=True)
+                    y, sums = _groupnorm_act(y, gn, True, conv_bias=cbias, channel_sums=True, partials=stats)
                     if defer_gate and nxt == n - 1:
                         x, gate = y, mods[nxt].gate(y, channel_sums=sums)
                     else:
@@ -219,18 +285,20 @@ class FusedSequential(nn.Sequential):
                     nxt += 1
                 elif (max_over_last and nxt == n and swish and y.dim() == 4
                       and _ops._B.groupnorm_max_supported(y.shape[-1])):
-                    x = _groupnorm_act(y, gn, True, conv_bias=m.bias, max_over_last=True)
+                    x = _groupnorm_act(y, gn, True, conv_bias=cbias, max_over_last=True)
                     reduced = True
                 else:
-                    x = _groupnorm_act(y, gn, swish, conv_bias=m.bias, partials=first_stats if pre is not None else None)
+                    x = _groupnorm_act(y, gn, swish, conv_bias=cbias, partials=stats)
                 i = nxt
             elif pre is not None:
-                x = pre if m.bias is None else pre + m.bias.view(1, -1, *([1] * (pre.dim() - 2)))
+                x = pre if (m.bias is None or pre_biased) else pre + m.bias.view(1, -1, *([1] * (pre.dim() - 2)))
+                pre = pre_stats = None
+                pre_biased = False
                 i += 1
             elif fusable and isinstance(m, nn.GroupNorm) and i + 1 < n and isinstance(mods[i + 1], Swish):
                 x = norm_act(m, x, True)
                 i += 2
-            elif (isinstance(m, Attention) and i + 1 < n and isinstance(mods[i + 1], SE3d) and pre is None
+            elif (isinstance(m, Attention) and i + 1 < n and isinstance(mods[i + 1], SE3d)
                   and m.fused_applicable(x)):
                 # the attention block hands the SE squeeze its per-channel sums (no three chained means over the grid)
                 y, sums = m.forward_fused(x, channel_sums=True)

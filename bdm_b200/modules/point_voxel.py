@@ -179,9 +179,12 @@ class _PVConvBase(nn.Module):
         if (CHANNELS_LAST_VOXELS and hasattr(_ops._B, "groupnorm_act_cl")
                 and _ops._B.groupnorm_cl_supported(self.out_channels, 8)):
             norm = self.voxel_layers[1]
+            second = next((m for m in list(self.voxel_layers)[2:] if isinstance(m, nn.Conv3d)), None)
             if (isinstance(norm, nn.GroupNorm) and _layers.FUSED_NORM_ACT
-                    and (self.out_channels // norm.num_groups) * vox.r ** 3 > 32768):
-                # group too large for the one-pass norm: the gather also emits the norm's statistics
+                    and ((self.out_channels // norm.num_groups) * vox.r ** 3 > 32768
+                         or (second is not None and _layers.conv3_tc05_applicable(second, norm, self.out_channels, vox.r)))):
+                # group too large for the one-pass norm, or the norm feeds the tcgen05 convolution (which wants the
+                # statistics up front): the gather also emits the norm's statistics
                 out, stats = _ops._B.sparse_conv3_gather(taps, plan, channels_last=True, stats=True)
                 return (out.permute(0, 4, 1, 2, 3), stats), norm_coords
             return _ops._B.sparse_conv3_gather(taps, plan, channels_last=True).permute(0, 4, 1, 2, 3), norm_coords

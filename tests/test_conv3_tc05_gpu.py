@@ -1,0 +1,185 @@
+"""GPU: the tcgen05 3x3x3 convolution route (csrc/conv3_tc05.cu) -- GroupNorm+Swish -> fp16 chunk planes ->
+implicit-GEMM convolution with bias and GroupNorm statistics -- against float64 torch, and against cuDNN's TF32
+convolution, which is what the reference runs here (modules/pvconv.py:75-88 under torch's default conv policy).
+
+Tolerance: the route rounds operands to 11 significant bits exactly like TF32 does, so its error against float64
+must not exceed cuDNN-TF32's error on the same input (x 1.5 for sampling noise), and both sit near 3e-4 of the
+output's peak; statistics are compared at 1e-5."""
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+# (batch, resolution, c_in, c_out): every template instance of the kernel, odd batches, ragged last units
+CASES = [(2, 8, 32, 32), (3, 16, 64, 64), (1, 32, 32, 32), (2, 16, 128, 128), (1, 32, 64, 64), (2, 8, 256, 128),
+         (2, 16, 64, 32), (5, 16, 32, 64), (3, 8, 32, 128), (1, 4, 64, 64)]
+
+
+def _inputs(b, r, cin, cout, seed, gamma_scale=1.0, w_scale=1.0):
+    import torch
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    x = torch.randn(b, r, r, r, cin, device="cuda", generator=g) * 1.7 + 0.3
+    cb = torch.randn(cin, device="cuda", generator=g) * 0.2
+    gamma = (torch.rand(cin, device="cuda", generator=g) + 0.5) * gamma_scale
+    beta = torch.randn(cin, device="cuda", generator=g) * 0.1 * gamma_scale
+    w = torch.randn(cout, cin, 3, 3, 3, device="cuda", generator=g) / (27 * cin) ** 0.5 * w_scale
+    bias = torch.randn(cout, device="cuda", generator=g) * 0.1 * w_scale * gamma_scale
+    return x, cb, gamma, beta, w, bias
+
+
+def _partials(x):
+    import torch
+    b, c = x.shape[0], x.shape[-1]
+    xs = x.reshape(b, -1, c).double()
+    return torch.stack([xs.sum(1), (xs * xs).sum(1)], dim=-1).reshape(b, 1, c, 2).contiguous()
+
+
+def _route(B, x, cb, gamma, beta, w, bias, groups=8, eps=1e-5):
+    b, r, cin = x.shape[0], x.shape[1], x.shape[-1]
+    prepared = B.conv3_tc05_prepare(w, gamma, beta, (cin // groups) * r ** 3)
+    planes = B.HalfPlanes(b, cin, r, x.device)
+    B.groupnorm_swish_half_planar(x, groups, gamma, beta, eps, True, cb, _partials(x), prepared, planes)
+    out, stats = B.conv3_tc05(planes, prepared, w.shape[0], bias=bias, stats=True)
+    return out, stats, planes, prepared
+
+
+def _reference64(x, cb, gamma, beta, w, bias, groups=8, eps=1e-5):
+    import torch
+    import torch.nn.functional as TF
+    xd = (x.double() + cb.double()).permute(0, 4, 1, 2, 3)
+    act = TF.group_norm(xd, groups, gamma.double(), beta.double(), eps)
+    act = act * torch.sigmoid(act)
+    return act, TF.conv3d(act, w.double(), bias.double(), padding=1).permute(0, 2, 3, 4, 1)
+
+
+@pytest.mark.parametrize("b,r,cin,cout", CASES)
+def test_conv3_tc05_vs_float64_and_cudnn_tf32(b, r, cin, cout, cuda_backend):
+    import torch
+    import torch.nn.functional as TF
+    B = cuda_backend
+    assert B.conv3_tc05_supported(cin, cout, r)
+    x, cb, gamma, beta, w, bias = _inputs(b, r, cin, cout, 1000 * b + r + cin)
+    out, stats, _, _ = _route(B, x, cb, gamma, beta, w, bias)
+    act, ref = _reference64(x, cb, gamma, beta, w, bias)
+    saved = torch.backends.cudnn.allow_tf32
+    try:
+        torch.backends.cudnn.allow_tf32 = True
+        tf32 = TF.conv3d(act.float().contiguous(memory_format=torch.channels_last_3d),
+                         w.contiguous(memory_format=torch.channels_last_3d), bias, padding=1).permute(0, 2, 3, 4, 1)
+    finally:
+        torch.backends.cudnn.allow_tf32 = saved
+    peak = ref.abs().max().item()
+    e_ours = (out.double() - ref).abs().max().item() / peak
+    e_tf32 = (tf32.double() - ref).abs().max().item() / peak
+    assert e_ours <= 1.5 * e_tf32 + 2e-6, (e_ours, e_tf32)
+    assert e_ours <= 1e-3, e_ours
+    # statistics of the result: per-group sums in the group's first channel slot, zeros elsewhere
+    od = out.double().reshape(b, -1, cout)
+    cg = cout // 8
+    want1 = od.sum(1).reshape(b, 8, cg).sum(-1)
+    want2 = (od * od).sum(1).reshape(b, 8, cg).sum(-1)
+    got = stats.reshape(b, 8, cg, 2)
+    assert ((got[:, :, 0, 0] - want1).abs() <= 1e-5 * (want2.sqrt() + 1)).all()
+    assert ((got[:, :, 0, 1] - want2).abs() <= 1e-5 * (want2 + 1)).all()
+    if cg > 1:
+        assert got[:, :, 1:].abs().max().item() == 0.0
+
+
+@pytest.mark.parametrize("b,r,c", [(2, 16, 64), (3, 8, 32), (1, 32, 128)])
+def test_half_planes_hold_the_activation_and_zero_pads(b, r, c, cuda_backend):
+    """decode the fp16 chunk planes back to [B,R,R,R,C]: GroupNorm+Swish to fp16 rounding; every other row is zero"""
+    import torch
+    import torch.nn.functional as TF
+    B = cuda_backend
+    x, cb, gamma, beta, w, bias = _inputs(b, r, c, c, 77 + r)
+    _, _, planes, prepared = _route(B, x, cb, gamma, beta, w, bias)
+    act_scale = prepared[:12].view(torch.float32)[1].item()
+    assert act_scale == 1.0
+    q = r + 1
+    guard = (q * q + q + 1 + 7) // 8 * 8
+    srows = (guard + q ** 3 + 7) // 8 * 8
+    data = planes.data                                            # [C/8, rows, 8]
+    full = data.permute(1, 0, 2).reshape(planes.rows, c)          # [rows, C]
+    want = TF.group_norm((x + cb).permute(0, 4, 1, 2, 3), 8, gamma, beta, 1e-5)
+    want = (want * torch.sigmoid(want)).permute(0, 2, 3, 4, 1)
+    mask = torch.zeros(planes.rows, dtype=torch.bool, device="cuda")
+    for i in range(b):
+        vol = full[guard + i * srows: guard + i * srows + q ** 3].reshape(q, q, q, c)
+        got = vol[:r, :r, :r].float()
+        assert (got - want[i]).abs().max().item() <= 1e-3 * want.abs().max().item()     # fp16: 2^-11 relative
+        assert vol[r].abs().max().item() == 0 and vol[:, r].abs().max().item() == 0 and vol[:, :, r].abs().max().item() == 0
+        m = torch.zeros(q, q, q, dtype=torch.bool, device="cuda")
+        m[:r, :r, :r] = True
+        mask[guard + i * srows: guard + i * srows + q ** 3] = m.reshape(-1)
+    assert full[~mask].abs().max().item() == 0
+
+
+def test_scaling_keeps_extreme_operands_in_range(cuda_backend):
+    """huge GroupNorm affine (activations beyond fp16's range without the scale) and tiny weights (below fp16's
+    normal range without the scale): same relative accuracy"""
+    import torch
+    B = cuda_backend
+    for gs, ws in ((3.0e3, 1.0), (1.0, 1.0e-7), (2.0e3, 1.0e-6)):
+        x, cb, gamma, beta, w, bias = _inputs(2, 16, 64, 64, 5, gamma_scale=gs, w_scale=ws)
+        out, _, _, prepared = _route(B, x, cb, gamma, beta, w, bias)
+        _, ref = _reference64(x, cb, gamma, beta, w, bias)
+        assert torch.isfinite(out).all()
+        err = (out.double() - ref).abs().max().item() / ref.abs().max().item()
+        assert err <= 1e-3, (gs, ws, err)
+        hdr = prepared[:12].view(torch.float32)
+        if gs > 100:
+            assert hdr[1].item() < 1.0      # activations were scaled down
+
+
+def test_voxel_stack_takes_the_tcgen05_route_and_matches_cudnn(cuda_backend):
+    """PVConv blocks at the network's (channels, resolution) pairs: default route (tcgen05 second convolution)
+    against the same block with the route off (cuDNN TF32) and against fp32 convolutions"""
+    import torch
+
+    import bdm_b200.modules.layers as L
+    import bdm_b200.modules.point_voxel as PV
+    B = cuda_backend
+    for cin, cout, n, r, attention in ((32, 32, 4096, 32, False), (64, 64, 2048, 32, False), (64, 128, 1024, 16, False),
+                                       (32, 64, 1024, 16, True)):
+        torch.manual_seed(cin + n)
+        blk = PV.PVConv(cin, cout, 3, r, attention=attention, with_se=True).cuda().eval()
+        feats = torch.randn(3, cin, n, device="cuda")
+        u = torch.randn(3, 3, n, device="cuda")
+        coords = u / u.norm(dim=1, keepdim=True) * (0.5 + 0.02 * torch.randn(3, 1, n, device="cuda"))
+        temb = torch.randn(3, 8, n, device="cuda")
+        saved = (L.CONV3_TC05, torch.backends.cudnn.allow_tf32)
+        try:
+            with torch.no_grad():
+                torch.backends.cudnn.allow_tf32 = True
+                L.CONV3_TC05 = True
+                n0 = B.LAUNCHES
+                B.profile_start()
+                y_tc = blk((feats, coords, temb))[0]
+                prof = B.profile_stop()
+                assert "conv3_tc05" in prof and "groupnorm_swish_half_planar" in prof, sorted(prof)
+                L.CONV3_TC05 = False
+                y_cudnn = blk((feats, coords, temb))[0]
+                torch.backends.cudnn.allow_tf32 = False
+                y_fp32 = blk((feats, coords, temb))[0]
+        finally:
+            L.CONV3_TC05, torch.backends.cudnn.allow_tf32 = saved
+        peak = y_fp32.abs().max().item()
+        e_tc = (y_tc - y_fp32).abs().max().item() / peak
+        e_cudnn = (y_cudnn - y_fp32).abs().max().item() / peak
+        assert e_tc <= max(2.0 * e_cudnn, 2e-4), (cin, cout, r, e_tc, e_cudnn)
+
+
+def test_route_is_off_when_tf32_convolutions_are_off(cuda_backend):
+    import torch
+
+    import bdm_b200.modules.layers as L
+    conv = torch.nn.Conv3d(64, 64, 3, padding=1).cuda()
+    gn = torch.nn.GroupNorm(8, 64).cuda()
+    saved = torch.backends.cudnn.allow_tf32
+    try:
+        torch.backends.cudnn.allow_tf32 = True
+        assert L.conv3_tc05_applicable(conv, gn, 64, 32)
+        assert not L.conv3_tc05_applicable(conv, gn, 64, 8)          # cuDNN is faster on 8^3 grids
+        torch.backends.cudnn.allow_tf32 = False
+        assert not L.conv3_tc05_applicable(conv, gn, 64, 32)
+    finally:
+        torch.backends.cudnn.allow_tf32 = saved

@@ -99,6 +99,11 @@ def one(b, r, cin, cout, accuracy=True, timing=True):
 
 
 if __name__ == "__main__":
+    if "--only" in sys.argv:      # --only B R C: one timing case (for ncu)
+        i = sys.argv.index("--only")
+        b, r, c = (int(v) for v in sys.argv[i + 1:i + 4])
+        one(b, r, c, c, accuracy=False, timing=True)
+        sys.exit(0)
     for (b, r, cin, cout) in ((2, 8, 32, 32), (3, 16, 64, 64), (2, 32, 32, 32), (2, 16, 128, 128), (1, 32, 64, 64), (2, 8, 256, 128),
                               (2, 16, 64, 32), (2, 16, 32, 64)):
         one(b, r, cin, cout, accuracy=True, timing=False)

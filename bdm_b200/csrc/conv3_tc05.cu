@@ -121,7 +121,7 @@ __host__ __device__ inline Geometry conv3_geometry(int b, int r) {
   g.sample_rows = ((long long)g.guard + (long long)g.q * g.p + 7) / 8 * 8;
   g.slab_rows = kUnitRows + 2 * g.q + 2;
   // the last unit of the last sample reads up to units*256 + P + Q + 1 rows past its sample's first position
-  g.total_rows = (long long)g.guard + (long long)b * g.sample_rows + (long long)g.units * kUnitRows + g.guard + 8;
+  g.total_rows = (long long)g.guard + (long long)b * g.sample_rows + (long long)(last_valid + 1 + 2 * kUnitRows) + g.guard + 8;
   return g;
 }
 
@@ -254,7 +254,8 @@ gn_apply_half_planar_kernel(int c, int r, int groups, int nchunks, int ntiles, f
   __syncthreads();
   const float act_scale = __ldg(header + 1);
   const int c8 = c >> 3, rpp = kApplyThreads / c8;
-  const int j = t % c8, r0 = t / c8;
+  const int j = t % c8, r0 = t / c8;              // load side: 8 channels (chunk j) of voxel r0 of a pass: 1 KB per warp
+  const int jw = t / rpp, vw = t % rpp;           // store side: voxel vw of chunk plane jw: 512 contiguous bytes per warp
   float2 co[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) co[i] = ab[8 * j + i];
@@ -264,9 +265,13 @@ gn_apply_half_planar_kernel(int c, int r, int groups, int nchunks, int ntiles, f
   per = (per + rpp - 1) / rpp * rpp;
   const long long lo = min((long long)tile * per, s), hi = min(lo + per, s);
   const float *px = x + (size_t)b * s * c + 8 * j;
-  __half *plane = xh + ((size_t)j * total_rows + (size_t)guard + (size_t)b * sample_rows) * 8;
-  auto emit = [&](long long row, const float4 &u, const float4 &w) {
-    float v[8] = {u.x, u.y, u.z, u.w, w.x, w.y, w.z, w.w};
+  __half *plane = xh + ((size_t)jw * total_rows + (size_t)guard + (size_t)b * sample_rows) * 8;
+  // A pass = rpp voxels x c8 chunks = 256 (voxel, chunk) pairs: loaded voxel-major (coalesced reads of the fp32 rows),
+  // transposed through shared memory, stored plane-major (coalesced writes of the fp16 chunk planes).
+  constexpr int UNR = 4;
+  __shared__ uint4 stage[UNR][kApplyThreads + 32];     // [chunk][rpp + 1] per pass: the +1 keeps the 8 chunks of a voxel in different banks
+  auto convert = [&](const float4 &u, const float4 &w) {
+    const float v[8] = {u.x, u.y, u.z, u.w, w.x, w.y, w.z, w.w};
     uint32_t h[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -275,23 +280,43 @@ gn_apply_half_planar_kernel(int c, int r, int groups, int nchunks, int ntiles, f
       const __half2 hh = __floats2half2_rn(a0 * act_scale, a1 * act_scale);
       h[i] = *reinterpret_cast<const uint32_t *>(&hh);
     }
-    const int vz = (int)row & (r - 1), vy = ((int)row >> sh) & (r - 1), vx = (int)row >> (2 * sh);
-    const long long p = ((long long)vx * q + vy) * q + vz;
-    *reinterpret_cast<uint4 *>(plane + (size_t)p * 8) = make_uint4(h[0], h[1], h[2], h[3]);
+    return make_uint4(h[0], h[1], h[2], h[3]);
   };
-  constexpr int UNR = 4;
-  long long row = lo + r0;
-  for (; row + (long long)(UNR - 1) * rpp < hi; row += (long long)UNR * rpp) {
-    float4 u[UNR], w[UNR];
+  auto dest = [&](long long row) {
+    const int vz = (int)row & (r - 1), vy = ((int)row >> sh) & (r - 1), vx = (int)row >> (2 * sh);
+    return plane + (size_t)(((long long)vx * q + vy) * q + vz) * 8;
+  };
+  const long long step = (long long)UNR * rpp;
+  long long base = lo;                             // first voxel of the current group of UNR passes
+  float4 u[UNR], w[UNR], un[UNR], wn[UNR];
+  auto load = [&](long long first, float4 (&a)[UNR], float4 (&bq)[UNR]) {
 #pragma unroll
     for (int k = 0; k < UNR; ++k) {
-      u[k] = ld_stream_f4(px + (size_t)(row + (long long)k * rpp) * c);
-      w[k] = ld_stream_f4(px + (size_t)(row + (long long)k * rpp) * c + 4);
+      const long long row = first + (long long)k * rpp + r0;
+      if (row < hi) {
+        a[k] = ld_stream_f4(px + (size_t)row * c);
+        bq[k] = ld_stream_f4(px + (size_t)row * c + 4);
+      }
     }
+  };
+  if (base < hi) load(base, u, w);
+  while (base < hi) {                              // uniform over the CTA
+    const long long nbase = base + step;
+    if (nbase < hi) load(nbase, un, wn);           // next group in flight while this one is converted and stored
 #pragma unroll
-    for (int k = 0; k < UNR; ++k) emit(row + (long long)k * rpp, u[k], w[k]);
+    for (int k = 0; k < UNR; ++k)
+      if (base + (long long)k * rpp + r0 < hi) stage[k][j * (rpp + 1) + r0] = convert(u[k], w[k]);
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < UNR; ++k) {
+      const long long row = base + (long long)k * rpp + vw;
+      if (row < hi) *reinterpret_cast<uint4 *>(dest(row)) = stage[k][jw * (rpp + 1) + vw];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < UNR; ++k) { u[k] = un[k]; w[k] = wn[k]; }
+    base = nbase;
   }
-  for (; row < hi; row += rpp) emit(row, ld_stream_f4(px + (size_t)row * c), ld_stream_f4(px + (size_t)row * c + 4));
 }
 
 // -------------------------------------------------------------------------------------------------------------
@@ -473,8 +498,15 @@ conv3_tc05_kernel(int b, int c_in, Geometry geo, int a_stage_bytes, const __half
         tmem_wait_ld();
         float f[32];
 #pragma unroll
+        for (int i4 = 0; i4 < 8; ++i4) {
+          const float4 bb = bias != nullptr ? __ldg(reinterpret_cast<const float4 *>(bias + c0) + i4) : make_float4(0.f, 0.f, 0.f, 0.f);
+          f[4 * i4] = fmaf(__uint_as_float(rr[4 * i4]), out_scale, bb.x);
+          f[4 * i4 + 1] = fmaf(__uint_as_float(rr[4 * i4 + 1]), out_scale, bb.y);
+          f[4 * i4 + 2] = fmaf(__uint_as_float(rr[4 * i4 + 2]), out_scale, bb.z);
+          f[4 * i4 + 3] = fmaf(__uint_as_float(rr[4 * i4 + 3]), out_scale, bb.w);
+        }
+#pragma unroll
         for (int i = 0; i < 32; ++i) {
-          f[i] = fmaf(__uint_as_float(rr[i]), out_scale, bias != nullptr ? __ldg(bias + c0 + i) : 0.0f);
           const float fv = valid ? f[i] : 0.0f;
           gs1[(c0 + i) / CG] += fv;
           gs2[(c0 + i) / CG] = fmaf(fv, fv, gs2[(c0 + i) / CG]);
@@ -488,19 +520,34 @@ conv3_tc05_kernel(int b, int c_in, Geometry geo, int a_stage_bytes, const __half
       tc_fence_before();
       bar_arrive(t_empty + buf);
       if (unit_stats != nullptr) {
+        // 16 values (sum, sum of squares of 8 groups) over 32 lanes as a halving butterfly: each step a lane hands half of
+        // what it still holds to its partner, so 8 + 4 + 2 + 1 + 1 = 16 shuffles instead of 16 x 5; fixed order
+        float v8[8], v4[4], v2[2], v1;
+        {
+          const bool up = (lane & 16) != 0;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-#pragma unroll
-          for (int d = 16; d >= 1; d >>= 1) {
-            gs1[i] += __shfl_xor_sync(0xffffffffu, gs1[i], d);
-            gs2[i] += __shfl_xor_sync(0xffffffffu, gs2[i], d);
+          for (int i = 0; i < 8; ++i) {    // value index k = 2 * group + (0: sum, 1: sum of squares); k < 8 <-> groups 0..3
+            const float lo_v = (i & 1) ? gs2[i >> 1] : gs1[i >> 1], hi_v = (i & 1) ? gs2[4 + (i >> 1)] : gs1[4 + (i >> 1)];
+            v8[i] = (up ? hi_v : lo_v) + __shfl_xor_sync(0xffffffffu, up ? lo_v : hi_v, 16);
           }
         }
-        float *rb = red + (buf * 8 + e) * 16;
-        if (lane == 0) {
+        {
+          const bool up = (lane & 8) != 0;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) { rb[2 * i] = gs1[i]; rb[2 * i + 1] = gs2[i]; }
+          for (int i = 0; i < 4; ++i) v4[i] = (up ? v8[i + 4] : v8[i]) + __shfl_xor_sync(0xffffffffu, up ? v8[i] : v8[i + 4], 8);
         }
+        {
+          const bool up = (lane & 4) != 0;
+#pragma unroll
+          for (int i = 0; i < 2; ++i) v2[i] = (up ? v4[i + 2] : v4[i]) + __shfl_xor_sync(0xffffffffu, up ? v4[i] : v4[i + 2], 4);
+        }
+        {
+          const bool up = (lane & 2) != 0;
+          v1 = (up ? v2[1] : v2[0]) + __shfl_xor_sync(0xffffffffu, up ? v2[0] : v2[1], 2);
+        }
+        v1 += __shfl_xor_sync(0xffffffffu, v1, 1);
+        float *rb = red + (buf * 8 + e) * 16;
+        if ((lane & 1) == 0) rb[((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1)] = v1;
         asm volatile("bar.sync 1, 256;" ::: "memory");
         if (e == 0 && lane < 16) {
           double a = 0.0;
@@ -522,20 +569,22 @@ conv3_tc05_kernel(int b, int c_in, Geometry geo, int a_stage_bytes, const __half
 
 // unit partials f64[b][units][8 groups][2] -> the GroupNorm kernels' producer-statistics format f64[b][1][c][2]:
 // the group's sums sit in its first channel's slot, the other channels hold zeros (the consumer adds the
-// channels of a group).  Fixed summation order: deterministic.
-__global__ void conv3_stats_fold_kernel(int units, int c, const double *__restrict__ unit_stats, double2 *__restrict__ stats) {
-  const int b = blockIdx.x, ch = threadIdx.x;
-  if (ch >= c) return;
+// channels of a group).  One warp per value, lanes stride the units, fixed shuffle tree: deterministic.
+__global__ void __launch_bounds__(512)
+conv3_stats_fold_kernel(int units, int c, const double *__restrict__ unit_stats, double2 *__restrict__ stats) {
+  __shared__ double sums[16];
+  const int b = blockIdx.x, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double a = 0.0;
+  for (int u = lane; u < units; u += 32) a += unit_stats[((size_t)b * units + u) * 16 + w];
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) a += __shfl_xor_sync(0xffffffffu, a, d);
+  if (lane == 0) sums[w] = a;
+  __syncthreads();
   const int cg = c / 8;
-  double s1 = 0.0, s2 = 0.0;
-  if (ch % cg == 0) {
+  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
     const int grp = ch / cg;
-    for (int u = 0; u < units; ++u) {
-      s1 += unit_stats[((size_t)b * units + u) * 16 + 2 * grp];
-      s2 += unit_stats[((size_t)b * units + u) * 16 + 2 * grp + 1];
-    }
+    stats[(size_t)b * c + ch] = ch % cg == 0 ? make_double2(sums[2 * grp], sums[2 * grp + 1]) : make_double2(0.0, 0.0);
   }
-  stats[(size_t)b * c + ch] = make_double2(s1, s2);
 }
 
 static inline bool supported(int c_in, int c_out, int r) {
@@ -653,6 +702,7 @@ extern "C" int bdm_conv3_tc05(int b, int c_in, int c_out, int r, const void *xh,
   const unsigned char *wp = static_cast<const unsigned char *>(prepared);
   int rc;
   const int kc = cv3::kc_of(c_in);
+  const int units = geo.units;
   if (c_out == 32 && kc == 32) rc = cv3::launch_conv<32, 32, 9>(b, c_in, geo, x, wp, bias, out, unit_stats, st);
   else if (c_out == 32) rc = cv3::launch_conv<32, 64, 3>(b, c_in, geo, x, wp, bias, out, unit_stats, st);
   else if (c_out == 64 && kc == 32) rc = cv3::launch_conv<64, 32, 3>(b, c_in, geo, x, wp, bias, out, unit_stats, st);
@@ -661,7 +711,7 @@ extern "C" int bdm_conv3_tc05(int b, int c_in, int c_out, int r, const void *xh,
   else rc = cv3::launch_conv<128, 64, 1>(b, c_in, geo, x, wp, bias, out, unit_stats, st);
   if (rc != BDM_OK) return rc;
   if (stats != nullptr) {
-    cv3::conv3_stats_fold_kernel<<<b, c_out, 0, st>>>(geo.units, c_out, unit_stats, reinterpret_cast<double2 *>(stats));
+    cv3::conv3_stats_fold_kernel<<<b, 512, 0, st>>>(units, c_out, unit_stats, reinterpret_cast<double2 *>(stats));
     BDM_RETURN_LAUNCH_STATUS();
   }
   return BDM_OK;

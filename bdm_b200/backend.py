@@ -805,6 +805,20 @@ def groupnorm_swish_half_planar(x, num_groups, weight, bias, eps, swish, conv_bi
     return planes
 
 
+@_op(2)
+def conv3_tc05_fill_planes(compact, plan, prepared, planes):
+    """per-occupied-voxel averages f32[B,C,N] (avg_voxelize_compact) + VoxelPlan -> `planes` (zeros at empty voxels),
+    scaled by a power of two derived on the device from max|average| and recorded in `prepared`."""
+    _chk_float(compact, "compact")
+    b, c, n = compact.shape
+    _req(b == plan.b and n == plan.n, "compact does not match the voxel plan")
+    _req(planes.b == b and planes.c == c and planes.r == plan.r and planes.data.device == compact.device, "planes do not match")
+    with _Launch(compact) as st:
+        _check(_L.bdm_conv3_tc05_fill_planes(b, c, n, plan.r, compact.data_ptr(), plan.workspace.data_ptr(), plan.workspace.numel(),
+                                             prepared.data_ptr(), planes.data.data_ptr(), planes.rows, st))
+    return planes
+
+
 @_op(1)
 def conv3_tc05(planes, prepared, c_out, bias=None, stats=False):
     """HalfPlanes + prepared weights -> f32[B,R,R,R,Cout] channels-last (= conv + bias) and, with stats, the result's

@@ -37,6 +37,7 @@
 #include <cuda_fp16.h>
 
 #include "common.cuh"
+#include "voxel_plan.cuh"
 
 namespace bdm {
 namespace cv3 {
@@ -99,7 +100,7 @@ __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ float swish_fast(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
 
 constexpr int kUnitRows = 256;        // output positions per unit (2 accumulators of 128)
-constexpr int kHeaderBytes = 256;     // prepared-weight header: float out_scale, float act_scale
+constexpr int kHeaderBytes = 256;     // prepared-weight header: f32 out_scale, act_scale, w_scale, 1/w_scale, u32 amax bits (dynamic scaling)
 constexpr int kAStages = 3;
 constexpr int kThreads = 384;         // 12 warps
 constexpr int kEpiThreads = 256;
@@ -173,6 +174,7 @@ conv3_prep_header_kernel(size_t nw, const float *__restrict__ w, int c_in, const
     header[0] = inv_w * inv_a;   // out_scale: accumulator -> convolution result
     header[1] = sa;              // act_scale: applied by the producer of xh
     header[2] = sw;
+    header[3] = inv_w;
   }
 }
 
@@ -316,6 +318,66 @@ gn_apply_half_planar_kernel(int c, int r, int groups, int nchunks, int ntiles, f
 #pragma unroll
     for (int k = 0; k < UNR; ++k) { u[k] = un[k]; w[k] = wn[k]; }
     base = nbase;
+  }
+}
+
+// -------------------------------------------------------------------------------------------------------------
+// A freshly voxelized cloud as the convolution's operand (the FIRST Conv3d of a PVConv block, modules/pvconv.py:75-76,
+// 91-97): per-occupied-voxel averages (bdm_avg_voxelize_compact, f32[b][c][n]) + the voxel plan's occupancy bitmask ->
+// every real voxel row of the fp16 chunk planes (zeros for empty voxels; occupancy changes from call to call, so
+// all of them are rewritten).  No normalisation precedes this convolution, so the activation scale is dynamic:
+// max|average| is reduced first (conv3_amax_kernel, one atomicMax per warp), every thread derives the power-of-two
+// scale from it, and one thread records it in the prepared header for the convolution's epilogue.
+// -------------------------------------------------------------------------------------------------------------
+__global__ void conv3_amax_kernel(size_t n4, const float4 *__restrict__ x, unsigned *__restrict__ amax_bits) {
+  float m = 0.0f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(x + i);
+    m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+  }
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, d));
+  if ((threadIdx.x & 31) == 0 && m > 0.0f) atomicMax(amax_bits, __float_as_uint(m));
+}
+
+// one warp per 32-voxel occupancy word (lane = voxel), looping over the chunk planes: 512-byte stores
+__global__ void __launch_bounds__(256)
+conv3_fill_planes_kernel(int c, int n, int r, VoxAuxLayout L, const unsigned char *__restrict__ plan_ws,
+                         const float *__restrict__ compact, float *__restrict__ header, __half *__restrict__ xh, int guard,
+                         long long sample_rows, long long total_rows) {
+  const int b = blockIdx.y, lane = threadIdx.x & 31;
+  const int word_idx = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const float amax = __uint_as_float(reinterpret_cast<const unsigned *>(header)[4]);
+  float inv_a;
+  const float sa = pow2_scale_to(amax, 13.0f, &inv_a);
+  if (blockIdx.x == 0 && b == 0 && threadIdx.x == 0) {
+    header[0] = header[3] * inv_a;
+    header[1] = sa;
+  }
+  if (word_idx >= L.nw) return;
+  const unsigned char *ws = plan_ws + (size_t)b * L.stride;
+  const uint32_t word = __ldg(reinterpret_cast<const uint32_t *>(ws + L.bitmask) + word_idx);
+  const int slot = (int)__ldg(reinterpret_cast<const uint16_t *>(ws + L.obase) + word_idx) + __popc(word & ((1u << lane) - 1u));
+  const bool occ = (word >> lane) & 1u;
+  const int v = word_idx * 32 + lane;
+  if (v >= r * r * r) return;
+  const int sh = 31 - __clz(r), q = r + 1;
+  const int vz = v & (r - 1), vy = (v >> sh) & (r - 1), vx = v >> (2 * sh);
+  const size_t row = (size_t)guard + (size_t)b * sample_rows + (size_t)(((long long)vx * q + vy) * q + vz);
+  const float *src = compact + (size_t)b * c * n + slot;
+  const int c8 = c >> 3;
+  for (int j = 0; j < c8; ++j) {
+    uint4 h = make_uint4(0u, 0u, 0u, 0u);
+    if (occ) {
+      float a[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) a[e] = __ldg(src + (size_t)(8 * j + e) * n) * sa;
+      const __half2 h0 = __floats2half2_rn(a[0], a[1]), h1 = __floats2half2_rn(a[2], a[3]);
+      const __half2 h2 = __floats2half2_rn(a[4], a[5]), h3 = __floats2half2_rn(a[6], a[7]);
+      h = make_uint4(*reinterpret_cast<const uint32_t *>(&h0), *reinterpret_cast<const uint32_t *>(&h1),
+                     *reinterpret_cast<const uint32_t *>(&h2), *reinterpret_cast<const uint32_t *>(&h3));
+    }
+    *reinterpret_cast<uint4 *>(xh + ((size_t)j * total_rows + row) * 8) = h;
   }
 }
 
@@ -671,6 +733,33 @@ extern "C" int bdm_groupnorm_swish_half_planar(int b, int c, int r, int groups, 
   cv3::gn_apply_half_planar_kernel<<<dim3(ntiles, b), cv3::kApplyThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       c, r, groups, chunks, ntiles, eps, swish, x, conv_bias, gamma, beta, reinterpret_cast<const double2 *>(partials),
       static_cast<const float *>(prepared), static_cast<__half *>(xh), geo.guard, geo.sample_rows, geo.total_rows);
+  BDM_RETURN_LAUNCH_STATUS();
+}
+
+/* compact f32[b][c][n] (bdm_avg_voxelize_compact) + the voxel plan (bdm_voxel_plan's workspace for the same b, n, r) ->
+ * xh; `prepared` (of the convolution that will read xh) receives the dynamic activation scale. */
+extern "C" int bdm_conv3_tc05_fill_planes(int b, int c, int n, int r, const float *compact, const void *plan_workspace,
+                                          size_t plan_workspace_bytes, void *prepared, void *xh, long long plane_rows,
+                                          bdm_stream_t stream) {
+  BDM_CHECK_SIZE(b >= 0 && b <= 65535 && c >= 8 && c % 8 == 0 && n >= 1 && r >= 4 && r <= 32 && (r & (r - 1)) == 0);
+  BDM_CHECK_SIZE(vox_fast_path(n, r * r * r) && ((size_t)c * n) % 4 == 0);
+  if (b == 0) return BDM_OK;
+  BDM_CHECK_PTR(compact); BDM_CHECK_PTR(prepared); BDM_CHECK_PTR(xh);
+  const cv3::Geometry geo = cv3::conv3_geometry(b, r);
+  BDM_CHECK_SIZE(plane_rows == geo.total_rows);
+  const VoxAuxLayout L = vox_aux_layout(n, r * r * r);
+  int rc = check_workspace(L, b, plan_workspace, plan_workspace_bytes);
+  if (rc != BDM_OK) return rc;
+  if (((reinterpret_cast<uintptr_t>(compact) | reinterpret_cast<uintptr_t>(xh) | reinterpret_cast<uintptr_t>(prepared)) & 15) != 0)
+    return BDM_ERR_MISALIGNED;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  float *header = static_cast<float *>(prepared);
+  cudaMemsetAsync(header + 4, 0, 4, st);
+  cv3::conv3_amax_kernel<<<2 * sm_count(), 256, 0, st>>>((size_t)b * c * n / 4, reinterpret_cast<const float4 *>(compact),
+                                                       reinterpret_cast<unsigned *>(header) + 4);
+  cv3::conv3_fill_planes_kernel<<<dim3((L.nw + 7) / 8, b), 256, 0, st>>>(
+      c, n, r, L, static_cast<const unsigned char *>(plan_workspace), compact, header, static_cast<__half *>(xh), geo.guard,
+      geo.sample_rows, geo.total_rows);
   BDM_RETURN_LAUNCH_STATUS();
 }
 

@@ -124,7 +124,7 @@ _HALF_PLANES = {}     # (B, C, R, device) -> backend.HalfPlanes: scratch between
                       # every block of that shape (pad rows are zero once and for all; stream order serialises reuse)
 
 
-def _half_planes(b, c, r, device):
+def half_planes(b, c, r, device):
     key = (int(b), int(c), int(r), str(device))
     planes = _HALF_PLANES.get(key)
     if planes is None:
@@ -132,15 +132,16 @@ def _half_planes(b, c, r, device):
     return planes
 
 
-def _conv3_prepared(conv, gn, group_elems):
-    """scales + fp16 weight stages of `conv` (whose input GroupNorm `gn` produces), cached per parameter version"""
-    params = (conv.weight, gn.weight, gn.bias)
+def conv3_prepared(conv, gn, group_elems):
+    """scales + fp16 weight stages of `conv` (whose input GroupNorm `gn` produces; gn None: the operand's producer
+    sets the activation scale itself, bdm_conv3_tc05_fill_planes), cached per parameter version"""
+    params = (conv.weight, gn.weight if gn is not None else None, gn.bias if gn is not None else None)
     key = tuple((p.data_ptr(), geometry.tensor_version(p), p.device) if p is not None else None for p in params) + (int(group_elems),)
     cached = getattr(conv, "_tc05_prepared", None)
     if cached is None or cached[0] != key:
         cached = (key, _ops._B.conv3_tc05_prepare(conv.weight.detach().contiguous(),
-                                                 gn.weight.detach() if gn.weight is not None else None,
-                                                 gn.bias.detach() if gn.bias is not None else None, group_elems))
+                                                 gn.weight.detach() if gn is not None and gn.weight is not None else None,
+                                                 gn.bias.detach() if gn is not None and gn.bias is not None else None, group_elems))
         conv._tc05_prepared = cached
     return cached[1]
 
@@ -234,11 +235,12 @@ class FusedSequential(nn.Sequential):
     statistics), norm + activation are one pass, the SE squeeze comes out of that same pass and a
     trailing max over neighbours replaces the full-size write.  Anything else runs module by module."""
 
-    def forward(self, x, max_over_last=False, first_output=None, defer_gate=False, first_stats=None):
+    def forward(self, x, max_over_last=False, first_output=None, defer_gate=False, first_stats=None, first_biased=False):
         """first_output: the bias-less output of self[0] (a conv) when the caller computed it by other
         means (PVConv's sparse first convolution); `x` is then ignored.
         first_stats: per-channel statistics of first_output made by its producer (sparse_conv3_gather), handed
         to the norm that follows so that it does not read the tensor a second time.
+        first_biased: first_output already includes self[0]'s bias (and first_stats are those of the biased tensor).
         defer_gate: when the stack ends in an SE3d gate, return (ungated grid, gate f32[B,C]) instead of
         multiplying the whole grid -- the caller applies the gate after its (linear) consumer."""
         mods = list(self)
@@ -246,7 +248,7 @@ class FusedSequential(nn.Sequential):
         i = 0
         reduced = False
         gate = None
-        pre, pre_stats, pre_biased = first_output, first_stats, False   # output of mods[i] made by other means
+        pre, pre_stats, pre_biased = first_output, first_stats, bool(first_biased)   # output of mods[i] made by other means
         while i < n:
             m = mods[i]
             fusable = _fusable(x if pre is None else pre)
@@ -268,8 +270,8 @@ class FusedSequential(nn.Sequential):
                         and conv3_tc05_applicable(mods[j], gn, y.shape[1], y.shape[2])):
                     conv2 = mods[j]
                     nb, nc, r = y.shape[0], y.shape[1], y.shape[2]
-                    prepared = _conv3_prepared(conv2, gn, (nc // gn.num_groups) * r ** 3)
-                    planes = _half_planes(nb, nc, r, y.device)
+                    prepared = conv3_prepared(conv2, gn, (nc // gn.num_groups) * r ** 3)
+                    planes = half_planes(nb, nc, r, y.device)
                     _ops._B.groupnorm_swish_half_planar(y.permute(0, 2, 3, 4, 1), gn.num_groups, gn.weight, gn.bias, gn.eps,
                                                         True, cbias, stats, prepared, planes)
                     out2, pre_stats = _ops._B.conv3_tc05(planes, prepared, conv2.out_channels, bias=conv2.bias, stats=True)

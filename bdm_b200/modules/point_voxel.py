@@ -29,6 +29,13 @@ DEFER_SE_GATE = os.environ.get("BDM_DEFER_SE_GATE", "1") != "0"
 # it, the fused norm kernels and the devoxelization read it, and cuDNN's Conv3d (whose tensor-core kernels are
 # NDHWC inside) stops wrapping two transposes around every call.  Same values; BDM_CHANNELS_LAST=0 disables.
 CHANNELS_LAST_VOXELS = os.environ.get("BDM_CHANNELS_LAST", "1") != "0"
+# First convolution on the tcgen05 kernel too (csrc/conv3_tc05.cu) where the dense product is cheaper than the
+# tap-product round trip of the sparse route: the occupied voxels' averages are scattered into the convolution's fp16
+# operand (zeros elsewhere), and the convolution emits the first norm's statistics.  Measured at 32 shapes (B200):
+# 64->64 at R=32 295 vs 363 us, 128->128 at R=16 ~125 vs 197 us, 32->32 at R=32 ~165 vs 196 us; wide inputs (390->32)
+# and the 8^3 grids stay on the sparse route.  BDM_DENSE_FIRST_TC05=0 disables.
+DENSE_FIRST_TC05 = os.environ.get("BDM_DENSE_FIRST_TC05", "1") != "0"
+DENSE_FIRST_TC05_MAX_CIN = int(os.environ.get("BDM_DENSE_FIRST_TC05_MAX_CIN", "128"))
 
 
 def normalized_voxel_coords(coords, resolution, normalize=True, eps=0):
@@ -159,6 +166,27 @@ class _PVConvBase(nn.Module):
                 and conv.padding == (1, 1, 1) and conv.dilation == (1, 1, 1) and conv.groups == 1
                 and conv.padding_mode == 'zeros')
 
+    def _dense_first_eligible(self, features):
+        """the sparse-eligible block's first convolution as a dense tcgen05 convolution (see DENSE_FIRST_TC05)"""
+        conv, norm, vox = self.voxel_layers[0], self.voxel_layers[1], self.voxelization
+        return (DENSE_FIRST_TC05 and CHANNELS_LAST_VOXELS and _layers.FUSED_NORM_ACT and _layers.CONV3_TC05
+                and hasattr(_ops._B, "conv3_tc05_fill_planes") and bool(torch.backends.cudnn.allow_tf32)
+                and isinstance(norm, nn.GroupNorm) and _ops._B.groupnorm_cl_supported(self.out_channels, 8)
+                and vox.r >= _layers.CONV3_TC05_MIN_R and conv.in_channels <= DENSE_FIRST_TC05_MAX_CIN
+                and conv.in_channels % 8 == 0 and (conv.in_channels * features.shape[2]) % 4 == 0
+                and _ops._B.conv3_tc05_supported(conv.in_channels, conv.out_channels, vox.r))
+
+    def _dense_first_conv(self, features, coords):
+        """-> ((output of voxel_layers[0] INCLUDING its bias, channels-last; its GroupNorm statistics; True), coords)"""
+        vox, conv = self.voxelization, self.voxel_layers[0]
+        norm_coords, _, plan = coordinate_plan(coords, vox.r, vox.normalize, vox.eps)
+        occupied = _ops._B.avg_voxelize_compact(features.contiguous(), plan)     # [B, Cin, N]
+        prepared = _layers.conv3_prepared(conv, None, 1)
+        planes = _layers.half_planes(features.shape[0], conv.in_channels, vox.r, features.device)
+        _ops._B.conv3_tc05_fill_planes(occupied, plan, prepared, planes)
+        out, stats = _ops._B.conv3_tc05(planes, prepared, conv.out_channels, bias=conv.bias, stats=True)
+        return (out.permute(0, 4, 1, 2, 3), stats, True), norm_coords
+
     def _tap_matrix(self, conv):
         """Conv3d weight [Cout,Cin,3,3,3] -> [Cin, 27*Cout] (column k*Cout+co), cached per weight version."""
         w = conv.weight
@@ -198,14 +226,19 @@ class _PVConvBase(nn.Module):
         defer = (DEFER_SE_GATE and features.is_cuda and not torch.is_grad_enabled()
                  and not _ops.REFERENCE_CALL_PATTERN and hasattr(_ops._B, "groupnorm_act"))
         first = first_stats = None
+        first_biased = False
         if self._sparse_eligible(features):
-            first, grid_coords = self._sparse_first_conv(features, coords)
+            if self._dense_first_eligible(features):
+                first, grid_coords = self._dense_first_conv(features, coords)
+            else:
+                first, grid_coords = self._sparse_first_conv(features, coords)
             if isinstance(first, tuple):
-                first, first_stats = first
+                first, first_stats, first_biased = (tuple(first) + (False,))[:3]
             grid = None
         else:
             grid, grid_coords = self.voxelization(features, coords)
-        grid = self.voxel_layers(grid, first_output=first, defer_gate=defer, first_stats=first_stats)
+        grid = self.voxel_layers(grid, first_output=first, defer_gate=defer, first_stats=first_stats,
+                                 first_biased=first_biased)
         gate = None
         if defer:
             grid, gate = grid

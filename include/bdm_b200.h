@@ -306,6 +306,9 @@ int bdm_groupnorm_act_cl(int b, int c, long long s, int groups, float eps, int s
  *       the activations for the fp16 scaling.  Once per weight version.
  *   bdm_groupnorm_swish_half_planar   x f32[b][r^3][c] channels-last + its producer's statistics partials
  *       f64[b][chunks][c][2] (of the bias-less tensor) -> act(group_norm(x + conv_bias)) * act_scale as xh.
+ *   bdm_conv3_tc05_fill_planes   the FIRST Conv3d's operand: per-occupied-voxel averages (bdm_avg_voxelize_compact)
+ *       + the voxel plan -> xh (zeros at empty voxels), scaled by a power of two derived from max|average| on
+ *       the device and recorded in `prepared` (prepare that convolution with gamma = beta = NULL, group_elems = 1).
  *   bdm_conv3_tc05   out f32[b][r^3][c_out] = conv(xh) + bias; stats (or NULL): f64[b][1][c_out][2], the result's
  *       GroupNorm(8) statistics in the layout bdm_groupnorm_act_cl(precomputed_chunks = 1) takes; workspace:
  *       bdm_conv3_tc05_workspace_bytes(b, r) bytes when stats != NULL.
@@ -321,6 +324,9 @@ int bdm_groupnorm_swish_half_planar(int b, int c, int r, int groups, float eps, 
                                     const float *conv_bias, const float *gamma, const float *beta,
                                     const double *partials, int chunks, const void *prepared, void *xh,
                                     long long plane_rows, bdm_stream_t stream);
+int bdm_conv3_tc05_fill_planes(int b, int c, int n, int r, const float *compact, const void *plan_workspace,
+                               size_t plan_workspace_bytes, void *prepared, void *xh, long long plane_rows,
+                               bdm_stream_t stream);
 int bdm_conv3_tc05(int b, int c_in, int c_out, int r, const void *xh, long long plane_rows, const void *prepared,
                    const float *bias, float *out, double *stats, void *workspace, size_t workspace_bytes,
                    bdm_stream_t stream);

@@ -168,6 +168,76 @@ def test_voxel_stack_takes_the_tcgen05_route_and_matches_cudnn(cuda_backend):
         assert e_tc <= max(2.0 * e_cudnn, 2e-4), (cin, cout, r, e_tc, e_cudnn)
 
 
+@pytest.mark.parametrize("b,c,n,r", [(3, 64, 2048, 32), (2, 32, 1000, 16), (2, 128, 1024, 16)])
+def test_fill_planes_from_a_voxelized_cloud(b, c, n, r, cuda_backend):
+    """occupied-voxel averages + plan -> fp16 planes == the dense voxel grid (fp16 rounding of the scaled values),
+    zeros at empty voxels and pads; the scale in the prepared header is the power of two the kernel derived"""
+    import numpy as np
+    import torch
+    from tests import cases
+    B = cuda_backend
+    rng = np.random.default_rng(b * 7 + r)
+    co = cases.cloud(rng, b, n, "shape")
+    vox, _ = cases.vox_coords(co, r)
+    plan = B.voxel_plan(torch.from_numpy(vox).cuda(), r)
+    feats = torch.randn(b, c, n, device="cuda") * 37.0
+    dense = B.avg_voxelize_fill(feats, plan).reshape(b, c, r, r, r)
+    w = torch.randn(c, c, 3, 3, 3, device="cuda")
+    prepared = B.conv3_tc05_prepare(w, None, None, 1)
+    planes = B.HalfPlanes(b, c, r, "cuda")
+    planes.data.fill_(7.0)                                     # stale contents of real rows must be overwritten
+    q = r + 1
+    guard = (q * q + q + 1 + 7) // 8 * 8
+    srows = (guard + q ** 3 + 7) // 8 * 8
+    B.conv3_tc05_fill_planes(B.avg_voxelize_compact(feats, plan), plan, prepared, planes)
+    hdr = prepared[:16].view(torch.float32)
+    act_scale = hdr[1].item()
+    amax = dense.abs().max().item()
+    assert 2 ** 13 <= amax * act_scale < 2 ** 14
+    assert hdr[0].item() == hdr[3].item() / act_scale
+    full = planes.data.permute(1, 0, 2).reshape(planes.rows, c).float()
+    for i in range(b):
+        vol = full[guard + i * srows: guard + i * srows + q ** 3].reshape(q, q, q, c)[:r, :r, :r]
+        want = dense[i].permute(1, 2, 3, 0) * act_scale
+        assert (vol - want).abs().max().item() <= 2 ** -10 * amax * act_scale
+        assert (vol[want == 0] == 0).all()
+
+
+def test_first_convolution_dense_route_matches_sparse_route(cuda_backend):
+    """block level: first convolution through the tcgen05 kernel (DENSE_FIRST_TC05) against the tap-product route"""
+    import torch
+
+    import bdm_b200.modules.point_voxel as PV
+    B = cuda_backend
+    for cin, cout, n, r in ((64, 64, 4096, 32), (128, 128, 1024, 16), (32, 32, 4096, 32), (128, 64, 1024, 16)):
+        torch.manual_seed(cin + r)
+        blk = PV.PVConv(cin, cout, 3, r, with_se=True).cuda().eval()
+        feats = torch.randn(2, cin, n, device="cuda") * 2.0
+        u = torch.randn(2, 3, n, device="cuda")
+        coords = u / u.norm(dim=1, keepdim=True) * (0.5 + 0.02 * torch.randn(2, 1, n, device="cuda"))
+        temb = torch.randn(2, 8, n, device="cuda")
+        saved = (PV.DENSE_FIRST_TC05, torch.backends.cudnn.allow_tf32)
+        try:
+            with torch.no_grad():
+                torch.backends.cudnn.allow_tf32 = True
+                PV.DENSE_FIRST_TC05 = True
+                assert blk._dense_first_eligible(feats)
+                B.profile_start()
+                y_dense = blk((feats, coords, temb))[0]
+                prof = B.profile_stop()
+                assert "conv3_tc05_fill_planes" in prof and len(prof["conv3_tc05"]) == 2 and "sparse_conv3_gather" not in prof
+                PV.DENSE_FIRST_TC05 = False
+                y_sparse = blk((feats, coords, temb))[0]
+                torch.backends.cudnn.allow_tf32 = False
+                y_fp32 = blk((feats, coords, temb))[0]
+        finally:
+            PV.DENSE_FIRST_TC05, torch.backends.cudnn.allow_tf32 = saved
+        peak = y_fp32.abs().max().item()
+        e_dense = (y_dense - y_fp32).abs().max().item() / peak
+        e_sparse = (y_sparse - y_fp32).abs().max().item() / peak
+        assert e_dense <= max(2.0 * e_sparse, 2e-4), (cin, cout, r, e_dense, e_sparse)
+
+
 def test_route_is_off_when_tf32_convolutions_are_off(cuda_backend):
     import torch
 

@@ -764,6 +764,9 @@ class HalfPlanes:
         self.rows = int(_L.bdm_conv3_tc05_plane_rows(self.b, self.r))
         self.data = torch.zeros((self.c // 8, self.rows, 8), dtype=torch.float16, device=device)
 
+    def describe(self):
+        return f"HalfPlanes(b={self.b}, c={self.c}, r={self.r})"
+
 
 @_op(2)
 def conv3_tc05_prepare(weight, gamma, beta, group_elems):

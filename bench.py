@@ -268,6 +268,11 @@ def algorithmic_work(op, shp):
     if op == "attention_qkv":                               # qkv [B,T,3C]
         b, t, c3 = shp[0]
         return "tensor", 4.0 * b * t * t * (c3 // 3), "flop"
+    if op == "conv3_tc05":                                  # (HalfPlanes, prepared, c_out): 27 taps x Cin x Cout MACs per voxel
+        pl, c_out = shp[0], int(shp[2])
+        return "tensor", 2.0 * pl.b * pl.r ** 3 * 27 * pl.c * c_out, "flop"
+    if op == "groupnorm_swish_half_planar":                 # f32 read + f16 write of the grid
+        return "hbm", 6.0 * _numel(shp[0]), "byte"
     if op == "groupnorm_act":
         x = shp[0]
         n = _numel(x)
@@ -302,7 +307,7 @@ def pick_roofline(prof, steps, ms_step, occupied, peaks):
     groups = {}
     for op, calls in prof.items():
         for ms, shp in calls:
-            key = (op, json.dumps(shp, default=lambda o: type(o).__name__))
+            key = (op, json.dumps(shp, default=lambda o: getattr(o, "describe", lambda: type(o).__name__)()))
             g = groups.setdefault(key, {"op": op, "shapes": shp, "ms": []})
             g["ms"].append(ms)
     ranked = sorted(groups.values(), key=lambda g: -sum(g["ms"]))
@@ -323,9 +328,14 @@ def pick_roofline(prof, steps, ms_step, occupied, peaks):
             ach, peak, u = units / (ms * 1e-3) / 1e9, peaks["hbm_gbs"], "GB/s"
         else:
             ach, peak, u = units / (ms * 1e-3) / 1e12, peaks["bf16_tflops_sustained"], "TFLOP/s"
-        shown = [list(s) if isinstance(s, tuple) else (s if isinstance(s, (int, float, str, bool, dict, type(None))) else type(s).__name__)
+        shown = [list(s) if isinstance(s, tuple) else (s if isinstance(s, (int, float, str, bool, dict, type(None)))
+                                                       else getattr(s, "describe", lambda: type(s).__name__)())
                  for s in shp]
         extra = {}
+        if op == "conv3_tc05":
+            extra = {"note": "algorithmic flops = 2*27*Cin*Cout per real voxel (the padded rows the flat layout also computes, "
+                             "6 % at R=32 / 13 % at R=16, are not counted); fp16 operands (11 significant bits, as TF32), "
+                             "fp32 accumulation; SS-mode MMA: the kernel is bound by shared-memory operand bandwidth (DESIGN.md)"}
         if op in ("attention", "attention_qkv"):
             # every fp32 product is three fp16 tensor-core products (lo*hi + hi*lo + hi*hi): the tensor pipe executes 3x
             extra = {"executed_tflops": 3.0 * ach, "frac_executed": 3.0 * ach / peak,

@@ -96,6 +96,12 @@ __host__ __device__ constexpr uint32_t instr_desc(int n) {
         "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),    \
         "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])     \
       : "r"(taddr))
+// true in exactly one (always the same) lane of a converged warp
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ float swish_fast(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
 
@@ -476,7 +482,10 @@ conv3_tc05_kernel(int b, int c_in, Geometry geo, int a_stage_bytes, const __half
     // constant; its lower word is (address >> 4) | (LBO >> 4) << 16, and since an activation row is 16 bytes a window
     // shift of n rows is simply +n on that word.  Taps and k-steps are unrolled: their offsets are immediates or one
     // of a few registers.
-    if (lane == 0) {
+    // The whole warp runs the (uniform) loops so that addresses and descriptor words live in uniform registers; one
+    // elected lane issues the MMAs and the commits (the per-lane version paid a register -> uniform-register move and
+    // a convergence loop in front of every MMA).
+    {
       constexpr uint32_t idesc = instr_desc(N);
       constexpr uint32_t desc_hi = (128u >> 4) | (1u << 14);           // SBO = 128 bytes, descriptor version 1
       int sa = 0, sw = 0; uint32_t pa = 0, pw = 0;
@@ -500,35 +509,39 @@ conv3_tc05_kernel(int b, int c_in, Geometry geo, int a_stage_bytes, const __half
               bar_wait(w_full + sw, pw);
               tc_fence_after();
               const uint32_t b_lo = (smem_u32(w_smem + sw * C::kWStageBytes) >> 4) | (b_lbo16 << 16);
+              __syncwarp();
+              if (elect_one()) {
 #pragma unroll
-              for (int j = 0; j < TG; ++j) {
-                const int tap = grp * TG + j;
-                const int dy = tap / 3, dz = tap - dy * 3;
-                const uint32_t a_tap = a_lo + (dy == 0 ? 0u : (dy == 1 ? q1 : q2)) + (uint32_t)dz;
+                for (int j = 0; j < TG; ++j) {
+                  const int tap = grp * TG + j;
+                  const int dy = tap / 3, dz = tap - dy * 3;
+                  const uint32_t a_tap = a_lo + (dy == 0 ? 0u : (dy == 1 ? q1 : q2)) + (uint32_t)dz;
 #pragma unroll
-                for (int t = 0; t < 2; ++t) {
+                  for (int t = 0; t < 2; ++t) {
 #pragma unroll
-                  for (int k = 0; k < C::kK16; ++k) {
-                    const uint32_t da_lo = a_tap + (uint32_t)(t * 128) + (uint32_t)k * kstep;
-                    const uint32_t db_lo = b_lo + (uint32_t)(j * (C::kTapBytes >> 4) + k * 2 * N);
-                    const uint32_t accumulate = (tap == 0 && k == 0) ? acc : 1u;
-                    asm volatile(
-                        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %5, 0;\n\t"
-                        "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %2};\n\t"
-                        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
-                        ::"r"(d0 + t * N), "r"(da_lo), "r"(desc_hi), "r"(db_lo), "r"(idesc), "r"(accumulate) : "memory");
+                    for (int k = 0; k < C::kK16; ++k) {
+                      const uint32_t da_lo = a_tap + (uint32_t)(t * 128) + (uint32_t)k * kstep;
+                      const uint32_t db_lo = b_lo + (uint32_t)(j * (C::kTapBytes >> 4) + k * 2 * N);
+                      const uint32_t accumulate = (tap == 0 && k == 0) ? acc : 1u;
+                      asm volatile(
+                          "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %5, 0;\n\t"
+                          "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %2};\n\t"
+                          "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
+                          ::"r"(d0 + t * N), "r"(da_lo), "r"(desc_hi), "r"(db_lo), "r"(idesc), "r"(accumulate) : "memory");
+                    }
                   }
                 }
+                umma_commit(w_empty + sw);
+                if (grp == C::kNG - 1) umma_commit(a_empty + sa);
+                if (grp == C::kNG - 1 && dx == 2 && kc == nkc - 1) umma_commit(t_full + buf);
               }
-              umma_commit(w_empty + sw);
+              __syncwarp();
               if (++sw == C::kWStages) { sw = 0; pw ^= 1; }
             }
             acc = 1;
-            umma_commit(a_empty + sa);
             if (++sa == kAStages) { sa = 0; pa ^= 1; }
           }
         }
-        umma_commit(t_full + buf);
       }
     }
   } else if (warp >= 4) {

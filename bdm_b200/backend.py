@@ -187,16 +187,24 @@ def avg_voxelize_fill(features, plan):
 
 
 @_op(1)
-def avg_voxelize_compact(features, plan):
+def avg_voxelize_compact(features, plan, amax_into=None):
     """features f32[B,C,N] + VoxelPlan -> f32[B,C,N]: column j = average of the j-th occupied voxel
-    (ascending voxel id), zero past the shape's occupied count."""
+    (ascending voxel id), zero past the shape's occupied count.
+    amax_into: a prepared conv3_tc05 weight buffer whose header also receives max|out| (the dynamic fp16 scale of
+    conv3_tc05_fill_planes(amax_ready=True))."""
     _chk_float(features, "features")
     b, c, n = features.shape
     _req(b == plan.b and n == plan.n, "features do not match the voxel plan")
     out = torch.empty((b, c, n), dtype=_F32, device=features.device)
     with _Launch(features) as st:
-        _check(_L.bdm_avg_voxelize_compact(b, c, n, plan.r, features.data_ptr(), out.data_ptr(),
-                                           plan.workspace.data_ptr(), plan.workspace.numel(), st))
+        if amax_into is not None:
+            _req(amax_into.is_cuda and amax_into.dtype == torch.uint8 and amax_into.numel() >= 256, "amax_into must be a prepared weight buffer")
+            _check(_L.bdm_avg_voxelize_compact_amax(b, c, n, plan.r, features.data_ptr(), out.data_ptr(),
+                                                    plan.workspace.data_ptr(), plan.workspace.numel(),
+                                                    amax_into.data_ptr() + 16, st))
+        else:
+            _check(_L.bdm_avg_voxelize_compact(b, c, n, plan.r, features.data_ptr(), out.data_ptr(),
+                                               plan.workspace.data_ptr(), plan.workspace.numel(), st))
     return out
 
 
@@ -808,17 +816,21 @@ def groupnorm_swish_half_planar(x, num_groups, weight, bias, eps, swish, conv_bi
     return planes
 
 
-@_op(2)
-def conv3_tc05_fill_planes(compact, plan, prepared, planes):
+@_op(1)
+def conv3_tc05_fill_planes(compact, plan, prepared, planes, amax_ready=False):
     """per-occupied-voxel averages f32[B,C,N] (avg_voxelize_compact) + VoxelPlan -> `planes` (zeros at empty voxels),
-    scaled by a power of two derived on the device from max|average| and recorded in `prepared`."""
+    scaled by a power of two derived on the device from max|average| and recorded in `prepared`.
+    amax_ready: avg_voxelize_compact(..., amax_into=prepared) already measured max|average|."""
+    if not amax_ready:
+        _count_launches(1)
     _chk_float(compact, "compact")
     b, c, n = compact.shape
     _req(b == plan.b and n == plan.n, "compact does not match the voxel plan")
     _req(planes.b == b and planes.c == c and planes.r == plan.r and planes.data.device == compact.device, "planes do not match")
     with _Launch(compact) as st:
         _check(_L.bdm_conv3_tc05_fill_planes(b, c, n, plan.r, compact.data_ptr(), plan.workspace.data_ptr(), plan.workspace.numel(),
-                                             prepared.data_ptr(), planes.data.data_ptr(), planes.rows, st))
+                                             prepared.data_ptr(), planes.data.data_ptr(), planes.rows,
+                                             1 if amax_ready else 0, st))
     return planes
 
 

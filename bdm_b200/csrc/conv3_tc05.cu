@@ -747,10 +747,11 @@ extern "C" int bdm_groupnorm_swish_half_planar(int b, int c, int r, int groups, 
 }
 
 /* compact f32[b][c][n] (bdm_avg_voxelize_compact) + the voxel plan (bdm_voxel_plan's workspace for the same b, n, r) ->
- * xh; `prepared` (of the convolution that will read xh) receives the dynamic activation scale. */
+ * xh; `prepared` (of the convolution that will read xh) receives the dynamic activation scale.  amax_ready != 0: word 4
+ * of `prepared` already holds the bit pattern of max|compact| (bdm_avg_voxelize_compact_amax wrote it). */
 extern "C" int bdm_conv3_tc05_fill_planes(int b, int c, int n, int r, const float *compact, const void *plan_workspace,
                                           size_t plan_workspace_bytes, void *prepared, void *xh, long long plane_rows,
-                                          bdm_stream_t stream) {
+                                          int amax_ready, bdm_stream_t stream) {
   BDM_CHECK_SIZE(b >= 0 && b <= 65535 && c >= 8 && c % 8 == 0 && n >= 1 && r >= 4 && r <= 32 && (r & (r - 1)) == 0);
   BDM_CHECK_SIZE(vox_fast_path(n, r * r * r) && ((size_t)c * n) % 4 == 0);
   if (b == 0) return BDM_OK;
@@ -764,9 +765,11 @@ extern "C" int bdm_conv3_tc05_fill_planes(int b, int c, int n, int r, const floa
     return BDM_ERR_MISALIGNED;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   float *header = static_cast<float *>(prepared);
-  cudaMemsetAsync(header + 4, 0, 4, st);
-  cv3::conv3_amax_kernel<<<2 * sm_count(), 256, 0, st>>>((size_t)b * c * n / 4, reinterpret_cast<const float4 *>(compact),
-                                                       reinterpret_cast<unsigned *>(header) + 4);
+  if (!amax_ready) {   // otherwise bdm_avg_voxelize_compact_amax already left max|average| in the header's word 4
+    cudaMemsetAsync(header + 4, 0, 4, st);
+    cv3::conv3_amax_kernel<<<2 * sm_count(), 256, 0, st>>>((size_t)b * c * n / 4, reinterpret_cast<const float4 *>(compact),
+                                                         reinterpret_cast<unsigned *>(header) + 4);
+  }
   cv3::conv3_fill_planes_kernel<<<dim3((L.nw + 7) / 8, b), 256, 0, st>>>(
       c, n, r, L, static_cast<const unsigned char *>(plan_workspace), compact, header, static_cast<__half *>(xh), geo.guard,
       geo.sample_rows, geo.total_rows);

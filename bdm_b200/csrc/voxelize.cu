@@ -192,7 +192,7 @@ vox_sort_kernel(int n, int r, const int *__restrict__ coords, int *__restrict__ 
 template <int CT, int VEC, bool COMPACT = false>
 __global__ void __launch_bounds__(kFillThreads)
 vox_fill_kernel(int c, int n, int r3, const float *__restrict__ feat, float *__restrict__ out,
-                const unsigned char *__restrict__ ws, VoxAuxLayout L) {
+                const unsigned char *__restrict__ ws, VoxAuxLayout L, unsigned *__restrict__ amax_bits = nullptr) {
   const int b = blockIdx.y;
   const int c0 = blockIdx.x * CT;
   const int tid = threadIdx.x;
@@ -275,10 +275,20 @@ vox_fill_kernel(int c, int n, int r3, const float *__restrict__ feat, float *__r
     // (c') sparse consumers (sparse_conv.cu) want only the occupied voxels: out[b][c][j] = average of the
     // j-th occupied voxel (ascending voxel id), zero-padded to n columns so the shape is static
     float *o = out + ((size_t)b * c + c0) * n;
+    float amax = 0.0f;
     for (int j = tid; j < n; j += kFillThreads) {
 #pragma unroll
       for (int cc = 0; cc < CT; ++cc)
-        if (c0 + cc < c) o[(size_t)cc * n + j] = j < nocc ? buf[cc * n + j] : 0.0f;
+        if (c0 + cc < c) {
+          const float v = j < nocc ? buf[cc * n + j] : 0.0f;
+          o[(size_t)cc * n + j] = v;
+          amax = fmaxf(amax, fabsf(v));
+        }
+    }
+    if (amax_bits != nullptr) {   // max |average| of the tensor for the fp16 consumer (conv3_tc05.cu): one atomic per warp
+#pragma unroll
+      for (int d = 16; d >= 1; d >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, d));
+      if ((tid & 31) == 0 && amax > 0.0f) atomicMax(amax_bits, __float_as_uint(amax));
     }
     return;
   }
@@ -371,14 +381,14 @@ __global__ void vox_grad_kernel(int c, int n, int s, const int *__restrict__ ind
 
 template <int CT, int VEC, bool COMPACT = false>
 static cudaError_t launch_fill(int b, int c, int n, int r3, const float *feat, float *out,
-                               const unsigned char *ws, const VoxAuxLayout &L, cudaStream_t st) {
+                               const unsigned char *ws, const VoxAuxLayout &L, cudaStream_t st, unsigned *amax_bits = nullptr) {
   const size_t smem = sizeof(float) * (size_t)CT * n + sizeof(uint32_t) * L.nw +
                       sizeof(uint16_t) * ((L.nw + 1) & ~1);
   auto kern = vox_fill_kernel<CT, VEC, COMPACT>;
   cudaError_t e0 = ensure_dynamic_smem(reinterpret_cast<const void *>(kern), smem);
   if (e0 != cudaSuccess) return e0;
   dim3 grid(ceil_div(c, CT), b);
-  kern<<<grid, kFillThreads, smem, st>>>(c, n, r3, feat, out, ws, L);
+  kern<<<grid, kFillThreads, smem, st>>>(c, n, r3, feat, out, ws, L, amax_bits);
   return cudaGetLastError();
 }
 
@@ -477,8 +487,11 @@ extern "C" int bdm_avg_voxelize_fill(int b, int c, int n, int r, const int *ind,
 // Step 2', sparse flavour: only the occupied voxels' averages, out[b][c][j] for the j-th occupied voxel of
 // shape b in ascending voxel id, columns nocc(b)..n-1 zero.  Same arithmetic as the dense fill (the values
 // are the dense grid's non-empty entries, bit for bit).  Needs the sorted plan (fast path sizes only).
-extern "C" int bdm_avg_voxelize_compact(int b, int c, int n, int r, const float *feat, float *out,
-                                        const void *workspace, size_t workspace_bytes, bdm_stream_t stream) {
+// amax_bits (or NULL): a device word that receives the bit pattern of max |out| (zeroed here first) -- the dynamic fp16
+// scale of bdm_conv3_tc05_fill_planes without a separate pass over the tensor.
+extern "C" int bdm_avg_voxelize_compact_amax(int b, int c, int n, int r, const float *feat, float *out,
+                                             const void *workspace, size_t workspace_bytes, unsigned *amax_bits,
+                                             bdm_stream_t stream) {
   using namespace bdm;
   BDM_CHECK_SIZE(b >= 0 && c >= 0 && n >= 1 && r >= 1);
   const long long r3ll = (long long)r * r * r;
@@ -491,16 +504,22 @@ extern "C" int bdm_avg_voxelize_compact(int b, int c, int n, int r, const float 
   if (rc != BDM_OK) return rc;
   const unsigned char *ws = static_cast<const unsigned char *>(workspace);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (amax_bits != nullptr) cudaMemsetAsync(amax_bits, 0, sizeof(unsigned), st);
   const int want = 2 * sm_count();
   int ct = 4;
   if (b * ceil_div(c, 4) < want) ct = 2;
   if (b * ceil_div(c, 2) < want) ct = 1;
   if (sizeof(float) * (size_t)ct * n > 160 * 1024) ct = (n > 8192) ? 1 : 2;
   cudaError_t e;
-  if (ct == 4) e = launch_fill<4, 4, true>(b, c, n, r3, feat, out, ws, L, st);
-  else if (ct == 2) e = launch_fill<2, 4, true>(b, c, n, r3, feat, out, ws, L, st);
-  else e = launch_fill<1, 4, true>(b, c, n, r3, feat, out, ws, L, st);
+  if (ct == 4) e = launch_fill<4, 4, true>(b, c, n, r3, feat, out, ws, L, st, amax_bits);
+  else if (ct == 2) e = launch_fill<2, 4, true>(b, c, n, r3, feat, out, ws, L, st, amax_bits);
+  else e = launch_fill<1, 4, true>(b, c, n, r3, feat, out, ws, L, st, amax_bits);
   return e == cudaSuccess ? BDM_OK : (int)e;
+}
+
+extern "C" int bdm_avg_voxelize_compact(int b, int c, int n, int r, const float *feat, float *out,
+                                        const void *workspace, size_t workspace_bytes, bdm_stream_t stream) {
+  return bdm_avg_voxelize_compact_amax(b, c, n, r, feat, out, workspace, workspace_bytes, nullptr, stream);
 }
 
 extern "C" int bdm_avg_voxelize(int b, int c, int n, int r, const int *coords, const float *feat,

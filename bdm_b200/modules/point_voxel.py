@@ -180,10 +180,10 @@ class _PVConvBase(nn.Module):
         """-> ((output of voxel_layers[0] INCLUDING its bias, channels-last; its GroupNorm statistics; True), coords)"""
         vox, conv = self.voxelization, self.voxel_layers[0]
         norm_coords, _, plan = coordinate_plan(coords, vox.r, vox.normalize, vox.eps)
-        occupied = _ops._B.avg_voxelize_compact(features.contiguous(), plan)     # [B, Cin, N]
         prepared = _layers.conv3_prepared(conv, None, 1)
+        occupied = _ops._B.avg_voxelize_compact(features.contiguous(), plan, amax_into=prepared)     # [B, Cin, N] + max|.|
         planes = _layers.half_planes(features.shape[0], conv.in_channels, vox.r, features.device)
-        _ops._B.conv3_tc05_fill_planes(occupied, plan, prepared, planes)
+        _ops._B.conv3_tc05_fill_planes(occupied, plan, prepared, planes, amax_ready=True)
         out, stats = _ops._B.conv3_tc05(planes, prepared, conv.out_channels, bias=conv.bias, stats=True)
         return (out.permute(0, 4, 1, 2, 3), stats, True), norm_coords
 

@@ -85,6 +85,11 @@ int bdm_avg_voxelize_fill(int b, int c, int n, int r, const int *ind, const int 
  *                              output per block of rows -- the GroupNorm statistics, made by the producer. */
 int bdm_avg_voxelize_compact(int b, int c, int n, int r, const float *feat, float *out,
                              const void *workspace, size_t workspace_bytes, bdm_stream_t stream);
+/* the same, also leaving the bit pattern of max|out| in *amax_bits (a device word, zeroed by the call first): the
+ * dynamic fp16 scale of bdm_conv3_tc05_fill_planes(amax_ready = 1) without another pass over the tensor */
+int bdm_avg_voxelize_compact_amax(int b, int c, int n, int r, const float *feat, float *out,
+                                  const void *workspace, size_t workspace_bytes, unsigned *amax_bits,
+                                  bdm_stream_t stream);
 int bdm_sparse_conv3_stats_blocks(int r);
 int bdm_sparse_conv3_gather(int b, int cout, int n, int r, const float *taps, const float *bias,
                             float *out, int channels_last, double *stats, const void *workspace,
@@ -308,7 +313,8 @@ int bdm_groupnorm_act_cl(int b, int c, long long s, int groups, float eps, int s
  *       f64[b][chunks][c][2] (of the bias-less tensor) -> act(group_norm(x + conv_bias)) * act_scale as xh.
  *   bdm_conv3_tc05_fill_planes   the FIRST Conv3d's operand: per-occupied-voxel averages (bdm_avg_voxelize_compact)
  *       + the voxel plan -> xh (zeros at empty voxels), scaled by a power of two derived from max|average| on
- *       the device and recorded in `prepared` (prepare that convolution with gamma = beta = NULL, group_elems = 1).
+ *       the device and recorded in `prepared` (prepare that convolution with gamma = beta = NULL, group_elems = 1);
+ *       amax_ready != 0: bdm_avg_voxelize_compact_amax already wrote max|average| to word 4 of `prepared`.
  *   bdm_conv3_tc05   out f32[b][r^3][c_out] = conv(xh) + bias; stats (or NULL): f64[b][1][c_out][2], the result's
  *       GroupNorm(8) statistics in the layout bdm_groupnorm_act_cl(precomputed_chunks = 1) takes; workspace:
  *       bdm_conv3_tc05_workspace_bytes(b, r) bytes when stats != NULL.
@@ -326,7 +332,7 @@ int bdm_groupnorm_swish_half_planar(int b, int c, int r, int groups, float eps, 
                                     long long plane_rows, bdm_stream_t stream);
 int bdm_conv3_tc05_fill_planes(int b, int c, int n, int r, const float *compact, const void *plan_workspace,
                                size_t plan_workspace_bytes, void *prepared, void *xh, long long plane_rows,
-                               bdm_stream_t stream);
+                               int amax_ready, bdm_stream_t stream);
 int bdm_conv3_tc05(int b, int c_in, int c_out, int r, const void *xh, long long plane_rows, const void *prepared,
                    const float *bias, float *out, double *stats, void *workspace, size_t workspace_bytes,
                    bdm_stream_t stream);

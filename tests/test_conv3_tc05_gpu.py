@@ -201,6 +201,13 @@ def test_fill_planes_from_a_voxelized_cloud(b, c, n, r, cuda_backend):
         want = dense[i].permute(1, 2, 3, 0) * act_scale
         assert (vol - want).abs().max().item() <= 2 ** -10 * amax * act_scale
         assert (vol[want == 0] == 0).all()
+    # the same with max|average| measured by the compact voxelize kernel itself: identical planes and scales
+    prepared2 = B.conv3_tc05_prepare(w, None, None, 1)
+    planes2 = B.HalfPlanes(b, c, r, "cuda")
+    planes2.data.fill_(7.0)
+    B.conv3_tc05_fill_planes(B.avg_voxelize_compact(feats, plan, amax_into=prepared2), plan, prepared2, planes2, amax_ready=True)
+    assert torch.equal(planes2.data, planes.data)
+    assert torch.equal(prepared2[:20], prepared[:20])
 
 
 def test_first_convolution_dense_route_matches_sparse_route(cuda_backend):

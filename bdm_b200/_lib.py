@@ -36,6 +36,9 @@ _PROTOS = {
     "bdm_sparse_conv3_gather": (_i, [_i, _i, _i, _i, _p, _p, _p, _i, _p, _p, _z, _p]),
     "bdm_sparse_conv3_stats_blocks": (_i, [_i]),
     "bdm_trilinear_devoxelize_cl": (_i, [_i, _i, _i, _i, _p, _p, _p, _p, _p, _p]),
+    "bdm_trilinear_devoxelize_cl_norm": (_i, [_i, _i, _i, _i, _p, _p, _p, _i, _p, _p, _p, _p]),
+    "bdm_groupnorm_cl_sums_tiles": (_i, [_i, _i, ctypes.c_longlong]),
+    "bdm_groupnorm_cl_sums": (_i, [_i, _i, ctypes.c_longlong, _i, _f, _i, _p, _p, _p, _p, _p, _i, _p, _p, _p]),
     "bdm_se_gate": (_i, [_i, _i, _i, _i, _f, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_longlong, _p, _p, _p, _i, _p, _p]),
     "bdm_avg_voxelize_grad": (_i, [_i, _i, _i, _i, _p, _p, _p, _p, _p]),
     "bdm_trilinear_devoxelize_workspace_bytes": (_z, [_i, _i, _i]),

@@ -234,9 +234,11 @@ def sparse_conv3_gather(taps, plan, bias=None, channels_last=False, stats=False)
 
 
 @_op(1)
-def trilinear_devoxelize_cl(grid, coords, resolution, gate=None, residual=None):
+def trilinear_devoxelize_cl(grid, coords, resolution, gate=None, residual=None, norm_coef=None, swish=True):
     """grid f32[B,R,R,R,C] (channels last) + float voxel coordinates f32[B,3,N] -> f32[B,C,N]; inference only.
-    gate f32[B,C] / residual f32[B,C,N]: out = devox * gate + residual (the tail of a PVConv block)."""
+    gate f32[B,C] / residual f32[B,C,N]: out = devox * gate + residual (the tail of a PVConv block).
+    norm_coef f32[B,C,2] (groupnorm_cl_sums): `grid` is un-normalised and every corner value goes through
+    act(x*A + B) first -- devoxelization of GroupNorm(+Swish)(grid) without materialising it."""
     _chk_float(grid, "grid")
     _chk_float(coords, "coords")
     b, c, n, r = grid.shape[0], grid.shape[-1], coords.shape[2], int(resolution)
@@ -247,12 +249,17 @@ def trilinear_devoxelize_cl(grid, coords, resolution, gate=None, residual=None):
     if residual is not None:
         _chk_float(residual, "residual")
         _req(tuple(residual.shape) == (b, c, n), "residual must be [B,C,N]")
+    if norm_coef is not None:
+        _chk_float(norm_coef, "norm_coef")
+        _req(tuple(norm_coef.shape) == (b, c, 2), "norm_coef must be [B,C,2]")
     out = torch.empty((b, c, n), dtype=_F32, device=grid.device)
     with _Launch(grid) as st:
-        _check(_L.bdm_trilinear_devoxelize_cl(b, c, n, r, coords.data_ptr(), grid.data_ptr(),
-                                              gate.data_ptr() if gate is not None else None,
-                                              residual.data_ptr() if residual is not None else None,
-                                              out.data_ptr(), st))
+        _check(_L.bdm_trilinear_devoxelize_cl_norm(b, c, n, r, coords.data_ptr(), grid.data_ptr(),
+                                                   norm_coef.data_ptr() if norm_coef is not None else None,
+                                                   1 if swish else 0,
+                                                   gate.data_ptr() if gate is not None else None,
+                                                   residual.data_ptr() if residual is not None else None,
+                                                   out.data_ptr(), st))
     return out
 
 
@@ -642,6 +649,29 @@ def groupnorm_act_cl(x, num_groups, weight, bias, eps, swish=True, conv_bias=Non
     if channel_sums:
         return y, sums.sum(dim=1)
     return y
+
+
+@_op(1)
+def groupnorm_cl_sums(x, num_groups, weight, bias, eps, swish, conv_bias, partials):
+    """x f32[B,*,C] channels-last + producer statistics f64[B,chunks,C,2] -> (tile sums f32[B,tiles,C] of
+    act(group_norm(x + conv_bias)) for se_gate, coefficients f32[B,C,2] = (A, B) with y = act(x*A + B)): the
+    normalised tensor itself is not written (trilinear_devoxelize_cl(norm_coef=) applies it on the fly)."""
+    _chk_float(x, "x")
+    b, c = x.shape[0], x.shape[-1]
+    for t_, nm in ((weight, "weight"), (bias, "bias"), (conv_bias, "conv_bias")):
+        _chk_channel_vector(t_, nm, c)
+    s = x.numel() // max(b * c, 1)
+    _req(partials.dtype == torch.float64 and partials.is_contiguous() and partials.dim() == 4 and partials.shape[0] == b
+         and partials.shape[2] == c and partials.shape[3] == 2, "partials must be f64[B,chunks,C,2]")
+    sums = torch.empty((b, _L.bdm_groupnorm_cl_sums_tiles(b, c, s), c), dtype=_F32, device=x.device)
+    coef = torch.empty((b, c, 2), dtype=_F32, device=x.device)
+    with _Launch(x) as st:
+        _check(_L.bdm_groupnorm_cl_sums(b, c, s, int(num_groups), float(eps), 1 if swish else 0, x.data_ptr(),
+                                        conv_bias.data_ptr() if conv_bias is not None else None,
+                                        weight.data_ptr() if weight is not None else None,
+                                        bias.data_ptr() if bias is not None else None, partials.data_ptr(),
+                                        int(partials.shape[1]), sums.data_ptr(), coef.data_ptr(), st))
+    return sums, coef
 
 
 def groupnorm_max_supported(u):

@@ -394,10 +394,16 @@ constexpr int kDevoxClWarps = 8;
 // PTS = points per CTA: 32 (128-byte output rows) when there are enough points to fill the GPU that way,
 // 8 (one point per warp) for the coarse stages, whose 64-1024 points per shape would otherwise leave most
 // SMs idle while each warp walks 4 points x C/32 dependent-latency steps.
-template <int PTS>
+// NORM: feat is the un-normalised output of the block's last convolution and every corner value goes through
+// y = swish(x * A + B) (coef[b][c] = (A, B), the GroupNorm + Swish of modules/pvconv.py:82-83 with the statistics
+// folded in) before it is weighted -- the same expression the stand-alone norm kernel evaluates, so the result is
+// bit-identical to devoxelizing the normalised grid, which is then never written.
+__device__ __forceinline__ float devox_swish(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
+template <int PTS, bool NORM = false>
 __global__ void __launch_bounds__(kDevoxClWarps * 32)
 devox_cl_kernel(int c, int n, int r, const float *__restrict__ coords, const float *__restrict__ feat,
-                const float *__restrict__ gate, const float *residual, float *outs) {
+                const float *__restrict__ gate, const float *residual, float *outs,
+                const float2 *__restrict__ coef = nullptr, int swish = 0) {
   extern __shared__ float tile[];   // [PTS][c + 1]
   const int b = blockIdx.y, i0 = blockIdx.x * PTS;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -413,10 +419,19 @@ devox_cl_kernel(int c, int n, int r, const float *__restrict__ coords, const flo
     devox_corners(__ldg(co + i), __ldg(co + i + n), __ldg(co + i + n + n), r, r2, k);
     devox_clamp_ids(k, (int)r3);
     for (int cc = lane; cc < c; cc += 32) {
-      const float f0 = __ldg(f + (size_t)k.id[0] * c + cc), f1 = __ldg(f + (size_t)k.id[1] * c + cc),
-                  f2 = __ldg(f + (size_t)k.id[2] * c + cc), f3 = __ldg(f + (size_t)k.id[3] * c + cc),
-                  f4 = __ldg(f + (size_t)k.id[4] * c + cc), f5 = __ldg(f + (size_t)k.id[5] * c + cc),
-                  f6 = __ldg(f + (size_t)k.id[6] * c + cc), f7 = __ldg(f + (size_t)k.id[7] * c + cc);
+      float f0 = __ldg(f + (size_t)k.id[0] * c + cc), f1 = __ldg(f + (size_t)k.id[1] * c + cc),
+            f2 = __ldg(f + (size_t)k.id[2] * c + cc), f3 = __ldg(f + (size_t)k.id[3] * c + cc),
+            f4 = __ldg(f + (size_t)k.id[4] * c + cc), f5 = __ldg(f + (size_t)k.id[5] * c + cc),
+            f6 = __ldg(f + (size_t)k.id[6] * c + cc), f7 = __ldg(f + (size_t)k.id[7] * c + cc);
+      if (NORM) {
+        const float2 ab = __ldg(coef + (size_t)b * c + cc);
+        f0 = fmaf(f0, ab.x, ab.y); f1 = fmaf(f1, ab.x, ab.y); f2 = fmaf(f2, ab.x, ab.y); f3 = fmaf(f3, ab.x, ab.y);
+        f4 = fmaf(f4, ab.x, ab.y); f5 = fmaf(f5, ab.x, ab.y); f6 = fmaf(f6, ab.x, ab.y); f7 = fmaf(f7, ab.x, ab.y);
+        if (swish) {
+          f0 = devox_swish(f0); f1 = devox_swish(f1); f2 = devox_swish(f2); f3 = devox_swish(f3);
+          f4 = devox_swish(f4); f5 = devox_swish(f5); f6 = devox_swish(f6); f7 = devox_swish(f7);
+        }
+      }
       float acc = __fmul_rn(k.w[1], f1);
       acc = __fmaf_rn(k.w[0], f0, acc);
       acc = __fmaf_rn(k.w[2], f2, acc);
@@ -629,25 +644,43 @@ extern "C" int bdm_trilinear_devoxelize_grad(int b, int c, int n, int r3, const 
 // Inference devoxelization from a channels-last grid feat f32[b][r^3][c] -> outs f32[b][c][n]; same
 // arithmetic (weights, corner order, fma chain) as bdm_trilinear_devoxelize.  Optional epilogue:
 // outs = devox * gate[b][c] + residual[b][c][n] (either may be NULL; residual may alias outs).
-extern "C" int bdm_trilinear_devoxelize_cl(int b, int c, int n, int r, const float *coords, const float *feat,
-                                           const float *gate, const float *residual, float *outs,
-                                           bdm_stream_t stream) {
+// coef (or NULL): f32[b][c][2] = (A, B); when given, feat is the un-normalised grid and every corner value is taken through
+// act(x * A + B) first (act = Swish when swish != 0): devoxelization of GroupNorm+Swish(feat) without that tensor.
+extern "C" int bdm_trilinear_devoxelize_cl_norm(int b, int c, int n, int r, const float *coords, const float *feat,
+                                                const float *coef, int swish, const float *gate, const float *residual,
+                                                float *outs, bdm_stream_t stream) {
   using namespace bdm;
   BDM_CHECK_SIZE(b >= 0 && c >= 0 && n >= 0 && r >= 1 && b <= 65535);
   BDM_CHECK_SIZE((long long)r * r * r <= 0x7fffffffLL && c <= 8192);
   if (b == 0 || c == 0 || n == 0) return BDM_OK;
   BDM_CHECK_PTR(coords); BDM_CHECK_PTR(feat); BDM_CHECK_PTR(outs);
+  if ((reinterpret_cast<uintptr_t>(coef) & 7) != 0) return BDM_ERR_MISALIGNED;
+  const float2 *cf = reinterpret_cast<const float2 *>(coef);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if ((long long)ceil_div(n, 32) * b >= 4LL * sm_count()) {
     const size_t smem = sizeof(float) * 32 * (size_t)(c + 1);
-    cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void *>(devox_cl_kernel<32>), smem);
+    cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void *>(devox_cl_kernel<32, false>), smem);
+    if (e == cudaSuccess) e = ensure_dynamic_smem(reinterpret_cast<const void *>(devox_cl_kernel<32, true>), smem);
     if (e != cudaSuccess) return (int)e;
-    devox_cl_kernel<32><<<dim3(ceil_div(n, 32), b), kDevoxClWarps * 32, smem, st>>>(c, n, r, coords, feat, gate, residual, outs);
+    if (cf != nullptr)
+      devox_cl_kernel<32, true><<<dim3(ceil_div(n, 32), b), kDevoxClWarps * 32, smem, st>>>(c, n, r, coords, feat, gate, residual, outs, cf, swish);
+    else
+      devox_cl_kernel<32, false><<<dim3(ceil_div(n, 32), b), kDevoxClWarps * 32, smem, st>>>(c, n, r, coords, feat, gate, residual, outs);
   } else {
     const size_t smem = sizeof(float) * 8 * (size_t)(c + 1);
-    cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void *>(devox_cl_kernel<8>), smem);
+    cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void *>(devox_cl_kernel<8, false>), smem);
+    if (e == cudaSuccess) e = ensure_dynamic_smem(reinterpret_cast<const void *>(devox_cl_kernel<8, true>), smem);
     if (e != cudaSuccess) return (int)e;
-    devox_cl_kernel<8><<<dim3(ceil_div(n, 8), b), kDevoxClWarps * 32, smem, st>>>(c, n, r, coords, feat, gate, residual, outs);
+    if (cf != nullptr)
+      devox_cl_kernel<8, true><<<dim3(ceil_div(n, 8), b), kDevoxClWarps * 32, smem, st>>>(c, n, r, coords, feat, gate, residual, outs, cf, swish);
+    else
+      devox_cl_kernel<8, false><<<dim3(ceil_div(n, 8), b), kDevoxClWarps * 32, smem, st>>>(c, n, r, coords, feat, gate, residual, outs);
   }
   BDM_RETURN_LAUNCH_STATUS();
+}
+
+extern "C" int bdm_trilinear_devoxelize_cl(int b, int c, int n, int r, const float *coords, const float *feat,
+                                           const float *gate, const float *residual, float *outs,
+                                           bdm_stream_t stream) {
+  return bdm_trilinear_devoxelize_cl_norm(b, c, n, r, coords, feat, nullptr, 0, gate, residual, outs, stream);
 }

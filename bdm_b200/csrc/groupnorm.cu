@@ -454,12 +454,15 @@ gn_cl_stats_kernel(int c, long long s, int nchunks, const float *__restrict__ x,
   }
 }
 
-template <bool SWISH, int UNR>
+// STORE == false: nothing is written back except the per-tile sums and (tile 0) the per-channel coefficients
+// coef[b][c] = (A, B) of y = act(x * A + B): the consumer normalises on the fly (bdm_trilinear_devoxelize_cl_norm).
+template <bool SWISH, int UNR, bool STORE = true>
 __global__ void __launch_bounds__(kClThreads)
 gn_cl_apply_kernel(int c, long long s, int groups, int nchunks, int pstride, int ntiles, float eps, int zero_shift,
                    const float *__restrict__ x, const float *__restrict__ conv_bias,
                    const float *__restrict__ gamma, const float *__restrict__ beta,
-                   const double2 *__restrict__ partials, float *__restrict__ y, float *__restrict__ tile_sums) {
+                   const double2 *__restrict__ partials, float *__restrict__ y, float *__restrict__ tile_sums,
+                   float2 *__restrict__ coef = nullptr) {
   __shared__ double2 chan[256];          // per-channel folded (sum, sumsq) of x + conv_bias
   __shared__ double2 grp[256];           // per-group (mean, rstd)
   __shared__ float2 ab[256];             // per-channel (A, B): y = act(x * A + B)
@@ -508,6 +511,7 @@ gn_cl_apply_kernel(int c, long long s, int groups, int nchunks, int pstride, int
     const float cb = conv_bias != nullptr ? conv_bias[t] : 0.0f;
     const float A = (float)g.y * ga;
     ab[t] = make_float2(A, (float)((double)be + ((double)cb - g.x) * (double)A));
+    if (!STORE && coef != nullptr && tile == 0) coef[(size_t)b * c + t] = ab[t];
   }
   __syncthreads();
   const int q = t % c4, r0 = t / c4;
@@ -541,8 +545,11 @@ gn_cl_apply_kernel(int c, long long s, int groups, int nchunks, int pstride, int
       for (int j = 0; j < UNR; ++j) {
         v[j].x = act(fmaf(v[j].x, p0.x, p0.y)); v[j].y = act(fmaf(v[j].y, p1.x, p1.y));
         v[j].z = act(fmaf(v[j].z, p2.x, p2.y)); v[j].w = act(fmaf(v[j].w, p3.x, p3.y));
-        *reinterpret_cast<float4 *>(py + (size_t)(row + (long long)j * rpp) * c + 4 * q) = v[j];
-        acc[0] += v[j].x; acc[1] += v[j].y; acc[2] += v[j].z; acc[3] += v[j].w;
+        if (STORE) *reinterpret_cast<float4 *>(py + (size_t)(row + (long long)j * rpp) * c + 4 * q) = v[j];
+        // (__fadd_rn: never contracted with the multiply inside the activation, so the sums are those of the rounded
+        // values whether or not they are also stored)
+        acc[0] = __fadd_rn(acc[0], v[j].x); acc[1] = __fadd_rn(acc[1], v[j].y);
+        acc[2] = __fadd_rn(acc[2], v[j].z); acc[3] = __fadd_rn(acc[3], v[j].w);
       }
       if (more) {
 #pragma unroll
@@ -556,8 +563,8 @@ gn_cl_apply_kernel(int c, long long s, int groups, int nchunks, int pstride, int
     float4 v = ld_stream_f4(px + (size_t)row * c + 4 * q);
     v.x = act(fmaf(v.x, p0.x, p0.y)); v.y = act(fmaf(v.y, p1.x, p1.y));
     v.z = act(fmaf(v.z, p2.x, p2.y)); v.w = act(fmaf(v.w, p3.x, p3.y));
-    *reinterpret_cast<float4 *>(py + (size_t)row * c + 4 * q) = v;
-    acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[3] += v.w;
+    if (STORE) *reinterpret_cast<float4 *>(py + (size_t)row * c + 4 * q) = v;
+    acc[0] = __fadd_rn(acc[0], v.x); acc[1] = __fadd_rn(acc[1], v.y); acc[2] = __fadd_rn(acc[2], v.z); acc[3] = __fadd_rn(acc[3], v.w);
   }
   if (tile_sums != nullptr) {   // per-tile, per-channel sums of y in fixed slots: deterministic
 #pragma unroll
@@ -985,6 +992,34 @@ extern "C" int bdm_groupnorm_act_cl(int b, int c, long long s, int groups, float
     gn_cl_apply_kernel<false, 4><<<dim3(ntiles, b), kClThreads, 0, st>>>(c, s, groups, nchunks, nchunks, ntiles, eps, 0, x, conv_bias,
                                                                     gamma, beta, partials, y, tile_sums);
   g_last_launches = 2;
+  BDM_RETURN_LAUNCH_STATUS();
+}
+
+// The statistics-only half of bdm_groupnorm_act_cl for a consumer that normalises on the fly: x f32[b][s][c] with producer
+// statistics partials f64[b][chunks][c][2] -> tile_sums f32[b][tiles][c] (tiles = bdm_groupnorm_cl_sums_tiles: the sums of
+// y = act(group_norm(x + conv_bias)) the SE gate needs) and coef f32[b][c][2] = (A, B) with y = act(x * A + B).  y itself is
+// never written: the pass reads x once.
+extern "C" int bdm_groupnorm_cl_sums_tiles(int b, int c, long long s) { return bdm::gn_cl_tiles(b, s, c); }
+extern "C" int bdm_groupnorm_cl_sums(int b, int c, long long s, int groups, float eps, int swish, const float *x,
+                                     const float *conv_bias, const float *gamma, const float *beta, const double *partials,
+                                     int chunks, float *tile_sums, float *coef, bdm_stream_t stream) {
+  using namespace bdm;
+  BDM_CHECK_SIZE(b >= 0 && s >= 0 && groups >= 1 && gn_cl_supported(c, groups) && b <= 65535 && chunks >= 1);
+  if (b == 0 || s == 0) return BDM_OK;
+  BDM_CHECK_PTR(x); BDM_CHECK_PTR(partials); BDM_CHECK_PTR(tile_sums); BDM_CHECK_PTR(coef);
+  if (((reinterpret_cast<uintptr_t>(partials) | reinterpret_cast<uintptr_t>(x)) & 15) != 0 ||
+      (reinterpret_cast<uintptr_t>(coef) & 7) != 0)
+    return BDM_ERR_MISALIGNED;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int ntiles = gn_cl_tiles(b, s, c);
+  const double2 *pp = reinterpret_cast<const double2 *>(partials);
+  float2 *cf = reinterpret_cast<float2 *>(coef);
+  if (swish)
+    gn_cl_apply_kernel<true, 4, false><<<dim3(ntiles, b), kClThreads, 0, st>>>(c, s, groups, chunks, chunks, ntiles, eps, 1, x, conv_bias,
+                                                                           gamma, beta, pp, nullptr, tile_sums, cf);
+  else
+    gn_cl_apply_kernel<false, 4, false><<<dim3(ntiles, b), kClThreads, 0, st>>>(c, s, groups, chunks, chunks, ntiles, eps, 1, x, conv_bias,
+                                                                            gamma, beta, pp, nullptr, tile_sums, cf);
   BDM_RETURN_LAUNCH_STATUS();
 }
 

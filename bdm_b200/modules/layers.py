@@ -29,6 +29,11 @@ FUSED_ATTENTION = os.environ.get("BDM_FUSED_ATTENTION", "1") != "0"
 # faster on the 8^3 grids: too few 128-row tiles for 148 SMs).  BDM_CONV3_TC05=0 disables.
 CONV3_TC05 = os.environ.get("BDM_CONV3_TC05", "1") != "0"
 CONV3_TC05_MIN_R = int(os.environ.get("BDM_CONV3_TC05_MIN_R", "16"))
+# Tail of a voxel stack whose last convolution made its own statistics: conv -> GroupNorm -> Swish -> SE -> devoxelize.
+# The normalised grid is never written: one read-only pass yields the SE squeeze sums and the per-channel (A, B) of
+# y = swish(x*A + B), and the devoxelization applies that to the 8 corner values it reads (bit-identical results).
+# BDM_FUSED_TAIL_NORM=0 disables.
+FUSED_TAIL_NORM = os.environ.get("BDM_FUSED_TAIL_NORM", "1") != "0"
 
 
 _TF32_LOCK = threading.RLock()
@@ -235,12 +240,16 @@ class FusedSequential(nn.Sequential):
     statistics), norm + activation are one pass, the SE squeeze comes out of that same pass and a
     trailing max over neighbours replaces the full-size write.  Anything else runs module by module."""
 
-    def forward(self, x, max_over_last=False, first_output=None, defer_gate=False, first_stats=None, first_biased=False):
+    def forward(self, x, max_over_last=False, first_output=None, defer_gate=False, first_stats=None, first_biased=False,
+                defer_norm=False):
         """first_output: the bias-less output of self[0] (a conv) when the caller computed it by other
         means (PVConv's sparse first convolution); `x` is then ignored.
         first_stats: per-channel statistics of first_output made by its producer (sparse_conv3_gather), handed
         to the norm that follows so that it does not read the tensor a second time.
         first_biased: first_output already includes self[0]'s bias (and first_stats are those of the biased tensor).
+        defer_norm (with defer_gate): when the stack ends in conv -> GroupNorm -> Swish -> SE3d and the conv's statistics
+        are known, return (UN-normalised conv output, gate, coefficients f32[B,C,2]) -- the caller's devoxelization applies
+        the norm + Swish to the values it reads (trilinear_devoxelize_cl(norm_coef=)).
         defer_gate: when the stack ends in an SE3d gate, return (ungated grid, gate f32[B,C]) instead of
         multiplying the whole grid -- the caller applies the gate after its (linear) consumer."""
         mods = list(self)
@@ -248,6 +257,7 @@ class FusedSequential(nn.Sequential):
         i = 0
         reduced = False
         gate = None
+        norm_coef = None
         pre, pre_stats, pre_biased = first_output, first_stats, bool(first_biased)   # output of mods[i] made by other means
         while i < n:
             m = mods[i]
@@ -278,7 +288,14 @@ class FusedSequential(nn.Sequential):
                     pre, pre_biased = out2.permute(0, 4, 1, 2, 3), True
                     i = j
                     continue
-                if nxt < n and isinstance(mods[nxt], SE3d) and swish:
+                if (nxt < n and isinstance(mods[nxt], SE3d) and swish and defer_norm and defer_gate and nxt == n - 1
+                        and FUSED_TAIL_NORM and stats is not None and is_channels_last_3d(y)
+                        and hasattr(_ops._B, "groupnorm_cl_sums") and _ops._B.groupnorm_cl_supported(y.shape[1], gn.num_groups)):
+                    sums, norm_coef = _ops._B.groupnorm_cl_sums(y.permute(0, 2, 3, 4, 1), gn.num_groups, gn.weight, gn.bias,
+                                                                gn.eps, True, cbias, stats)
+                    x, gate = y, mods[nxt].gate(y, channel_sums=sums)
+                    nxt += 1
+                elif nxt < n and isinstance(mods[nxt], SE3d) and swish:
                     y, sums = _groupnorm_act(y, gn, True, conv_bias=cbias, channel_sums=True, partials=stats)
                     if defer_gate and nxt == n - 1:
                         x, gate = y, mods[nxt].gate(y, channel_sums=sums)
@@ -318,7 +335,7 @@ class FusedSequential(nn.Sequential):
         if max_over_last and not reduced:
             x = x.max(dim=-1).values
         if defer_gate:
-            return x, gate
+            return (x, gate, norm_coef) if defer_norm else (x, gate)
         return x
 
 

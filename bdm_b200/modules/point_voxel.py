@@ -238,15 +238,18 @@ class _PVConvBase(nn.Module):
         else:
             grid, grid_coords = self.voxelization(features, coords)
         grid = self.voxel_layers(grid, first_output=first, defer_gate=defer, first_stats=first_stats,
-                                 first_biased=first_biased)
-        gate = None
+                                 first_biased=first_biased, defer_norm=defer)
+        gate = norm_coef = None
         if defer:
-            grid, gate = grid
+            grid, gate, norm_coef = grid
         if _layers.is_channels_last_3d(grid) and not torch.is_grad_enabled():
-            # channels-last branch: devoxelize, SE gate and the residual add of the point branch in one kernel
+            # channels-last branch: (last norm + Swish,) devoxelize, SE gate and the residual add of the point branch in
+            # one kernel
             fused = _ops._B.trilinear_devoxelize_cl(grid.permute(0, 2, 3, 4, 1), grid_coords.contiguous(), self.resolution,
-                                                    gate=gate, residual=self.point_features(features).contiguous())
+                                                    gate=gate, residual=self.point_features(features).contiguous(),
+                                                    norm_coef=norm_coef)
             return fused, coords, temb
+        assert norm_coef is None
         from_voxels = F.trilinear_devoxelize(grid, grid_coords, self.resolution, self.training)
         if gate is not None:
             return torch.addcmul(self.point_features(features), from_voxels, gate[:, :, None]), coords, temb

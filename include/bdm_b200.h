@@ -119,6 +119,12 @@ int bdm_trilinear_devoxelize(int b, int c, int n, int r, int is_training, const 
  * optional epilogue of the PVConv block: outs = devox * gate[b,c] + residual[b,c,n] (NULL = skip) */
 int bdm_trilinear_devoxelize_cl(int b, int c, int n, int r, const float *coords, const float *feat,
                                 const float *gate, const float *residual, float *outs, bdm_stream_t stream);
+/* the same from the UN-normalised grid: coef f32[b][c][2] = (A, B) with y = act(x*A + B) (act = Swish when swish != 0;
+ * bdm_groupnorm_cl_sums produces coef) is applied to every corner value before the interpolation -- bit-identical to
+ * devoxelizing bdm_groupnorm_act_cl's output, which is then never written (modules/pvconv.py:82-83, 95-97) */
+int bdm_trilinear_devoxelize_cl_norm(int b, int c, int n, int r, const float *coords, const float *feat,
+                                     const float *coef, int swish, const float *gate, const float *residual,
+                                     float *outs, bdm_stream_t stream);
 /* replaces trilinear_devoxelize_grad (trilinear_devox.cuh:9-11): grad_x f32[b,c,r3] is zeroed here */
 int bdm_trilinear_devoxelize_grad(int b, int c, int n, int r3, const int *inds, const float *wgts,
                                   const float *grad_y, float *grad_x, bdm_stream_t stream);
@@ -295,6 +301,14 @@ int bdm_groupnorm_act_cl(int b, int c, long long s, int groups, float eps, int s
                          bdm_stream_t stream);
 /* precomputed_chunks > 0: workspace holds the producer's statistics f64[b,precomputed_chunks,c,2] (see
  * bdm_sparse_conv3_gather) and the statistics pass over x is skipped. */
+/* Statistics-only half for a consumer that normalises on the fly (bdm_trilinear_devoxelize_cl_norm): x + producer
+ * statistics partials f64[b,chunks,c,2] -> tile_sums f32[b,tiles,c] (tiles = bdm_groupnorm_cl_sums_tiles; sums of
+ * y = act(group_norm(x + conv_bias)), what bdm_se_gate takes) and coef f32[b,c,2] = (A, B) with y = act(x*A + B).
+ * One read of x, nothing else written. */
+int bdm_groupnorm_cl_sums_tiles(int b, int c, long long s);
+int bdm_groupnorm_cl_sums(int b, int c, long long s, int groups, float eps, int swish, const float *x,
+                          const float *conv_bias, const float *gamma, const float *beta, const double *partials,
+                          int chunks, float *tile_sums, float *coef, bdm_stream_t stream);
 
 /* ---- dense side: the 3x3x3 convolution of the voxel branch on the 5th-generation tensor cores -------------------
  * replaces the second nn.Conv3d(c, c, 3, padding=1) of a PVConv block's voxel_layers (modules/pvconv.py:75-88), which

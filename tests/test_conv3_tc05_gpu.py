@@ -245,6 +245,68 @@ def test_first_convolution_dense_route_matches_sparse_route(cuda_backend):
         assert e_dense <= max(2.0 * e_sparse, 2e-4), (cin, cout, r, e_dense, e_sparse)
 
 
+@pytest.mark.parametrize("b,c,r,n", [(3, 64, 32, 4096), (2, 32, 16, 1000), (2, 128, 16, 1024), (1, 256, 8, 64)])
+def test_norm_on_the_fly_devoxelize_is_bit_identical(b, c, r, n, cuda_backend):
+    """groupnorm_cl_sums + trilinear_devoxelize_cl(norm_coef=) == groupnorm_act_cl -> trilinear_devoxelize_cl, bit for
+    bit: SE squeeze sums, and the devoxelized, gated, residual-added features"""
+    import torch
+    B = cuda_backend
+    g = torch.Generator(device="cuda").manual_seed(b + c + r)
+    x = torch.randn(b, r, r, r, c, device="cuda", generator=g) * 2.0 + 0.5
+    gamma = torch.rand(c, device="cuda", generator=g) + 0.5
+    beta = torch.randn(c, device="cuda", generator=g) * 0.2
+    coords = torch.rand(b, 3, n, device="cuda", generator=g) * (r - 1)
+    gate = torch.rand(b, c, device="cuda", generator=g)
+    res = torch.randn(b, c, n, device="cuda", generator=g)
+    xs = x.reshape(b, -1, c).double()
+    cg = c // 8
+    part = torch.zeros(b, 1, c, 2, dtype=torch.float64, device="cuda")      # per-group sums in the group's first slot
+    part[:, 0, ::cg, 0] = xs.sum(1).reshape(b, 8, cg).sum(-1)
+    part[:, 0, ::cg, 1] = (xs * xs).sum(1).reshape(b, 8, cg).sum(-1)
+    xf = x.reshape(b, -1, c)
+    y, sums_ref = B.groupnorm_act_cl(xf, 8, gamma, beta, 1e-5, True, channel_sums="tiles", partials=part)
+    want = B.trilinear_devoxelize_cl(y.reshape(b, r, r, r, c), coords, r, gate=gate, residual=res)
+    sums, coef = B.groupnorm_cl_sums(xf, 8, gamma, beta, 1e-5, True, None, part)
+    got = B.trilinear_devoxelize_cl(x, coords, r, gate=gate, residual=res, norm_coef=coef)
+    if sums_ref.shape == sums.shape:       # (small groups take the one-pass norm kernel, which reports whole sums)
+        assert torch.equal(sums, sums_ref)
+    else:
+        assert torch.allclose(sums.sum(1), sums_ref.sum(1), rtol=1e-5, atol=1e-3)
+        y2 = torch.nn.functional.group_norm(x.permute(0, 4, 1, 2, 3), 8, gamma, beta, 1e-5)
+        want = B.trilinear_devoxelize_cl((y2 * torch.sigmoid(y2)).permute(0, 2, 3, 4, 1).contiguous(), coords, r, gate=gate, residual=res)
+        assert (got - want).abs().max().item() <= 1e-5 * want.abs().max().item()
+        return
+    assert torch.equal(got, want)
+
+
+def test_block_with_fused_tail_is_bit_identical(cuda_backend):
+    import torch
+
+    import bdm_b200.modules.layers as L
+    import bdm_b200.modules.point_voxel as PV
+    B = cuda_backend
+    for cin, cout, n, r in ((64, 64, 4096, 32), (128, 128, 1024, 16), (32, 32, 2048, 32)):
+        torch.manual_seed(cin + r + 1)
+        blk = PV.PVConv(cin, cout, 3, r, with_se=True).cuda().eval()
+        feats = torch.randn(2, cin, n, device="cuda")
+        u = torch.randn(2, 3, n, device="cuda")
+        coords = u / u.norm(dim=1, keepdim=True) * (0.5 + 0.02 * torch.randn(2, 1, n, device="cuda"))
+        temb = torch.randn(2, 8, n, device="cuda")
+        saved = L.FUSED_TAIL_NORM
+        try:
+            with torch.no_grad():
+                L.FUSED_TAIL_NORM = True
+                B.profile_start()
+                y_fused = blk((feats, coords, temb))[0]
+                prof = B.profile_stop()
+                assert "groupnorm_cl_sums" in prof, sorted(prof)
+                L.FUSED_TAIL_NORM = False
+                y_plain = blk((feats, coords, temb))[0]
+        finally:
+            L.FUSED_TAIL_NORM = saved
+        assert torch.equal(y_fused, y_plain), (cin, cout, r, (y_fused - y_plain).abs().max().item())
+
+
 def test_route_is_off_when_tf32_convolutions_are_off(cuda_backend):
     import torch
 

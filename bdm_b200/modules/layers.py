@@ -34,6 +34,10 @@ CONV3_TC05_MIN_R = int(os.environ.get("BDM_CONV3_TC05_MIN_R", "16"))
 # y = swish(x*A + B), and the devoxelization applies that to the 8 corner values it reads (bit-identical results).
 # BDM_FUSED_TAIL_NORM=0 disables.
 FUSED_TAIL_NORM = os.environ.get("BDM_FUSED_TAIL_NORM", "1") != "0"
+# ... only on grids of at least this many voxels per side: the devoxelization then evaluates Swish 8 times per point
+# instead of once per voxel (MUFU-bound: +35 us at R=32 / C=64 / 4096 points against -42 us for the norm pass; on the 16^3
+# grids, where 8 * points = 2 * voxels, it loses)
+FUSED_TAIL_NORM_MIN_R = int(os.environ.get("BDM_FUSED_TAIL_NORM_MIN_R", "32"))
 
 
 _TF32_LOCK = threading.RLock()
@@ -289,7 +293,7 @@ class FusedSequential(nn.Sequential):
                     i = j
                     continue
                 if (nxt < n and isinstance(mods[nxt], SE3d) and swish and defer_norm and defer_gate and nxt == n - 1
-                        and FUSED_TAIL_NORM and stats is not None and is_channels_last_3d(y)
+                        and FUSED_TAIL_NORM and y.shape[-1] >= FUSED_TAIL_NORM_MIN_R and stats is not None and is_channels_last_3d(y)
                         and hasattr(_ops._B, "groupnorm_cl_sums") and _ops._B.groupnorm_cl_supported(y.shape[1], gn.num_groups)):
                     sums, norm_coef = _ops._B.groupnorm_cl_sums(y.permute(0, 2, 3, 4, 1), gn.num_groups, gn.weight, gn.bias,
                                                                 gn.eps, True, cbias, stats)

@@ -292,10 +292,10 @@ def test_block_with_fused_tail_is_bit_identical(cuda_backend):
         u = torch.randn(2, 3, n, device="cuda")
         coords = u / u.norm(dim=1, keepdim=True) * (0.5 + 0.02 * torch.randn(2, 1, n, device="cuda"))
         temb = torch.randn(2, 8, n, device="cuda")
-        saved = L.FUSED_TAIL_NORM
+        saved = (L.FUSED_TAIL_NORM, L.FUSED_TAIL_NORM_MIN_R)
         try:
             with torch.no_grad():
-                L.FUSED_TAIL_NORM = True
+                L.FUSED_TAIL_NORM, L.FUSED_TAIL_NORM_MIN_R = True, 16
                 B.profile_start()
                 y_fused = blk((feats, coords, temb))[0]
                 prof = B.profile_stop()
@@ -303,7 +303,7 @@ def test_block_with_fused_tail_is_bit_identical(cuda_backend):
                 L.FUSED_TAIL_NORM = False
                 y_plain = blk((feats, coords, temb))[0]
         finally:
-            L.FUSED_TAIL_NORM = saved
+            L.FUSED_TAIL_NORM, L.FUSED_TAIL_NORM_MIN_R = saved
         assert torch.equal(y_fused, y_plain), (cin, cout, r, (y_fused - y_plain).abs().max().item())
 
 

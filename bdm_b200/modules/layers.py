@@ -194,6 +194,25 @@ def conv_no_bias_concat(m, parts):
     return y
 
 
+# A 1x1 convolution over 3 + C grouped channels (35, 67, 131, 259 in the SA stages) has a reduction length that is not a
+# multiple of 4, which sends cuBLAS to its SIMT / split kernels (122 us for 35 -> 32 channels over 32 x 1024 x 32 columns,
+# against ~65 us of HBM time).  When the consumer is the fused conv -> norm route, BallQuery allocates the grouped tensor
+# with the channel count rounded up to a multiple of 4 (zero planes at the end) and the convolution multiplies by a
+# zero-padded weight: same sums, aligned tensor-op GEMM.  BDM_PAD_GROUPED=0 disables.
+PAD_GROUPED_CHANNELS = os.environ.get("BDM_PAD_GROUPED", "1") != "0"
+
+
+def padded_channels(c):
+    return (int(c) + 3) & ~3
+
+
+def pads_grouped_channels(t, first_conv):
+    """may a grouped tensor built for `first_conv` from CUDA tensor `t` carry zero-padded channels?"""
+    return (PAD_GROUPED_CHANNELS and FUSED_NORM_ACT and t.is_cuda and t.dtype == torch.float32
+            and not torch.is_grad_enabled() and not _ops.REFERENCE_CALL_PATTERN and hasattr(_ops._B, "groupnorm_act")
+            and _pointwise(first_conv) and first_conv.bias is not None and first_conv.in_channels % 4 != 0)
+
+
 def _pointwise(m):
     return (isinstance(m, (nn.Conv1d, nn.Conv2d)) and all(k == 1 for k in m.kernel_size)
             and all(v == 1 for v in m.stride) and all(v == 0 for v in m.padding)
@@ -207,6 +226,23 @@ def conv_no_bias(m, x):
     tail costs two GEMM launches and no copy of x.  TF32 follows the conv policy (cudnn.allow_tf32), as for
     every other convolution of the network."""
     cin = m.in_channels
+    if _pointwise(m) and x.shape[1] != cin:
+        # zero-padded input channels (BallQuery pads 3 + C to a multiple of 4 for exactly this): one aligned
+        # tensor-op GEMM against the weight padded with zero columns (cached)
+        cpad = x.shape[1]
+        assert cpad == padded_channels(cin) and x.is_contiguous()
+        w = m.weight
+        key = (w.data_ptr(), geometry.tensor_version(w), w.device, cpad)
+        cached = getattr(m, "_padded_weight", None)
+        if cached is None or cached[0] != key:
+            w2 = torch.zeros((m.out_channels, cpad), dtype=w.dtype, device=w.device)
+            w2[:, :cin] = w.detach().reshape(m.out_channels, cin)
+            cached = (key, w2)
+            m._padded_weight = cached
+        nb = x.shape[0]
+        with matmul_precision_of_convs():
+            y = torch.matmul(cached[1], x.reshape(nb, cpad, -1))
+        return y.reshape(nb, m.out_channels, *x.shape[2:])
     if isinstance(m, nn.Conv3d) and is_channels_last_3d(x):
         # channels-last activations: hand cuDNN the weight in the same format (cached), so that it neither
         # transposes the weight on every call nor the activations around the kernel

@@ -21,7 +21,9 @@ class BallQuery(nn.Module):
         self.num_neighbors = num_neighbors
         self.include_coordinates = include_coordinates
 
-    def forward(self, points_coords, centers_coords, temb, points_features=None):
+    def forward(self, points_coords, centers_coords, temb, points_features=None, pad_channels=False):
+        """pad_channels: the caller's first 1x1 convolution accepts a grouped tensor whose channel count is rounded up to
+        a multiple of 4 with zero planes (layers.conv_no_bias); only honoured on the fused inference route."""
         pts, cen = points_coords.contiguous(), centers_coords.contiguous()
         nbr = F.ball_query(cen, pts, self.radius, self.num_neighbors)          # int32[B,M,U]
         if (points_features is not None and self.include_coordinates and pts.is_cuda and not torch.is_grad_enabled()
@@ -30,8 +32,11 @@ class BallQuery(nn.Module):
             # inference: both groupings write straight into the concatenated tensor, centres subtracted on
             # the way (same values as grouping -> broadcast subtract -> cat, two full-size passes less)
             feats = points_features.contiguous()
-            grouped = torch.empty((pts.shape[0], 3 + feats.shape[1], nbr.shape[1], nbr.shape[2]),
-                                  dtype=torch.float32, device=pts.device)
+            channels = 3 + feats.shape[1]
+            total = _layers.padded_channels(channels) if pad_channels else channels
+            grouped = torch.empty((pts.shape[0], total, nbr.shape[1], nbr.shape[2]), dtype=torch.float32, device=pts.device)
+            if total > channels:
+                grouped[:, channels:].zero_()
             _ops._B.grouping_into(pts, nbr, grouped, 0, centers=cen)
             _ops._B.grouping_into(feats, nbr, grouped, 3)
             return grouped, F.group_time_embedding(temb, nbr)
@@ -104,7 +109,9 @@ class PointNetSAModule(nn.Module):
         features, coords, temb = inputs
         centers = F.furthest_point_sample(coords, self.num_centers)
         if len(self.groupers) == 1:
-            grouped, temb = self.groupers[0](coords, centers, temb, features)
+            first_conv = self.mlps[0].layers[0]
+            grouped, temb = self.groupers[0](coords, centers, temb, features,
+                                             pad_channels=features is not None and _layers.pads_grouped_channels(features, first_conv))
             first = self.mlps[0].forward_max(grouped)   # == mlp(grouped).max(dim=-1).values
         else:
             first = None

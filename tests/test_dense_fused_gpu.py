@@ -445,3 +445,31 @@ def test_attention_block_on_channels_last_grid(cuda_backend):
     assert torch.equal(y1s, y1)
     want_sums = y0.double().flatten(2).sum(-1)
     assert (sums.sum(dim=1).double() - want_sums).abs().max().item() <= 1e-5 * want_sums.abs().max().item()
+
+
+@pytest.mark.parametrize("cin,widths,m,u,n", [(32, (32, 64), 256, 32, 1024), (64, (64, 128), 64, 16, 256), (128, (128,), 16, 8, 64)])
+def test_grouped_channels_padded_to_a_multiple_of_four(cin, widths, m, u, n, cuda_backend):
+    """SA module with the grouped tensor's 3 + C channels zero-padded to a multiple of 4 (aligned GEMM against a
+    zero-padded weight) == the unpadded route; fp32 GEMMs on both sides: 1e-5 of the output's peak"""
+    import torch
+
+    import bdm_b200.modules.layers as L
+    from bdm_b200.modules.pointnet2 import PointNetSAModule
+    torch.manual_seed(cin + m)
+    sa = PointNetSAModule(m, 0.4, u, cin, list(widths)).cuda().eval()
+    feats = torch.randn(3, cin, n, device="cuda")
+    coords = torch.rand(3, 3, n, device="cuda")
+    temb = torch.randn(3, 8, n, device="cuda")
+    saved = (L.PAD_GROUPED_CHANNELS, torch.backends.cudnn.allow_tf32)
+    try:
+        torch.backends.cudnn.allow_tf32 = False
+        with torch.no_grad():
+            L.PAD_GROUPED_CHANNELS = True
+            assert L.pads_grouped_channels(feats, sa.mlps[0].layers[0])
+            y_pad = sa((feats, coords, temb))[0]
+            L.PAD_GROUPED_CHANNELS = False
+            y_ref = sa((feats, coords, temb))[0]
+    finally:
+        L.PAD_GROUPED_CHANNELS, torch.backends.cudnn.allow_tf32 = saved
+    err = (y_pad - y_ref).abs().max().item() / y_ref.abs().max().item()
+    assert err <= 1e-5, err

@@ -660,7 +660,7 @@ conv3_stats_fold_kernel(int units, int c, const double *__restrict__ unit_stats,
 }
 
 static inline bool supported(int c_in, int c_out, int r) {
-  const bool pow2 = r >= 4 && r <= 64 && (r & (r - 1)) == 0;
+  const bool pow2 = r >= 4 && r <= 32 && (r & (r - 1)) == 0;   // r = 64: the three activation slabs no longer fit 227 KB
   return pow2 && (c_out == 32 || c_out == 64 || c_out == 128) && (c_in == 32 || (c_in >= 64 && c_in % 64 == 0 && c_in <= 512));
 }
 static inline int kc_of(int c_in) { return c_in == 32 ? 32 : 64; }

@@ -27,7 +27,8 @@ for name, us in half:
     a[0] += 1
     a[1] += us
 total = sum(a[1] for a in agg.values())
-ours = sum(a[1] for k, a in agg.items() if k.startswith("bdm::"))
+OURS = ("bdm::", "cv3::", "tc05::", "gnc::")      # namespaces of libbdm_b200.so's kernels as ncu prints them
+ours = sum(a[1] for k, a in agg.items() if k.startswith(OURS))
 print(f"# {'window of the bench command (graph replays)' if len(half) == len(launches) else 'One PC^2 iteration, eager'} (B={__import__('os').environ.get('BDM_BATCH', '32')}, N=4096), serialised under ncu: {len(half)} launches, {total / 1e3:.2f} ms of kernel time")
 print(f"# libbdm_b200 kernels: {ours / 1e3:.3f} ms = {ours / total * 100:.1f} % of the step's kernel time")
 print("| kernel | launches | total us | share % |")

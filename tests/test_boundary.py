@@ -58,6 +58,37 @@ def test_argument_errors_do_not_need_a_gpu():
     assert L.bdm_avg_voxelize_compact(1, 4, 64, 64, None, None, None, 0, None) == -2         # needs the sorted plan (r^3 <= 32768)
 
 
+def test_conv3_tc05_geometry_and_argument_errors_need_no_gpu():
+    """flat padded grid of csrc/conv3_tc05.cu: plane rows, units and the shape restrictions, all host-side"""
+    from bdm_b200 import _lib
+    L = _lib.lib
+    for r in (4, 8, 16, 32):
+        q = r + 1
+        guard = (q * q + q + 1 + 7) // 8 * 8
+        sample_rows = (guard + q ** 3 + 7) // 8 * 8
+        last_valid = ((r - 1) * q + (r - 1)) * q + (r - 1)
+        assert L.bdm_conv3_tc05_units(r) == (last_valid + 1 + 255) // 256
+        for b in (1, 3, 32):
+            rows = L.bdm_conv3_tc05_plane_rows(b, r)
+            # every sample's positions plus the rows its last 256-row unit reads beyond them fit
+            assert rows >= guard + b * sample_rows + guard
+            assert rows >= guard + (b - 1) * sample_rows + L.bdm_conv3_tc05_units(r) * 256 + q * q + q + 1
+    assert L.bdm_conv3_tc05_supported(64, 64, 32) == 1 and L.bdm_conv3_tc05_supported(32, 128, 16) == 1
+    assert L.bdm_conv3_tc05_supported(390, 32, 32) == 0      # reduction length: 32 or a multiple of 64
+    assert L.bdm_conv3_tc05_supported(64, 256, 8) == 0       # 256 accumulator columns do not double-buffer in TMEM
+    assert L.bdm_conv3_tc05_supported(64, 64, 12) == 0 and L.bdm_conv3_tc05_supported(64, 64, 64) == 0
+    assert L.bdm_conv3_tc05_weight_bytes(64, 64) == 256 + 27 * 64 * 64 * 2
+    rows = L.bdm_conv3_tc05_plane_rows(2, 16)
+    assert L.bdm_conv3_tc05(2, 390, 32, 16, None, rows, None, None, None, None, None, 0, None) == -2     # unsupported widths
+    assert L.bdm_conv3_tc05(2, 64, 64, 16, None, rows, None, None, None, None, None, 0, None) == -1      # NULL operands
+    assert L.bdm_conv3_tc05(0, 64, 64, 16, None, rows, None, None, None, None, None, 0, None) == 0       # empty batch
+    assert L.bdm_conv3_tc05_prepare(48, 64, None, None, None, 1, None, 0, None) == -2
+    assert L.bdm_groupnorm_swish_half_planar(2, 64, 12, 8, 1e-5, 1, None, None, None, None, None, 1, None, None, rows, None) == -2
+    assert L.bdm_conv3_tc05_fill_planes(2, 64, 1024, 64, None, None, 0, None, None, rows, 0, None) == -2  # needs the plan (r <= 32)
+    assert L.bdm_groupnorm_cl_sums(2, 48, 512, 8, 1e-5, 1, None, None, None, None, None, 1, None, None, None) == -2
+    assert L.bdm_trilinear_devoxelize_cl_norm(0, 64, 128, 16, None, None, None, 1, None, None, None, None) == 0
+
+
 def test_product_never_imports_oracle():
     """A product path that routes through the oracle voids every parity claim: forbid it textually."""
     offenders = []

@@ -78,9 +78,10 @@ _PROTOS = {
     "bdm_conv3_tc05_workspace_bytes": (_z, [_i, _i]),
     "bdm_conv3_tc05_prepare": (_i, [_i, _i, _p, _p, _p, ctypes.c_longlong, _p, _z, _p]),
     "bdm_groupnorm_swish_half_planar": (_i, [_i, _i, _i, _i, _f, _i, _p, _p, _p, _p, _p, _i, _p, _p, ctypes.c_longlong, _p]),
-    "bdm_conv3_tc05_fill_planes": (_i, [_i, _i, _i, _i, _p, _p, _z, _p, _p, ctypes.c_longlong, _i, _p]),
+    "bdm_conv3_tc05_fill_planes": (_i, [_i, _i, _i, _i, _p, _p, _z, _p, _p, ctypes.c_longlong, _i, _p, _p]),
+    "bdm_conv3_tc05_occ_words": (_i, [_i]),
     "bdm_avg_voxelize_compact_amax": (_i, [_i, _i, _i, _i, _p, _p, _p, _z, _p, _p]),
-    "bdm_conv3_tc05": (_i, [_i, _i, _i, _i, _p, ctypes.c_longlong, _p, _p, _p, _p, _p, _z, _p]),
+    "bdm_conv3_tc05": (_i, [_i, _i, _i, _i, _p, ctypes.c_longlong, _p, _p, _p, _p, _p, _z, _p, _p]),
 }
 
 EXPORTS = tuple(_PROTOS)

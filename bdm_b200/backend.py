@@ -795,12 +795,14 @@ def conv3_tc05_supported(c_in, c_out, resolution):
 class HalfPlanes:
     """fp16 chunk planes [C/8, rows, 8] of the flat padded grid for (batch, resolution): the convolution's operand.
     Zero-filled at creation; producers write real voxels only, so pad rows stay zero for the buffer's lifetime."""
-    __slots__ = ("b", "c", "r", "rows", "data")
+    __slots__ = ("b", "c", "r", "rows", "data", "occ")
 
     def __init__(self, b, c, r, device):
         self.b, self.c, self.r = int(b), int(c), int(r)
         self.rows = int(_L.bdm_conv3_tc05_plane_rows(self.b, self.r))
         self.data = torch.zeros((self.c // 8, self.rows, 8), dtype=torch.float16, device=device)
+        # one bit per non-zero row (conv3_tc05_fill_planes): lets conv3_tc05(sparse=True) skip all-zero tap windows
+        self.occ = torch.zeros((self.b, int(_L.bdm_conv3_tc05_occ_words(self.r))), dtype=torch.int32, device=device)
 
     def describe(self):
         return f"HalfPlanes(b={self.b}, c={self.c}, r={self.r})"
@@ -860,14 +862,16 @@ def conv3_tc05_fill_planes(compact, plan, prepared, planes, amax_ready=False):
     with _Launch(compact) as st:
         _check(_L.bdm_conv3_tc05_fill_planes(b, c, n, plan.r, compact.data_ptr(), plan.workspace.data_ptr(), plan.workspace.numel(),
                                              prepared.data_ptr(), planes.data.data_ptr(), planes.rows,
-                                             1 if amax_ready else 0, st))
+                                             1 if amax_ready else 0, planes.occ.data_ptr(), st))
     return planes
 
 
 @_op(1)
-def conv3_tc05(planes, prepared, c_out, bias=None, stats=False):
+def conv3_tc05(planes, prepared, c_out, bias=None, stats=False, sparse=False):
     """HalfPlanes + prepared weights -> f32[B,R,R,R,Cout] channels-last (= conv + bias) and, with stats, the result's
-    GroupNorm(8) statistics f64[B,1,Cout,2] for groupnorm_act_cl(partials=)."""
+    GroupNorm(8) statistics f64[B,1,Cout,2] for groupnorm_act_cl(partials=).
+    sparse: the planes were just written by conv3_tc05_fill_planes (whose occupancy bits are current): tap windows that
+    hold only zero rows are skipped.  Exact: the skipped products are zeros."""
     b, r, c_in = planes.b, planes.r, planes.c
     dev = planes.data.device
     _chk_channel_vector(bias, "bias", c_out)
@@ -883,5 +887,5 @@ def conv3_tc05(planes, prepared, c_out, bias=None, stats=False):
         _check(_L.bdm_conv3_tc05(b, c_in, int(c_out), r, planes.data.data_ptr(), planes.rows, prepared.data_ptr(),
                                  bias.data_ptr() if bias is not None else None, out.data_ptr(),
                                  part.data_ptr() if part is not None else None, ws.data_ptr() if ws is not None else None,
-                                 ws_bytes, st))
+                                 ws_bytes, planes.occ.data_ptr() if sparse else None, st))
     return (out, part) if stats else out

@@ -347,7 +347,7 @@ __global__ void conv3_amax_kernel(size_t n4, const float4 *__restrict__ x, unsig
 __global__ void __launch_bounds__(256)
 conv3_fill_planes_kernel(int c, int n, int r, VoxAuxLayout L, const unsigned char *__restrict__ plan_ws,
                          const float *__restrict__ compact, float *__restrict__ header, __half *__restrict__ xh, int guard,
-                         long long sample_rows, long long total_rows) {
+                         long long sample_rows, long long total_rows, uint32_t *__restrict__ occ_bits, int occ_words) {
   const int b = blockIdx.y, lane = threadIdx.x & 31;
   const int word_idx = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const float amax = __uint_as_float(reinterpret_cast<const unsigned *>(header)[4]);
@@ -366,7 +366,10 @@ conv3_fill_planes_kernel(int c, int n, int r, VoxAuxLayout L, const unsigned cha
   if (v >= r * r * r) return;
   const int sh = 31 - __clz(r), q = r + 1;
   const int vz = v & (r - 1), vy = (v >> sh) & (r - 1), vx = v >> (2 * sh);
-  const size_t row = (size_t)guard + (size_t)b * sample_rows + (size_t)(((long long)vx * q + vy) * q + vz);
+  const int p = (vx * q + vy) * q + vz;
+  const size_t row = (size_t)guard + (size_t)b * sample_rows + (size_t)p;
+  if (occ_bits != nullptr && occ)   // one bit per non-zero flat row (zeroed by the launcher): lets the convolution skip all-zero windows
+    atomicOr(occ_bits + (size_t)b * occ_words + ((guard + p) >> 5), 1u << ((guard + p) & 31));
   const float *src = compact + (size_t)b * c * n + slot;
   const int c8 = c >> 3;
   for (int j = 0; j < c8; ++j) {
@@ -387,6 +390,37 @@ conv3_fill_planes_kernel(int c, int n, int r, VoxAuxLayout L, const unsigned cha
 // -------------------------------------------------------------------------------------------------------------
 // the convolution
 // -------------------------------------------------------------------------------------------------------------
+// Occupancy of the flat rows of one sample, one bit per row (row index includes the guard): set by
+// conv3_fill_planes_kernel for the occupied voxels of a freshly voxelized cloud.  window_mask() -> bit dx*3+dy is set iff
+// the 258-row window [unit row 0 + (dx-1)*P + (dy-1)*Q - 1, +258) that the three dz taps of (dx, dy) read holds any
+// non-zero row.  Executed by a whole (converged) warp: the 9 windows x up to 10 words are spread over the lanes and
+// combined with one REDUX.  occ == NULL: everything is treated as occupied.
+constexpr int kOccSlackRows = 1024;     // rows past a sample's stride that a unit's windows may reach into
+__host__ __device__ inline int occ_words_per_sample(const Geometry &g) { return (int)((g.sample_rows + kOccSlackRows + 31) / 32); }
+__device__ __forceinline__ uint32_t window_mask(const uint32_t *__restrict__ occ, const Geometry &geo, int smp, int u, int lane) {
+  if (occ == nullptr) return 0x1FFu;
+  const uint32_t *o = occ + (size_t)smp * occ_words_per_sample(geo);
+  uint32_t m = 0;
+#pragma unroll
+  for (int rnd = 0; rnd < 3; ++rnd) {
+    const int idx = rnd * 32 + lane;             // (window, word) pair
+    if (idx < 90) {
+      const int wdw = idx / 10, k = idx - wdw * 10;
+      const int dx = wdw / 3, dy = wdw - dx * 3;
+      const int first = geo.guard + u * kUnitRows + (dx - 1) * geo.p + (dy - 1) * geo.q - 1;      // >= 0: guard >= P + Q + 1
+      const int last = first + kUnitRows + 1;                                                      // inclusive
+      const int w = (first >> 5) + k;
+      if (w <= (last >> 5)) {
+        uint32_t bits = __ldg(o + w);
+        if (w == (first >> 5)) bits &= 0xffffffffu << (first & 31);
+        if (w == (last >> 5)) bits &= 0xffffffffu >> (31 - (last & 31));
+        if (bits != 0u) m |= 1u << wdw;
+      }
+    }
+  }
+  return __reduce_or_sync(0xffffffffu, m);
+}
+
 template <int N, int KC, int TG>
 struct Cfg {
   static constexpr int kChunks = KC / 8;
@@ -403,7 +437,7 @@ template <int N, int KC, int TG>
 __global__ void __launch_bounds__(kThreads, 1)
 conv3_tc05_kernel(int b, int c_in, Geometry geo, int a_stage_bytes, const __half *__restrict__ xh,
                   const unsigned char *__restrict__ wprep, const float *__restrict__ bias,
-                  float *__restrict__ out, double *__restrict__ unit_stats) {
+                  float *__restrict__ out, double *__restrict__ unit_stats, const uint32_t *__restrict__ occ) {
   using C = Cfg<N, KC, TG>;
   extern __shared__ __align__(1024) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -418,6 +452,7 @@ conv3_tc05_kernel(int b, int c_in, Geometry geo, int a_stage_bytes, const __half
   uint64_t *t_full = w_empty + C::kWStages, *t_empty = t_full + 2;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + C::kNumBars);
   float *red = reinterpret_cast<float *>(tmem_slot + 4);        // [2][8 warps][16]
+  volatile uint32_t *unit_empty = tmem_slot + 2;                // [2]: no MMA was issued for the unit in this accumulator buffer
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kAStages; ++s) { bar_init(a_full + s, 1); bar_init(a_empty + s, 1); }
@@ -436,40 +471,60 @@ conv3_tc05_kernel(int b, int c_in, Geometry geo, int a_stage_bytes, const __half
 
   if (warp == 0) {
     // ===================== A producer =====================
-    if (lane == 0) {
+    // (the warp runs the unit loop together for window_mask(); lane 0 does the waiting and the copies)
+    {
       int sa = 0; uint32_t pa = 0;
       const uint32_t slab_bytes = (uint32_t)slab_rows * 16u;
       for (int g = blockIdx.x; g < total_units; g += gridDim.x) {
         const int smp = g / geo.units, u = g - smp * geo.units;
+        const uint32_t wm = window_mask(occ, geo, smp, u, lane);
         const long long row_base = (long long)geo.guard + (long long)smp * geo.sample_rows + (long long)u * kUnitRows;
         for (int dx = 0; dx < 3; ++dx) {
+          if (((wm >> (3 * dx)) & 7u) == 0u) continue;          // an all-zero slab: nothing to multiply
           const long long src_row = row_base + (long long)(dx - 1) * geo.p - geo.q - 1;
           for (int kc = 0; kc < nkc; ++kc) {
-            bar_wait(a_empty + sa, pa ^ 1);
-            bar_expect_tx(a_full + sa, C::kChunks * slab_bytes);
-            const uint32_t dst = smem_u32(a_smem + sa * a_stage_bytes);
+            if (lane == 0) {
+              bar_wait(a_empty + sa, pa ^ 1);
+              bar_expect_tx(a_full + sa, C::kChunks * slab_bytes);
+              const uint32_t dst = smem_u32(a_smem + sa * a_stage_bytes);
 #pragma unroll
-            for (int j = 0; j < C::kChunks; ++j)
-              tma_load(dst + j * slab_bytes, xh + ((size_t)(kc * C::kChunks + j) * geo.total_rows + (size_t)src_row) * 8,
-                       slab_bytes, a_full + sa);
+              for (int j = 0; j < C::kChunks; ++j)
+                tma_load(dst + j * slab_bytes, xh + ((size_t)(kc * C::kChunks + j) * geo.total_rows + (size_t)src_row) * 8,
+                         slab_bytes, a_full + sa);
+            }
             if (++sa == kAStages) { sa = 0; pa ^= 1; }
           }
         }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
     // ===================== W producer =====================
-    if (lane == 0) {
+    {
       int sw = 0; uint32_t pw = 0;
-      const int stages_per_unit = 3 * nkc * C::kNG;
       const unsigned char *wsrc = wprep + kHeaderBytes;
       for (int g = blockIdx.x; g < total_units; g += gridDim.x) {
-        for (int s = 0; s < stages_per_unit; ++s) {
-          bar_wait(w_empty + sw, pw ^ 1);
-          bar_expect_tx(w_full + sw, C::kWStageBytes);
-          tma_load(smem_u32(w_smem + sw * C::kWStageBytes), wsrc + (size_t)s * C::kWStageBytes, C::kWStageBytes, w_full + sw);
-          if (++sw == C::kWStages) { sw = 0; pw ^= 1; }
+        const int smp = g / geo.units, u = g - smp * geo.units;
+        const uint32_t wm = window_mask(occ, geo, smp, u, lane);
+        for (int dx = 0; dx < 3; ++dx) {
+          const uint32_t sm = (wm >> (3 * dx)) & 7u;
+          if (sm == 0u) continue;
+          for (int kc = 0; kc < nkc; ++kc) {
+            for (int grp = 0; grp < C::kNG; ++grp) {
+              // taps of a stage: TG = 9 -> the whole dx plane, 3 -> one dy row, 1 -> one tap (dy = grp / 3)
+              const uint32_t need = TG == 9 ? sm : (TG == 3 ? (sm >> grp) & 1u : (sm >> (grp / 3)) & 1u);
+              if (need == 0u) continue;
+              if (lane == 0) {
+                const int s = (dx * nkc + kc) * C::kNG + grp;
+                bar_wait(w_empty + sw, pw ^ 1);
+                bar_expect_tx(w_full + sw, C::kWStageBytes);
+                tma_load(smem_u32(w_smem + sw * C::kWStageBytes), wsrc + (size_t)s * C::kWStageBytes, C::kWStageBytes, w_full + sw);
+              }
+              if (++sw == C::kWStages) { sw = 0; pw ^= 1; }
+            }
+          }
         }
+        __syncwarp();
       }
     }
   } else if (warp == 2) {
@@ -492,26 +547,34 @@ conv3_tc05_kernel(int b, int c_in, Geometry geo, int a_stage_bytes, const __half
       int it = 0;
       for (int g = blockIdx.x; g < total_units; g += gridDim.x, ++it) {
         const int buf = it & 1;
+        const int smp = g / geo.units, u = g - smp * geo.units;
+        const uint32_t wm = window_mask(occ, geo, smp, u, lane);      // windows of all-zero rows are skipped, loads and MMAs
         bar_wait(t_empty + buf, ((it >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t d0 = tmem + buf * 2 * N;
-        uint32_t acc = 0;
+        uint32_t acc = 0;                                             // 0 until the unit's first MMA has been issued
         for (int dx = 0; dx < 3; ++dx) {
+          const uint32_t sm = (wm >> (3 * dx)) & 7u;
+          if (sm == 0u) continue;
           for (int kc = 0; kc < nkc; ++kc) {
             bar_wait(a_full + sa, pa);
             tc_fence_after();
             const uint32_t a_lo = (smem_u32(a_smem + sa * a_stage_bytes) >> 4) | (a_lbo16 << 16);
 #pragma unroll
             for (int grp = 0; grp < C::kNG; ++grp) {
+              const uint32_t need = TG == 9 ? sm : (TG == 3 ? (sm >> grp) & 1u : (sm >> (grp / 3)) & 1u);
+              if (need == 0u) continue;
               bar_wait(w_full + sw, pw);
               tc_fence_after();
               const uint32_t b_lo = (smem_u32(w_smem + sw * C::kWStageBytes) >> 4) | (b_lbo16 << 16);
               __syncwarp();
               if (elect_one()) {
+                uint32_t first = acc;                                  // accumulate flag of the next tap's k = 0 MMAs
 #pragma unroll
                 for (int j = 0; j < TG; ++j) {
                   const int tap = grp * TG + j;
                   const int dy = tap / 3, dz = tap - dy * 3;
+                  if (((sm >> dy) & 1u) == 0u) continue;               // (only TG = 9 stages mix dy rows)
                   const uint32_t a_tap = a_lo + (dy == 0 ? 0u : (dy == 1 ? q1 : q2)) + (uint32_t)dz;
 #pragma unroll
                   for (int t = 0; t < 2; ++t) {
@@ -519,7 +582,7 @@ conv3_tc05_kernel(int b, int c_in, Geometry geo, int a_stage_bytes, const __half
                     for (int k = 0; k < C::kK16; ++k) {
                       const uint32_t da_lo = a_tap + (uint32_t)(t * 128) + (uint32_t)k * kstep;
                       const uint32_t db_lo = b_lo + (uint32_t)(j * (C::kTapBytes >> 4) + k * 2 * N);
-                      const uint32_t accumulate = (tap == 0 && k == 0) ? acc : 1u;
+                      const uint32_t accumulate = k == 0 ? first : 1u;
                       asm volatile(
                           "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %5, 0;\n\t"
                           "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %2};\n\t"
@@ -527,18 +590,26 @@ conv3_tc05_kernel(int b, int c_in, Geometry geo, int a_stage_bytes, const __half
                           ::"r"(d0 + t * N), "r"(da_lo), "r"(desc_hi), "r"(db_lo), "r"(idesc), "r"(accumulate) : "memory");
                     }
                   }
+                  first = 1u;
                 }
                 umma_commit(w_empty + sw);
-                if (grp == C::kNG - 1) umma_commit(a_empty + sa);
-                if (grp == C::kNG - 1 && dx == 2 && kc == nkc - 1) umma_commit(t_full + buf);
               }
               __syncwarp();
+              acc = 1;                                                 // a needed stage always issues at least one tap
               if (++sw == C::kWStages) { sw = 0; pw ^= 1; }
             }
-            acc = 1;
+            if (elect_one()) umma_commit(a_empty + sa);
+            __syncwarp();
             if (++sa == kAStages) { sa = 0; pa ^= 1; }
           }
         }
+        if (elect_one()) {
+          unit_empty[buf] = acc == 0u ? 1u : 0u;
+          __threadfence_block();
+          if (acc != 0u) umma_commit(t_full + buf);
+          else bar_arrive(t_full + buf);                               // nothing was multiplied: the result is the bias
+        }
+        __syncwarp();
       }
     }
   } else if (warp >= 4) {
@@ -562,12 +633,18 @@ conv3_tc05_kernel(int b, int c_in, Geometry geo, int a_stage_bytes, const __half
       for (int i = 0; i < 8; ++i) gs1[i] = gs2[i] = 0.0f;
       bar_wait(t_full + buf, (it >> 1) & 1);
       tc_fence_after();
+      const bool empty = unit_empty[buf] != 0u;       // all of the unit's windows were zero rows: accumulators were not written
       const uint32_t taddr = tmem + ((uint32_t)(qd * 32) << 16) + buf * 2 * N + t * N;
 #pragma unroll
       for (int c0 = 0; c0 < N; c0 += 32) {
         uint32_t rr[32];
-        BDM_CV3_TMEM_LD32(rr, taddr + c0);
-        tmem_wait_ld();
+        if (!empty) {
+          BDM_CV3_TMEM_LD32(rr, taddr + c0);
+          tmem_wait_ld();
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) rr[i] = 0u;
+        }
         float f[32];
 #pragma unroll
         for (int i4 = 0; i4 < 8; ++i4) {
@@ -583,10 +660,13 @@ conv3_tc05_kernel(int b, int c_in, Geometry geo, int a_stage_bytes, const __half
           gs1[(c0 + i) / CG] += fv;
           gs2[(c0 + i) / CG] = fmaf(fv, fv, gs2[(c0 + i) / CG]);
         }
-        if (valid) {
+        if (valid) {   // 256-bit stores: every lane writes whole 32-byte sectors of its row (128-bit stores at this 4N-byte
+                       // lane stride make two partial-sector requests per sector; the store floor is 160 us at C=64, R=32)
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            *reinterpret_cast<float4 *>(dst + c0 + 4 * i) = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+          for (int i = 0; i < 4; ++i)
+            asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + c0 + 8 * i), "f"(f[8 * i]),
+                         "f"(f[8 * i + 1]), "f"(f[8 * i + 2]), "f"(f[8 * i + 3]), "f"(f[8 * i + 4]), "f"(f[8 * i + 5]),
+                         "f"(f[8 * i + 6]), "f"(f[8 * i + 7]) : "memory");
         }
       }
       tc_fence_before();
@@ -671,7 +751,7 @@ static inline int tg_of(int c_in, int c_out) {      // taps per weight stage: ke
 
 template <int N, int KC, int TG>
 static int launch_conv(int b, int c_in, const Geometry &geo, const __half *xh, const unsigned char *wprep, const float *bias,
-                       float *out, double *unit_stats, cudaStream_t st) {
+                       float *out, double *unit_stats, const uint32_t *occ, cudaStream_t st) {
   using C = Cfg<N, KC, TG>;
   const int a_stage_bytes = (int)align_up((size_t)C::kChunks * geo.slab_rows * 16, 128);
   const size_t smem_bytes = (size_t)kAStages * a_stage_bytes + (size_t)C::kWStages * C::kWStageBytes + C::kNumBars * 8 + 16 +
@@ -681,7 +761,7 @@ static int launch_conv(int b, int c_in, const Geometry &geo, const __half *xh, c
   if (e != cudaSuccess) return (int)e;
   const int total_units = b * geo.units;
   const int grid = total_units < sm_count() ? total_units : sm_count();
-  conv3_tc05_kernel<N, KC, TG><<<grid, kThreads, smem_bytes, st>>>(b, c_in, geo, a_stage_bytes, xh, wprep, bias, out, unit_stats);
+  conv3_tc05_kernel<N, KC, TG><<<grid, kThreads, smem_bytes, st>>>(b, c_in, geo, a_stage_bytes, xh, wprep, bias, out, unit_stats, occ);
   BDM_RETURN_LAUNCH_STATUS();
 }
 
@@ -748,10 +828,16 @@ extern "C" int bdm_groupnorm_swish_half_planar(int b, int c, int r, int groups, 
 
 /* compact f32[b][c][n] (bdm_avg_voxelize_compact) + the voxel plan (bdm_voxel_plan's workspace for the same b, n, r) ->
  * xh; `prepared` (of the convolution that will read xh) receives the dynamic activation scale.  amax_ready != 0: word 4
- * of `prepared` already holds the bit pattern of max|compact| (bdm_avg_voxelize_compact_amax wrote it). */
+ * of `prepared` already holds the bit pattern of max|compact| (bdm_avg_voxelize_compact_amax wrote it).
+ * occ (or NULL): u32[b][bdm_conv3_tc05_occ_words(r)] receives one bit per non-zero row of every sample; handed to
+ * bdm_conv3_tc05 it lets the convolution skip the windows that hold only zeros (a third of them at r = 32). */
+extern "C" int bdm_conv3_tc05_occ_words(int r) {
+  if (r <= 0) return 0;
+  return cv3::occ_words_per_sample(cv3::conv3_geometry(1, r));
+}
 extern "C" int bdm_conv3_tc05_fill_planes(int b, int c, int n, int r, const float *compact, const void *plan_workspace,
                                           size_t plan_workspace_bytes, void *prepared, void *xh, long long plane_rows,
-                                          int amax_ready, bdm_stream_t stream) {
+                                          int amax_ready, unsigned *occ, bdm_stream_t stream) {
   BDM_CHECK_SIZE(b >= 0 && b <= 65535 && c >= 8 && c % 8 == 0 && n >= 1 && r >= 4 && r <= 32 && (r & (r - 1)) == 0);
   BDM_CHECK_SIZE(vox_fast_path(n, r * r * r) && ((size_t)c * n) % 4 == 0);
   if (b == 0) return BDM_OK;
@@ -770,9 +856,11 @@ extern "C" int bdm_conv3_tc05_fill_planes(int b, int c, int n, int r, const floa
     cv3::conv3_amax_kernel<<<2 * sm_count(), 256, 0, st>>>((size_t)b * c * n / 4, reinterpret_cast<const float4 *>(compact),
                                                          reinterpret_cast<unsigned *>(header) + 4);
   }
+  const int occ_words = cv3::occ_words_per_sample(geo);
+  if (occ != nullptr) cudaMemsetAsync(occ, 0, sizeof(unsigned) * (size_t)b * occ_words, st);
   cv3::conv3_fill_planes_kernel<<<dim3((L.nw + 7) / 8, b), 256, 0, st>>>(
       c, n, r, L, static_cast<const unsigned char *>(plan_workspace), compact, header, static_cast<__half *>(xh), geo.guard,
-      geo.sample_rows, geo.total_rows);
+      geo.sample_rows, geo.total_rows, occ, occ_words);
   BDM_RETURN_LAUNCH_STATUS();
 }
 
@@ -785,7 +873,7 @@ extern "C" size_t bdm_conv3_tc05_workspace_bytes(int b, int r) {
 }
 extern "C" int bdm_conv3_tc05(int b, int c_in, int c_out, int r, const void *xh, long long plane_rows, const void *prepared,
                               const float *bias, float *out, double *stats, void *workspace, size_t workspace_bytes,
-                              bdm_stream_t stream) {
+                              const unsigned *occ, bdm_stream_t stream) {
   BDM_CHECK_SIZE(b >= 0 && cv3::supported(c_in, c_out, r));
   if (b == 0) return BDM_OK;
   BDM_CHECK_PTR(xh); BDM_CHECK_PTR(prepared); BDM_CHECK_PTR(out);
@@ -805,12 +893,12 @@ extern "C" int bdm_conv3_tc05(int b, int c_in, int c_out, int r, const void *xh,
   int rc;
   const int kc = cv3::kc_of(c_in);
   const int units = geo.units;
-  if (c_out == 32 && kc == 32) rc = cv3::launch_conv<32, 32, 9>(b, c_in, geo, x, wp, bias, out, unit_stats, st);
-  else if (c_out == 32) rc = cv3::launch_conv<32, 64, 3>(b, c_in, geo, x, wp, bias, out, unit_stats, st);
-  else if (c_out == 64 && kc == 32) rc = cv3::launch_conv<64, 32, 3>(b, c_in, geo, x, wp, bias, out, unit_stats, st);
-  else if (c_out == 64) rc = cv3::launch_conv<64, 64, 3>(b, c_in, geo, x, wp, bias, out, unit_stats, st);
-  else if (kc == 32) rc = cv3::launch_conv<128, 32, 3>(b, c_in, geo, x, wp, bias, out, unit_stats, st);
-  else rc = cv3::launch_conv<128, 64, 1>(b, c_in, geo, x, wp, bias, out, unit_stats, st);
+  if (c_out == 32 && kc == 32) rc = cv3::launch_conv<32, 32, 9>(b, c_in, geo, x, wp, bias, out, unit_stats, occ, st);
+  else if (c_out == 32) rc = cv3::launch_conv<32, 64, 3>(b, c_in, geo, x, wp, bias, out, unit_stats, occ, st);
+  else if (c_out == 64 && kc == 32) rc = cv3::launch_conv<64, 32, 3>(b, c_in, geo, x, wp, bias, out, unit_stats, occ, st);
+  else if (c_out == 64) rc = cv3::launch_conv<64, 64, 3>(b, c_in, geo, x, wp, bias, out, unit_stats, occ, st);
+  else if (kc == 32) rc = cv3::launch_conv<128, 32, 3>(b, c_in, geo, x, wp, bias, out, unit_stats, occ, st);
+  else rc = cv3::launch_conv<128, 64, 1>(b, c_in, geo, x, wp, bias, out, unit_stats, occ, st);
   if (rc != BDM_OK) return rc;
   if (stats != nullptr) {
     cv3::conv3_stats_fold_kernel<<<b, 512, 0, st>>>(units, c_out, unit_stats, reinterpret_cast<double2 *>(stats));

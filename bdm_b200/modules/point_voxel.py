@@ -36,6 +36,9 @@ CHANNELS_LAST_VOXELS = os.environ.get("BDM_CHANNELS_LAST", "1") != "0"
 # and the 8^3 grids stay on the sparse route.  BDM_DENSE_FIRST_TC05=0 disables.
 DENSE_FIRST_TC05 = os.environ.get("BDM_DENSE_FIRST_TC05", "1") != "0"
 DENSE_FIRST_TC05_MAX_CIN = int(os.environ.get("BDM_DENSE_FIRST_TC05_MAX_CIN", "128"))
+# ... and there the kernel skips the tap windows (258 flat rows x one (dx, dy)) that hold no occupied voxel: 31-44 % of
+# them at R=32 along the sampling trajectory, 4-16 % at R=16.  Exact (the skipped products are zeros).  BDM_CONV3_SKIP_EMPTY=0.
+SKIP_EMPTY_WINDOWS = os.environ.get("BDM_CONV3_SKIP_EMPTY", "1") != "0"
 
 
 def normalized_voxel_coords(coords, resolution, normalize=True, eps=0):
@@ -184,7 +187,8 @@ class _PVConvBase(nn.Module):
         occupied = _ops._B.avg_voxelize_compact(features.contiguous(), plan, amax_into=prepared)     # [B, Cin, N] + max|.|
         planes = _layers.half_planes(features.shape[0], conv.in_channels, vox.r, features.device)
         _ops._B.conv3_tc05_fill_planes(occupied, plan, prepared, planes, amax_ready=True)
-        out, stats = _ops._B.conv3_tc05(planes, prepared, conv.out_channels, bias=conv.bias, stats=True)
+        out, stats = _ops._B.conv3_tc05(planes, prepared, conv.out_channels, bias=conv.bias, stats=True,
+                                        sparse=SKIP_EMPTY_WINDOWS)
         return (out.permute(0, 4, 1, 2, 3), stats, True), norm_coords
 
     def _tap_matrix(self, conv):

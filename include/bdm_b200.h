@@ -329,6 +329,9 @@ int bdm_groupnorm_cl_sums(int b, int c, long long s, int groups, float eps, int 
  *       + the voxel plan -> xh (zeros at empty voxels), scaled by a power of two derived from max|average| on
  *       the device and recorded in `prepared` (prepare that convolution with gamma = beta = NULL, group_elems = 1);
  *       amax_ready != 0: bdm_avg_voxelize_compact_amax already wrote max|average| to word 4 of `prepared`.
+ *       occ (or NULL): u32[b][bdm_conv3_tc05_occ_words(r)], one bit per non-zero row; passed on to bdm_conv3_tc05 it
+ *       makes the convolution skip (loads and MMAs) the tap windows that hold only zero rows -- exact, since those
+ *       products are zeros (NULL there = dense operand).
  *   bdm_conv3_tc05   out f32[b][r^3][c_out] = conv(xh) + bias; stats (or NULL): f64[b][1][c_out][2], the result's
  *       GroupNorm(8) statistics in the layout bdm_groupnorm_act_cl(precomputed_chunks = 1) takes; workspace:
  *       bdm_conv3_tc05_workspace_bytes(b, r) bytes when stats != NULL.
@@ -346,10 +349,11 @@ int bdm_groupnorm_swish_half_planar(int b, int c, int r, int groups, float eps, 
                                     long long plane_rows, bdm_stream_t stream);
 int bdm_conv3_tc05_fill_planes(int b, int c, int n, int r, const float *compact, const void *plan_workspace,
                                size_t plan_workspace_bytes, void *prepared, void *xh, long long plane_rows,
-                               int amax_ready, bdm_stream_t stream);
+                               int amax_ready, unsigned *occ, bdm_stream_t stream);
+int bdm_conv3_tc05_occ_words(int r);
 int bdm_conv3_tc05(int b, int c_in, int c_out, int r, const void *xh, long long plane_rows, const void *prepared,
                    const float *bias, float *out, double *stats, void *workspace, size_t workspace_bytes,
-                   bdm_stream_t stream);
+                   const unsigned *occ, bdm_stream_t stream);
 
 #ifdef __cplusplus
 }

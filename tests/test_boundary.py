@@ -79,12 +79,12 @@ def test_conv3_tc05_geometry_and_argument_errors_need_no_gpu():
     assert L.bdm_conv3_tc05_supported(64, 64, 12) == 0 and L.bdm_conv3_tc05_supported(64, 64, 64) == 0
     assert L.bdm_conv3_tc05_weight_bytes(64, 64) == 256 + 27 * 64 * 64 * 2
     rows = L.bdm_conv3_tc05_plane_rows(2, 16)
-    assert L.bdm_conv3_tc05(2, 390, 32, 16, None, rows, None, None, None, None, None, 0, None) == -2     # unsupported widths
-    assert L.bdm_conv3_tc05(2, 64, 64, 16, None, rows, None, None, None, None, None, 0, None) == -1      # NULL operands
-    assert L.bdm_conv3_tc05(0, 64, 64, 16, None, rows, None, None, None, None, None, 0, None) == 0       # empty batch
+    assert L.bdm_conv3_tc05(2, 390, 32, 16, None, rows, None, None, None, None, None, 0, None, None) == -2     # unsupported widths
+    assert L.bdm_conv3_tc05(2, 64, 64, 16, None, rows, None, None, None, None, None, 0, None, None) == -1      # NULL operands
+    assert L.bdm_conv3_tc05(0, 64, 64, 16, None, rows, None, None, None, None, None, 0, None, None) == 0       # empty batch
     assert L.bdm_conv3_tc05_prepare(48, 64, None, None, None, 1, None, 0, None) == -2
     assert L.bdm_groupnorm_swish_half_planar(2, 64, 12, 8, 1e-5, 1, None, None, None, None, None, 1, None, None, rows, None) == -2
-    assert L.bdm_conv3_tc05_fill_planes(2, 64, 1024, 64, None, None, 0, None, None, rows, 0, None) == -2  # needs the plan (r <= 32)
+    assert L.bdm_conv3_tc05_fill_planes(2, 64, 1024, 64, None, None, 0, None, None, rows, 0, None, None) == -2  # needs the plan (r <= 32)
     assert L.bdm_groupnorm_cl_sums(2, 48, 512, 8, 1e-5, 1, None, None, None, None, None, 1, None, None, None) == -2
     assert L.bdm_trilinear_devoxelize_cl_norm(0, 64, 128, 16, None, None, None, 1, None, None, None, None) == 0
 

@@ -210,6 +210,46 @@ def test_fill_planes_from_a_voxelized_cloud(b, c, n, r, cuda_backend):
     assert torch.equal(prepared2[:20], prepared[:20])
 
 
+@pytest.mark.parametrize("b,cin,cout,n,r,regime", [(3, 64, 64, 4096, 32, "shape"), (2, 32, 32, 4096, 32, "noise"), (2, 128, 128, 1024, 16, "shape"),
+                                                    (2, 64, 32, 300, 32, "shape"), (1, 64, 64, 8, 16, "shape")])
+def test_skipping_empty_windows_is_exact(b, cin, cout, n, r, regime, cuda_backend):
+    """conv3_tc05(sparse=True) -- loads and MMAs of all-zero tap windows skipped via the occupancy bits the plane
+    writer leaves -- is bit-identical to the dense pass over the same planes (the skipped products are zeros), down
+    to a cloud of 8 points where almost every unit is skipped entirely"""
+    import numpy as np
+    import torch
+    from tests import cases
+    B = cuda_backend
+    rng = np.random.default_rng(b + cin + n)
+    co = cases.cloud(rng, b, n, regime)
+    vox, _ = cases.vox_coords(co, r)
+    plan = B.voxel_plan(torch.from_numpy(vox).cuda(), r)
+    feats = torch.randn(b, cin, n, device="cuda")
+    w = torch.randn(cout, cin, 3, 3, 3, device="cuda") / (27 * cin) ** 0.5
+    bias = torch.randn(cout, device="cuda")
+    prepared = B.conv3_tc05_prepare(w, None, None, 1)
+    planes = B.HalfPlanes(b, cin, r, "cuda")
+    B.conv3_tc05_fill_planes(B.avg_voxelize_compact(feats, plan, amax_into=prepared), plan, prepared, planes, amax_ready=True)
+    # the occupancy bits are exactly the non-zero rows' positions
+    q = r + 1
+    guard = (q * q + q + 1 + 7) // 8 * 8
+    bits = planes.occ.cpu().numpy().view(np.uint32)
+    for i in range(b):
+        p = np.unique((vox[i, 0].astype(np.int64) * q + vox[i, 1]) * q + vox[i, 2]) + guard
+        want = np.zeros(bits.shape[1] * 32, dtype=bool)
+        want[p] = True
+        got = np.unpackbits(bits[i].view(np.uint8), bitorder="little").astype(bool)
+        assert (got == want).all()
+    dense, st_d = B.conv3_tc05(planes, prepared, cout, bias=bias, stats=True, sparse=False)
+    sparse, st_s = B.conv3_tc05(planes, prepared, cout, bias=bias, stats=True, sparse=True)
+    assert torch.equal(dense, sparse)
+    assert torch.equal(st_d, st_s)
+    # and both are the convolution of the voxelized grid
+    grid = B.avg_voxelize_fill(feats, plan).reshape(b, cin, r, r, r)
+    ref = torch.nn.functional.conv3d(grid.double(), w.double(), bias.double(), padding=1).permute(0, 2, 3, 4, 1)
+    assert (sparse.double() - ref).abs().max().item() <= 1e-3 * ref.abs().max().item()
+
+
 def test_first_convolution_dense_route_matches_sparse_route(cuda_backend):
     """block level: first convolution through the tcgen05 kernel (DENSE_FIRST_TC05) against the tap-product route"""
     import torch

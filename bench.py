@@ -554,6 +554,10 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": value, "unit": "shapes/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
         "ms_per_step": ms_job, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "precision": "fp32 activations and accumulation throughout; convolution / 1x1-convolution operands carry 11 significant "
+                     "bits as in the reference under torch's default TF32 conv policy (TF32 in cuDNN / cuBLAS; fp16 after a "
+                     "power-of-two scaling in the tcgen05 3x3x3 convolutions); attention is fp32-equivalent (fp16 hi/lo split, "
+                     "3 products); sparse ops are fp32, integer outputs bit-exact",
         "data": "synthetic", "config": workload_config(mode, world, B),
         "clocks": clocks.summary(),
         "e2e": {"value": e2e_value, "unit": "shapes/s", "ms_per_step": ms_e2e, "steps": k_e2e,

@@ -324,6 +324,103 @@ gn_apply_half_planar_kernel(int c, int r, int groups, int nchunks, int ntiles, f
   }
 }
 
+// Warp-level version for C = 32 / 64 / 128 (C4 = C/4 <= 32 float4 per voxel): a warp owns tiles of 32 consecutive voxels.
+// Load: C4 instructions, each 512 contiguous bytes of the fp32 rows (lane = (voxel, quad) pair, the quad -- hence the
+// coefficients -- fixed per lane); convert; 8-byte stores into the warp's private [chunk plane][33 voxels][16 bytes]
+// slab; then C/8 instructions of lane = voxel: a 16-byte shared load and a 16-byte global store, 512 contiguous bytes of
+// one fp16 plane per instruction.  No block-wide barrier after the prologue.
+template <int C4>
+__global__ void __launch_bounds__(kApplyThreads)
+gn_apply_half_planar_warp_kernel(int r, int groups, int nchunks, int ntiles, float eps, int swish,
+                                 const float *__restrict__ x, const float *__restrict__ conv_bias,
+                                 const float *__restrict__ gamma, const float *__restrict__ beta,
+                                 const double2 *__restrict__ partials, const float *__restrict__ header,
+                                 __half *__restrict__ xh, int guard, long long sample_rows, long long total_rows) {
+  constexpr int c = 4 * C4, C8 = C4 / 2, VPI = 32 / C4;      // channels, chunk planes, voxels per load instruction
+  __shared__ double2 slice[kApplyThreads];
+  __shared__ double2 chan[c];
+  __shared__ double2 grp[32];
+  __shared__ float2 ab[c];
+  extern __shared__ __align__(16) unsigned char dyn[];       // [8 warps][C8][33][16 bytes]
+  const int b = blockIdx.y, tile = blockIdx.x, t = threadIdx.x;
+  const int cg = c / groups;
+  const long long s = (long long)r * r * r;
+  {
+    const int nsl = kApplyThreads / c, tc = t % c, sl = t / c;
+    double S1 = 0.0, S2 = 0.0;
+    for (int ch = sl; ch < nchunks; ch += nsl) {
+      const double2 v = partials[((size_t)b * nchunks + ch) * c + tc];
+      S1 += v.x; S2 += v.y;
+    }
+    slice[t] = make_double2(S1, S2);
+  }
+  __syncthreads();
+  if (t < c) {
+    double S1 = 0.0, S2 = 0.0;
+    for (int sl = 0; sl < kApplyThreads / c; ++sl) { S1 += slice[sl * c + t].x; S2 += slice[sl * c + t].y; }
+    const double tt = conv_bias != nullptr ? (double)conv_bias[t] : 0.0;
+    const double ds = (double)s;
+    chan[t] = make_double2(S1 + ds * tt, S2 + 2.0 * tt * S1 + ds * tt * tt);
+  }
+  __syncthreads();
+  if (t < groups) {
+    double S1 = 0.0, S2 = 0.0;
+    for (int j = 0; j < cg; ++j) { S1 += chan[t * cg + j].x; S2 += chan[t * cg + j].y; }
+    const double n = (double)cg * (double)s;
+    const double mean = S1 / n;
+    const double var = fmax(S2 / n - mean * mean, 0.0);
+    grp[t] = make_double2(mean, 1.0 / sqrt(var + (double)eps));
+  }
+  __syncthreads();
+  if (t < c) {
+    const double2 g = grp[t / cg];
+    const float ga = gamma != nullptr ? gamma[t] : 1.0f;
+    const float be = beta != nullptr ? beta[t] : 0.0f;
+    const float cb = conv_bias != nullptr ? conv_bias[t] : 0.0f;
+    const float A = (float)g.y * ga;
+    ab[t] = make_float2(A, (float)((double)be + ((double)cb - g.x) * (double)A));
+  }
+  __syncthreads();
+  const float act_scale = __ldg(header + 1);
+  const int warp = t >> 5, lane = t & 31;
+  const int qd = lane % C4, vsub = lane / C4;                  // this lane's quad of channels and voxel within a load
+  const float2 k0 = ab[4 * qd], k1 = ab[4 * qd + 1], k2 = ab[4 * qd + 2], k3 = ab[4 * qd + 3];
+  const int q = r + 1;
+  const int sh = 31 - __clz(r);
+  uint2 *slab = reinterpret_cast<uint2 *>(dyn) + (size_t)warp * C8 * 33 * 2;
+  long long per = (s + ntiles - 1) / ntiles;
+  per = (per + 31) / 32 * 32;
+  const long long lo = min((long long)tile * per, s), hi = min(lo + per, s);
+  const float *px = x + (size_t)b * s * c;
+  __half *planes = xh + ((size_t)guard + (size_t)b * sample_rows) * 8;
+  for (long long v0 = lo + 32LL * warp; v0 < hi; v0 += 32LL * (kApplyThreads / 32)) {
+    float4 u[C4];
+#pragma unroll
+    for (int k = 0; k < C4; ++k) {
+      const long long v = v0 + k * VPI + vsub;
+      if (v < hi) u[k] = ld_stream_f4(px + (size_t)v * c + 4 * qd);
+    }
+#pragma unroll
+    for (int k = 0; k < C4; ++k) {
+      float a0 = fmaf(u[k].x, k0.x, k0.y), a1 = fmaf(u[k].y, k1.x, k1.y), a2 = fmaf(u[k].z, k2.x, k2.y), a3 = fmaf(u[k].w, k3.x, k3.y);
+      if (swish) { a0 = swish_fast(a0); a1 = swish_fast(a1); a2 = swish_fast(a2); a3 = swish_fast(a3); }
+      const __half2 h0 = __floats2half2_rn(a0 * act_scale, a1 * act_scale), h1 = __floats2half2_rn(a2 * act_scale, a3 * act_scale);
+      slab[((qd >> 1) * 33 + k * VPI + vsub) * 2 + (qd & 1)] =
+          make_uint2(*reinterpret_cast<const uint32_t *>(&h0), *reinterpret_cast<const uint32_t *>(&h1));
+    }
+    __syncwarp();
+    const long long v = v0 + lane;
+    if (v < hi) {
+      const int vz = (int)v & (r - 1), vy = ((int)v >> sh) & (r - 1), vx = (int)v >> (2 * sh);
+      __half *dst = planes + (size_t)(((long long)vx * q + vy) * q + vz) * 8;
+#pragma unroll
+      for (int j = 0; j < C8; ++j)
+        *reinterpret_cast<uint4 *>(dst + (size_t)j * total_rows * 8) = *reinterpret_cast<const uint4 *>(&slab[(j * 33 + lane) * 2]);
+    }
+    __syncwarp();
+  }
+}
+
 // -------------------------------------------------------------------------------------------------------------
 // A freshly voxelized cloud as the convolution's operand (the FIRST Conv3d of a PVConv block, modules/pvconv.py:75-76,
 // 91-97): per-occupied-voxel averages (bdm_avg_voxelize_compact, f32[b][c][n]) + the voxel plan's occupancy bitmask ->
@@ -820,6 +917,30 @@ extern "C" int bdm_groupnorm_swish_half_planar(int b, int c, int r, int groups, 
   long long want = ((long long)8 * sm_count() + b - 1) / b;
   long long maxt = (s + 4LL * rpp - 1) / (4LL * rpp);
   const int ntiles = (int)(want < maxt ? (want < 1 ? 1 : want) : (maxt < 1 ? 1 : maxt));
+  if (c == 32 || c == 64 || c == 128) {   // warp-level kernel: no block barriers in the streaming loop
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const double2 *pp = reinterpret_cast<const double2 *>(partials);
+    const float *hd = static_cast<const float *>(prepared);
+    __half *xp = static_cast<__half *>(xh);
+    long long wt = ((long long)6 * sm_count() + b - 1) / b;
+    long long mt = (s + 255) / 256;
+    const int nt = (int)(wt < mt ? (wt < 1 ? 1 : wt) : (mt < 1 ? 1 : mt));
+    const size_t smem = (size_t)8 * (c / 8) * 33 * 16;
+    cudaError_t e = cudaSuccess;
+    if (c == 32) {
+      cv3::gn_apply_half_planar_warp_kernel<8><<<dim3(nt, b), cv3::kApplyThreads, smem, st>>>(
+          r, groups, chunks, nt, eps, swish, x, conv_bias, gamma, beta, pp, hd, xp, geo.guard, geo.sample_rows, geo.total_rows);
+    } else if (c == 64) {
+      cv3::gn_apply_half_planar_warp_kernel<16><<<dim3(nt, b), cv3::kApplyThreads, smem, st>>>(
+          r, groups, chunks, nt, eps, swish, x, conv_bias, gamma, beta, pp, hd, xp, geo.guard, geo.sample_rows, geo.total_rows);
+    } else {
+      e = ensure_dynamic_smem(reinterpret_cast<const void *>(cv3::gn_apply_half_planar_warp_kernel<32>), smem);
+      if (e != cudaSuccess) return (int)e;
+      cv3::gn_apply_half_planar_warp_kernel<32><<<dim3(nt, b), cv3::kApplyThreads, smem, st>>>(
+          r, groups, chunks, nt, eps, swish, x, conv_bias, gamma, beta, pp, hd, xp, geo.guard, geo.sample_rows, geo.total_rows);
+    }
+    BDM_RETURN_LAUNCH_STATUS();
+  }
   cv3::gn_apply_half_planar_kernel<<<dim3(ntiles, b), cv3::kApplyThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       c, r, groups, chunks, ntiles, eps, swish, x, conv_bias, gamma, beta, reinterpret_cast<const double2 *>(partials),
       static_cast<const float *>(prepared), static_cast<__half *>(xh), geo.guard, geo.sample_rows, geo.total_rows);

@@ -394,19 +394,23 @@ gn_apply_half_planar_warp_kernel(int r, int groups, int nchunks, int ntiles, flo
   const float *px = x + (size_t)b * s * c;
   __half *planes = xh + ((size_t)guard + (size_t)b * sample_rows) * 8;
   for (long long v0 = lo + 32LL * warp; v0 < hi; v0 += 32LL * (kApplyThreads / 32)) {
-    float4 u[C4];
+    constexpr int KB = C4 < 16 ? C4 : 16;                    // load instructions in flight per lane (64 registers)
 #pragma unroll
-    for (int k = 0; k < C4; ++k) {
-      const long long v = v0 + k * VPI + vsub;
-      if (v < hi) u[k] = ld_stream_f4(px + (size_t)v * c + 4 * qd);
-    }
+    for (int kb = 0; kb < C4; kb += KB) {
+      float4 u[KB];
 #pragma unroll
-    for (int k = 0; k < C4; ++k) {
-      float a0 = fmaf(u[k].x, k0.x, k0.y), a1 = fmaf(u[k].y, k1.x, k1.y), a2 = fmaf(u[k].z, k2.x, k2.y), a3 = fmaf(u[k].w, k3.x, k3.y);
-      if (swish) { a0 = swish_fast(a0); a1 = swish_fast(a1); a2 = swish_fast(a2); a3 = swish_fast(a3); }
-      const __half2 h0 = __floats2half2_rn(a0 * act_scale, a1 * act_scale), h1 = __floats2half2_rn(a2 * act_scale, a3 * act_scale);
-      slab[((qd >> 1) * 33 + k * VPI + vsub) * 2 + (qd & 1)] =
-          make_uint2(*reinterpret_cast<const uint32_t *>(&h0), *reinterpret_cast<const uint32_t *>(&h1));
+      for (int i = 0; i < KB; ++i) {
+        const long long v = v0 + (kb + i) * VPI + vsub;
+        if (v < hi) u[i] = ld_stream_f4(px + (size_t)v * c + 4 * qd);
+      }
+#pragma unroll
+      for (int i = 0; i < KB; ++i) {
+        float a0 = fmaf(u[i].x, k0.x, k0.y), a1 = fmaf(u[i].y, k1.x, k1.y), a2 = fmaf(u[i].z, k2.x, k2.y), a3 = fmaf(u[i].w, k3.x, k3.y);
+        if (swish) { a0 = swish_fast(a0); a1 = swish_fast(a1); a2 = swish_fast(a2); a3 = swish_fast(a3); }
+        const __half2 h0 = __floats2half2_rn(a0 * act_scale, a1 * act_scale), h1 = __floats2half2_rn(a2 * act_scale, a3 * act_scale);
+        slab[((qd >> 1) * 33 + (kb + i) * VPI + vsub) * 2 + (qd & 1)] =
+            make_uint2(*reinterpret_cast<const uint32_t *>(&h0), *reinterpret_cast<const uint32_t *>(&h1));
+      }
     }
     __syncwarp();
     const long long v = v0 + lane;

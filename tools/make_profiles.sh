@@ -21,6 +21,15 @@ for spec in "attention:attention_tc05_kernel" "sparse_conv:sparse_conv3_gather" 
   cp /tmp/ncu_$op.ncu-rep gpurun_out/prof/ 2>/dev/null
 done
 python tools/ncu_summary.py /tmp/ncu_*.ncu-rep > gpurun_out/prof/ncu_kernels.md 2>&1
+# 3b. the tcgen05 convolution, one capture per kernel instance of the step (B R C)
+for c in "32 32 64" "32 16 128" "32 32 32"; do
+  n=$(echo $c | tr " " "_")
+  timeout 300 ncu --set full --clock-control none --import-source on -k regex:conv3_tc05_kernel -s 2 -c 1 -o gpurun_out/prof/conv3_$n -f \
+      python tools/conv3_check.py --only $c > /dev/null 2>&1
+done
+python tools/ncu_summary.py gpurun_out/prof/conv3_*.ncu-rep > gpurun_out/prof/ncu_conv3_tc05.md 2>&1
+timeout 300 python tools/conv3_check.py > gpurun_out/prof/conv3_check.log 2>&1
+timeout 300 python tools/conv3_sparse_time.py > gpurun_out/prof/conv3_sparse_time.log 2>&1
 # 4. op-level timings and the stand-alone probes
 timeout 300 python tools/gn_bench.py > gpurun_out/prof/gn_bench.log 2>&1
 timeout 300 python tools/attn_bench.py > gpurun_out/prof/attn_bench.log 2>&1

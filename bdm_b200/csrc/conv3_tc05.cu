@@ -28,12 +28,16 @@
 //              (dy, dz) windows, KC/8 bulk copies into a 3-stage ring.
 //   warp 1     one thread: W producer.  Weights are pre-arranged (conv3_tc05_prep) as the exact shared-memory image of
 //              each (dx, chunk, tap group) stage; one bulk copy per stage into a ring.
-//   warp 2     one thread: issues the MMAs (2 tiles x taps x K/16 per stage), commits stages back to the producers.
+//   warp 2     issues the MMAs (2 tiles x taps x K/16 per stage) and commits stages back to the producers: the warp
+//              runs the loops together (descriptor words in uniform registers), one elected lane issues.
 //   warp 3     TMEM allocation.
 //   warps 4-11 epilogue: thread = output row = TMEM lane; scale, + bias, GroupNorm statistics of the result
-//              (per-group sum / sum of squares, reduced per unit, no atomics), channels-last fp32 store of the real
-//              voxels.  Accumulators are double-buffered (2 x 2 x N TMEM columns), so the epilogue of unit i overlaps
-//              the MMAs of unit i+1.
+//              (per-group sum / sum of squares, reduced per unit, no atomics), channels-last fp32 rows of the real
+//              voxels written with 256-bit stores.  Accumulators are double-buffered (2 x 2 x N TMEM columns), so the
+//              epilogue of unit i overlaps the MMAs of unit i+1.
+// For the FIRST convolution of a block the operand is a freshly voxelized cloud (conv3_fill_planes_kernel): mostly zero
+// rows.  The writer leaves one occupancy bit per row; every role derives the same 9-bit mask of non-empty (dx, dy)
+// windows per unit and the loads and MMAs of the empty ones are skipped (exact: those products are zeros).
 #include <cuda_fp16.h>
 
 #include "common.cuh"

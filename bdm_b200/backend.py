@@ -631,9 +631,8 @@ def groupnorm_act_cl(x, num_groups, weight, bias, eps, swish=True, conv_bias=Non
         sums = torch.empty((b, _L.bdm_groupnorm_cl_tiles(b, c, s, int(num_groups)), c), dtype=_F32, device=dev)
     chunks = 0
     if partials is not None:
-        _req(partials.dtype == torch.float64 and partials.is_contiguous() and partials.dim() == 4
-             and partials.shape[0] == b and partials.shape[2] == c and partials.shape[3] == 2, "partials must be f64[B,chunks,C,2]")
-        ws, chunks, ws_bytes = partials, int(partials.shape[1]), partials.numel() * 8
+        ws, chunks = _partials_args(partials, b, c, int(num_groups), conv_bias)
+        ws_bytes = ws.numel() * 8
     else:
         ws = _workspace(_L.bdm_groupnorm_cl_workspace_bytes(b, c, s), dev)
         ws_bytes = ws.numel()
@@ -661,16 +660,15 @@ def groupnorm_cl_sums(x, num_groups, weight, bias, eps, swish, conv_bias, partia
     for t_, nm in ((weight, "weight"), (bias, "bias"), (conv_bias, "conv_bias")):
         _chk_channel_vector(t_, nm, c)
     s = x.numel() // max(b * c, 1)
-    _req(partials.dtype == torch.float64 and partials.is_contiguous() and partials.dim() == 4 and partials.shape[0] == b
-         and partials.shape[2] == c and partials.shape[3] == 2, "partials must be f64[B,chunks,C,2]")
+    pt, chunks = _partials_args(partials, b, c, int(num_groups), conv_bias)
     sums = torch.empty((b, _L.bdm_groupnorm_cl_sums_tiles(b, c, s), c), dtype=_F32, device=x.device)
     coef = torch.empty((b, c, 2), dtype=_F32, device=x.device)
     with _Launch(x) as st:
         _check(_L.bdm_groupnorm_cl_sums(b, c, s, int(num_groups), float(eps), 1 if swish else 0, x.data_ptr(),
                                         conv_bias.data_ptr() if conv_bias is not None else None,
                                         weight.data_ptr() if weight is not None else None,
-                                        bias.data_ptr() if bias is not None else None, partials.data_ptr(),
-                                        int(partials.shape[1]), sums.data_ptr(), coef.data_ptr(), st))
+                                        bias.data_ptr() if bias is not None else None, pt.data_ptr(),
+                                        chunks, sums.data_ptr(), coef.data_ptr(), st))
     return sums, coef
 
 
@@ -792,6 +790,29 @@ def conv3_tc05_supported(c_in, c_out, resolution):
     return bool(_L.bdm_conv3_tc05_supported(int(c_in), int(c_out), int(resolution)))
 
 
+class GroupStats:
+    """Group-level producer statistics f64[B,blocks,groups,2] -- (sum, sum of squares) per normalisation group over
+    disjoint blocks of voxels, of the tensor as it is (bias included) -- as conv3_tc05(stats="groups") leaves them per
+    unit; groupnorm_act_cl / groupnorm_cl_sums / groupnorm_swish_half_planar fold them in their prologue."""
+    __slots__ = ("data",)
+
+    def __init__(self, data):
+        self.data = data
+
+
+def _partials_args(partials, b, c, groups, conv_bias):
+    """-> (tensor, chunks argument of the C entry): per-channel partials f64[B,chunks,C,2] -> +chunks; GroupStats -> -blocks"""
+    if isinstance(partials, GroupStats):
+        t = partials.data
+        _req(t.dtype == torch.float64 and t.is_contiguous() and t.dim() == 4 and t.shape[0] == b and t.shape[2] == groups
+             and t.shape[3] == 2, "group statistics must be f64[B,blocks,groups,2]")
+        _req(conv_bias is None, "group statistics already include the bias")
+        return t, -int(t.shape[1])
+    _req(partials.dtype == torch.float64 and partials.is_contiguous() and partials.dim() == 4 and partials.shape[0] == b
+         and partials.shape[2] == c and partials.shape[3] == 2, "partials must be f64[B,chunks,C,2]")
+    return partials, int(partials.shape[1])
+
+
 class HalfPlanes:
     """fp16 chunk planes [C/8, rows, 8] of the flat padded grid for (batch, resolution): the convolution's operand.
     Zero-filled at creation; producers write real voxels only, so pad rows stay zero for the buffer's lifetime."""
@@ -836,14 +857,13 @@ def groupnorm_swish_half_planar(x, num_groups, weight, bias, eps, swish, conv_bi
     _req(planes.b == b and planes.c == c and planes.r == r and planes.data.device == x.device, "planes do not match x")
     for t_, nm in ((weight, "weight"), (bias, "bias"), (conv_bias, "conv_bias")):
         _chk_channel_vector(t_, nm, c)
-    _req(partials.dtype == torch.float64 and partials.is_contiguous() and partials.dim() == 4 and partials.shape[0] == b
-         and partials.shape[2] == c and partials.shape[3] == 2, "partials must be f64[B,chunks,C,2]")
+    pt, chunks = _partials_args(partials, b, c, int(num_groups), conv_bias)
     with _Launch(x) as st:
         _check(_L.bdm_groupnorm_swish_half_planar(b, c, r, int(num_groups), float(eps), 1 if swish else 0, x.data_ptr(),
                                                   conv_bias.data_ptr() if conv_bias is not None else None,
                                                   weight.data_ptr() if weight is not None else None,
-                                                  bias.data_ptr() if bias is not None else None, partials.data_ptr(),
-                                                  int(partials.shape[1]), prepared.data_ptr(), planes.data.data_ptr(),
+                                                  bias.data_ptr() if bias is not None else None, pt.data_ptr(),
+                                                  chunks, prepared.data_ptr(), planes.data.data_ptr(),
                                                   planes.rows, st))
     return planes
 
@@ -878,7 +898,9 @@ def conv3_tc05(planes, prepared, c_out, bias=None, stats=False, sparse=False):
     out = torch.empty((b, r, r, r, c_out), dtype=_F32, device=dev)
     part = ws = None
     ws_bytes = 0
-    if stats:
+    if stats == "groups":       # the per-unit group partials as they are: no folding kernel (see GroupStats)
+        part = torch.empty((b, int(_L.bdm_conv3_tc05_units(r)), 8, 2), dtype=torch.float64, device=dev)
+    elif stats:
         part = torch.empty((b, 1, c_out, 2), dtype=torch.float64, device=dev)
         ws_bytes = int(_L.bdm_conv3_tc05_workspace_bytes(b, r))
         ws = _workspace(ws_bytes, dev)
@@ -888,4 +910,6 @@ def conv3_tc05(planes, prepared, c_out, bias=None, stats=False, sparse=False):
                                  bias.data_ptr() if bias is not None else None, out.data_ptr(),
                                  part.data_ptr() if part is not None else None, ws.data_ptr() if ws is not None else None,
                                  ws_bytes, planes.occ.data_ptr() if sparse else None, st))
+    if stats == "groups":
+        return out, GroupStats(part)
     return (out, part) if stats else out

@@ -215,6 +215,30 @@ conv3_prep_weights_kernel(int c_in, int c_out, int kc_size, int tg, const float 
 // store); a warp reads 1 KB of consecutive voxels.
 // -------------------------------------------------------------------------------------------------------------
 constexpr int kApplyThreads = 256;
+// group-level producer statistics f64[b][blocks][groups][2] -> per-channel table (the group's sums in its first channel's
+// slot, zeros in the others); see groupnorm.cu
+__device__ __forceinline__ void fold_group_partials(const double2 *__restrict__ gp, int b, int blocks, int groups, int c, int cg,
+                                                    double2 *slice /* [256] */, double2 *chan /* [c] */) {
+  const int t = threadIdx.x;
+  const int nsl = 256 / groups, g = t % groups, sl = t / groups;
+  double S1 = 0.0, S2 = 0.0;
+  if (sl < nsl) {
+    for (int blk = sl; blk < blocks; blk += nsl) {
+      const double2 v = gp[((size_t)b * blocks + blk) * groups + g];
+      S1 += v.x; S2 += v.y;
+    }
+  }
+  slice[t] = make_double2(S1, S2);
+  __syncthreads();
+  if (t < c) {
+    double A1 = 0.0, A2 = 0.0;
+    if (t % cg == 0) {
+      for (int k = 0; k < nsl; ++k) { A1 += slice[k * groups + t / cg].x; A2 += slice[k * groups + t / cg].y; }
+    }
+    chan[t] = make_double2(A1, A2);
+  }
+  __syncthreads();
+}
 __global__ void __launch_bounds__(kApplyThreads)
 gn_apply_half_planar_kernel(int c, int r, int groups, int nchunks, int ntiles, float eps, int swish,
                             const float *__restrict__ x, const float *__restrict__ conv_bias,
@@ -228,6 +252,9 @@ gn_apply_half_planar_kernel(int c, int r, int groups, int nchunks, int ntiles, f
   const int b = blockIdx.y, tile = blockIdx.x, t = threadIdx.x;
   const int cg = c / groups;
   const long long s = (long long)r * r * r;
+  if (nchunks < 0) {
+    fold_group_partials(partials, b, -nchunks, groups, c, cg, slice, chan);     // group-level statistics (bias included)
+  } else {
   {
     const int nsl = kApplyThreads / c, tc = t % c, sl = t / c;
     double S1 = 0.0, S2 = 0.0;
@@ -246,6 +273,7 @@ gn_apply_half_planar_kernel(int c, int r, int groups, int nchunks, int ntiles, f
     chan[t] = make_double2(S1 + ds * tt, S2 + 2.0 * tt * S1 + ds * tt * tt);
   }
   __syncthreads();
+  }
   if (t < groups) {
     double S1 = 0.0, S2 = 0.0;
     for (int j = 0; j < cg; ++j) { S1 += chan[t * cg + j].x; S2 += chan[t * cg + j].y; }
@@ -349,6 +377,9 @@ gn_apply_half_planar_warp_kernel(int r, int groups, int nchunks, int ntiles, flo
   const int b = blockIdx.y, tile = blockIdx.x, t = threadIdx.x;
   const int cg = c / groups;
   const long long s = (long long)r * r * r;
+  if (nchunks < 0) {
+    fold_group_partials(partials, b, -nchunks, groups, c, cg, slice, chan);     // group-level statistics (bias included)
+  } else {
   {
     const int nsl = kApplyThreads / c, tc = t % c, sl = t / c;
     double S1 = 0.0, S2 = 0.0;
@@ -367,6 +398,7 @@ gn_apply_half_planar_warp_kernel(int r, int groups, int nchunks, int ntiles, flo
     chan[t] = make_double2(S1 + ds * tt, S2 + 2.0 * tt * S1 + ds * tt * tt);
   }
   __syncthreads();
+  }
   if (t < groups) {
     double S1 = 0.0, S2 = 0.0;
     for (int j = 0; j < cg; ++j) { S1 += chan[t * cg + j].x; S2 += chan[t * cg + j].y; }
@@ -914,7 +946,8 @@ extern "C" int bdm_groupnorm_swish_half_planar(int b, int c, int r, int groups, 
                                                const double *partials, int chunks, const void *prepared, void *xh,
                                                long long plane_rows, bdm_stream_t stream) {
   BDM_CHECK_SIZE(b >= 0 && b <= 65535 && c >= 8 && c % 8 == 0 && c <= 256 && 256 % c == 0 && groups >= 1 && groups <= 32 &&
-                 c % groups == 0 && chunks >= 1 && r >= 2 && r <= 64 && (r & (r - 1)) == 0);
+                 c % groups == 0 && chunks != 0 && r >= 2 && r <= 64 && (r & (r - 1)) == 0);
+  BDM_CHECK_SIZE(chunks > 0 || conv_bias == nullptr);      // chunks < 0: -chunks blocks of group partials f64[b][blocks][groups][2]
   if (b == 0) return BDM_OK;
   BDM_CHECK_PTR(x); BDM_CHECK_PTR(partials); BDM_CHECK_PTR(prepared); BDM_CHECK_PTR(xh);
   const cv3::Geometry geo = cv3::conv3_geometry(b, r);
@@ -1011,10 +1044,12 @@ extern "C" int bdm_conv3_tc05(int b, int c_in, int c_out, int r, const void *xh,
   if (((reinterpret_cast<uintptr_t>(xh) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(prepared)) & 15) != 0)
     return BDM_ERR_MISALIGNED;
   double *unit_stats = nullptr;
-  if (stats != nullptr) {
-    BDM_CHECK_PTR(workspace);
+  const bool fold = stats != nullptr && workspace != nullptr;
+  if (fold) {
     if (workspace_bytes < bdm_conv3_tc05_workspace_bytes(b, r)) return BDM_ERR_WORKSPACE_TOO_SMALL;
     unit_stats = static_cast<double *>(workspace);
+  } else if (stats != nullptr) {
+    unit_stats = stats;          // the caller takes the per-unit group partials f64[b][units][8][2] as they are
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const __half *x = static_cast<const __half *>(xh);
@@ -1029,7 +1064,7 @@ extern "C" int bdm_conv3_tc05(int b, int c_in, int c_out, int r, const void *xh,
   else if (kc == 32) rc = cv3::launch_conv<128, 32, 3>(b, c_in, geo, x, wp, bias, out, unit_stats, occ, st);
   else rc = cv3::launch_conv<128, 64, 1>(b, c_in, geo, x, wp, bias, out, unit_stats, occ, st);
   if (rc != BDM_OK) return rc;
-  if (stats != nullptr) {
+  if (fold) {
     cv3::conv3_stats_fold_kernel<<<b, 512, 0, st>>>(units, c_out, unit_stats, reinterpret_cast<double2 *>(stats));
     BDM_RETURN_LAUNCH_STATUS();
   }

@@ -454,6 +454,32 @@ gn_cl_stats_kernel(int c, long long s, int nchunks, const float *__restrict__ x,
   }
 }
 
+// Producer statistics at group level, f64[b][blocks][groups][2] = (sum, sum of squares) of the tensor the norm is applied to
+// (bias included) over disjoint blocks of voxels -- what bdm_conv3_tc05 leaves per unit.  Folded by 256 threads into the
+// per-channel table the kernels below work from: the group's sums in its first channel's slot, zeros in the others.
+__device__ __forceinline__ void fold_group_partials(const double2 *__restrict__ gp, int b, int blocks, int groups, int c, int cg,
+                                                    double2 *slice /* [256] */, double2 *chan /* [c] */) {
+  const int t = threadIdx.x;
+  const int nsl = 256 / groups, g = t % groups, sl = t / groups;
+  double S1 = 0.0, S2 = 0.0;
+  if (sl < nsl) {
+    for (int blk = sl; blk < blocks; blk += nsl) {
+      const double2 v = gp[((size_t)b * blocks + blk) * groups + g];
+      S1 += v.x; S2 += v.y;
+    }
+  }
+  slice[t] = make_double2(S1, S2);
+  __syncthreads();
+  if (t < c) {
+    double A1 = 0.0, A2 = 0.0;
+    if (t % cg == 0) {
+      for (int k = 0; k < nsl; ++k) { A1 += slice[k * groups + t / cg].x; A2 += slice[k * groups + t / cg].y; }
+    }
+    chan[t] = make_double2(A1, A2);
+  }
+  __syncthreads();
+}
+
 // STORE == false: nothing is written back except the per-tile sums and (tile 0) the per-channel coefficients
 // coef[b][c] = (A, B) of y = act(x * A + B): the consumer normalises on the fly (bdm_trilinear_devoxelize_cl_norm).
 template <bool SWISH, int UNR, bool STORE = true>
@@ -471,30 +497,34 @@ gn_cl_apply_kernel(int c, long long s, int groups, int nchunks, int pstride, int
   const int c4 = c >> 2, rpp = kClThreads / c4, cg = c / groups;
   const float *px = x + (size_t)b * s * c;
   const int t = threadIdx.x;
-  {
-    // the sample's partial moments, folded by all 256 threads: thread (channel t % c, slice t / c) sums every
-    // (256/c)-th block, the slices are combined in order below (producer-made statistics come in up to 128 blocks;
-    // with c threads alone this prologue cost every CTA several microseconds)
-    const int nsl = kClThreads / c, tc = t % c, sl = t / c;
-    double S1 = 0.0, S2 = 0.0;
-    for (int ch = sl; ch < nchunks; ch += nsl) {
-      const double2 v = partials[((size_t)b * pstride + ch) * c + tc];   // pstride = blocks per sample in memory
-      S1 += v.x; S2 += v.y;
+  if (nchunks < 0) {
+    fold_group_partials(partials, b, -nchunks, groups, c, cg, grp, chan);      // group-level producer statistics (bias included)
+  } else {
+    {
+      // the sample's partial moments, folded by all 256 threads: thread (channel t % c, slice t / c) sums every
+      // (256/c)-th block, the slices are combined in order below (producer-made statistics come in up to 128 blocks;
+      // with c threads alone this prologue cost every CTA several microseconds)
+      const int nsl = kClThreads / c, tc = t % c, sl = t / c;
+      double S1 = 0.0, S2 = 0.0;
+      for (int ch = sl; ch < nchunks; ch += nsl) {
+        const double2 v = partials[((size_t)b * pstride + ch) * c + tc];   // pstride = blocks per sample in memory
+        S1 += v.x; S2 += v.y;
+      }
+      grp[t] = make_double2(S1, S2);          // grp doubles as the slice buffer until the group fold below
     }
-    grp[t] = make_double2(S1, S2);          // grp doubles as the slice buffer until the group fold below
+    __syncthreads();
+    if (t < c) {
+      // true sums of (x + bias) from the shifted partials: with tt = k_c + bias_c,
+      //   sum = S1 + s*tt,  sumsq = S2 + 2*tt*S1 + s*tt^2
+      double S1 = 0.0, S2 = 0.0;
+      for (int sl = 0; sl < kClThreads / c; ++sl) { S1 += grp[sl * c + t].x; S2 += grp[sl * c + t].y; }
+      double tt = zero_shift ? 0.0 : (double)__ldg(px + t);   // producer-made partials are of x itself
+      if (conv_bias != nullptr) tt += (double)conv_bias[t];
+      const double ds = (double)s;
+      chan[t] = make_double2(S1 + ds * tt, S2 + 2.0 * tt * S1 + ds * tt * tt);
+    }
+    __syncthreads();
   }
-  __syncthreads();
-  if (t < c) {
-    // true sums of (x + bias) from the shifted partials: with tt = k_c + bias_c,
-    //   sum = S1 + s*tt,  sumsq = S2 + 2*tt*S1 + s*tt^2
-    double S1 = 0.0, S2 = 0.0;
-    for (int sl = 0; sl < kClThreads / c; ++sl) { S1 += grp[sl * c + t].x; S2 += grp[sl * c + t].y; }
-    double tt = zero_shift ? 0.0 : (double)__ldg(px + t);   // producer-made partials are of x itself
-    if (conv_bias != nullptr) tt += (double)conv_bias[t];
-    const double ds = (double)s;
-    chan[t] = make_double2(S1 + ds * tt, S2 + 2.0 * tt * S1 + ds * tt * tt);
-  }
-  __syncthreads();
   if (t < groups) {
     double S1 = 0.0, S2 = 0.0;
     for (int j = 0; j < cg; ++j) { S1 += chan[t * cg + j].x; S2 += chan[t * cg + j].y; }
@@ -936,13 +966,16 @@ extern "C" int bdm_groupnorm_act_cl(int b, int c, long long s, int groups, float
                                     float *tile_sums, void *workspace, size_t workspace_bytes,
                                     int precomputed_chunks, bdm_stream_t stream) {
   using namespace bdm;
-  BDM_CHECK_SIZE(b >= 0 && s >= 0 && groups >= 1 && gn_cl_supported(c, groups) && b <= 65535 && precomputed_chunks >= 0);
+  BDM_CHECK_SIZE(b >= 0 && s >= 0 && groups >= 1 && gn_cl_supported(c, groups) && b <= 65535);
+  BDM_CHECK_SIZE(precomputed_chunks >= 0 || (conv_bias == nullptr && groups <= 32));   // group partials include the bias
   if (b == 0 || s == 0) return BDM_OK;
   BDM_CHECK_PTR(x); BDM_CHECK_PTR(y); BDM_CHECK_PTR(workspace);
   // (a group small enough for the one-pass kernel ignores producer statistics: one read either way, and the
   // tile count reported by bdm_groupnorm_cl_tiles stays consistent)
-  if (precomputed_chunks > 0 && !gn_cl_onepass(b, c, s, groups)) {
-    if (workspace_bytes < sizeof(double2) * (size_t)b * precomputed_chunks * c) return BDM_ERR_WORKSPACE_TOO_SMALL;
+  if (precomputed_chunks != 0 && !gn_cl_onepass(b, c, s, groups)) {
+    const size_t need = precomputed_chunks > 0 ? sizeof(double2) * (size_t)b * precomputed_chunks * c
+                                               : sizeof(double2) * (size_t)b * (size_t)(-precomputed_chunks) * groups;
+    if (workspace_bytes < need) return BDM_ERR_WORKSPACE_TOO_SMALL;
     if (((reinterpret_cast<uintptr_t>(workspace) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) != 0)
       return BDM_ERR_MISALIGNED;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -1004,7 +1037,8 @@ extern "C" int bdm_groupnorm_cl_sums(int b, int c, long long s, int groups, floa
                                      const float *conv_bias, const float *gamma, const float *beta, const double *partials,
                                      int chunks, float *tile_sums, float *coef, bdm_stream_t stream) {
   using namespace bdm;
-  BDM_CHECK_SIZE(b >= 0 && s >= 0 && groups >= 1 && gn_cl_supported(c, groups) && b <= 65535 && chunks >= 1);
+  BDM_CHECK_SIZE(b >= 0 && s >= 0 && groups >= 1 && gn_cl_supported(c, groups) && b <= 65535 && chunks != 0);
+  BDM_CHECK_SIZE(chunks > 0 || (conv_bias == nullptr && groups <= 32));      // chunks < 0: -chunks blocks of group partials
   if (b == 0 || s == 0) return BDM_OK;
   BDM_CHECK_PTR(x); BDM_CHECK_PTR(partials); BDM_CHECK_PTR(tile_sums); BDM_CHECK_PTR(coef);
   if (((reinterpret_cast<uintptr_t>(partials) | reinterpret_cast<uintptr_t>(x)) & 15) != 0 ||

@@ -29,6 +29,9 @@ FUSED_ATTENTION = os.environ.get("BDM_FUSED_ATTENTION", "1") != "0"
 # faster on the 8^3 grids: too few 128-row tiles for 148 SMs).  BDM_CONV3_TC05=0 disables.
 CONV3_TC05 = os.environ.get("BDM_CONV3_TC05", "1") != "0"
 CONV3_TC05_MIN_R = int(os.environ.get("BDM_CONV3_TC05_MIN_R", "16"))
+# the convolution's per-unit group statistics go to the next norm as they are ("groups": its prologue folds them) instead
+# of through a folding kernel (True); BDM_CONV3_GROUP_STATS=0 selects the latter
+CONV3_STATS = "groups" if os.environ.get("BDM_CONV3_GROUP_STATS", "1") != "0" else True
 # Tail of a voxel stack whose last convolution made its own statistics: conv -> GroupNorm -> Swish -> SE -> devoxelize.
 # The normalised grid is never written: one read-only pass yields the SE squeeze sums and the per-channel (A, B) of
 # y = swish(x*A + B), and the devoxelization applies that to the 8 corner values it reads (bit-identical results).
@@ -324,7 +327,7 @@ class FusedSequential(nn.Sequential):
                     planes = half_planes(nb, nc, r, y.device)
                     _ops._B.groupnorm_swish_half_planar(y.permute(0, 2, 3, 4, 1), gn.num_groups, gn.weight, gn.bias, gn.eps,
                                                         True, cbias, stats, prepared, planes)
-                    out2, pre_stats = _ops._B.conv3_tc05(planes, prepared, conv2.out_channels, bias=conv2.bias, stats=True)
+                    out2, pre_stats = _ops._B.conv3_tc05(planes, prepared, conv2.out_channels, bias=conv2.bias, stats=CONV3_STATS)
                     pre, pre_biased = out2.permute(0, 4, 1, 2, 3), True
                     i = j
                     continue

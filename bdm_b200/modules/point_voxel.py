@@ -187,7 +187,7 @@ class _PVConvBase(nn.Module):
         occupied = _ops._B.avg_voxelize_compact(features.contiguous(), plan, amax_into=prepared)     # [B, Cin, N] + max|.|
         planes = _layers.half_planes(features.shape[0], conv.in_channels, vox.r, features.device)
         _ops._B.conv3_tc05_fill_planes(occupied, plan, prepared, planes, amax_ready=True)
-        out, stats = _ops._B.conv3_tc05(planes, prepared, conv.out_channels, bias=conv.bias, stats=True,
+        out, stats = _ops._B.conv3_tc05(planes, prepared, conv.out_channels, bias=conv.bias, stats=_layers.CONV3_STATS,
                                         sparse=SKIP_EMPTY_WINDOWS)
         return (out.permute(0, 4, 1, 2, 3), stats, True), norm_coords
 

@@ -300,7 +300,11 @@ int bdm_groupnorm_act_cl(int b, int c, long long s, int groups, float eps, int s
                          float *tile_sums, void *workspace, size_t workspace_bytes, int precomputed_chunks,
                          bdm_stream_t stream);
 /* precomputed_chunks > 0: workspace holds the producer's statistics f64[b,precomputed_chunks,c,2] (see
- * bdm_sparse_conv3_gather) and the statistics pass over x is skipped. */
+ * bdm_sparse_conv3_gather) and the statistics pass over x is skipped.
+ * precomputed_chunks < 0: workspace holds GROUP-level producer statistics f64[b,-precomputed_chunks,groups,2] -- (sum, sum
+ * of squares) per normalisation group over disjoint blocks of voxels, of the tensor as it is (conv_bias must be NULL):
+ * what bdm_conv3_tc05 writes per unit.  The same convention holds for `chunks` of bdm_groupnorm_cl_sums and
+ * bdm_groupnorm_swish_half_planar. */
 /* Statistics-only half for a consumer that normalises on the fly (bdm_trilinear_devoxelize_cl_norm): x + producer
  * statistics partials f64[b,chunks,c,2] -> tile_sums f32[b,tiles,c] (tiles = bdm_groupnorm_cl_sums_tiles; sums of
  * y = act(group_norm(x + conv_bias)), what bdm_se_gate takes) and coef f32[b,c,2] = (A, B) with y = act(x*A + B).
@@ -332,9 +336,11 @@ int bdm_groupnorm_cl_sums(int b, int c, long long s, int groups, float eps, int 
  *       occ (or NULL): u32[b][bdm_conv3_tc05_occ_words(r)], one bit per non-zero row; passed on to bdm_conv3_tc05 it
  *       makes the convolution skip (loads and MMAs) the tap windows that hold only zero rows -- exact, since those
  *       products are zeros (NULL there = dense operand).
- *   bdm_conv3_tc05   out f32[b][r^3][c_out] = conv(xh) + bias; stats (or NULL): f64[b][1][c_out][2], the result's
- *       GroupNorm(8) statistics in the layout bdm_groupnorm_act_cl(precomputed_chunks = 1) takes; workspace:
- *       bdm_conv3_tc05_workspace_bytes(b, r) bytes when stats != NULL.
+ *   bdm_conv3_tc05   out f32[b][r^3][c_out] = conv(xh) + bias; stats (or NULL): the result's GroupNorm(8) statistics.
+ *       With workspace (bdm_conv3_tc05_workspace_bytes(b, r) bytes): f64[b][1][c_out][2] in the layout
+ *       bdm_groupnorm_act_cl(precomputed_chunks = 1) takes (one more small kernel folds the units).  With workspace
+ *       NULL: the per-unit group partials themselves, f64[b][bdm_conv3_tc05_units(r)][8][2], for
+ *       precomputed_chunks = -bdm_conv3_tc05_units(r) (no extra kernel).
  * c_out in {32, 64, 128}, c_in = 32 or a multiple of 64, r a power of two (bdm_conv3_tc05_supported). */
 int bdm_conv3_tc05_supported(int c_in, int c_out, int r);
 long long bdm_conv3_tc05_plane_rows(int b, int r);

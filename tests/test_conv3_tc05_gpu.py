@@ -84,6 +84,35 @@ def test_conv3_tc05_vs_float64_and_cudnn_tf32(b, r, cin, cout, cuda_backend):
         assert got[:, :, 1:].abs().max().item() == 0.0
 
 
+@pytest.mark.parametrize("b,r,c", [(3, 32, 64), (2, 16, 128), (2, 32, 32)])
+def test_group_statistics_go_to_the_consumers_unfolded(b, r, c, cuda_backend):
+    """conv3_tc05(stats="groups") leaves its per-unit group partials; every consumer folds them in its prologue and must
+    agree with the folded form (stats=True) to rounding of the double sums"""
+    import torch
+    B = cuda_backend
+    x, cb, gamma, beta, w, bias = _inputs(b, r, c, c, 31 + r + c)
+    prepared = B.conv3_tc05_prepare(w, gamma, beta, (c // 8) * r ** 3)
+    planes = B.HalfPlanes(b, c, r, x.device)
+    B.groupnorm_swish_half_planar(x, 8, gamma, beta, 1e-5, True, cb, _partials(x), prepared, planes)
+    out, folded = B.conv3_tc05(planes, prepared, c, bias=bias, stats=True)
+    out2, groups = B.conv3_tc05(planes, prepared, c, bias=bias, stats="groups")
+    assert torch.equal(out, out2)
+    cg = c // 8
+    assert torch.allclose(groups.data.sum(1), folded[:, 0, ::cg], rtol=1e-12, atol=0)
+    of = out.reshape(b, -1, c)
+    y1, s1 = B.groupnorm_act_cl(of, 8, gamma, beta, 1e-5, True, channel_sums="tiles", partials=folded)
+    y2, s2 = B.groupnorm_act_cl(of, 8, gamma, beta, 1e-5, True, channel_sums="tiles", partials=groups)
+    assert (y1 - y2).abs().max().item() <= 1e-6 * y1.abs().max().item()
+    assert torch.allclose(s1, s2, rtol=1e-5, atol=1e-4)
+    t1, c1 = B.groupnorm_cl_sums(of, 8, gamma, beta, 1e-5, True, None, folded)
+    t2, c2 = B.groupnorm_cl_sums(of, 8, gamma, beta, 1e-5, True, None, groups)
+    assert torch.allclose(c1, c2, rtol=1e-6, atol=1e-7)
+    p1, p2 = B.HalfPlanes(b, c, r, x.device), B.HalfPlanes(b, c, r, x.device)
+    B.groupnorm_swish_half_planar(out, 8, gamma, beta, 1e-5, True, None, folded, prepared, p1)
+    B.groupnorm_swish_half_planar(out, 8, gamma, beta, 1e-5, True, None, groups, prepared, p2)
+    assert (p1.data.float() - p2.data.float()).abs().max().item() <= 2e-3 * p1.data.float().abs().max().item()
+
+
 @pytest.mark.parametrize("b,r,c", [(2, 16, 64), (3, 8, 32), (1, 32, 128)])
 def test_half_planes_hold_the_activation_and_zero_pads(b, r, c, cuda_backend):
     """decode the fp16 chunk planes back to [B,R,R,R,C]: GroupNorm+Swish to fp16 rounding; every other row is zero"""

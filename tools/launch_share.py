@@ -18,7 +18,7 @@ for r in rows[hdr_i + 1:]:
     unit = r[ui]
     us = v * {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(unit, 1e-3)
     launches.append((r[ki], us))
-half = launches if (len(sys.argv) > 2 and sys.argv[2] == "all") else launches[len(launches) // 2:]
+half = launches     # (the step list holds exactly one iteration: tools/step_launches.py brackets it with cudaProfilerStart/Stop)
 agg = collections.OrderedDict()
 for name, us in half:
     short = re.sub(r"\(.*", "", name).replace("void ", "")
@@ -29,7 +29,7 @@ for name, us in half:
 total = sum(a[1] for a in agg.values())
 OURS = ("bdm::", "cv3::", "tc05::", "gnc::")      # namespaces of libbdm_b200.so's kernels as ncu prints them
 ours = sum(a[1] for k, a in agg.items() if k.startswith(OURS))
-print(f"# {'window of the bench command (graph replays)' if len(half) == len(launches) else 'One PC^2 iteration, eager'} (B={__import__('os').environ.get('BDM_BATCH', '32')}, N=4096), serialised under ncu: {len(half)} launches, {total / 1e3:.2f} ms of kernel time")
+print(f"# {'window of the bench command (graph replays)' if (len(sys.argv) > 2 and sys.argv[2] == 'all') else 'One PC^2 iteration, eager'} (B={__import__('os').environ.get('BDM_BATCH', '32')}, N=4096), serialised under ncu: {len(half)} launches, {total / 1e3:.2f} ms of kernel time")
 print(f"# libbdm_b200 kernels: {ours / 1e3:.3f} ms = {ours / total * 100:.1f} % of the step's kernel time")
 print("| kernel | launches | total us | share % |")
 print("|---|---|---|---|")

@@ -4,7 +4,7 @@
 mkdir -p gpurun_out/prof
 export BDM_BATCH=32
 # 1. every launch of one eager PC^2 sampler iteration (B = 32) with its device time
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/prof/step_launches.csv \
+timeout 600 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/prof/step_launches.csv \
     python tools/step_launches.py > /dev/null 2>&1
 python tools/launch_share.py gpurun_out/prof/step_launches.csv > gpurun_out/prof/step_launch_share.md
 # 2. a window of ~2 sampler iterations (graph replays) out of the middle of the bench command's second warm-up job

@@ -377,6 +377,35 @@ def test_block_with_fused_tail_is_bit_identical(cuda_backend):
         assert torch.equal(y_fused, y_plain), (cin, cout, r, (y_fused - y_plain).abs().max().item())
 
 
+def test_prepared_weights_follow_in_place_updates(cuda_backend):
+    """the fp16 weight stages are cached per parameter version: an in-place update of a convolution's weight (or of the
+    GroupNorm affine that bounds its activations) must be picked up by the next forward"""
+    import torch
+
+    import bdm_b200.modules.point_voxel as PV
+    torch.manual_seed(3)
+    blk = PV.PVConv(64, 64, 3, 32, with_se=True).cuda().eval()
+    feats = torch.randn(2, 64, 4096, device="cuda")
+    u = torch.randn(2, 3, 4096, device="cuda")
+    coords = u / u.norm(dim=1, keepdim=True) * 0.5
+    temb = torch.randn(2, 8, 4096, device="cuda")
+    saved = torch.backends.cudnn.allow_tf32
+    try:
+        torch.backends.cudnn.allow_tf32 = True
+        with torch.no_grad():
+            y0 = blk((feats, coords, temb))[0].clone()
+            assert torch.equal(blk((feats, coords, temb))[0], y0)                   # deterministic, cache hit
+            for conv in (blk.voxel_layers[0], blk.voxel_layers[4]):
+                conv.weight.mul_(1.5)                                                # in place: same storage, new version
+            y1 = blk((feats, coords, temb))[0]
+            torch.backends.cudnn.allow_tf32 = False                                  # cuDNN fp32 with the updated weights
+            y_ref = blk((feats, coords, temb))[0]
+    finally:
+        torch.backends.cudnn.allow_tf32 = saved
+    assert (y1 - y0).abs().max().item() > 1e-3 * y0.abs().max().item()
+    assert (y1 - y_ref).abs().max().item() <= 2e-3 * y_ref.abs().max().item()
+
+
 def test_route_is_off_when_tf32_convolutions_are_off(cuda_backend):
     import torch
 

@@ -73,7 +73,7 @@ _PROTOS = {
     "bdm_sampler_update": (_i, [ctypes.c_longlong, _i, _p, _p, _p, _p, _i, _p, _p, _p]),
     "bdm_conv3_tc05_supported": (_i, [_i, _i, _i]),
     "bdm_conv3_tc05_plane_rows": (ctypes.c_longlong, [_i, _i]),
-    "bdm_conv3_tc05_units": (_i, [_i]),
+    "bdm_conv3_tc05_units": (_i, [_i, _i, _i]),
     "bdm_conv3_tc05_weight_bytes": (_z, [_i, _i]),
     "bdm_conv3_tc05_workspace_bytes": (_z, [_i, _i]),
     "bdm_conv3_tc05_prepare": (_i, [_i, _i, _p, _p, _p, ctypes.c_longlong, _p, _z, _p]),

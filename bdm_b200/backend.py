@@ -899,7 +899,7 @@ def conv3_tc05(planes, prepared, c_out, bias=None, stats=False, sparse=False):
     part = ws = None
     ws_bytes = 0
     if stats == "groups":       # the per-unit group partials as they are: no folding kernel (see GroupStats)
-        part = torch.empty((b, int(_L.bdm_conv3_tc05_units(r)), 8, 2), dtype=torch.float64, device=dev)
+        part = torch.empty((b, int(_L.bdm_conv3_tc05_units(c_in, int(c_out), r)), 8, 2), dtype=torch.float64, device=dev)
     elif stats:
         part = torch.empty((b, 1, c_out, 2), dtype=torch.float64, device=dev)
         ws_bytes = int(_L.bdm_conv3_tc05_workspace_bytes(b, r))

@@ -40,6 +40,8 @@
 // windows per unit and the loads and MMAs of the empty ones are skipped (exact: those products are zeros).
 #include <cuda_fp16.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 #include "voxel_plan.cuh"
 
@@ -119,6 +121,7 @@ struct Geometry {
   int r, q, p;                // resolution, Q = r+1, P = Q^2
   int guard;                  // zero rows in front of every sample (>= P + Q + 1, multiple of 8)
   int units;                  // units per sample
+  int units_pair;             // ... of the tap-pairing kernel instances (255 outputs per unit)
   long long sample_rows;      // row stride between samples
   long long total_rows;       // rows of one chunk plane
   int slab_rows;              // rows of an A stage: 256 + 2Q + 2
@@ -129,6 +132,7 @@ __host__ __device__ inline Geometry conv3_geometry(int b, int r) {
   g.guard = (g.p + g.q + 1 + 7) / 8 * 8;
   const int last_valid = ((r - 1) * g.q + (r - 1)) * g.q + (r - 1);
   g.units = (last_valid + 1 + kUnitRows - 1) / kUnitRows;
+  g.units_pair = (last_valid + 1 + kUnitRows - 2) / (kUnitRows - 1);
   g.sample_rows = ((long long)g.guard + (long long)g.q * g.p + 7) / 8 * 8;
   g.slab_rows = kUnitRows + 2 * g.q + 2;
   // the last unit of the last sample reads up to units*256 + P + Q + 1 rows past its sample's first position
@@ -189,20 +193,40 @@ conv3_prep_header_kernel(size_t nw, const float *__restrict__ w, int c_in, const
 }
 
 __global__ void __launch_bounds__(256)
-conv3_prep_weights_kernel(int c_in, int c_out, int kc_size, int tg, const float *__restrict__ w,
+conv3_prep_weights_kernel(int c_in, int c_out, int kc_size, int tg, int pair, const float *__restrict__ w,
                           const float *__restrict__ header, __half *__restrict__ out) {
   const float sw = header[2];
   const int nkc = c_in / kc_size, ng = 9 / tg, chunks = kc_size / 8;
   const size_t total = (size_t)27 * c_in * c_out;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     size_t rest = i;
+    int n, c, j, grp, kc, dx;
     const int e = (int)(rest % 8); rest /= 8;
-    const int n = (int)(rest % c_out); rest /= c_out;
-    const int c = (int)(rest % chunks); rest /= chunks;
-    const int j = (int)(rest % tg); rest /= tg;
-    const int grp = (int)(rest % ng); rest /= ng;
-    const int kc = (int)(rest % nkc); rest /= nkc;
-    const int dx = (int)rest;
+    if (pair) {
+      // stage (dx, kc, dy): [chunk][2 c_out rows: dz = 0 then dz = +1][8 halves], then [chunk][c_out rows: dz = -1][8 halves]
+      const int stage_elems = 3 * c_out * chunks;            // 16-byte rows per stage
+      const int in_stage = (int)(rest % stage_elems); rest /= stage_elems;
+      if (in_stage < 2 * c_out * chunks) {
+        c = in_stage / (2 * c_out);
+        const int row = in_stage - c * 2 * c_out;
+        j = row < c_out ? 1 : 2;
+        n = row < c_out ? row : row - c_out;
+      } else {
+        const int q = in_stage - 2 * c_out * chunks;
+        c = q / c_out; n = q - c * c_out; j = 0;
+      }
+      grp = (int)(rest % 3); rest /= 3;
+      kc = (int)(rest % nkc); rest /= nkc;
+      dx = (int)rest;
+      tg = 3;
+    } else {
+      n = (int)(rest % c_out); rest /= c_out;
+      c = (int)(rest % chunks); rest /= chunks;
+      j = (int)(rest % tg); rest /= tg;
+      grp = (int)(rest % ng); rest /= ng;
+      kc = (int)(rest % nkc); rest /= nkc;
+      dx = (int)rest;
+    }
     const int ci = kc * kc_size + c * 8 + e;
     const int tap = dx * 9 + grp * tg + j;
     out[i] = __float2half_rn(__ldg(w + ((size_t)n * c_in + ci) * 27 + tap) * sw);
@@ -534,7 +558,8 @@ conv3_fill_planes_kernel(int c, int n, int r, VoxAuxLayout L, const unsigned cha
 // combined with one REDUX.  occ == NULL: everything is treated as occupied.
 constexpr int kOccSlackRows = 1024;     // rows past a sample's stride that a unit's windows may reach into
 __host__ __device__ inline int occ_words_per_sample(const Geometry &g) { return (int)((g.sample_rows + kOccSlackRows + 31) / 32); }
-__device__ __forceinline__ uint32_t window_mask(const uint32_t *__restrict__ occ, const Geometry &geo, int smp, int u, int lane) {
+__device__ __forceinline__ uint32_t window_mask(const uint32_t *__restrict__ occ, const Geometry &geo, int smp, int u, int lane,
+                                                int uout = kUnitRows) {
   if (occ == nullptr) return 0x1FFu;
   const uint32_t *o = occ + (size_t)smp * occ_words_per_sample(geo);
   uint32_t m = 0;
@@ -544,7 +569,7 @@ __device__ __forceinline__ uint32_t window_mask(const uint32_t *__restrict__ occ
     if (idx < 90) {
       const int wdw = idx / 10, k = idx - wdw * 10;
       const int dx = wdw / 3, dy = wdw - dx * 3;
-      const int first = geo.guard + u * kUnitRows + (dx - 1) * geo.p + (dy - 1) * geo.q - 1;      // >= 0: guard >= P + Q + 1
+      const int first = geo.guard + u * uout + (dx - 1) * geo.p + (dy - 1) * geo.q - 1;           // >= 0: guard >= P + Q + 1
       const int last = first + kUnitRows + 1;                                                      // inclusive
       const int w = (first >> 5) + k;
       if (w <= (last >> 5)) {
@@ -558,28 +583,39 @@ __device__ __forceinline__ uint32_t window_mask(const uint32_t *__restrict__ occ
   return __reduce_or_sync(0xffffffffu, m);
 }
 
-template <int N, int KC, int TG>
+// PAIR (N <= 64, TG = 3): the dz = 0 and dz = +1 taps of a (dx, dy) pair share ONE activation window -- B = [W(dz=0); W(dz=+1)]
+// is a 2N-row operand and one MMA of N' = 2N fills two column blocks, `main` and `side` -- and the dz = -1 tap is a
+// second MMA of N columns into `main` with the window shifted by one row, as before.  Per (dx, dy), tile and K-step that
+// is 8 + 6 KB of shared-memory operands instead of 3 x 6 KB: the kernel is bound by exactly that traffic.  The side
+// block belongs one row further down, out[m] = main[m] + side[m+1]: the epilogue takes it from the next lane (one
+// shuffle per column) and, for a warp's last lane, from a row the next warp leaves in shared memory; a unit therefore
+// yields rows 0..254 of its 256.
+template <int N, int KC, int TG, bool PAIR = false>
 struct Cfg {
+  static_assert(!PAIR || (TG == 3 && N <= 64), "tap pairing: one (dx, dy) row of taps per stage, 8N <= 512 TMEM columns");
+  static constexpr int kUOut = PAIR ? kUnitRows - 1 : kUnitRows;      // output rows per unit
+  static constexpr int kDCols = PAIR ? 2 * N : N;                    // TMEM columns per tile
   static constexpr int kChunks = KC / 8;
   static constexpr int kK16 = KC / 16;
   static constexpr int kNG = 9 / TG;
   static constexpr int kTapBytes = N * KC * 2;
   static constexpr int kWStageBytes = TG * kTapBytes;
   static constexpr int kWStages = kWStageBytes <= 16 * 1024 ? 4 : 3;
-  static constexpr int kTmemCols = 4 * N;          // 2 buffers x 2 tiles x N
+  static constexpr int kTmemCols = 4 * kDCols;     // 2 buffers x 2 tiles x columns per tile
   static constexpr int kNumBars = 2 * kAStages + 2 * kWStages + 4;
 };
 
-template <int N, int KC, int TG>
+template <int N, int KC, int TG, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
 conv3_tc05_kernel(int b, int c_in, Geometry geo, int a_stage_bytes, const __half *__restrict__ xh,
                   const unsigned char *__restrict__ wprep, const float *__restrict__ bias,
                   float *__restrict__ out, double *__restrict__ unit_stats, const uint32_t *__restrict__ occ) {
-  using C = Cfg<N, KC, TG>;
+  using C = Cfg<N, KC, TG, PAIR>;
   extern __shared__ __align__(1024) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkc = c_in / KC;
-  const int total_units = b * geo.units;
+  const int units = PAIR ? geo.units_pair : geo.units;
+  const int total_units = b * units;
   const int slab_rows = geo.slab_rows;
 
   unsigned char *a_smem = smem;
@@ -589,6 +625,7 @@ conv3_tc05_kernel(int b, int c_in, Geometry geo, int a_stage_bytes, const __half
   uint64_t *t_full = w_empty + C::kWStages, *t_empty = t_full + 2;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + C::kNumBars);
   float *red = reinterpret_cast<float *>(tmem_slot + 4);        // [2][8 warps][16]
+  float *edge = red + 2 * 8 * 16;                               // PAIR: [8 warps][N], the side row of every warp's first lane
   volatile uint32_t *unit_empty = tmem_slot + 2;                // [2]: no MMA was issued for the unit in this accumulator buffer
 
   if (threadIdx.x == 0) {
@@ -613,9 +650,9 @@ conv3_tc05_kernel(int b, int c_in, Geometry geo, int a_stage_bytes, const __half
       int sa = 0; uint32_t pa = 0;
       const uint32_t slab_bytes = (uint32_t)slab_rows * 16u;
       for (int g = blockIdx.x; g < total_units; g += gridDim.x) {
-        const int smp = g / geo.units, u = g - smp * geo.units;
-        const uint32_t wm = window_mask(occ, geo, smp, u, lane);
-        const long long row_base = (long long)geo.guard + (long long)smp * geo.sample_rows + (long long)u * kUnitRows;
+        const int smp = g / units, u = g - smp * units;
+        const uint32_t wm = window_mask(occ, geo, smp, u, lane, C::kUOut);
+        const long long row_base = (long long)geo.guard + (long long)smp * geo.sample_rows + (long long)u * C::kUOut;
         for (int dx = 0; dx < 3; ++dx) {
           if (((wm >> (3 * dx)) & 7u) == 0u) continue;          // an all-zero slab: nothing to multiply
           const long long src_row = row_base + (long long)(dx - 1) * geo.p - geo.q - 1;
@@ -641,8 +678,8 @@ conv3_tc05_kernel(int b, int c_in, Geometry geo, int a_stage_bytes, const __half
       int sw = 0; uint32_t pw = 0;
       const unsigned char *wsrc = wprep + kHeaderBytes;
       for (int g = blockIdx.x; g < total_units; g += gridDim.x) {
-        const int smp = g / geo.units, u = g - smp * geo.units;
-        const uint32_t wm = window_mask(occ, geo, smp, u, lane);
+        const int smp = g / units, u = g - smp * units;
+        const uint32_t wm = window_mask(occ, geo, smp, u, lane, C::kUOut);
         for (int dx = 0; dx < 3; ++dx) {
           const uint32_t sm = (wm >> (3 * dx)) & 7u;
           if (sm == 0u) continue;
@@ -684,11 +721,11 @@ conv3_tc05_kernel(int b, int c_in, Geometry geo, int a_stage_bytes, const __half
       int it = 0;
       for (int g = blockIdx.x; g < total_units; g += gridDim.x, ++it) {
         const int buf = it & 1;
-        const int smp = g / geo.units, u = g - smp * geo.units;
-        const uint32_t wm = window_mask(occ, geo, smp, u, lane);      // windows of all-zero rows are skipped, loads and MMAs
+        const int smp = g / units, u = g - smp * units;
+        const uint32_t wm = window_mask(occ, geo, smp, u, lane, C::kUOut);      // windows of all-zero rows are skipped, loads and MMAs
         bar_wait(t_empty + buf, ((it >> 1) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t d0 = tmem + buf * 2 * N;
+        const uint32_t d0 = tmem + buf * 2 * C::kDCols;
         uint32_t acc = 0;                                             // 0 until the unit's first MMA has been issued
         for (int dx = 0; dx < 3; ++dx) {
           const uint32_t sm = (wm >> (3 * dx)) & 7u;
@@ -707,6 +744,37 @@ conv3_tc05_kernel(int b, int c_in, Geometry geo, int a_stage_bytes, const __half
               __syncwarp();
               if (elect_one()) {
                 uint32_t first = acc;                                  // accumulate flag of the next tap's k = 0 MMAs
+                if constexpr (PAIR) {
+                  // stage = the three dz taps of (dx, dy = grp): [pair image: 2N rows = W(dz=0) | W(dz=+1)][single image: W(dz=-1)]
+                  constexpr uint32_t idesc_pair = instr_desc(2 * N);
+                  const uint32_t a_row = a_lo + (grp == 0 ? 0u : (grp == 1 ? q1 : q2));
+                  const uint32_t bp_lo = (b_lo & 0xffffu) | ((uint32_t)(2 * N) << 16);          // LBO = 2N rows of 16 bytes
+                  const uint32_t bs_lo = b_lo + (uint32_t)((2 * C::kTapBytes) >> 4);
+#pragma unroll
+                  for (int t = 0; t < 2; ++t) {
+#pragma unroll
+                    for (int k = 0; k < C::kK16; ++k) {       // dz = 0 (main) and dz = +1 (side): window at row offset +1
+                      const uint32_t da_lo = a_row + 1u + (uint32_t)(t * 128) + (uint32_t)k * kstep;
+                      const uint32_t db_lo = bp_lo + (uint32_t)(k * 2 * 2 * N);
+                      const uint32_t accumulate = k == 0 ? first : 1u;
+                      asm volatile(
+                          "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %5, 0;\n\t"
+                          "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %2};\n\t"
+                          "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
+                          ::"r"(d0 + t * C::kDCols), "r"(da_lo), "r"(desc_hi), "r"(db_lo), "r"(idesc_pair), "r"(accumulate) : "memory");
+                    }
+#pragma unroll
+                    for (int k = 0; k < C::kK16; ++k) {       // dz = -1 into main: window at row offset 0
+                      const uint32_t da_lo = a_row + (uint32_t)(t * 128) + (uint32_t)k * kstep;
+                      const uint32_t db_lo = bs_lo + (uint32_t)(k * 2 * N);
+                      asm volatile(
+                          "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %5, 0;\n\t"
+                          "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %2};\n\t"
+                          "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
+                          ::"r"(d0 + t * C::kDCols), "r"(da_lo), "r"(desc_hi), "r"(db_lo), "r"(idesc), "r"(1u) : "memory");
+                    }
+                  }
+                } else {
 #pragma unroll
                 for (int j = 0; j < TG; ++j) {
                   const int tap = grp * TG + j;
@@ -728,6 +796,7 @@ conv3_tc05_kernel(int b, int c_in, Geometry geo, int a_stage_bytes, const __half
                     }
                   }
                   first = 1u;
+                }
                 }
                 umma_commit(w_empty + sw);
               }
@@ -759,11 +828,11 @@ conv3_tc05_kernel(int b, int c_in, Geometry geo, int a_stage_bytes, const __half
     int it = 0;
     for (int g = blockIdx.x; g < total_units; g += gridDim.x, ++it) {
       const int buf = it & 1;
-      const int smp = g / geo.units, u = g - smp * geo.units;
+      const int smp = g / units, u = g - smp * units;
       const int m = t * 128 + qd * 32 + lane;
-      const int p = u * kUnitRows + m;
+      const int p = u * C::kUOut + m;
       const int z = p % q, xy = p / q, y = xy % q, x = xy / q;
-      const bool valid = x < r && y < r && z < r;
+      const bool valid = x < r && y < r && z < r && m < C::kUOut;
       float *dst = out + ((size_t)smp * s3 + ((size_t)x * r + y) * r + z) * N;
       float gs1[8], gs2[8];
 #pragma unroll
@@ -771,13 +840,48 @@ conv3_tc05_kernel(int b, int c_in, Geometry geo, int a_stage_bytes, const __half
       bar_wait(t_full + buf, (it >> 1) & 1);
       tc_fence_after();
       const bool empty = unit_empty[buf] != 0u;       // all of the unit's windows were zero rows: accumulators were not written
-      const uint32_t taddr = tmem + ((uint32_t)(qd * 32) << 16) + buf * 2 * N + t * N;
+      const uint32_t taddr = tmem + ((uint32_t)(qd * 32) << 16) + buf * 2 * C::kDCols + t * C::kDCols;
+      if constexpr (PAIR) {
+        // the side row of this warp's first lane is what the previous warp's last lane adds to its main row
+        if (!empty) {
+#pragma unroll
+          for (int c0 = 0; c0 < N; c0 += 32) {
+            uint32_t ss[32];
+            BDM_CV3_TMEM_LD32(ss, taddr + N + c0);
+            tmem_wait_ld();
+            if (lane == 0) {
+#pragma unroll
+              for (int i4 = 0; i4 < 8; ++i4)
+                *reinterpret_cast<uint4 *>(edge + e * N + c0 + 4 * i4) = make_uint4(ss[4 * i4], ss[4 * i4 + 1], ss[4 * i4 + 2], ss[4 * i4 + 3]);
+            }
+          }
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+        }
+      }
+      const float *edge_next = edge + (e < 7 ? e + 1 : 7) * N;
 #pragma unroll
       for (int c0 = 0; c0 < N; c0 += 32) {
         uint32_t rr[32];
         if (!empty) {
           BDM_CV3_TMEM_LD32(rr, taddr + c0);
-          tmem_wait_ld();
+          if constexpr (PAIR) {
+            uint32_t ss[32];
+            BDM_CV3_TMEM_LD32(ss, taddr + N + c0);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i4 = 0; i4 < 8; ++i4) {
+              const float4 ev = *reinterpret_cast<const float4 *>(edge_next + c0 + 4 * i4);     // same address in every lane
+              const float en[4] = {ev.x, ev.y, ev.z, ev.w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                float sd = __shfl_down_sync(0xffffffffu, __uint_as_float(ss[4 * i4 + i]), 1);
+                sd = lane == 31 ? en[i] : sd;
+                rr[4 * i4 + i] = __float_as_uint(__uint_as_float(rr[4 * i4 + i]) + sd);
+              }
+            }
+          } else {
+            tmem_wait_ld();
+          }
         } else {
 #pragma unroll
           for (int i = 0; i < 32; ++i) rr[i] = 0u;
@@ -808,6 +912,7 @@ conv3_tc05_kernel(int b, int c_in, Geometry geo, int a_stage_bytes, const __half
       }
       tc_fence_before();
       bar_arrive(t_empty + buf);
+      if (PAIR && unit_stats == nullptr) asm volatile("bar.sync 1, 256;" ::: "memory");     // `edge` is rewritten by the next unit
       if (unit_stats != nullptr) {
         // 16 values (sum, sum of squares of 8 groups) over 32 lanes as a halving butterfly: each step a lane hands half of
         // what it still holds to its partner, so 8 + 4 + 2 + 1 + 1 = 16 shuffles instead of 16 x 5; fixed order
@@ -886,20 +991,30 @@ static inline int tg_of(int c_in, int c_out) {      // taps per weight stage: ke
   return tap_bytes <= 2048 ? 9 : (tap_bytes <= 8192 ? 3 : 1);
 }
 
-template <int N, int KC, int TG>
+template <int N, int KC, int TG, bool PAIR = false>
 static int launch_conv(int b, int c_in, const Geometry &geo, const __half *xh, const unsigned char *wprep, const float *bias,
                        float *out, double *unit_stats, const uint32_t *occ, cudaStream_t st) {
-  using C = Cfg<N, KC, TG>;
+  using C = Cfg<N, KC, TG, PAIR>;
   const int a_stage_bytes = (int)align_up((size_t)C::kChunks * geo.slab_rows * 16, 128);
   const size_t smem_bytes = (size_t)kAStages * a_stage_bytes + (size_t)C::kWStages * C::kWStageBytes + C::kNumBars * 8 + 16 +
-                            2 * 8 * 16 * sizeof(float);
+                            2 * 8 * 16 * sizeof(float) + (PAIR ? 8 * N * sizeof(float) : 0);
   if (smem_bytes > 227 * 1024) return BDM_ERR_BAD_SIZE;
-  cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void *>(conv3_tc05_kernel<N, KC, TG>), smem_bytes);
+  cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void *>(conv3_tc05_kernel<N, KC, TG, PAIR>), smem_bytes);
   if (e != cudaSuccess) return (int)e;
-  const int total_units = b * geo.units;
+  const int total_units = b * (PAIR ? geo.units_pair : geo.units);
   const int grid = total_units < sm_count() ? total_units : sm_count();
-  conv3_tc05_kernel<N, KC, TG><<<grid, kThreads, smem_bytes, st>>>(b, c_in, geo, a_stage_bytes, xh, wprep, bias, out, unit_stats, occ);
+  conv3_tc05_kernel<N, KC, TG, PAIR><<<grid, kThreads, smem_bytes, st>>>(b, c_in, geo, a_stage_bytes, xh, wprep, bias, out, unit_stats, occ);
   BDM_RETURN_LAUNCH_STATUS();
+}
+
+// tap pairing (see Cfg): on for c_out <= 64 with 64-channel... any chunking; BDM_CONV3_PAIR=0 keeps one MMA per tap
+static bool pair_mode(int c_in, int c_out) {
+  static const bool on = [] {
+    const char *e = std::getenv("BDM_CONV3_PAIR");
+    return e == nullptr || e[0] != '0';
+  }();
+  (void)c_in;
+  return on && c_out <= 64;
 }
 
 }  // namespace cv3
@@ -914,9 +1029,11 @@ extern "C" long long bdm_conv3_tc05_plane_rows(int b, int r) {
   if (b <= 0 || r <= 0) return 0;
   return cv3::conv3_geometry(b, r).total_rows;
 }
-extern "C" int bdm_conv3_tc05_units(int r) {
+/* units (blocks of the per-unit group statistics) the convolution c_in -> c_out works in at resolution r */
+extern "C" int bdm_conv3_tc05_units(int c_in, int c_out, int r) {
   if (r <= 0) return 0;
-  return cv3::conv3_geometry(1, r).units;
+  const cv3::Geometry g = cv3::conv3_geometry(1, r);
+  return cv3::pair_mode(c_in, c_out) ? g.units_pair : g.units;
 }
 extern "C" size_t bdm_conv3_tc05_weight_bytes(int c_in, int c_out) {
   if (c_in <= 0 || c_out <= 0) return 0;
@@ -936,7 +1053,7 @@ extern "C" int bdm_conv3_tc05_prepare(int c_in, int c_out, const float *weight, 
   const size_t total = (size_t)27 * c_in * c_out;
   const int blocks = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
   cv3::conv3_prep_weights_kernel<<<blocks, 256, 0, st>>>(
-      c_in, c_out, cv3::kc_of(c_in), cv3::tg_of(c_in, c_out), weight, header,
+      c_in, c_out, cv3::kc_of(c_in), cv3::pair_mode(c_in, c_out) ? 3 : cv3::tg_of(c_in, c_out), cv3::pair_mode(c_in, c_out) ? 1 : 0, weight, header,
       reinterpret_cast<__half *>(static_cast<unsigned char *>(prepared) + cv3::kHeaderBytes));
   BDM_RETURN_LAUNCH_STATUS();
 }
@@ -1031,7 +1148,7 @@ extern "C" int bdm_conv3_tc05_fill_planes(int b, int c, int n, int r, const floa
  * (8 groups); workspace: b * units * 16 doubles when stats != NULL. */
 extern "C" size_t bdm_conv3_tc05_workspace_bytes(int b, int r) {
   if (b <= 0 || r <= 0) return 16;
-  return (size_t)b * cv3::conv3_geometry(b, r).units * 16 * sizeof(double);
+  return (size_t)b * cv3::conv3_geometry(b, r).units_pair * 16 * sizeof(double);     // units_pair >= units
 }
 extern "C" int bdm_conv3_tc05(int b, int c_in, int c_out, int r, const void *xh, long long plane_rows, const void *prepared,
                               const float *bias, float *out, double *stats, void *workspace, size_t workspace_bytes,
@@ -1040,7 +1157,7 @@ extern "C" int bdm_conv3_tc05(int b, int c_in, int c_out, int r, const void *xh,
   if (b == 0) return BDM_OK;
   BDM_CHECK_PTR(xh); BDM_CHECK_PTR(prepared); BDM_CHECK_PTR(out);
   const cv3::Geometry geo = cv3::conv3_geometry(b, r);
-  BDM_CHECK_SIZE(plane_rows == geo.total_rows && (long long)b * geo.units < 0x7fffffffLL);
+  BDM_CHECK_SIZE(plane_rows == geo.total_rows && (long long)b * geo.units_pair < 0x7fffffffLL);
   if (((reinterpret_cast<uintptr_t>(xh) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(prepared)) & 15) != 0)
     return BDM_ERR_MISALIGNED;
   double *unit_stats = nullptr;
@@ -1056,8 +1173,13 @@ extern "C" int bdm_conv3_tc05(int b, int c_in, int c_out, int r, const void *xh,
   const unsigned char *wp = static_cast<const unsigned char *>(prepared);
   int rc;
   const int kc = cv3::kc_of(c_in);
-  const int units = geo.units;
-  if (c_out == 32 && kc == 32) rc = cv3::launch_conv<32, 32, 9>(b, c_in, geo, x, wp, bias, out, unit_stats, occ, st);
+  const bool pair = cv3::pair_mode(c_in, c_out);
+  const int units = pair ? geo.units_pair : geo.units;
+  if (pair && c_out == 32 && kc == 32) rc = cv3::launch_conv<32, 32, 3, true>(b, c_in, geo, x, wp, bias, out, unit_stats, occ, st);
+  else if (pair && c_out == 32) rc = cv3::launch_conv<32, 64, 3, true>(b, c_in, geo, x, wp, bias, out, unit_stats, occ, st);
+  else if (pair && kc == 32) rc = cv3::launch_conv<64, 32, 3, true>(b, c_in, geo, x, wp, bias, out, unit_stats, occ, st);
+  else if (pair) rc = cv3::launch_conv<64, 64, 3, true>(b, c_in, geo, x, wp, bias, out, unit_stats, occ, st);
+  else if (c_out == 32 && kc == 32) rc = cv3::launch_conv<32, 32, 9>(b, c_in, geo, x, wp, bias, out, unit_stats, occ, st);
   else if (c_out == 32) rc = cv3::launch_conv<32, 64, 3>(b, c_in, geo, x, wp, bias, out, unit_stats, occ, st);
   else if (c_out == 64 && kc == 32) rc = cv3::launch_conv<64, 32, 3>(b, c_in, geo, x, wp, bias, out, unit_stats, occ, st);
   else if (c_out == 64) rc = cv3::launch_conv<64, 64, 3>(b, c_in, geo, x, wp, bias, out, unit_stats, occ, st);

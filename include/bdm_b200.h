@@ -339,12 +339,12 @@ int bdm_groupnorm_cl_sums(int b, int c, long long s, int groups, float eps, int 
  *   bdm_conv3_tc05   out f32[b][r^3][c_out] = conv(xh) + bias; stats (or NULL): the result's GroupNorm(8) statistics.
  *       With workspace (bdm_conv3_tc05_workspace_bytes(b, r) bytes): f64[b][1][c_out][2] in the layout
  *       bdm_groupnorm_act_cl(precomputed_chunks = 1) takes (one more small kernel folds the units).  With workspace
- *       NULL: the per-unit group partials themselves, f64[b][bdm_conv3_tc05_units(r)][8][2], for
- *       precomputed_chunks = -bdm_conv3_tc05_units(r) (no extra kernel).
+ *       NULL: the per-unit group partials themselves, f64[b][bdm_conv3_tc05_units(c_in, c_out, r)][8][2], for
+ *       precomputed_chunks = -bdm_conv3_tc05_units(c_in, c_out, r) (no extra kernel).
  * c_out in {32, 64, 128}, c_in = 32 or a multiple of 64, r a power of two (bdm_conv3_tc05_supported). */
 int bdm_conv3_tc05_supported(int c_in, int c_out, int r);
 long long bdm_conv3_tc05_plane_rows(int b, int r);
-int bdm_conv3_tc05_units(int r);
+int bdm_conv3_tc05_units(int c_in, int c_out, int r);
 size_t bdm_conv3_tc05_weight_bytes(int c_in, int c_out);
 size_t bdm_conv3_tc05_workspace_bytes(int b, int r);
 int bdm_conv3_tc05_prepare(int c_in, int c_out, const float *weight, const float *gamma, const float *beta,

@@ -67,12 +67,14 @@ def test_conv3_tc05_geometry_and_argument_errors_need_no_gpu():
         guard = (q * q + q + 1 + 7) // 8 * 8
         sample_rows = (guard + q ** 3 + 7) // 8 * 8
         last_valid = ((r - 1) * q + (r - 1)) * q + (r - 1)
-        assert L.bdm_conv3_tc05_units(r) == (last_valid + 1 + 255) // 256
+        assert L.bdm_conv3_tc05_units(128, 128, r) == (last_valid + 1 + 255) // 256          # one MMA per tap: 256 rows per unit
+        assert L.bdm_conv3_tc05_units(64, 64, r) in ((last_valid + 1 + 255) // 256, (last_valid + 1 + 254) // 255)  # tap pairing: 255
         for b in (1, 3, 32):
             rows = L.bdm_conv3_tc05_plane_rows(b, r)
             # every sample's positions plus the rows its last 256-row unit reads beyond them fit
             assert rows >= guard + b * sample_rows + guard
-            assert rows >= guard + (b - 1) * sample_rows + L.bdm_conv3_tc05_units(r) * 256 + q * q + q + 1
+            for cc in (64, 128):
+                assert rows >= guard + (b - 1) * sample_rows + L.bdm_conv3_tc05_units(cc, cc, r) * 256 + q * q + q + 1
     assert L.bdm_conv3_tc05_supported(64, 64, 32) == 1 and L.bdm_conv3_tc05_supported(32, 128, 16) == 1
     assert L.bdm_conv3_tc05_supported(390, 32, 32) == 0      # reduction length: 32 or a multiple of 64
     assert L.bdm_conv3_tc05_supported(64, 256, 8) == 0       # 256 accumulator columns do not double-buffer in TMEM

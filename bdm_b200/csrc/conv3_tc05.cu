@@ -592,7 +592,7 @@ __device__ __forceinline__ uint32_t window_mask(const uint32_t *__restrict__ occ
 // yields rows 0..254 of its 256.
 template <int N, int KC, int TG, bool PAIR = false>
 struct Cfg {
-  static_assert(!PAIR || (TG == 3 && N <= 64), "tap pairing: one (dx, dy) row of taps per stage, 8N <= 512 TMEM columns");
+  static_assert(!PAIR || ((TG == 3 || TG == 9) && N <= 64), "tap pairing: whole (dx, dy) rows of taps per stage, 8N <= 512 TMEM columns");
   static constexpr int kUOut = PAIR ? kUnitRows - 1 : kUnitRows;      // output rows per unit
   static constexpr int kDCols = PAIR ? 2 * N : N;                    // TMEM columns per tile
   static constexpr int kChunks = KC / 8;
@@ -745,34 +745,41 @@ conv3_tc05_kernel(int b, int c_in, Geometry geo, int a_stage_bytes, const __half
               if (elect_one()) {
                 uint32_t first = acc;                                  // accumulate flag of the next tap's k = 0 MMAs
                 if constexpr (PAIR) {
-                  // stage = the three dz taps of (dx, dy = grp): [pair image: 2N rows = W(dz=0) | W(dz=+1)][single image: W(dz=-1)]
+                  // stage = TG / 3 rows of taps (dx, dy), each [pair image: 2N rows = W(dz=0) | W(dz=+1)][single image: W(dz=-1)]
                   constexpr uint32_t idesc_pair = instr_desc(2 * N);
-                  const uint32_t a_row = a_lo + (grp == 0 ? 0u : (grp == 1 ? q1 : q2));
-                  const uint32_t bp_lo = (b_lo & 0xffffu) | ((uint32_t)(2 * N) << 16);          // LBO = 2N rows of 16 bytes
-                  const uint32_t bs_lo = b_lo + (uint32_t)((2 * C::kTapBytes) >> 4);
 #pragma unroll
-                  for (int t = 0; t < 2; ++t) {
+                  for (int sg = 0; sg < TG / 3; ++sg) {
+                    const int dy = grp * (TG / 3) + sg;
+                    if (((sm >> dy) & 1u) == 0u) continue;
+                    const uint32_t a_row = a_lo + (dy == 0 ? 0u : (dy == 1 ? q1 : q2));
+                    const uint32_t bg_lo = b_lo + (uint32_t)(sg * ((3 * C::kTapBytes) >> 4));
+                    const uint32_t bp_lo = (bg_lo & 0xffffu) | ((uint32_t)(2 * N) << 16);        // LBO = 2N rows of 16 bytes
+                    const uint32_t bs_lo = bg_lo + (uint32_t)((2 * C::kTapBytes) >> 4);
 #pragma unroll
-                    for (int k = 0; k < C::kK16; ++k) {       // dz = 0 (main) and dz = +1 (side): window at row offset +1
-                      const uint32_t da_lo = a_row + 1u + (uint32_t)(t * 128) + (uint32_t)k * kstep;
-                      const uint32_t db_lo = bp_lo + (uint32_t)(k * 2 * 2 * N);
-                      const uint32_t accumulate = k == 0 ? first : 1u;
-                      asm volatile(
-                          "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %5, 0;\n\t"
-                          "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %2};\n\t"
-                          "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
-                          ::"r"(d0 + t * C::kDCols), "r"(da_lo), "r"(desc_hi), "r"(db_lo), "r"(idesc_pair), "r"(accumulate) : "memory");
+                    for (int t = 0; t < 2; ++t) {
+#pragma unroll
+                      for (int k = 0; k < C::kK16; ++k) {       // dz = 0 (main) and dz = +1 (side): window at row offset +1
+                        const uint32_t da_lo = a_row + 1u + (uint32_t)(t * 128) + (uint32_t)k * kstep;
+                        const uint32_t db_lo = bp_lo + (uint32_t)(k * 2 * 2 * N);
+                        const uint32_t accumulate = k == 0 ? first : 1u;
+                        asm volatile(
+                            "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %5, 0;\n\t"
+                            "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %2};\n\t"
+                            "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
+                            ::"r"(d0 + t * C::kDCols), "r"(da_lo), "r"(desc_hi), "r"(db_lo), "r"(idesc_pair), "r"(accumulate) : "memory");
+                      }
+#pragma unroll
+                      for (int k = 0; k < C::kK16; ++k) {       // dz = -1 into main: window at row offset 0
+                        const uint32_t da_lo = a_row + (uint32_t)(t * 128) + (uint32_t)k * kstep;
+                        const uint32_t db_lo = bs_lo + (uint32_t)(k * 2 * N);
+                        asm volatile(
+                            "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %5, 0;\n\t"
+                            "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %2};\n\t"
+                            "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
+                            ::"r"(d0 + t * C::kDCols), "r"(da_lo), "r"(desc_hi), "r"(db_lo), "r"(idesc), "r"(1u) : "memory");
+                      }
                     }
-#pragma unroll
-                    for (int k = 0; k < C::kK16; ++k) {       // dz = -1 into main: window at row offset 0
-                      const uint32_t da_lo = a_row + (uint32_t)(t * 128) + (uint32_t)k * kstep;
-                      const uint32_t db_lo = bs_lo + (uint32_t)(k * 2 * N);
-                      asm volatile(
-                          "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %5, 0;\n\t"
-                          "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %2};\n\t"
-                          "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
-                          ::"r"(d0 + t * C::kDCols), "r"(da_lo), "r"(desc_hi), "r"(db_lo), "r"(idesc), "r"(1u) : "memory");
-                    }
+                    first = 1u;
                   }
                 } else {
 #pragma unroll
@@ -1175,7 +1182,7 @@ extern "C" int bdm_conv3_tc05(int b, int c_in, int c_out, int r, const void *xh,
   const int kc = cv3::kc_of(c_in);
   const bool pair = cv3::pair_mode(c_in, c_out);
   const int units = pair ? geo.units_pair : geo.units;
-  if (pair && c_out == 32 && kc == 32) rc = cv3::launch_conv<32, 32, 3, true>(b, c_in, geo, x, wp, bias, out, unit_stats, occ, st);
+  if (pair && c_out == 32 && kc == 32) rc = cv3::launch_conv<32, 32, 9, true>(b, c_in, geo, x, wp, bias, out, unit_stats, occ, st);
   else if (pair && c_out == 32) rc = cv3::launch_conv<32, 64, 3, true>(b, c_in, geo, x, wp, bias, out, unit_stats, occ, st);
   else if (pair && kc == 32) rc = cv3::launch_conv<64, 32, 3, true>(b, c_in, geo, x, wp, bias, out, unit_stats, occ, st);
   else if (pair) rc = cv3::launch_conv<64, 64, 3, true>(b, c_in, geo, x, wp, bias, out, unit_stats, occ, st);

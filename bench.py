@@ -595,10 +595,14 @@ def run_ours(args):
                 "libbdm_b200_kernels_per_replay": sampler.graph_launches_per_step,
                 "note": "random-init weights: the metric values only exercise the evaluation path"},
         "implementation": {
-            "sparse_first_conv": "PVConv blocks: voxelize -> Conv3d replaced by compact averages -> GEMM (TF32 like the "
-                                 "Conv3d) -> sparse_conv3_gather; BDM_SPARSE_CONV=0 restores the dense route",
-            "dense_layers": "second Conv3d of a block and 1x1 convs: torch (cuDNN/cuBLAS, PyTorch default TF32 conv policy); conv "
-                            "bias + GroupNorm + Swish (+ SE squeeze, + max over neighbours), attention: libbdm_b200",
+            "conv3_tc05": "3x3x3 convolutions on 16^3 / 32^3 grids: libbdm_b200's tcgen05 implicit GEMM (fp16 chunk planes, TMEM "
+                          "accumulators, bias + GroupNorm statistics in the epilogue); a block's first convolution reads planes "
+                          "scattered from the compact voxel averages and skips all-zero tap windows (c_in <= 128)",
+            "sparse_first_conv": "first convolution of the 8^3 blocks and of the 390-channel input block: compact averages -> GEMM "
+                                 "(cuBLAS, TF32 like the Conv3d) -> sparse_conv3_gather; BDM_SPARSE_CONV=0 restores the dense route",
+            "dense_layers": "second Conv3d of the 8^3 blocks (cuDNN) and 1x1 convs (cuBLAS): torch, PyTorch default TF32 conv policy; "
+                            "conv bias + GroupNorm + Swish (+ SE squeeze, + max over neighbours, + devoxelize), attention (tcgen05): "
+                            "libbdm_b200",
         },
     }
 

@@ -227,13 +227,21 @@ gn_apply_kernel(int c, long long s, int groups, int nchunks, float eps, int tile
         idx[j] = i0 + (long long)j * kGnThreads + threadIdx.x;
         if (idx[j] < hi) v[j] = ld_stream_f4(px + 4 * idx[j]);
       }
+      // v -> fma(v, A, B) is monotone and Swish falls to its minimum (at -1.278) and rises from it: the largest
+      // activated value of a run belongs to its largest or to its smallest input -- two activations per run instead of
+      // u (the MUFU pipe, not memory, bounded this loop)
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        float best = ninf;
-        if (idx[j] < hi)
-          best = fmaxf(fmaxf(act(fmaf(v[j].x, A, Bc)), act(fmaf(v[j].y, A, Bc))), fmaxf(act(fmaf(v[j].z, A, Bc)), act(fmaf(v[j].w, A, Bc))));
-        for (int d = 1; d < lpr; d <<= 1) best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, d));
-        if (idx[j] < hi && (threadIdx.x & (lpr - 1)) == 0) py[idx[j] / lpr] = best;
+        float hi_v = ninf, lo_v = -ninf;
+        if (idx[j] < hi) {
+          hi_v = fmaxf(fmaxf(v[j].x, v[j].y), fmaxf(v[j].z, v[j].w));
+          lo_v = fminf(fminf(v[j].x, v[j].y), fminf(v[j].z, v[j].w));
+        }
+        for (int d = 1; d < lpr; d <<= 1) {
+          hi_v = fmaxf(hi_v, __shfl_xor_sync(0xffffffffu, hi_v, d));
+          lo_v = fminf(lo_v, __shfl_xor_sync(0xffffffffu, lo_v, d));
+        }
+        if (idx[j] < hi && (threadIdx.x & (lpr - 1)) == 0) py[idx[j] / lpr] = fmaxf(act(fmaf(hi_v, A, Bc)), act(fmaf(lo_v, A, Bc)));
       }
     }
   }

@@ -144,15 +144,22 @@ gn_cluster_kernel(int c, int s, int groups, float eps, int u, int per4, const fl
     float *py = y + ((size_t)sample * c + ch0) * (size_t)(s / u);
     for (int i0 = 0; i0 < m4; i0 += kCfThreads) {
       const int i = i0 + tid;
-      float best = -__int_as_float(0x7f800000);
+      // the largest activated value of a run belongs to its largest or its smallest input (fma monotone, Swish
+      // unimodal): two activations per run instead of u
+      const float inf = __int_as_float(0x7f800000);
+      float hi_v = -inf, lo_v = inf;
+      float2 p = make_float2(0.0f, 0.0f);
       if (i < m4) {
         const float4 v = tile[i];
-        const float2 p = ab[(4 * (lo4 + i)) / s];
-        best = fmaxf(fmaxf(act(fmaf(v.x, p.x, p.y)), act(fmaf(v.y, p.x, p.y))),
-                     fmaxf(act(fmaf(v.z, p.x, p.y)), act(fmaf(v.w, p.x, p.y))));
+        p = ab[(4 * (lo4 + i)) / s];
+        hi_v = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
+        lo_v = fminf(fminf(v.x, v.y), fminf(v.z, v.w));
       }
-      for (int d = 1; d < lpr; d <<= 1) best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, d));
-      if (i < m4 && (tid & (lpr - 1)) == 0) py[(lo4 + i) / lpr] = best;
+      for (int d = 1; d < lpr; d <<= 1) {
+        hi_v = fmaxf(hi_v, __shfl_xor_sync(0xffffffffu, hi_v, d));
+        lo_v = fminf(lo_v, __shfl_xor_sync(0xffffffffu, lo_v, d));
+      }
+      if (i < m4 && (tid & (lpr - 1)) == 0) py[(lo4 + i) / lpr] = fmaxf(act(fmaf(hi_v, p.x, p.y)), act(fmaf(lo_v, p.x, p.y)));
     }
   }
 }

@@ -583,7 +583,8 @@ __device__ __forceinline__ uint32_t window_mask(const uint32_t *__restrict__ occ
   return __reduce_or_sync(0xffffffffu, m);
 }
 
-// PAIR (N <= 64, TG = 3): the dz = 0 and dz = +1 taps of a (dx, dy) pair share ONE activation window -- B = [W(dz=0); W(dz=+1)]
+// PAIR (N <= 64; a weight stage holds TG / 3 = 1 or 3 (dx, dy) rows of taps -- 3 for the 32-channel instance, whose
+// 6 KB rows were too small a unit of work for the MMA warp's per-stage waits): the dz = 0 and dz = +1 taps of a (dx, dy) pair share ONE activation window -- B = [W(dz=0); W(dz=+1)]
 // is a 2N-row operand and one MMA of N' = 2N fills two column blocks, `main` and `side` -- and the dz = -1 tap is a
 // second MMA of N columns into `main` with the window shifted by one row, as before.  Per (dx, dy), tile and K-step that
 // is 8 + 6 KB of shared-memory operands instead of 3 x 6 KB: the kernel is bound by exactly that traffic.  The side

@@ -134,6 +134,19 @@ def _voxel_stack(c_in, c_out, k, attention, dropout, with_se, with_se_relu, make
     return FusedSequential(*seq)
 
 
+POINT_BRANCH_STREAM = os.environ.get("BDM_POINT_STREAM", "1") != "0"
+_POINT_STREAMS = {}
+
+
+def _point_stream(device):
+    dev = torch.device(device)
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    st = _POINT_STREAMS.get(key)
+    if st is None:
+        st = _POINT_STREAMS[key] = torch.cuda.Stream(device=dev)
+    return st
+
+
 class _PVConvBase(nn.Module):
     def __init__(self, in_channels, out_channels, kernel_size, resolution, normalize, eps):
         super().__init__()
@@ -231,6 +244,14 @@ class _PVConvBase(nn.Module):
                  and not _ops.REFERENCE_CALL_PATTERN and hasattr(_ops._B, "groupnorm_act"))
         first = first_stats = None
         first_biased = False
+        # the point branch reads only `features`: issued on a second stream at the top of the block, its small GEMM and norm
+        # kernels fill the SMs the voxel branch's narrow kernels (plans, SE gates, kernel tails) leave idle
+        point_branch = side = None
+        if defer and POINT_BRANCH_STREAM and features.dtype == torch.float32:
+            side = _point_stream(features.device)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                point_branch = self.point_features(features).contiguous()
         if self._sparse_eligible(features):
             if self._dense_first_eligible(features):
                 first, grid_coords = self._dense_first_conv(features, coords)
@@ -250,14 +271,23 @@ class _PVConvBase(nn.Module):
             # channels-last branch: (last norm + Swish,) devoxelize, SE gate and the residual add of the point branch in
             # one kernel
             fused = _ops._B.trilinear_devoxelize_cl(grid.permute(0, 2, 3, 4, 1), grid_coords.contiguous(), self.resolution,
-                                                    gate=gate, residual=self.point_features(features).contiguous(),
+                                                    gate=gate, residual=self._point_branch(features, point_branch, side),
                                                     norm_coef=norm_coef)
             return fused, coords, temb
         assert norm_coef is None
         from_voxels = F.trilinear_devoxelize(grid, grid_coords, self.resolution, self.training)
         if gate is not None:
-            return torch.addcmul(self.point_features(features), from_voxels, gate[:, :, None]), coords, temb
-        return from_voxels + self.point_features(features), coords, temb
+            return torch.addcmul(self._point_branch(features, point_branch, side), from_voxels, gate[:, :, None]), coords, temb
+        return from_voxels + self._point_branch(features, point_branch, side), coords, temb
+
+    def _point_branch(self, features, ahead, side):
+        """the point branch: computed here, or joined from the second stream forward() started it on"""
+        if ahead is None:
+            return self.point_features(features).contiguous()
+        main = torch.cuda.current_stream()
+        main.wait_stream(side)
+        ahead.record_stream(main)
+        return ahead
 
 
 class PVConv(_PVConvBase):

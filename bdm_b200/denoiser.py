@@ -21,6 +21,7 @@ including its quirks, because they decide the parameter shapes:
     of a list it has just shadowed), so FP PVConvs never carry attention;
   * the SA module's input width counts the time embedding only when the stage has no PVConv (:118).
 """
+import contextlib
 import math
 import os
 
@@ -31,7 +32,7 @@ from . import functional as F
 from .functional import geometry
 from .functional import ops as _ops
 from .modules import Attention, PointNetAModule, PointNetFPModule, PointNetSAModule, PVConv, SharedMLP
-from .modules.point_voxel import coordinate_plan
+from .modules.point_voxel import _point_stream, coordinate_plan
 
 # ((conv out_channels, num_blocks, voxel_resolution) | None, (num_centers, radius, num_neighbors, mlp widths))
 SA_BLOCKS = [
@@ -206,21 +207,43 @@ def plan_geometry_ahead(cache, sa_layers, fp_layers, coords):
 
 
 PLAN_AHEAD = os.environ.get("BDM_PLAN_AHEAD", "1") != "0"   # module switch (tests / A-B timing)
+TEMB_STREAM = os.environ.get("BDM_TEMB_STREAM", "1") != "0"
 
 
 def _ahead_enabled(x):
     return PLAN_AHEAD and x.is_cuda and not torch.is_grad_enabled() and not _ops.REFERENCE_CALL_PATTERN
 
 
-def _encode(sa_layers, features, coords, temb):
-    """Run the SA pyramid; returns the bottleneck state and the per-stage (coords, input features)."""
+def _encode(sa_layers, features, coords, temb, temb_stream=None):
+    """Run the SA pyramid; returns the bottleneck state and the per-stage (coords, input features).
+    temb_stream: the stream `temb` is still being computed on (PVCNN2.forward); PVConv blocks only pass the embedding
+    along, so the main stream joins in front of the first part that reads it."""
     coords_per_stage, feats_per_stage = [], []
     for i, stage in enumerate(sa_layers):
         feats_per_stage.append(features)
         coords_per_stage.append(coords)
+        if temb_stream is not None and i == 0:
+            state = (features, coords, temb)
+            for part in _stage_parts(stage):
+                if temb_stream is not None and not isinstance(part, PVConv):
+                    temb_stream = _join(temb_stream, temb)
+                state = part(state)
+            features, coords, temb = state
+            continue
+        if temb_stream is not None:
+            temb_stream = _join(temb_stream, temb)
         stage_in = features if i == 0 else torch.cat([features, temb], dim=1)
         features, coords, temb = stage((stage_in, coords, temb))
+    if temb_stream is not None:
+        _join(temb_stream, temb)
     return features, coords, temb, coords_per_stage, feats_per_stage
+
+
+def _join(stream, tensor):
+    main = torch.cuda.current_stream()
+    main.wait_stream(stream)
+    tensor.record_stream(main)
+    return None
 
 
 def _decode(fp_layers, features, coords, temb, coords_per_stage, skips_per_stage):
@@ -257,13 +280,20 @@ class PVCNN2(nn.Module):
         self.embedf = _time_mlp(embed_dim)
 
     def forward(self, inputs, t):
-        temb = self.embedf(timestep_embedding(self.embed_dim, t, inputs.device).float())
-        temb = temb[:, :, None].expand(-1, -1, inputs.shape[-1])
+        temb_stream = None
+        if TEMB_STREAM and _ahead_enabled(inputs) and t.is_cuda:
+            # the time MLP is ten tiny launches that depend on t alone: on the second stream, next to the first block
+            temb_stream = _point_stream(inputs.device)
+            temb_stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(temb_stream) if temb_stream is not None else contextlib.nullcontext():
+            temb = self.embedf(timestep_embedding(self.embed_dim, t, inputs.device).float())
+            temb = temb[:, :, None].expand(-1, -1, inputs.shape[-1])
         coords = inputs[:, :3, :].contiguous()
         with geometry.scope(_ahead_enabled(inputs)) as cache:
             if cache is not None:
                 plan_geometry_ahead(cache, self.sa_layers, self.fp_layers, coords)
-            features, coords, temb, coords_per_stage, feats_per_stage = _encode(self.sa_layers, inputs, coords, temb)
+            features, coords, temb, coords_per_stage, feats_per_stage = _encode(self.sa_layers, inputs, coords, temb,
+                                                                                 temb_stream)
             feats_per_stage[0] = inputs[:, 3:, :]   # a view: the FP stage's torch.cat copies it anyway
             if self.global_att is not None:
                 features = self.global_att(features)

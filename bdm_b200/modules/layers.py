@@ -504,9 +504,48 @@ class Attention(nn.Module):
             return out[0].view((nb,) + spatial + (nc,)).permute(0, 4, 1, 2, 3), out[1]
         return out.view((nb,) + spatial + (nc,)).permute(0, 4, 1, 2, 3)
 
+    # -- inference on CUDA over a short point set (the bottleneck: [B,512,16]): seven launches instead of thirteen ----------
+    def small_applicable(self, x):
+        return (FUSED_ATTENTION and _fusable(x) and x.dim() == 3 and x.is_contiguous() and x.shape[2] <= 64
+                and x.shape[2] % 4 == 0 and hasattr(_ops._B, "groupnorm_act")
+                and all(isinstance(m, nn.Conv1d) and _pointwise(m) and m.bias is not None
+                        for m in (self.q, self.k, self.v, self.out)) and isinstance(self.norm, nn.GroupNorm))
+
+    def _small_weights(self):
+        """[Wq;Wk;Wv] f32[3C,C], their biases f32[1,3C,1], Wo f32[C,C]; cached per weight version"""
+        params = (self.q.weight, self.k.weight, self.v.weight, self.out.weight, self.q.bias, self.k.bias, self.v.bias)
+        key = tuple((p.data_ptr(), geometry.tensor_version(p), p.device) for p in params)
+        cached = getattr(self, "_small", None)
+        if cached is None or cached[0] != key:
+            c = self.q.weight.shape[0]
+            wqkv = torch.cat([m.weight.detach().reshape(c, c) for m in (self.q, self.k, self.v)], dim=0).contiguous()
+            bqkv = torch.cat([m.bias.detach() for m in (self.q, self.k, self.v)]).reshape(1, 3 * c, 1).contiguous()
+            cached = (key, wqkv, bqkv, self.out.weight.detach().reshape(c, c).contiguous())
+            self._small = cached
+        return cached[1:]
+
+    def forward_small(self, x):
+        """x f32[B,C,T], T <= 64: one GEMM for q | k | v + one bias add, the two attention matmuls and the softmax as the
+        reference orders them, one GEMM that adds the residual, and the norm kernel (out-conv bias folded in, + Swish).
+        The reference (and the plain route below) runs 4 convolutions, 4 bias kernels, a residual add and a SIMT GEMM for
+        the transposed q here (modules/pvconv.py:40-63)."""
+        nb, nc, _ = x.shape
+        wqkv, bqkv, wo = self._small_weights()
+        with matmul_precision_of_convs():                                   # they stand in for 1x1 convolutions
+            qkv = torch.matmul(wqkv, x)                                     # [B,3C,T]
+        qkv += bqkv
+        q, k, v = qkv[:, :nc], qkv[:, nc:2 * nc], qkv[:, 2 * nc:]
+        attn = self.sm(torch.matmul(q.transpose(1, 2), k))                  # [B,T,T]
+        mixed = torch.matmul(v, attn.transpose(1, 2))                       # [B,C,T]
+        with matmul_precision_of_convs():
+            y = torch.baddbmm(x, wo.expand(nb, -1, -1), mixed)              # residual + out projection (bias: below)
+        return _groupnorm_act(y, self.norm, True, conv_bias=self.out.bias)
+
     def forward(self, x):
         if self.fused_applicable(x):
             return self.forward_fused(x)
+        if self.small_applicable(x):
+            return self.forward_small(x)
         nb, nc = x.shape[:2]
         q, k, v = (proj(x).reshape(nb, nc, -1) for proj in (self.q, self.k, self.v))
         if (FUSED_ATTENTION and _fusable(x) and hasattr(_ops._B, "attention")

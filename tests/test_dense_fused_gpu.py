@@ -228,6 +228,36 @@ def test_attention_block_fused_kernel(cuda_backend):
     assert (y1 - y0).abs().max().item() <= 1e-5 * y0.abs().max().item()
 
 
+@pytest.mark.parametrize("b,c,t", [(32, 512, 16), (3, 64, 64), (2, 128, 4)])
+def test_attention_block_short_point_set(b, c, t, cuda_backend):
+    """Attention(D=1) on the bottleneck's short point set: the seven-launch route (one q|k|v GEMM, residual folded into
+    the out-projection GEMM, out-conv bias folded into the norm) against the module-by-module route, fp32 both."""
+    import torch
+
+    import bdm_b200.modules.layers as L
+    torch.manual_seed(c + t)
+    blk = L.Attention(c, 8, D=1).cuda().eval()
+    x = torch.randn(b, c, t, device="cuda")
+    saved = (L.FUSED_ATTENTION, torch.backends.cudnn.allow_tf32)
+    try:
+        torch.backends.cudnn.allow_tf32 = False
+        with torch.no_grad():
+            assert blk.small_applicable(x)
+            y1 = blk(x)
+            L.FUSED_ATTENTION = False
+            y0 = blk(x)
+            assert not blk.small_applicable(x)
+            ref = blk.double()(x.double())
+    finally:
+        L.FUSED_ATTENTION, torch.backends.cudnn.allow_tf32 = saved
+        blk.float()
+    peak = ref.abs().max().item()
+    e1 = (y1.double() - ref).abs().max().item() / peak
+    e0 = (y0.double() - ref).abs().max().item() / peak
+    assert y1.shape == y0.shape and y1.is_contiguous()
+    assert e1 <= max(3 * e0, 1e-5), (e1, e0)
+
+
 def test_fp_module_without_concatenation(cuda_backend):
     """PointNetFPModule: first conv over (interpolated, skip) separately == conv over their concatenation"""
     import torch

@@ -295,6 +295,7 @@ class PVCNN2(nn.Module):
             features, coords, temb, coords_per_stage, feats_per_stage = _encode(self.sa_layers, inputs, coords, temb,
                                                                                  temb_stream)
             feats_per_stage[0] = inputs[:, 3:, :]   # a view: the FP stage's torch.cat copies it anyway
+            feats_per_stage[0]._bdm_slice_of = (inputs, 3)    # (layers.conv_no_bias_concat may widen it to an aligned width)
             if self.global_att is not None:
                 features = self.global_att(features)
             features = _decode(self.fp_layers, features, coords, temb, coords_per_stage, feats_per_stage)

@@ -165,10 +165,37 @@ def conv_no_bias_concat(m, parts):
     blocks (batch stride free).  PointNetFPModule uses it for cat([interpolated, skip]) -- at the last FP
     stage the skip tensor alone is 100 MB."""
     w = m.weight
-    key = (w.data_ptr(), geometry.tensor_version(w), w.device, tuple(p.shape[1] for p in parts))
+    # A part that is a channel slice base[:, c0:] of a wider tensor (the network input minus its coordinates: 387 of 390
+    # channels) and whose width is not a multiple of 4 is widened downwards to the next multiple -- base[:, c0 - e:] --
+    # against e zero columns in the weight: the same sums from ONE aligned tensor-op GEMM instead of an aligned head plus
+    # a SIMT tail that re-reads and re-writes the whole output for 3 channels (36 us at the last FP stage).  The caller
+    # vouches for the extra channels being ordinary data (`_bdm_slice_of` = (base, c0), set by PVCNN2.forward).
+    front = []
+    eff = []
+    for p in parts:
+        e = (-p.shape[1]) % 4
+        origin = getattr(p, "_bdm_slice_of", None)
+        if (e and origin is not None and p.shape[1] >= SPLIT_MIN_CHANNELS and origin[1] >= e and p.shape[2] % 4 == 0
+                and origin[0].is_contiguous() and origin[0].shape[1] == origin[1] + p.shape[1]):
+            eff.append(origin[0][:, origin[1] - e:])
+            front.append(e)
+        else:
+            eff.append(p)
+            front.append(0)
+    parts = eff
+    key = (w.data_ptr(), geometry.tensor_version(w), w.device, tuple(p.shape[1] for p in parts), tuple(front))
     cached = getattr(m, "_concat_weight", None)
     if cached is None or cached[0] != key:
         w2 = w.detach().reshape(m.out_channels, m.in_channels)
+        if any(front):
+            cols, src = [], 0
+            for p, e in zip(parts, front):
+                if e:
+                    cols.append(w2.new_zeros((m.out_channels, e)))
+                cols.append(w2[:, src:src + p.shape[1] - e])
+                src += p.shape[1] - e
+            assert src == m.in_channels
+            w2 = torch.cat(cols, dim=1)
         pieces, off = [], 0
         for p in parts:
             ci = p.shape[1]
@@ -177,7 +204,7 @@ def conv_no_bias_concat(m, parts):
             if head < ci:
                 pieces.append((off + head, ci - head, w2[:, off + head:off + ci].contiguous()))
             off += ci
-        assert off == m.in_channels
+        assert off == m.in_channels + sum(front)
         cached = (key, pieces)
         m._concat_weight = cached
     nb = parts[0].shape[0]

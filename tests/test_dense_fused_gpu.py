@@ -277,11 +277,18 @@ def test_fp_module_without_concatenation(cuda_backend):
         torch.backends.cudnn.allow_tf32 = False
         with torch.no_grad():
             y1 = fp((pts, cen, cen_feats, skip, temb))[0]
+            # the denoiser marks the skip view as a slice of the network input: its 390 channels are then read as
+            # full[:, 1:] (392, aligned) against two zero weight columns -- one GEMM, same sums
+            wide = full[:, 3:, :]
+            wide._bdm_slice_of = (full, 3)
+            y2 = fp((pts, cen, cen_feats, wide, temb))[0]
+            assert fp.mlp.layers[0]._concat_weight[0][-1] == (0, 2)
             L.FUSED_NORM_ACT = False             # module-by-module route, with torch.cat
             y0 = fp((pts, cen, cen_feats, skip, temb))[0]
     finally:
         L.FUSED_NORM_ACT, torch.backends.cudnn.allow_tf32 = saved
     assert (y1 - y0).abs().max().item() <= 1e-5 * y0.abs().max().item()
+    assert (y2 - y0).abs().max().item() <= 1e-5 * y0.abs().max().item()
 
 
 @pytest.mark.parametrize("swish", [True, False])

@@ -273,7 +273,9 @@ gn_apply_half_planar_kernel(int c, int r, int groups, int nchunks, int ntiles, f
   __shared__ double2 chan[256];
   __shared__ double2 grp[32];
   __shared__ float2 ab[256];
-  const int b = blockIdx.y, tile = blockIdx.x, t = threadIdx.x;
+  // back to front: the convolution that produced x wrote it front to back, so the end of x is what L2 still holds -- and
+  // the convolution that reads xh next starts at the front, which this kernel then writes last
+  const int b = gridDim.y - 1 - blockIdx.y, tile = gridDim.x - 1 - blockIdx.x, t = threadIdx.x;
   const int cg = c / groups;
   const long long s = (long long)r * r * r;
   if (nchunks < 0) {
@@ -398,7 +400,9 @@ gn_apply_half_planar_warp_kernel(int r, int groups, int nchunks, int ntiles, flo
   __shared__ double2 grp[32];
   __shared__ float2 ab[c];
   extern __shared__ __align__(16) unsigned char dyn[];       // [8 warps][C8][33][16 bytes]
-  const int b = blockIdx.y, tile = blockIdx.x, t = threadIdx.x;
+  // back to front: the convolution that produced x wrote it front to back, so the end of x is what L2 still holds -- and
+  // the convolution that reads xh next starts at the front, which this kernel then writes last
+  const int b = gridDim.y - 1 - blockIdx.y, tile = gridDim.x - 1 - blockIdx.x, t = threadIdx.x;
   const int cg = c / groups;
   const long long s = (long long)r * r * r;
   if (nchunks < 0) {

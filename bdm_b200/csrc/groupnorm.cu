@@ -35,8 +35,10 @@ static thread_local int g_last_launches = 0;
 
 __global__ void __launch_bounds__(kGnThreads)
 gn_stats_kernel(long long row_len, int nchunks, const float *__restrict__ x, double2 *__restrict__ partials) {
-  const long long row = blockIdx.y;
-  const int chunk = blockIdx.x;
+  // CTAs are dispatched in ascending block order; the tensor was written front to back by its producer, so its END is what
+  // the 126 MB L2 still holds: walk it back to front
+  const long long row = gridDim.y - 1 - blockIdx.y;
+  const int chunk = gridDim.x - 1 - blockIdx.x;
   long long per = (row_len + nchunks - 1) / nchunks;
   per = (per + 3) & ~3LL;  // chunks start on 16-byte boundaries when the row does
   const long long lo = min(chunk * per, row_len), hi = min(lo + per, row_len);
@@ -501,7 +503,7 @@ gn_cl_apply_kernel(int c, long long s, int groups, int nchunks, int pstride, int
   __shared__ double2 grp[256];           // per-group (mean, rstd)
   __shared__ float2 ab[256];             // per-channel (A, B): y = act(x * A + B)
   __shared__ float sums[kClThreads * 4]; // [rows per pass][c] for the SE squeeze
-  const int b = blockIdx.y, tile = blockIdx.x;
+  const int b = gridDim.y - 1 - blockIdx.y, tile = gridDim.x - 1 - blockIdx.x;     // back to front: see gn_stats_kernel
   const int c4 = c >> 2, rpp = kClThreads / c4, cg = c / groups;
   const float *px = x + (size_t)b * s * c;
   const int t = threadIdx.x;

@@ -192,3 +192,41 @@ def test_sampler_drops_graphs_on_reassignment():
     s._graphs["x"] = 1
     s.pc2_net = object()
     assert not s._graphs
+
+
+def test_concat_conv_widens_a_misaligned_channel_slice():
+    """layers.conv_no_bias_concat: a part marked as the channel slice base[:, c0:] of a wider tensor whose width is not a
+    multiple of 4 is read as base[:, c0 - e:] against e zero weight columns (one aligned GEMM); same sums as the
+    convolution over the concatenation.  Unmarked parts, slices without room below them and non-contiguous bases keep
+    the head + tail split."""
+    import torch
+    import torch.nn as nn
+
+    from bdm_b200.modules import layers as L
+    torch.manual_seed(0)
+    conv = nn.Conv1d(64 + 387, 128, 1)
+    full = torch.randn(2, 390, 32)
+    up = torch.randn(2, 64, 32)
+    with torch.no_grad():
+        want = conv._conv_forward(torch.cat([up, full[:, 3:, :]], 1), conv.weight, None)
+        plain = L.conv_no_bias_concat(conv, [up, full[:, 3:, :]])
+        assert conv._concat_weight[0][-1] == (0, 0)
+        marked = full[:, 3:, :]
+        marked._bdm_slice_of = (full, 3)
+        wide = L.conv_no_bias_concat(conv, [up, marked])
+        assert conv._concat_weight[0][-2:] == ((64, 388), (0, 1))
+        assert [(off, width) for off, width, _ in conv._concat_weight[1]] == [(0, 64), (64, 388)]
+        # no room below the slice / a base that is not plain-contiguous: not widened
+        conv2 = nn.Conv1d(387, 16, 1)
+        low = full[:, :387, :]
+        low._bdm_slice_of = (full, 0)
+        L.conv_no_bias_concat(conv2, [low])
+        assert conv2._concat_weight[0][-1] == (0,)
+        strided = full.transpose(1, 2).contiguous().transpose(1, 2)       # [2, 390, 32] with channel stride 1
+        part = strided[:, 3:, :]
+        part._bdm_slice_of = (strided, 3)
+        L.conv_no_bias_concat(conv2, [part.contiguous()])                # (the unmarked copy: plain route)
+        assert conv2._concat_weight[0][-1] == (0,)
+    scale = want.abs().max().item()
+    assert (plain - want).abs().max().item() <= 1e-5 * scale
+    assert (wide - want).abs().max().item() <= 1e-5 * scale

@@ -248,8 +248,9 @@ def _join(stream, tensor):
 
 def _decode(fp_layers, features, coords, temb, coords_per_stage, skips_per_stage):
     for fp_idx, stage in enumerate(fp_layers):
-        features, coords, temb = stage((coords_per_stage[-1 - fp_idx], coords, torch.cat([features, temb], dim=1),
-                                        skips_per_stage[-1 - fp_idx], temb))
+        joined = torch.cat([features, temb], dim=1)
+        joined._bdm_tail_is = temb      # (PointNetFPModule: the interpolated embedding is the tail of the interpolated `joined`)
+        features, coords, temb = stage((coords_per_stage[-1 - fp_idx], coords, joined, skips_per_stage[-1 - fp_idx], temb))
     return features
 
 

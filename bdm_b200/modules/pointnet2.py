@@ -155,7 +155,13 @@ class PointNetFPModule(nn.Module):
         else:
             idx, w = F.three_nn_search(points_coords, centers_coords)
             up = F.three_nn_interpolate(centers_features, idx, w)
-            up_temb = F.three_nn_interpolate(temb, idx, w)
+            width = temb.shape[1]
+            if width > 0 and getattr(centers_features, "_bdm_tail_is", None) is temb and centers_features.shape[1] > width:
+                # the caller concatenated [features, temb] (denoiser._decode marks it): the interpolated embedding is the
+                # tail of `up` -- the same kernel on the same rows, so the same bits -- and needs no second interpolation
+                up_temb = up[:, -width:, :]
+            else:
+                up_temb = F.three_nn_interpolate(temb, idx, w)
         if skip is not None:
             first = self.mlp.layers[0]
             if (_layers._fusable(up) and _layers._pointwise(first) and isinstance(first, nn.Conv1d)

@@ -83,9 +83,10 @@ def test_denoiser_runs_on_oracle_backend(oracle_backend):
     assert names.count("furthest_point_sampling") == 4
     assert names.count("ball_query") == 4
     # the reference does 12 groupings and 8 three-NN calls per forward; the mirror drops the 4 groupings
-    # of the point-constant time embedding and searches once per FP stage
+    # of the point-constant time embedding, searches once per FP stage and interpolates once per FP stage (the
+    # interpolated time embedding is the tail of the interpolated [features, temb])
     assert names.count("grouping_forward") == 8
-    assert names.count("three_nn_search") == 4 and names.count("three_nn_interpolate") == 8
+    assert names.count("three_nn_search") == 4 and names.count("three_nn_interpolate") == 4
 
 
 @needs_ref
@@ -230,3 +231,38 @@ def test_concat_conv_widens_a_misaligned_channel_slice():
     scale = want.abs().max().item()
     assert (plain - want).abs().max().item() <= 1e-5 * scale
     assert (wide - want).abs().max().item() <= 1e-5 * scale
+
+
+def test_fp_stages_reuse_the_interpolated_embedding(oracle_backend, monkeypatch):
+    """denoiser._decode marks cat([features, temb]); PointNetFPModule then takes the interpolated time embedding from the
+    tail of the interpolated concatenation instead of interpolating temb a second time: same bits, half the calls."""
+    import bdm_b200.functional as F
+    from bdm_b200 import denoiser
+    from bdm_b200.denoiser import PVCNN2_PC2
+    torch.manual_seed(3)
+    net = PVCNN2_PC2(num_classes=3, embed_dim=64, extra_feature_channels=5).eval()
+    x, t = _small_inputs(seed=7)
+    calls = []
+    original = F.three_nn_interpolate
+
+    def counting(feats, idx, w):
+        calls.append(int(feats.shape[1]))
+        return original(feats, idx, w)
+
+    monkeypatch.setattr(F, "three_nn_interpolate", counting)
+    with torch.no_grad():
+        got = net(x, t)
+    marked_calls = list(calls)
+    calls.clear()
+
+    def unmarked_decode(fp_layers, features, coords, temb, coords_per_stage, skips_per_stage):
+        for fp_idx, stage in enumerate(fp_layers):
+            features, coords, temb = stage((coords_per_stage[-1 - fp_idx], coords, torch.cat([features, temb], dim=1),
+                                            skips_per_stage[-1 - fp_idx], temb))
+        return features
+
+    monkeypatch.setattr(denoiser, "_decode", unmarked_decode)
+    with torch.no_grad():
+        want = net(x, t)
+    assert torch.equal(got, want)
+    assert len(marked_calls) == len(net.fp_layers) and len(calls) == 2 * len(net.fp_layers)

@@ -275,6 +275,8 @@ int bdm_attention_qkv(int b, int c, int t, const float *qkv, int ld, const float
  *   max_over_u == 0: y f32[b,c,s]; tile_sums (or NULL) f32[b*c, bdm_groupnorm_tiles(b,c,s)] receives
  *                    per-tile sums of y (sum them for the channel total).
  *   max_over_u == U (power of two, 4..128, divides s): y f32[b,c,s/U] = max over each run of U values.
+ *                    (evaluated as max(act(largest input), act(smallest input)) of the run: the affine map is
+ *                    monotone and Swish unimodal, so one of the two extremes carries the maximum)
  * workspace: bdm_groupnorm_workspace_bytes(b,c,s) bytes, 16-byte aligned. */
 size_t bdm_groupnorm_workspace_bytes(int b, int c, long long s);
 int bdm_groupnorm_tiles(int b, int c, long long s);
